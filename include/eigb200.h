@@ -1,0 +1,187 @@
+/*
+ * eigb200.h -- C ABI of libeigb200.so: the B200 (sm_100a) implementation of the eigenvalue-analysis hot path of
+ * "Task-Level Insights from Eigenvalues across Sequence Models" (reference: analysis/eval_eig.py + models/).
+ *
+ * The reference has no FFI of its own (it is pure Python); each entry point below replaces ONE operator
+ * boundary of the reference and cites it.  Conventions, identical for every function:
+ *
+ *   - extern "C", plain pointers and sizes, no framework types.  `stream` is a cudaStream_t passed as void*.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; nothing is allocated or freed here;
+ *     scratch is passed in by the caller (sizes documented per function).
+ *   - calls only ENQUEUE work on `stream` and return; no host synchronisation, no hidden streams.
+ *   - return value: 0 on success, negative EIGB200_E* on failure; eigb200_last_error() gives a thread-local message.
+ *   - tensors are row-major and dense unless a row stride (`ld*`, in elements) is given.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with EIGB200_ECUDA.
+ *
+ * Bin-count layout shared by all histogram outputs ("counts"):  int32 [..., EIGB200_NSLOT = 8]
+ *   slots 0 .. nthr   : the nthr+1 radius bins of threshold_analysis (analysis/eval_eig.py:335-362):
+ *                       bin 0 = 0 <= v <= thr[0]; bin j = thr[j-1] <= v <= thr[j] (closed on both ends, so a value equal
+ *                       to a threshold is counted twice); bin nthr = v > thr[nthr-1].   nthr <= 6.
+ *   slot 7            : number of values whose PHASE falls in the first phase bin [0, thr_phase[0]]: for the real
+ *                       non-negative Mamba-2 eigenvalues that is "not NaN" (eval_eig.py:614-618), for attention eta it is
+ *                       "finite" because the reference bins 0*eta (eval_eig.py:673-674).
+ *   counts are ACCUMULATED with integer atomics: zero the buffer first (eigb200_zero_i32 or cudaMemsetAsync).
+ *
+ * compare_mode selects the NumPy promotion the threshold compare reproduces:
+ *   EIGB200_CMP_F64 (NumPy >= 2: value widened to float64)  |  EIGB200_CMP_F32 (pinned numpy 1.24.1: threshold rounded
+ *   to the value's float32).  They differ only for values within 1 ulp of an edge.
+ */
+#ifndef EIGB200_H_
+#define EIGB200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EIGB200_VERSION 100
+#define EIGB200_NSLOT 8
+
+enum { EIGB200_OK = 0, EIGB200_EINVAL = -1, EIGB200_ECUDA = -2, EIGB200_EUNSUPPORTED = -3 };
+enum { EIGB200_CMP_F64 = 0, EIGB200_CMP_F32 = 1 };
+/* norm_fn of get_eig_att_norm (analysis/eval_eig.py:142-151) */
+enum { EIGB200_NORM_EXP = 0, EIGB200_NORM_ELU = 1, EIGB200_NORM_SOFTPLUS = 2, EIGB200_NORM_SIGMOID = 3 };
+/* ratio orientation for eigb200_ratio_hist */
+enum { EIGB200_RATIO_NONE = 0, EIGB200_RATIO_NEXT_OVER_CUR = 1, EIGB200_RATIO_CUR_OVER_NEXT = 2 };
+/* element types */
+enum { EIGB200_F32 = 0, EIGB200_F64 = 1, EIGB200_BF16 = 2 };
+/* epilogues of eigb200_linear */
+enum { EIGB200_EPI_NONE = 0, EIGB200_EPI_GELU = 1, EIGB200_EPI_GLU_RESIDUAL = 2, EIGB200_EPI_RESIDUAL = 3 };
+/* math mode of eigb200_linear */
+enum { EIGB200_GEMM_AUTO = 0, EIGB200_GEMM_SIMT_F32 = 1, EIGB200_GEMM_TC_3XTF32 = 2, EIGB200_GEMM_TC_TF32 = 3 };
+
+int         eigb200_version(void);
+const char* eigb200_last_error(void);
+/* sm_count / cc of device `dev`; EIGB200_ECUDA if there is no CUDA device. */
+int         eigb200_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor);
+/* cudaSetDevice for this library's (statically linked) CUDA runtime; call it from the thread that launches. */
+int         eigb200_set_device(int dev);
+int         eigb200_zero_i32(void* stream, int32_t* d_buf, size_t n);
+
+/* ---- K1: fused gate-projection -> discretisation -> eigenvalue -> bin counts --------------------------------------
+ * Replaces get_eig_mamba2(x, layer) (analysis/eval_eig.py:176-190) + the radius/phase threshold_analysis of its
+ * output (:605-618, :335-362).  lambda[b,t,h] = exp(softplus(x[b,t,:] . W_dt[h,:] + dt_bias[h]) * -exp(A_log[h])).
+ *   d_x      (B,T,D) float32 (x_dtype EIGB200_F32) or bfloat16 (EIGB200_BF16), D % 4 == 0 (bf16: D % 8 == 0), 16-byte aligned
+ *   d_W_dt   (H,D)   float32: rows [d_inner + 2*ngroups*d_state, +nheads) of in_proj.weight (models/mamba.py:62-64)
+ *   d_lam    (B,T,H) float32 out, may be NULL (statistics only)
+ *   d_counts (B,H,8) int32 accumulated, may be NULL */
+int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
+                       const float* d_W_dt, const float* d_dt_bias, const float* d_A_log, int H,
+                       float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+
+/* get_eig_mamba2_LTI (analysis/eval_eig.py:192-205): lambda[h] = exp(beta[h] * -softplus(A[h])), broadcast over (B,T).
+ * d_lam (B,T,H) may be NULL; d_counts (B,H,8) accumulated. */
+int eigb200_mamba2_lti_eig(void* stream, const float* d_A, const float* d_beta, int64_t B, int64_t T, int H,
+                           float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+
+/* ---- K1': normalised-attention gate  n[b,t,h] = exp(-norm_fn(x . W_n[h] + b_n[h] (+ offset[h])))  in float32 --------
+ * First half of get_eig_att_norm (analysis/eval_eig.py:154-163); W_n/b_n are rows [D + 2*d_qk, +H) of Wvqkn
+ * (models/norm_attention.py:201-203, :233-235); d_offset may be NULL.  d_n (B,T,H) float32 out.
+ * Follow with eigb200_ratio_hist(..., EIGB200_F32, EIGB200_RATIO_NEXT_OVER_CUR) for eta (:165-169). */
+int eigb200_normattn_gate(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
+                          const float* d_W_n, const float* d_b_n, const float* d_offset, int H, int norm_fn,
+                          float* d_n);
+
+/* ---- K1'': linear-attention normaliser  nu[b,t,h] = phi(q_t) . sum_{s<=t} phi(k_s),  phi = elu + 1 -------------------
+ * O(T) form of the (B,T,T,H) score tensor of get_eig_att_linear (analysis/eval_eig.py:109-126); prefix sum and dot product
+ * in float64.  q/k: raw projections, element (b,t,h,i) at d_q[(b*T + t)*ld + h*d + i] (so they can live inside the
+ * Wqkv output, q at column 0 and k at column d_qk).  d_nu (B,T,H) float64 out.
+ * Follow with eigb200_ratio_hist(..., EIGB200_F64, EIGB200_RATIO_CUR_OVER_NEXT) (:127-130). */
+int eigb200_linattn_nu(void* stream, const float* d_q, const float* d_k, int64_t ld, int64_t B, int64_t T, int H, int d,
+                       double* d_nu);
+
+/* Softmax-attention normaliser with the reference's multiplicative-mask quirk (analysis/eval_eig.py:57-90):
+ * m_t = max(max_{s<=t} q_t.k_s, 0 if t<T-1);  nu_t = sum_{s<=t} exp(q_t.k_s - m_t) + (T-1-t).  Streaming, no (B,T,T,H) tensor.
+ * d_nu (B,T,H) float64, d_m (B,T,H) float32.  eta_t = nu_t/nu_{t+1} * exp(m_t - m_{t+1}) is formed by eigb200_softmax_eta. */
+int eigb200_softmax_nu(void* stream, const float* d_q, const float* d_k, int64_t ld, int64_t B, int64_t T, int H, int d,
+                       double* d_nu, float* d_m);
+int eigb200_softmax_eta(void* stream, const double* d_nu, const float* d_m, int64_t B, int64_t T, int H,
+                        double* d_eta, int32_t* d_counts, const double* thresholds, int nthr);
+
+/* ---- ratios + threshold statistics ----------------------------------------------------------------------------------
+ * a: (B,N,inner) of `dtype` (EIGB200_F32 / EIGB200_F64).  mode NONE: v = a[b,n,i] (N values per (b,i));
+ * NEXT_OVER_CUR: v = z(a[b,n+1,i]) / z(a[b,n,i]); CUR_OVER_NEXT: v = z(a[b,n,i]) / z(a[b,n+1,i])  (N-1 values),
+ * z(u) = 2e-23 if u == 0 else u (analysis/eval_eig.py:127, :167), computed in float64.
+ * d_out: values written as float64 (ratio modes) -- (B,N-1,inner), may be NULL.   d_counts (B,inner,8) accumulated.
+ * With mode NONE this is threshold_analysis itself (analysis/eval_eig.py:335-362) for a (B,N,H*L) array. */
+int eigb200_ratio_hist(void* stream, const void* d_a, int dtype, int mode, int64_t B, int64_t N, int64_t inner,
+                       double* d_out, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+
+/* Batch moments of the bin counts: sum_b c and sum_b c^2 (int64) -- the only cross-sample (and cross-GPU) quantities
+ * behind np.mean / np.std over the batch axis (analysis/eval_eig.py:620-623, :677-680).  d_counts (B,inner,8);
+ * d_sum, d_sumsq (inner,8) int64, overwritten. */
+int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq);
+
+/* ---- K2a: diagonal complex recurrence  h_t = lam * h_{t-1} + Bu_t  ---------------------------------------------------
+ * What jax.lax.associative_scan(binary_operator_diag, (Lambda_elements, Bu_elements)) evaluates (models/lru.py:14-19, :95;
+ * models/s5.py:51-62, :82, :85 with reverse).  complex64 as interleaved (re,im) float pairs.
+ * d_lam (P), d_Bu (B,T,P), d_h (B,T,P); reverse != 0 runs t = T-1..0. */
+int eigb200_diag_scan(void* stream, const float* d_lam, const float* d_Bu, float* d_h, int64_t B, int64_t T, int P, int reverse);
+
+/* ---- K2b: SSD selective scan --------------------------------------------------------------------------------------------
+ * mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=D, z=None) at its call site models/mamba.py:138-150:
+ *   h_t[h,p,n] = exp(dt_t[h] A[h]) h_{t-1}[h,p,n] + dt_t[h] B_t[g,n] x_t[h,p];   y_t[h,p] = sum_n C_t[g,n] h_t[h,p,n] + D[h] x_t[h,p]
+ * x (B,T,H*P) row stride ldx; dt (B,T,H) (already softplus'ed); Bm, Cm (B,T,G*N) row stride ldbc; y (B,T,H*P) row stride ldy.
+ * d_final_state (B,H,P,N) may be NULL. */
+int eigb200_ssd_scan(void* stream, const float* d_x, int64_t ldx, const float* d_dt, const float* d_A,
+                     const float* d_Bm, const float* d_Cm, int64_t ldbc, const float* d_D,
+                     float* d_y, int64_t ldy, float* d_final_state,
+                     int64_t B, int64_t T, int H, int P, int G, int N);
+
+/* Fused depthwise causal conv (k taps, padding k-1, truncate) + SiLU on xBC, softplus(dt + dt_bias), then the SSD scan, reading
+ * the in_proj output once (models/mamba.py:123-150).  d_xbcdt (B,T,ldz) = [x (H*P) | B (G*N) | C (G*N) | dt (H)];
+ * d_conv_w (H*P + 2*G*N, k), d_conv_b (H*P + 2*G*N); kconv <= 4 (0 = no conv).  y (B,T,H*P) row stride ldy. */
+int eigb200_mamba_conv_ssd(void* stream, const float* d_xbcdt, int64_t ldz, const float* d_conv_w, const float* d_conv_b, int kconv,
+                           const float* d_dt_bias, const float* d_A_log, const float* d_D,
+                           float* d_y, int64_t ldy, int64_t B, int64_t T, int H, int P, int G, int N);
+
+/* ---- K3: S4 DPLR discretisation + batched nonsymmetric eigenvalues ---------------------------------------------------
+ * eigb200_dplr_abar: A-bar of discrete_DPLR (analysis/eval_eig.py:254-274; models/s4.py:16-36) for nmat parameter sets:
+ * d_Lambda, d_P, d_Q (nmat,N) complex64, d_step (nmat) float32 -> d_Abar (nmat,N,N) complex64 row-major.  N <= 64.
+ * eigb200_eigvals_c64: np.linalg.eigvals(Ad) (analysis/eval_eig.py:296) for nmat dense complex64 N x N matrices (N <= 64), one warp
+ * per matrix: Hessenberg reduction + shifted QR.  d_A is overwritten.  d_eig (nmat,N) complex64 (unordered, like LAPACK);
+ * d_info (nmat) int32: 0 = converged, >0 = number of eigenvalues not converged. */
+int eigb200_dplr_abar(void* stream, const float* d_Lambda, const float* d_P, const float* d_Q, const float* d_step,
+                      int64_t nmat, int N, float* d_Abar);
+int eigb200_eigvals_c64(void* stream, float* d_A, int64_t nmat, int N, float* d_eig, int32_t* d_info);
+
+/* ---- K4 + block glue: what propagates activations from one layer to the next ---------------------------------------
+ * eigb200_linear: C = epilogue(A W^T + bias) -- nn.Linear (models/mamba.py:64,109; common.py:53; attention.py:120; ...).
+ *   A (M,K) row stride lda, W (N,K) dense (torch layout), bias (N) or NULL, C (M,Nout) row stride ldc.
+ *   EPI_NONE: Nout = N.  EPI_GELU: exact-erf GELU (models/mamba.py:318, :333).  EPI_RESIDUAL: C = A W^T + bias + R.
+ *   EPI_GLU_RESIDUAL: N = 2*Nout, C = z[:, :Nout] * sigmoid(z[:, Nout:]) + R  (GLU, models/common.py:55-58, + skip, mamba.py:337),
+ *   R (M,Nout) row stride ldr (NULL = no residual).
+ *   mode: SIMT_F32 = fp32 FFMA; TC_3XTF32 = tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy); AUTO picks.
+ *   d_workspace/workspace_bytes: eigb200_linear_workspace_bytes(N, K) bytes (split weights for the tensor-core path). */
+size_t eigb200_linear_workspace_bytes(int N, int K);
+int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
+                   float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
+                   int64_t M, int N, int K, int epilogue, int mode, void* d_workspace, size_t workspace_bytes);
+
+/* TokenEmbeddings.forward (models/common.py:160-176): out[b,t,:] = word[ids[b,t],:] (+ pos[t,:] if d_pos != NULL). ids int64. */
+int eigb200_embedding(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,
+                      int64_t B, int64_t T, int D, int64_t vocab);
+/* nn.LayerNorm over the last axis, eps inside the sqrt, biased variance (models/mamba.py:321; transformer.py:84). */
+int eigb200_layernorm(void* stream, const float* d_x, const float* d_w, const float* d_b, float eps, float* d_out, int64_t rows, int D);
+/* Depthwise causal conv1d (k taps, padding k-1, truncated to T) + SiLU over x (B,T,C) row stride ldx -> out row stride ldo
+ * (models/attention.py:153-156; norm_attention.py:236-239).  k <= 8. */
+int eigb200_conv_silu(void* stream, const float* d_x, int64_t ldx, const float* d_w, const float* d_b, int k,
+                      float* d_out, int64_t ldo, int64_t B, int64_t T, int C);
+/* Causal linear attention in O(T) form -- SelfLinAttention / SelfNormAttention (models/attention.py:63-83; norm_attention.py:61-89).
+ * q,k (B,T,H,d), v (B,T,H,dv) inside one projection buffer of row stride ld; phi_elu != 0 applies elu+1 to q,k.
+ * normalise: 1 = divide by phi(q_t).sum_s phi(k_s) (linear attention), 0 = multiply by d_gate[b,t,h] (norm attention, may be NULL).
+ * kscale multiplies k (scale_B).  out (B,T,H*dv) row stride ldo. */
+int eigb200_linattn_forward(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld,
+                            const float* d_gate, int phi_elu, int normalise, float kscale,
+                            float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv);
+/* elementwise helpers of the transformer block (models/transformer.py:90-111): out = a + b; out = y * silu(z) etc. */
+int eigb200_add(void* stream, const float* d_a, const float* d_b, float* d_out, int64_t n);
+int eigb200_mul_silu(void* stream, const float* d_y, const float* d_z, float* d_out, int64_t n);
+int eigb200_gelu(void* stream, const float* d_x, float* d_out, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIGB200_H_ */

@@ -1,0 +1,109 @@
+// common.cuh -- shared device/host helpers for libeigb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/eigb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libeigb200 is written for sm_100a (B200) only"
+#endif
+
+namespace eigb200 {
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+int  num_sms();
+
+#define EIGB_CHECK_ARG(cond, ...)                                  \
+  do { if (!(cond)) { ::eigb200::set_error(__VA_ARGS__); return EIGB200_EINVAL; } } while (0)
+#define EIGB_CUDA(call)                                            \
+  do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ::eigb200::cuda_fail(e__, #call); } while (0)
+#define EIGB_LAUNCH_CHECK(name)                                    \
+  do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return ::eigb200::cuda_fail(e__, name); } while (0)
+
+// ---- threshold edges ------------------------------------------------------------------------------------------
+// nb = nthr + 1 bins.  Bins 0..nb-2 are closed intervals [lo, hi]; bin nb-1 is v > gt.
+// For float32 values the edges are chosen on the host so that a float32 compare reproduces either the float64
+// compare NumPy >= 2 performs (lo = ceil32(thr), hi = floor32(thr)) or the float32 compare of NumPy 1.24.
+struct EdgesF { float lo[7]; float hi[7]; float gt; int nb; };
+struct EdgesD { double lo[7]; double hi[7]; double gt; int nb; };
+int make_edges_f(const double* thr, int nthr, int compare_mode, EdgesF* e);
+int make_edges_d(const double* thr, int nthr, EdgesD* e);
+
+// ---- device helpers -------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// torch.nn.functional.softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
+// torch.nn.functional.elu(alpha=1)
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + expf(-z)); }
+// nn.GELU() exact form
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f)); }
+
+// Per-thread bin bookkeeping.  c[0..6]: closed bins (unused ones have lo=+inf, hi=-inf so they never fire),
+// c[7]: the open last bin (v > gt), c[8]: phase-bin-0 count.  flush_bins() maps them onto the 8 output slots.
+#define EIGB_NCNT 9
+__device__ __forceinline__ void bin_f32(float v, const EdgesF& e, int (&c)[EIGB_NCNT]) {
+#pragma unroll
+  for (int j = 0; j < 7; ++j) c[j] += (v >= e.lo[j] && v <= e.hi[j]) ? 1 : 0;
+  c[7] += (v > e.gt) ? 1 : 0;
+}
+__device__ __forceinline__ void bin_f64(double v, const EdgesD& e, int (&c)[EIGB_NCNT]) {
+#pragma unroll
+  for (int j = 0; j < 7; ++j) c[j] += (v >= e.lo[j] && v <= e.hi[j]) ? 1 : 0;
+  c[7] += (v > e.gt) ? 1 : 0;
+}
+// slot index of per-thread counter j for a histogram with nb bins
+__device__ __forceinline__ int slot_of(int j, int nb) { return j < 7 ? j : (j == 7 ? nb - 1 : 7); }
+
+// Butterfly "transpose-reduce": every lane holds N partial sums v[0..N); on return v[0] is the full 32-lane sum of
+// partial index (lane >> (5 - log2 N)).  N*(1 - 1/N) + (5 - log2 N) shuffles instead of 5*N.
+template <int N>
+__device__ __forceinline__ float transpose_reduce(float (&v)[N], int lane) {
+  static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two <= 32");
+  int off = 16;
+#pragma unroll
+  for (int m = N / 2; m >= 1; m >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const float send = up ? v[i] : v[i + m];
+      const float keep = up ? v[i + m] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+template <int N> struct Log2 { static constexpr int value = 1 + Log2<N / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+#endif  // __CUDACC__
+
+}  // namespace eigb200

@@ -1,0 +1,397 @@
+// k1_eigen.cu -- K1 family: fused gate-projection -> discretisation -> eigenvalue -> on-device bin counts.
+//
+// Reference operators replaced (see include/eigb200.h for the per-entry citations):
+//   get_eig_mamba2 / get_eig_mamba2_LTI / get_eig_att_norm (first half)   analysis/eval_eig.py:137-205
+//   threshold_analysis                                                      analysis/eval_eig.py:335-362
+//
+// Roofline: HBM.  Algorithmic bytes per eigenvalue = D*s/H (read x once) + 4 (write lambda); ~0.5 flop/B.
+// Data layout: x (B,T,D) row-major, rows 16-byte aligned.  One warp owns a contiguous run of rows of one sequence,
+// walks it R=4 rows at a time (4 independent 128-bit streaming loads per lane in flight per 128 columns), keeps the
+// H gate rows of W in shared memory (one LDS.128 feeds 4 rows), reduces the R*HT partial dot products with a
+// butterfly transpose-reduce so that lane (r,h) ends up with exactly one full dot product, applies the
+// transcendental epilogue once per eigenvalue, stores lambda coalesced and bins it in registers.  Bin counts are
+// flushed once per CTA with integer atomics (order independent => bit reproducible).
+#include "common.cuh"
+
+namespace eigb200 {
+
+constexpr int K1_R = 4;          // rows per warp iteration
+constexpr int K1_WARPS = 4;      // warps per CTA
+
+enum { K1_EPI_MAMBA2 = 0, K1_EPI_NORMGATE = 1 };
+
+struct K1Params {
+  const void* x; const float* W; const float* p0; const float* p1; const float* p2;   // W (H,D); per-head vectors
+  float* out; int* counts;
+  int T, D, H, rows_per_warp, norm_fn;
+  EdgesF e;
+};
+
+template <bool BF16> struct XLoad;
+template <> struct XLoad<false> {
+  static constexpr int VEC = 4;                      // floats per 128-bit load
+  __device__ static __forceinline__ void load(const void* row, int c, float (&v)[8]) {
+    float4 t = ldg_stream_f4(reinterpret_cast<const float4*>(row) + c);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct XLoad<true> {
+  static constexpr int VEC = 8;                      // bf16 per 128-bit load
+  __device__ static __forceinline__ void load(const void* row, int c, float (&v)[8]) {
+    uint4 t = ldg_stream_u4(reinterpret_cast<const uint4*>(row) + c);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+
+__device__ __forceinline__ float norm_fn_apply(int fn, float z) {
+  switch (fn) {
+    case EIGB200_NORM_EXP: return expf(z);
+    case EIGB200_NORM_ELU: return elu_f(z);
+    case EIGB200_NORM_SOFTPLUS: return softplus_f(z);
+    default: return sigmoid_f(z);
+  }
+}
+
+template <int HT, bool BF16, int EPI>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p) {
+  constexpr int VEC = XLoad<BF16>::VEC;
+  constexpr int NV = K1_R * HT;                       // partial sums per lane
+  constexpr int SH = 5 - Log2<NV>::value;             // lanes sharing one result = 1 << SH
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                                   // [HT][D]
+  __shared__ int hist[HT][EIGB200_NSLOT];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int hbase = blockIdx.z * HT;
+  const int D = p.D, T = p.T, H = p.H;
+
+  for (int i = threadIdx.x; i < HT * D; i += blockDim.x) {
+    const int h = i / D, c = i - h * D;
+    Ws[i] = (hbase + h < H) ? p.W[(size_t)(hbase + h) * D + c] : 0.f;
+  }
+  if (threadIdx.x < HT * EIGB200_NSLOT) (&hist[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+
+  // this lane's (row-in-group, head) after the transpose-reduce
+  const int idx = lane >> SH;
+  const int r_own = idx / HT, h_own = idx - r_own * HT;
+  const int hg = hbase + h_own;
+  const bool lead = (lane & ((1 << SH) - 1)) == 0 && hg < H;
+  float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+  if (hg < H) {
+    if (EPI == K1_EPI_MAMBA2) { e0 = p.p0[hg]; e1 = -expf(p.p1[hg]); }               // dt_bias, A = -exp(A_log)
+    else { e0 = p.p0[hg] + (p.p2 ? p.p2[hg] : 0.f); }                                  // bias (+ offset)
+  }
+  // NOTE: the reference adds bias inside the Linear and the offset afterwards, both in fp32: (dot + b) + offset.
+  const float bias_only = (EPI == K1_EPI_NORMGATE && hg < H) ? p.p0[hg] : 0.f;
+  const float offs_only = (EPI == K1_EPI_NORMGATE && hg < H && p.p2) ? p.p2[hg] : 0.f;
+  (void)e0;
+
+  int cnt[EIGB_NCNT];
+#pragma unroll
+  for (int j = 0; j < EIGB_NCNT; ++j) cnt[j] = 0;
+
+  const int wid = blockIdx.x * K1_WARPS + warp;
+  const int t0 = wid * p.rows_per_warp;
+  const int t1 = min(T, t0 + p.rows_per_warp);
+  const size_t row_bytes = (size_t)D * (BF16 ? 2 : 4);
+  const char* xb = reinterpret_cast<const char*>(p.x) + (size_t)b * T * row_bytes;
+  const int nvec = D / VEC;
+  const float4* Ws4 = reinterpret_cast<const float4*>(Ws);
+
+  for (int t = t0; t < t1; t += K1_R) {
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    const char* rows[K1_R];
+#pragma unroll
+    for (int r = 0; r < K1_R; ++r) rows[r] = xb + (size_t)min(t + r, t1 - 1) * row_bytes;   // clamp: tail rows re-read a valid row
+#pragma unroll 2
+    for (int c = lane; c < nvec; c += 32) {
+      float xv[K1_R][8];
+#pragma unroll
+      for (int r = 0; r < K1_R; ++r) XLoad<BF16>::load(rows[r], c, xv[r]);
+#pragma unroll
+      for (int h = 0; h < HT; ++h) {
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) {
+          const float4 w = Ws4[(h * D + c * VEC) / 4 + q];
+#pragma unroll
+          for (int r = 0; r < K1_R; ++r) {
+            float a = acc[r * HT + h];
+            a = fmaf(xv[r][4 * q + 0], w.x, a);
+            a = fmaf(xv[r][4 * q + 1], w.y, a);
+            a = fmaf(xv[r][4 * q + 2], w.z, a);
+            a = fmaf(xv[r][4 * q + 3], w.w, a);
+            acc[r * HT + h] = a;
+          }
+        }
+      }
+    }
+    const float dot = transpose_reduce<NV>(acc, lane);
+    const int row = t + r_own;
+    if (lead && row < t1) {
+      float val;
+      if (EPI == K1_EPI_MAMBA2) {
+        const float dt = softplus_f(dot + e0);
+        val = expf(dt * e1);
+      } else {
+        const float raw = (dot + bias_only) + offs_only;
+        val = expf(-norm_fn_apply(p.norm_fn, raw));
+      }
+      if (p.out) p.out[((size_t)b * T + row) * H + hg] = val;
+      if (EPI == K1_EPI_MAMBA2) {
+        bin_f32(val, p.e, cnt);
+        cnt[8] += (val == val) ? 1 : 0;                 // arctan2(0, lambda) = 0 unless lambda is NaN
+      }
+    }
+  }
+
+  if (EPI == K1_EPI_MAMBA2 && p.counts) {
+    if (lead) {
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j)
+        if (cnt[j]) atomicAdd(&hist[h_own][slot_of(j, p.e.nb)], cnt[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < HT * EIGB200_NSLOT) {
+      const int h = threadIdx.x / EIGB200_NSLOT, s = threadIdx.x % EIGB200_NSLOT;
+      const int v = hist[h][s];
+      if (v && hbase + h < H) atomicAdd(&p.counts[((size_t)b * H + hbase + h) * EIGB200_NSLOT + s], v);
+    }
+  }
+}
+
+template <bool BF16, int EPI>
+static int launch_k1(cudaStream_t st, const K1Params& p, int64_t B) {
+  int ht = 1;
+  while (ht < p.H && ht < 8) ht <<= 1;
+  const int hgroups = (p.H + ht - 1) / ht;
+  // rows per warp: aim for >= 8 CTAs per SM overall, but never fewer than 2 iterations per warp
+  const int64_t target_ctas = (int64_t)num_sms() * 16;
+  int ctas_per_seq = (int)((target_ctas + B * hgroups - 1) / (B * hgroups));
+  const int max_cps = (p.T + K1_WARPS * 2 * K1_R - 1) / (K1_WARPS * 2 * K1_R);
+  if (ctas_per_seq > max_cps) ctas_per_seq = max_cps;
+  if (ctas_per_seq < 1) ctas_per_seq = 1;
+  K1Params q = p;
+  int rpw = (p.T + ctas_per_seq * K1_WARPS - 1) / (ctas_per_seq * K1_WARPS);
+  rpw = (rpw + K1_R - 1) / K1_R * K1_R;
+  q.rows_per_warp = rpw;
+  ctas_per_seq = (p.T + rpw * K1_WARPS - 1) / (rpw * K1_WARPS);
+  dim3 grid(ctas_per_seq, (unsigned)B, hgroups), block(K1_WARPS * 32);
+  EIGB_CHECK_ARG(B <= 65535, "k1: batch %lld exceeds grid.y limit 65535; split the call", (long long)B);
+  const size_t smem = (size_t)ht * p.D * sizeof(float);
+#define K1_CASE(HT_)                                                                                              \
+  case HT_: {                                                                                                     \
+    if (smem > 48 * 1024)                                                                                         \
+      EIGB_CUDA(cudaFuncSetAttribute(k1_gate_kernel<HT_, BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k1_gate_kernel<HT_, BF16, EPI><<<grid, block, smem, st>>>(q);                                                 \
+  } break;
+  switch (ht) { K1_CASE(1) K1_CASE(2) K1_CASE(4) K1_CASE(8) default: set_error("k1: bad head tile"); return EIGB200_EINVAL; }
+#undef K1_CASE
+  EIGB_LAUNCH_CHECK("k1_gate_kernel");
+  return EIGB200_OK;
+}
+
+// ---- LTI: parameter-only eigenvalues broadcast over (B,T) ------------------------------------------------------
+__global__ void k1_lti_kernel(const float* A, const float* beta, int64_t BT, int T, int H, float* lam, int* counts, EdgesF e) {
+  // one thread per head computes lambda and its bins once; the broadcast store is a plain grid-stride fill
+  __shared__ float lam_s[256];
+  for (int h = threadIdx.x; h < H; h += blockDim.x) lam_s[h] = expf(beta[h] * -softplus_f(A[h]));
+  __syncthreads();
+  if (lam) {
+    const int64_t n = BT * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) lam[i] = lam_s[i % H];
+  }
+  if (counts) {
+    const int64_t Bn = BT / T;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Bn * H; i += (int64_t)gridDim.x * blockDim.x) {
+      const int h = (int)(i % H);
+      int c[EIGB_NCNT];
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j) c[j] = 0;
+      bin_f32(lam_s[h], e, c);
+      c[8] = (lam_s[h] == lam_s[h]) ? 1 : 0;
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j)
+        if (c[j]) atomicAdd(&counts[i * EIGB200_NSLOT + slot_of(j, e.nb)], c[j] * T);
+    }
+  }
+}
+
+// ---- ratios + bins over a (B,N,inner) array -------------------------------------------------------------------------
+struct RatioParams {
+  const void* a; double* out; int* counts;
+  int64_t N, inner; int mode; int chunk;             // chunk = values of n handled per CTA
+  EdgesF ef; EdgesD ed; int cmp_f32_on_f32;
+};
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) ratio_hist_kernel(const RatioParams p) {
+  // thread -> fixed inner index i (stride S is a multiple of `inner` when inner <= 256) so that bin counters live in registers
+  extern __shared__ int hist_s[];                     // [min(inner,256)][8]
+  const int64_t inner = p.inner;
+  const int b = blockIdx.y;
+  const int64_t Nout = p.mode == EIGB200_RATIO_NONE ? p.N : p.N - 1;
+  const int64_t n0 = (int64_t)blockIdx.x * p.chunk, n1 = min(Nout, n0 + p.chunk);
+  const TIn* a = reinterpret_cast<const TIn*>(p.a) + (size_t)b * p.N * inner;
+  const bool small = inner <= 256;
+  const int per = small ? (int)(256 / inner) : 1;     // n-values handled per CTA step
+  const int S = small ? per * (int)inner : 256;
+  if (small) { for (int i = threadIdx.x; i < inner * EIGB200_NSLOT; i += blockDim.x) hist_s[i] = 0; __syncthreads(); }
+  int cnt[EIGB_NCNT];
+#pragma unroll
+  for (int j = 0; j < EIGB_NCNT; ++j) cnt[j] = 0;
+  const int nb = p.ed.nb;
+  if ((int)threadIdx.x < S) {
+    const int64_t total = (n1 - n0) * inner;
+    for (int64_t k = threadIdx.x; k < total; k += S) {
+      const int64_t e = n0 * inner + k;
+      double v; float vf = 0.f;
+      if (p.mode == EIGB200_RATIO_NONE) {
+        v = (double)a[e]; vf = (float)a[e];
+      } else {
+        double u0 = (double)a[e], u1 = (double)a[e + inner];
+        if (u0 == 0.0) u0 = 2e-23;
+        if (u1 == 0.0) u1 = 2e-23;
+        v = p.mode == EIGB200_RATIO_NEXT_OVER_CUR ? u1 / u0 : u0 / u1;
+        if (p.out) p.out[(size_t)b * Nout * inner + e] = v;
+      }
+      int c[EIGB_NCNT];
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j) c[j] = 0;
+      if (sizeof(TIn) == 4 && p.mode == EIGB200_RATIO_NONE) bin_f32(vf, p.ef, c); else bin_f64(v, p.ed, c);
+      c[8] = (v - v == 0.0) ? 1 : 0;                   // finite: 0*v lands in the first phase bin (eval_eig.py:673-674)
+      if (small) {
+#pragma unroll
+        for (int j = 0; j < EIGB_NCNT; ++j) cnt[j] += c[j];
+      } else {
+        const int64_t i = e % inner;
+#pragma unroll
+        for (int j = 0; j < EIGB_NCNT; ++j)
+          if (c[j]) atomicAdd(&p.counts[((size_t)b * inner + i) * EIGB200_NSLOT + slot_of(j, nb)], c[j]);
+      }
+    }
+    if (small && p.counts) {
+      const int i = threadIdx.x % (int)inner;
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j)
+        if (cnt[j]) atomicAdd(&hist_s[i * EIGB200_NSLOT + slot_of(j, nb)], cnt[j]);
+    }
+  }
+  if (small && p.counts) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < inner * EIGB200_NSLOT; i += blockDim.x)
+      if (hist_s[i]) atomicAdd(&p.counts[(size_t)b * inner * EIGB200_NSLOT + i], hist_s[i]);
+  }
+}
+
+__global__ void count_moments_kernel(const int* counts, int64_t B, int64_t inner8, long long* sum, long long* sumsq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inner8) return;
+  long long s = 0, s2 = 0;
+  for (int64_t b = 0; b < B; ++b) { const long long c = counts[b * inner8 + i]; s += c; s2 += c * c; }
+  sum[i] = s; sumsq[i] = s2;
+}
+
+__global__ void zero_i32_kernel(int* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0;
+}
+
+}  // namespace eigb200
+
+using namespace eigb200;
+
+extern "C" int eigb200_zero_i32(void* stream, int32_t* d_buf, size_t n) {
+  EIGB_CHECK_ARG(d_buf || n == 0, "zero_i32: null buffer");
+  if (n == 0) return EIGB200_OK;
+  EIGB_CUDA(cudaMemsetAsync(d_buf, 0, n * sizeof(int32_t), (cudaStream_t)stream));
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
+                                  const float* d_W_dt, const float* d_dt_bias, const float* d_A_log, int H,
+                                  float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+  EIGB_CHECK_ARG(d_x && d_W_dt && d_dt_bias && d_A_log, "mamba2_eig: null input pointer");
+  EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && H > 0, "mamba2_eig: bad shape B=%lld T=%lld D=%d H=%d", (long long)B, (long long)T, D, H);
+  EIGB_CHECK_ARG(x_dtype == EIGB200_F32 || x_dtype == EIGB200_BF16, "mamba2_eig: x_dtype must be F32 or BF16");
+  EIGB_CHECK_ARG(D % (x_dtype == EIGB200_BF16 ? 8 : 4) == 0, "mamba2_eig: D=%d must be a multiple of %d (128-bit rows)", D, x_dtype == EIGB200_BF16 ? 8 : 4);
+  EIGB_CHECK_ARG(((uintptr_t)d_x & 15) == 0, "mamba2_eig: x must be 16-byte aligned");
+  EIGB_CHECK_ARG(T < (1LL << 31), "mamba2_eig: T too large");
+  K1Params p{};
+  p.x = d_x; p.W = d_W_dt; p.p0 = d_dt_bias; p.p1 = d_A_log; p.p2 = nullptr; p.out = d_lam; p.counts = d_counts;
+  p.T = (int)T; p.D = D; p.H = H; p.norm_fn = 0;
+  if (d_counts) { int rc = make_edges_f(thresholds, nthr, compare_mode, &p.e); if (rc) return rc; }
+  else { double one = 1.0; make_edges_f(&one, 1, 0, &p.e); }
+  return x_dtype == EIGB200_BF16 ? launch_k1<true, K1_EPI_MAMBA2>((cudaStream_t)stream, p, B)
+                                 : launch_k1<false, K1_EPI_MAMBA2>((cudaStream_t)stream, p, B);
+}
+
+extern "C" int eigb200_normattn_gate(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
+                                     const float* d_W_n, const float* d_b_n, const float* d_offset, int H, int norm_fn,
+                                     float* d_n) {
+  EIGB_CHECK_ARG(d_x && d_W_n && d_b_n && d_n, "normattn_gate: null pointer");
+  EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && H > 0, "normattn_gate: bad shape");
+  EIGB_CHECK_ARG(norm_fn >= EIGB200_NORM_EXP && norm_fn <= EIGB200_NORM_SIGMOID, "normalization function %d not implemented!", norm_fn);
+  EIGB_CHECK_ARG(x_dtype == EIGB200_F32 || x_dtype == EIGB200_BF16, "normattn_gate: x_dtype must be F32 or BF16");
+  EIGB_CHECK_ARG(D % (x_dtype == EIGB200_BF16 ? 8 : 4) == 0, "normattn_gate: D=%d must be a multiple of %d", D, x_dtype == EIGB200_BF16 ? 8 : 4);
+  EIGB_CHECK_ARG(((uintptr_t)d_x & 15) == 0, "normattn_gate: x must be 16-byte aligned");
+  K1Params p{};
+  p.x = d_x; p.W = d_W_n; p.p0 = d_b_n; p.p1 = nullptr; p.p2 = d_offset; p.out = d_n; p.counts = nullptr;
+  p.T = (int)T; p.D = D; p.H = H; p.norm_fn = norm_fn;
+  double one = 1.0; make_edges_f(&one, 1, 0, &p.e);
+  return x_dtype == EIGB200_BF16 ? launch_k1<true, K1_EPI_NORMGATE>((cudaStream_t)stream, p, B)
+                                 : launch_k1<false, K1_EPI_NORMGATE>((cudaStream_t)stream, p, B);
+}
+
+extern "C" int eigb200_mamba2_lti_eig(void* stream, const float* d_A, const float* d_beta, int64_t B, int64_t T, int H,
+                                      float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+  EIGB_CHECK_ARG(d_A && d_beta, "mamba2_lti_eig: null pointer");
+  EIGB_CHECK_ARG(B > 0 && T > 0 && H > 0 && H <= 256, "mamba2_lti_eig: bad shape (H <= 256)");
+  EdgesF e; double one = 1.0;
+  if (d_counts) { int rc = make_edges_f(thresholds, nthr, compare_mode, &e); if (rc) return rc; } else make_edges_f(&one, 1, 0, &e);
+  const int64_t n = B * T * H;
+  int grid = (int)((n + 255) / 256); if (grid > num_sms() * 8) grid = num_sms() * 8; if (grid < 1) grid = 1;
+  k1_lti_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_A, d_beta, B * T, (int)T, H, d_lam, d_counts, e);
+  EIGB_LAUNCH_CHECK("k1_lti_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_ratio_hist(void* stream, const void* d_a, int dtype, int mode, int64_t B, int64_t N, int64_t inner,
+                                  double* d_out, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+  EIGB_CHECK_ARG(d_a, "ratio_hist: null input");
+  EIGB_CHECK_ARG(dtype == EIGB200_F32 || dtype == EIGB200_F64, "ratio_hist: dtype must be F32 or F64");
+  EIGB_CHECK_ARG(mode >= EIGB200_RATIO_NONE && mode <= EIGB200_RATIO_CUR_OVER_NEXT, "ratio_hist: bad mode %d", mode);
+  EIGB_CHECK_ARG(B > 0 && inner > 0 && N > (mode == EIGB200_RATIO_NONE ? 0 : 1), "ratio_hist: bad shape");
+  EIGB_CHECK_ARG(B <= 65535, "ratio_hist: batch exceeds 65535; split the call");
+  RatioParams p{};
+  p.a = d_a; p.out = d_out; p.counts = d_counts; p.N = N; p.inner = inner; p.mode = mode;
+  int rc = make_edges_d(thresholds, nthr, &p.ed); if (rc) return rc;
+  rc = make_edges_f(thresholds, nthr, compare_mode, &p.ef); if (rc) return rc;
+  if (dtype == EIGB200_F32 && mode == EIGB200_RATIO_NONE && compare_mode == EIGB200_CMP_F64) { /* ef already encodes the f64 compare */ }
+  const int64_t Nout = mode == EIGB200_RATIO_NONE ? N : N - 1;
+  // CTAs per sequence: enough to fill the machine, at least ~2048 values per CTA
+  int64_t per_seq = ((int64_t)num_sms() * 8 + B - 1) / B;
+  const int64_t max_ps = (Nout * inner + 2047) / 2048;
+  if (per_seq > max_ps) per_seq = max_ps;
+  if (per_seq < 1) per_seq = 1;
+  p.chunk = (int)((Nout + per_seq - 1) / per_seq);
+  per_seq = (Nout + p.chunk - 1) / p.chunk;
+  dim3 grid((unsigned)per_seq, (unsigned)B);
+  const size_t smem = inner <= 256 ? (size_t)inner * EIGB200_NSLOT * sizeof(int) : 0;
+  if (dtype == EIGB200_F32) ratio_hist_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  else ratio_hist_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  EIGB_LAUNCH_CHECK("ratio_hist_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq) {
+  EIGB_CHECK_ARG(d_counts && d_sum && d_sumsq && B > 0 && inner > 0, "count_moments: bad arguments");
+  const int64_t n = inner * EIGB200_NSLOT;
+  count_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_counts, B, n, (long long*)d_sum, (long long*)d_sumsq);
+  EIGB_LAUNCH_CHECK("count_moments_kernel");
+  return EIGB200_OK;
+}
