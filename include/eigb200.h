@@ -120,6 +120,11 @@ int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int6
  * d_lam (P), d_Bu (B,T,P), d_h (B,T,P); reverse != 0 runs t = T-1..0. */
 int eigb200_diag_scan(void* stream, const float* d_lam, const float* d_Bu, float* d_h, int64_t B, int64_t T, int P, int reverse);
 
+/* Parameter-only eigenvalues of the diagonal SSMs, get_eigvals_ssm("lru"|"s5") (analysis/eval_eig.py:303-329) and the
+ * discretisations of models/s5.py:16-47.  kind 0 LRU: (p0,p1) = (nu_log, theta_log); kind 1 S5 zero-order hold, kind 2 S5 bilinear:
+ * (p0,p1,p2) = (Lambda_re, Lambda_im, log_step).  All (P) float32; d_lam (P) complex64. */
+int eigb200_ssm_lambda(void* stream, int kind, const float* d_p0, const float* d_p1, const float* d_p2, int P, float* d_lam);
+
 /* ---- K2b: SSD selective scan --------------------------------------------------------------------------------------------
  * mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=D, z=None) at its call site models/mamba.py:138-150:
  *   h_t[h,p,n] = exp(dt_t[h] A[h]) h_{t-1}[h,p,n] + dt_t[h] B_t[g,n] x_t[h,p];   y_t[h,p] = sum_n C_t[g,n] h_t[h,p,n] + D[h] x_t[h,p]
@@ -180,6 +185,8 @@ int eigb200_linattn_forward(void* stream, const float* d_q, const float* d_k, co
 int eigb200_add(void* stream, const float* d_a, const float* d_b, float* d_out, int64_t n);
 int eigb200_mul_silu(void* stream, const float* d_y, const float* d_z, float* d_out, int64_t n);
 int eigb200_gelu(void* stream, const float* d_x, float* d_out, int64_t n);
+/* out[m,j] = a[m,j] * s[j]: the D * u feed-through of LRU / S5 (models/lru.py:97; s5.py:247-248). */
+int eigb200_scale_cols(void* stream, const float* d_a, const float* d_s, float* d_out, int64_t rows, int cols);
 
 #ifdef __cplusplus
 }

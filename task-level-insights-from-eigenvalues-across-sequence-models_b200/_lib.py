@@ -49,6 +49,8 @@ SIGNATURES = {
     "eigb200_add": [_vp, _vp, _vp, _vp, _i64],
     "eigb200_mul_silu": [_vp, _vp, _vp, _vp, _i64],
     "eigb200_gelu": [_vp, _vp, _vp, _i64],
+    "eigb200_scale_cols": [_vp, _vp, _vp, _vp, _i64, _i],
+    "eigb200_ssm_lambda": [_vp, _i, _vp, _vp, _vp, _i, _vp],
 }
 _RESTYPES = {"eigb200_last_error": C.c_char_p, "eigb200_linear_workspace_bytes": C.c_size_t}
 

@@ -1,0 +1,305 @@
+"""`eval_eig` -- drop-in for analysis/eval_eig.py:462-857 on the eigb200 kernels.
+
+Same signature, same return tuple, same files on disk (10 .npy + used_config.yaml under save_path+name, and
+./percentage_file.txt), same quirks: the extractor of layer i is applied to the OUTPUT of block i (eval_eig.py:512-517);
+`model_config.pop("layer")` mutates the caller's dict (:479); only the first batch of `loader` is analysed (:502); bins are
+closed on both ends (:350, :359).  What differs is where the work happens: activations, eigenvalues and bin counts stay
+in HBM; the eigenvalue array is copied to the host once, at the end, because the reference returns it.
+
+Optional analysis-YAML keys beyond the reference's {batch_size, save_path} (defaults preserve reference behaviour):
+  materialize_eig: bool = True   copy eig / eig_init to the host and save them (False: statistics only, eig = None)
+  compare: "float64" | "float32" NumPy promotion reproduced by the threshold compare
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import yaml
+
+from . import _lib as L
+from . import dist as D
+from . import extractors as E
+from . import layers as Ly
+from . import ops
+from . import ssm
+
+thresholds_radius = E.THRESHOLDS_RADIUS
+thresholds_phase = E.THRESHOLDS_PHASE
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# device passes
+# ----------------------------------------------------------------------------------------------------------------------
+
+class PassResult:
+    """eig: device tensor (L, B, T', H) or None; counts: (L, B, H, 8) int32 device tensor; n_per_seq = T'."""
+
+    def __init__(self, eig, counts, n_per_seq, x_last):
+        self.eig, self.counts, self.n_per_seq, self.x_last = eig, counts, n_per_seq, x_last
+
+    def eig_host(self):
+        """(B, T', H, L) numpy, the reference's layout (np.concatenate along the last axis, eval_eig.py:524-526)."""
+        if self.eig is None:
+            return None
+        return np.ascontiguousarray(self.eig.permute(1, 2, 3, 0).cpu().numpy())
+
+
+def mamba_pass(model: "Ly.MambaDev", X, pseudoLTI=False, want_eig=True, compare="float64") -> PassResult:
+    """eval_eig.py:501-526 / :575-600 for one batch on the current device."""
+    x = model.encoder(X)
+    B, T, _ = x.shape
+    H = model.blocks[0].mamba.nheads
+    nl = len(model.blocks)
+    eig = torch.empty(nl, B, T, H, dtype=torch.float32, device=x.device) if want_eig else None
+    counts = torch.zeros(nl, B, H, ops.NSLOT, dtype=torch.int32, device=x.device)
+    for i, blk in enumerate(model.blocks):
+        x = blk(x)
+        if pseudoLTI:
+            lam, _ = E.get_eig_mamba2_LTI_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare)
+            if want_eig:
+                eig[i].copy_(lam)
+        else:
+            E.get_eig_mamba2_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=eig[i] if want_eig else None)
+    return PassResult(eig, counts, T, x)
+
+
+def transformer_pass(model: "Ly.TransformerDev", X, cfg, want_eig=True, compare="float64") -> PassResult:
+    """eval_eig.py:528-564 / :627-663."""
+    x = model.encoder(X)
+    B, T, _ = x.shape
+    H, dqk, dm = cfg["num_heads"], cfg["state_dim"], cfg["hidden_dim"]
+    nl = len(model.layers)
+    eig = torch.empty(nl, B, T - 1, H, dtype=torch.float64, device=x.device) if want_eig else None
+    counts = torch.zeros(nl, B, H, ops.NSLOT, dtype=torch.int32, device=x.device)
+    fn = cfg["attention_fn"]
+    for i, layer in enumerate(model.layers):
+        x = layer(x)
+        if fn == "lin-attention":
+            att = layer.attention
+            qk = ops.linear(x, att.W_qk, att.b_qk)
+            nu = ops.linattn_nu(qk, 2 * dqk, B, T, H, att.head_dim, dqk)
+            ops.ratio_hist(nu, L.RATIO_CUR_OVER_NEXT, want_out=want_eig, counts=counts[i], compare=compare, out=eig[i] if want_eig else None)
+        elif fn == "norm-attention":
+            att = layer.attention
+            n = ops.normattn_gate(x, att.W_n, att.b_n, att.inner_attn.offset if cfg["offset"] else None, cfg["norm_fn"])
+            ops.ratio_hist(n, L.RATIO_NEXT_OVER_CUR, want_out=want_eig, counts=counts[i], compare=compare, out=eig[i] if want_eig else None)
+        elif fn == "sm-attention":
+            raise NotImplementedError("sm-attention analysis is SURVEY 8f row f3 (next); not on the eigb200 path in this build")
+        else:
+            raise RuntimeError("{0} is not a valid model option".format(fn))
+    return PassResult(eig, counts, T - 1, x)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# report files (byte-compatible with create_file_percentage(_ssm), eval_eig.py:393-459)
+# ----------------------------------------------------------------------------------------------------------------------
+
+def create_file_percentage(thr_radius, percentage, percentage_init, percentage_mean, percentage_init_mean, percentage_std,
+                           percentage_init_std, path="percentage_file.txt"):
+    nheads, nlayers = np.shape(percentage)[2], np.shape(percentage)[3]
+    batch_selection = np.array([0, 2, 4, 6])
+    lines = []
+
+    def emit(*parts):
+        lines.append(" ".join(str(p) for p in parts))
+
+    emit("threshold radius:", thr_radius, "\n")
+    emit("batch selection:", batch_selection, "\n")
+    for bi, b in enumerate(batch_selection):
+        for h in range(nheads):
+            for tag, arr in (("radius init: ", percentage_init), ("radius: ", percentage)):
+                for l in range(nlayers):
+                    emit("percentage batch dimension", b, "head", h, "layer", l, tag, np.round(arr[:, b, h, l], 1))
+            if bi == 0:
+                for stat, a_init, a in (("mean", percentage_init_mean, percentage_mean), ("std", percentage_init_std, percentage_std)):
+                    for tag, arr in (("radius init: ", a_init), ("radius: ", a)):
+                        for l in range(nlayers):
+                            emit("percentage batch %s head" % stat, h, "layer", l, tag, np.round(arr[:, h, l], 1))
+            emit("\n")
+        emit("\n")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def create_file_percentage_ssm(thr_radius, thr_phase, percentage, percentage_init, percentage_phase, percentage_phase_init,
+                               path="percentage_file.txt"):
+    nlayers = np.shape(percentage)[1]
+    lines = []
+
+    def emit(*parts):
+        lines.append(" ".join(str(p) for p in parts))
+
+    emit("threshold radius:", thr_radius, "\n")
+    emit("threshold phase:", thr_phase, "\n")
+    blocks = (("radius init: ", percentage_init), ("radius: ", percentage), ("phase init: ", percentage_phase_init), ("phase: ", percentage_phase))
+    for k, (tag, arr) in enumerate(blocks):
+        for l in range(nlayers):
+            emit("percentage layer", l, tag, np.round(arr[:, l], 1))
+        if k < len(blocks) - 1:
+            emit("\n")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+RESULT_FILES = ["eig", "eig_init", "percentage", "percentage_init", "percentage_phase", "percentage_phase_init",
+                "percentage_mean", "percentage_init_mean", "percentage_std", "percentage_init_std"]
+
+
+def _save_results(args, conf_args, wandb_config, data_config, model_config, train_config, perf, arrays: Dict[str, object]):
+    """eval_eig.py:750-851: W&B artifact or 10 .npy + used_config.yaml under save_path + name_model."""
+    path_to_percentage_file = os.path.abspath(os.getcwd()) + "/percentage_file.txt"
+    dim_conv = model_config["dim_conv"] if "dim_conv" in model_config else 0
+    if wandb_config is not None:
+        import tempfile
+        import wandb
+        print("Saving artifact on W&B....")
+        base = data_config["name"] + "{0}-dmodel{1}-seed{4}-num_layers{5}-dqk{2}-conv_dim{6}-lr{3}".format(
+            wandb_config["name"], model_config["hidden_dim"], model_config["state_dim"], train_config["lr"], args["seed"],
+            model_config["num_layers"], dim_conv)
+        name_model = base + "-perf{0:0.3f}".format(perf)
+        wandb.init(group="artifact_upload", entity=wandb_config["entity"], project=wandb_config["project"],
+                   name="upload" + name_model, job_type="add-dataset")
+        artifact = wandb.Artifact(name="eigen_values_" + base, type="dataset")
+        art_names = ["eigen_values_", "eigen_values_init_", "percentage_", "percentage_init_", "percentage_phase_",
+                     "percentage_pase_init_", "percentage_mean_", "percentage_init_mean_", "percentage_std_", "percentage_init_std_"]
+        with tempfile.TemporaryDirectory() as tmpdir:
+            for fname, aname in zip(RESULT_FILES, art_names):
+                pth = os.path.join(tmpdir, fname + ".npy")
+                np.save(pth, arrays[fname])
+                artifact.add_file(local_path=pth, name=aname + name_model)
+            cfg_path = os.path.join(tmpdir, "used_config.yaml")
+            with open(cfg_path, "w") as file:
+                yaml.dump(args, file, default_flow_style=False, sort_keys=False)
+            artifact.add_file(local_path=path_to_percentage_file, name="percentage_file_" + name_model)
+            artifact.add_file(local_path=cfg_path, name="used_config-" + name_model)
+            artifact.save()
+        try:
+            wandb.finish()
+        except Exception:
+            pass
+        return None
+    print("Saving artifact locally....")
+    save_path = conf_args["save_path"] if "save_path" in conf_args else ""
+    base = data_config["name"] + "dmodel{0}-seed{3}-num_layers{4}-dqk{1}-conv_dim{5}-lr{2}".format(
+        model_config["hidden_dim"], model_config["state_dim"], train_config["lr"], args["seed"], model_config["num_layers"], dim_conv)
+    out_dir = save_path + base + "-perf{0:0.3f}".format(perf)
+    try:
+        os.mkdir(out_dir)
+        print(f"Directory '{out_dir}' created successfully.")
+    except FileExistsError:
+        print(f"Directory '{out_dir}' already exists.")
+    except PermissionError:
+        print(f"Permission denied: Unable to create '{out_dir}'.")
+    except Exception as e:
+        print(f"An error occurred: {e}")
+    for fname in RESULT_FILES:
+        np.save(os.path.join(out_dir, fname + ".npy"), arrays[fname])
+    with open(os.path.join(out_dir, "used_config.yaml"), "w") as file:
+        yaml.dump(args, file, default_flow_style=False, sort_keys=False)
+    return out_dir
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the entry point
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _first_batch(loader, device, lo=None, hi=None):
+    X, y, _ = next(iter(loader))                                           # eval_eig.py:502 -- first batch only
+    if lo is not None:
+        X = X[lo:hi]
+    if not torch.cuda.is_available():
+        raise L.Eigb200Error("eval_eig needs a CUDA device (the reference refuses to run without one too, launch.py:63-64)")
+    return X.to(device, non_blocking=True)
+
+
+def _load_torch_checkpoint(path):
+    return torch.load(path, weights_only=True, map_location="cpu")          # eval_eig.py:569
+
+
+def eval_eig(args, conf_args, wandb_config, data_config, loader, path_file, perf):
+    model_config = args["model"]
+    train_config = args["train"]
+    data_config = args["dataset"]
+    seed = args["seed"]
+    batch_size = conf_args["batch_size"]
+    num_layers = model_config["num_layers"]
+    pseudoLTI = model_config["pseudoLTI"] if "pseudoLTI" in model_config else False
+    materialize = conf_args.get("materialize_eig", True)
+    compare = conf_args.get("compare", "float64")
+
+    path = path_file if os.path.isabs(path_file) else os.path.abspath(os.getcwd()) + "/" + path_file
+    layer_type = model_config.pop("layer")                                   # mutates the caller's dict, like :479
+
+    rank, world = D.rank_world()
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+
+    if layer_type in ["mamba", "transformer"]:
+        num_heads = model_config["num_heads"]
+        lo, hi = D.shard_bounds(batch_size, rank, world) if world > 1 else (0, batch_size)
+
+        def run(state_dict):
+            X = _first_batch(loader, device, lo if world > 1 else None, hi if world > 1 else None)
+            if layer_type == "mamba":
+                model = Ly.MambaDev(model_config, state_dict, device)
+                res = mamba_pass(model, X, pseudoLTI, want_eig=materialize, compare=compare)
+            else:
+                model = Ly.TransformerDev(model_config, state_dict, device)
+                res = transformer_pass(model, X, model_config, want_eig=materialize, compare=compare)
+            counts = D.allreduce_counts(res.counts, batch_size, lo, batch_axis=1)          # the one exchange step
+            eig = res.eig
+            if eig is not None and world > 1:
+                eig = D.gather_batch(eig, batch_size, lo, batch_axis=1)
+            res.eig, res.counts = eig, counts
+            return res
+
+        # init pass: the reference constructs the model under torch.manual_seed(seed) (:484-497)
+        if layer_type == "mamba":
+            init_sd = Ly.init_mamba_state_dict(model_config, seed)
+        else:
+            init_sd = Ly.init_transformer_state_dict(model_config, seed)
+        res_init = run(init_sd)
+        res = run(_load_torch_checkpoint(path))                                             # :569-600 / :627-663
+
+        nb_r, nb_p = len(thresholds_radius) + 1, len(thresholds_phase) + 1
+        c_init = res_init.counts.cpu().numpy(); c = res.counts.cpu().numpy()
+        n_per = res.n_per_seq
+        percentage_init = E.percentages_from_counts(c_init, n_per, nb_r)
+        percentage = E.percentages_from_counts(c, n_per, nb_r)
+        percentage_phase_init = E.phase_percentages_from_counts(c_init, n_per, nb_p)
+        percentage_phase = E.phase_percentages_from_counts(c, n_per, nb_p)
+        percentage_init_mean = np.mean(percentage_init, axis=1); percentage_init_std = np.std(percentage_init, axis=1)
+        percentage_mean = np.mean(percentage, axis=1); percentage_std = np.std(percentage, axis=1)
+        eig_init = res_init.eig_host(); eig = res.eig_host()
+        if rank == 0:
+            create_file_percentage(thresholds_radius, percentage, percentage_init, percentage_mean, percentage_init_mean,
+                                   percentage_std, percentage_init_std)
+
+    elif layer_type in ["lru", "s4", "s5"]:
+        SEQ_LEN = model_config["seq_len"]
+        dim_idx = 1                                                                          # :689
+        init_layers = ssm.get_init_layers_ssm(seed, data_config, train_config, model_config, SEQ_LEN, layer_type, batch_size)
+        trained_layers = ssm.get_trained_layers_ssm(path)
+        eig_init = np.concatenate([ssm.get_eigvals_ssm(layer_type, init_layers, i, dim_idx, SEQ_LEN) for i in range(num_layers)], axis=-1)
+        eig = np.concatenate([ssm.get_eigvals_ssm(layer_type, trained_layers, i, dim_idx, SEQ_LEN) for i in range(num_layers)], axis=-1)
+        rad_init, ph_init = ssm.radius_phase(eig_init)
+        rad, ph = ssm.radius_phase(eig)
+        percentage_init = E.threshold_analysis_ssm(rad_init, thresholds_radius, num_layers, compare)
+        percentage = E.threshold_analysis_ssm(rad, thresholds_radius, num_layers, compare)
+        percentage_phase_init = E.threshold_analysis_ssm(ph_init, thresholds_phase, num_layers, compare)
+        percentage_phase = E.threshold_analysis_ssm(ph, thresholds_phase, num_layers, compare)
+        percentage_init_mean = percentage_init_std = percentage_mean = percentage_std = 0   # :740-743
+        if rank == 0:
+            create_file_percentage_ssm(thresholds_radius, thresholds_phase, percentage, percentage_init, percentage_phase, percentage_phase_init)
+    else:
+        raise RuntimeError("{0} is not a valid model option".format(layer_type))             # :748
+
+    if rank == 0:
+        _save_results(args, conf_args, wandb_config, data_config, model_config, train_config, perf,
+                      dict(eig=eig, eig_init=eig_init, percentage=percentage, percentage_init=percentage_init,
+                           percentage_phase=percentage_phase, percentage_phase_init=percentage_phase_init,
+                           percentage_mean=percentage_mean, percentage_init_mean=percentage_init_mean,
+                           percentage_std=percentage_std, percentage_init_std=percentage_init_std))
+    return eig, eig_init, percentage, percentage_init, percentage_phase, percentage_phase_init

@@ -1,0 +1,11 @@
+// gemm_simt.cuh -- fp32 FFMA GEMM  C = epilogue(A W^T + bias)  (exact-fp32 path; also the checker for the tcgen05 path).
+#pragma once
+#include "common.cuh"
+namespace eigb200 {
+struct LinearParams {
+  const float* A; int64_t lda; const float* W; const float* bias;
+  float* C; int64_t ldc; const float* R; int64_t ldr;
+  int64_t M; int N, K, epilogue;
+};
+int launch_linear_simt(cudaStream_t st, const LinearParams& p);
+}  // namespace eigb200

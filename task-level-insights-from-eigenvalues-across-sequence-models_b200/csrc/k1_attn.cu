@@ -1,0 +1,172 @@
+// k1_attn.cu -- K1'': linear-attention normaliser nu_t (O(T) prefix form of the reference's (B,T,T,H) score tensor) and
+// the causal linear-attention layer forward in recurrent form.
+//
+// Reference operators:
+//   get_eig_att_linear  analysis/eval_eig.py:97-135   nu_t = sum_{s<=t} phi(q_t).phi(k_s), phi = elu+1   (scores materialised O(T^2))
+//   SelfLinAttention.forward  models/attention.py:63-83    kv cumsum materialised as (B,T,H,d,dv)
+//   SelfNormAttention.forward models/norm_attention.py:61-89
+// Roofline: HBM for nu (2*d*4 bytes read per eigenvalue, 8 written); FMA-pipe for the layer forward (2*d*dv FMA per token).
+#include "common.cuh"
+
+namespace eigb200 {
+
+// ---- nu: CTA per (b,h); 8 warps split T into contiguous ranges; two passes (range sums, then the walk) -------------------
+constexpr int NU_WARPS = 8;
+constexpr int NU_DMAX = 8;            // channels per lane (d <= 256)
+
+__global__ void __launch_bounds__(NU_WARPS * 32) linattn_nu_kernel(const float* __restrict__ q, const float* __restrict__ k, int64_t ld,
+                                                                   int64_t T, int H, int d, double* __restrict__ nu) {
+  __shared__ double part[NU_WARPS][NU_DMAX * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int64_t per = (T + NU_WARPS - 1) / NU_WARPS;
+  const int64_t t0 = min(T, warp * per), t1 = min(T, t0 + per);
+  const float* qb = q + ((size_t)b * T) * ld + (size_t)h * d;
+  const float* kb = k + ((size_t)b * T) * ld + (size_t)h * d;
+  double S[NU_DMAX];
+#pragma unroll
+  for (int i = 0; i < NU_DMAX; ++i) S[i] = 0.0;
+  for (int64_t t = t0; t < t1; ++t) {
+#pragma unroll
+    for (int i = 0; i < NU_DMAX; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) S[i] += (double)(elu_f(__ldg(kb + t * ld + c)) + 1.f);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NU_DMAX; ++i) part[warp][lane + 32 * i] = S[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NU_DMAX; ++i) {
+    double acc = 0.0;
+    for (int w = 0; w < warp; ++w) acc += part[w][lane + 32 * i];
+    S[i] = acc;                                                    // exclusive prefix: state before this warp's range
+  }
+  for (int64_t t = t0; t < t1; ++t) {
+    double dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < NU_DMAX; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) {
+        S[i] += (double)(elu_f(__ldg(kb + t * ld + c)) + 1.f);
+        dot += (double)(elu_f(__ldg(qb + t * ld + c)) + 1.f) * S[i];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) nu[((size_t)b * T + t) * H + h] = dot;
+  }
+}
+
+// ---- layer forward: CTA per (b,h); thread (g, j) owns RI rows of column j of the d x dv state ----------------------
+constexpr int LA_THREADS = 256;
+constexpr int LA_TC = 16;             // tokens per staging round
+
+struct LinAttnParams {
+  const float* q; const float* k; const float* v; int64_t ld; const float* gate;
+  int phi_elu, normalise; float kscale;
+  float* out; int64_t ldo; int64_t T; int H, d, dv;
+};
+
+template <int RI>
+__global__ void __launch_bounds__(LA_THREADS) linattn_forward_kernel(const LinAttnParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = p.d, dv = p.dv;
+  const int groups = LA_THREADS / dv;
+  float* qs = sm;                                  // [TC][d]
+  float* ks = qs + LA_TC * d;                      // [TC][d]
+  float* vs = ks + LA_TC * d;                      // [TC][dv]
+  float* pn = vs + LA_TC * dv;                     // [TC][groups][dv] partial numerators
+  float* pd = pn + LA_TC * groups * dv;            // [TC][groups]     partial denominators
+  const int tid = threadIdx.x;
+  const int g = tid / dv, j = tid - g * dv;
+  const int i0 = g * RI;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const size_t rowbase = (size_t)b * p.T;
+  const float* qb = p.q + (size_t)h * d;
+  const float* kb = p.k + (size_t)h * d;
+  const float* vb = p.v + (size_t)h * dv;
+
+  float kv[RI], ksum[RI];
+#pragma unroll
+  for (int i = 0; i < RI; ++i) { kv[i] = 0.f; ksum[i] = 0.f; }
+
+  for (int64_t t0 = 0; t0 < p.T; t0 += LA_TC) {
+    const int tc = (int)min((int64_t)LA_TC, p.T - t0);
+    __syncthreads();
+    for (int i = tid; i < tc * d; i += LA_THREADS) {
+      const int r = i / d, c = i - r * d;
+      float qv = __ldg(qb + (rowbase + t0 + r) * p.ld + c), kvv = __ldg(kb + (rowbase + t0 + r) * p.ld + c);
+      if (p.phi_elu) { qv = elu_f(qv) + 1.f; kvv = elu_f(kvv) + 1.f; }
+      qs[i] = qv; ks[i] = kvv;
+    }
+    for (int i = tid; i < tc * dv; i += LA_THREADS) {
+      const int r = i / dv, c = i - r * dv;
+      vs[i] = __ldg(vb + (rowbase + t0 + r) * p.ld + c);
+    }
+    __syncthreads();
+    for (int tt = 0; tt < tc; ++tt) {
+      const float vj = vs[tt * dv + j];
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        const float ki = ks[tt * d + i0 + i], qi = qs[tt * d + i0 + i];
+        kv[i] = fmaf(ki * p.kscale, vj, kv[i]);
+        num = fmaf(qi, kv[i], num);
+        if (p.normalise) { ksum[i] += ki; den = fmaf(qi, ksum[i], den); }
+      }
+      pn[(tt * groups + g) * dv + j] = num;
+      if (p.normalise && j == 0) pd[tt * groups + g] = den;
+    }
+    __syncthreads();
+    for (int i = tid; i < tc * dv; i += LA_THREADS) {
+      const int r = i / dv, c = i - r * dv;
+      float num = 0.f;
+      for (int gg = 0; gg < groups; ++gg) num += pn[(r * groups + gg) * dv + c];
+      float scale = 1.f;
+      if (p.normalise) {
+        float den = 0.f;
+        for (int gg = 0; gg < groups; ++gg) den += pd[r * groups + gg];
+        scale = 1.f / den;                                      // n.pow(-1) (models/attention.py:79)
+      } else if (p.gate) scale = __ldg(p.gate + (rowbase + t0 + r) * p.H + h);
+      p.out[(rowbase + t0 + r) * p.ldo + (size_t)h * dv + c] = scale * num;
+    }
+  }
+}
+
+}  // namespace eigb200
+
+using namespace eigb200;
+
+extern "C" int eigb200_linattn_nu(void* stream, const float* d_q, const float* d_k, int64_t ld, int64_t B, int64_t T, int H, int d, double* d_nu) {
+  EIGB_CHECK_ARG(d_q && d_k && d_nu, "linattn_nu: null pointer");
+  EIGB_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && H > 0 && d > 0, "linattn_nu: bad shape");
+  EIGB_CHECK_ARG(d <= 32 * NU_DMAX, "linattn_nu: head dim %d > %d", d, 32 * NU_DMAX);
+  dim3 grid(H, (unsigned)B);
+  linattn_nu_kernel<<<grid, NU_WARPS * 32, 0, (cudaStream_t)stream>>>(d_q, d_k, ld, T, H, d, d_nu);
+  EIGB_LAUNCH_CHECK("linattn_nu_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_linattn_forward(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld,
+                                       const float* d_gate, int phi_elu, int normalise, float kscale,
+                                       float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv) {
+  EIGB_CHECK_ARG(d_q && d_k && d_v && d_out, "linattn_forward: null pointer");
+  EIGB_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && H > 0 && d > 0 && dv > 0, "linattn_forward: bad shape");
+  EIGB_CHECK_ARG(dv <= LA_THREADS && (dv & (dv - 1)) == 0, "linattn_forward: value head dim %d must be a power of two <= 256", dv);
+  const int groups = LA_THREADS / dv;
+  EIGB_CHECK_ARG(d % groups == 0, "linattn_forward: key head dim %d must be a multiple of %d (= 256 / dv)", d, groups);
+  const int ri = d / groups;
+  EIGB_CHECK_ARG(ri >= 1 && ri <= 64 && (ri & (ri - 1)) == 0, "linattn_forward: d*dv/256 = %d must be a power of two <= 64", ri);
+  LinAttnParams p{d_q, d_k, d_v, ld, d_gate, phi_elu, normalise, kscale, d_out, ldo, T, H, d, dv};
+  const size_t smem = sizeof(float) * ((size_t)LA_TC * (2 * d + dv) + (size_t)LA_TC * groups * dv + (size_t)LA_TC * groups);
+  dim3 grid(H, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LA_CASE(RI_) case RI_: \
+    if (smem > 48 * 1024) EIGB_CUDA(cudaFuncSetAttribute(linattn_forward_kernel<RI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    linattn_forward_kernel<RI_><<<grid, LA_THREADS, smem, st>>>(p); break;
+  switch (ri) { LA_CASE(1) LA_CASE(2) LA_CASE(4) LA_CASE(8) LA_CASE(16) LA_CASE(32) LA_CASE(64) default: break; }
+#undef LA_CASE
+  EIGB_LAUNCH_CHECK("linattn_forward_kernel");
+  return EIGB200_OK;
+}

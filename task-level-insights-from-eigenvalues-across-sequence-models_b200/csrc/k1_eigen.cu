@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p
       }
       if (p.out) p.out[((size_t)b * T + row) * H + hg] = val;
       if (EPI == K1_EPI_MAMBA2) {
-        bin_f32(val, p.e, cnt);
+        // the reference bins the float32 radius sqrt(fl(re^2) + fl(im^2)) of the real lambda (eval_eig.py:605-606)
+        bin_f32(sqrtf(__fmul_rn(val, val)), p.e, cnt);
         cnt[8] += (val == val) ? 1 : 0;                 // arctan2(0, lambda) = 0 unless lambda is NaN
       }
     }
@@ -213,7 +214,7 @@ __global__ void k1_lti_kernel(const float* A, const float* beta, int64_t BT, int
       int c[EIGB_NCNT];
 #pragma unroll
       for (int j = 0; j < EIGB_NCNT; ++j) c[j] = 0;
-      bin_f32(lam_s[h], e, c);
+      bin_f32(sqrtf(__fmul_rn(lam_s[h], lam_s[h])), e, c);
       c[8] = (lam_s[h] == lam_s[h]) ? 1 : 0;
 #pragma unroll
       for (int j = 0; j < EIGB_NCNT; ++j)

@@ -1,0 +1,28 @@
+// linear_api.cu -- eigb200_linear: argument checking and dispatch between the FFMA path and the tcgen05 path.
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+using namespace eigb200;
+
+extern "C" size_t eigb200_linear_workspace_bytes(int N, int K) { return tc_workspace_bytes(N, K); }
+
+extern "C" int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
+                              float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
+                              int64_t M, int N, int K, int epilogue, int mode, void* d_workspace, size_t workspace_bytes) {
+  EIGB_CHECK_ARG(d_A && d_W && d_C, "linear: null pointer");
+  EIGB_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  EIGB_CHECK_ARG(epilogue >= EIGB200_EPI_NONE && epilogue <= EIGB200_EPI_RESIDUAL, "linear: unknown epilogue %d", epilogue);
+  EIGB_CHECK_ARG(epilogue != EIGB200_EPI_GLU_RESIDUAL || N % 2 == 0, "linear: GLU epilogue needs an even N");
+  const int nout = epilogue == EIGB200_EPI_GLU_RESIDUAL ? N / 2 : N;
+  EIGB_CHECK_ARG(lda >= K && ldc >= nout && (!d_R || ldr >= nout), "linear: row stride smaller than the row");
+  LinearParams p{d_A, lda, d_W, d_bias, d_C, ldc, d_R, ldr, M, N, K, epilogue};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == EIGB200_GEMM_SIMT_F32) return launch_linear_simt(st, p);
+  const bool tc_ok = tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes(N, K);
+  if (mode == EIGB200_GEMM_TC_3XTF32 || mode == EIGB200_GEMM_TC_TF32) {
+    if (!tc_ok) { set_error("linear: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda); return EIGB200_EUNSUPPORTED; }
+    return launch_linear_tc(st, p, mode == EIGB200_GEMM_TC_TF32 ? 1 : 3, d_workspace);
+  }
+  EIGB_CHECK_ARG(mode == EIGB200_GEMM_AUTO, "linear: unknown mode %d", mode);
+  if (tc_ok && M >= 1024) return launch_linear_tc(st, p, 3, d_workspace);
+  return launch_linear_simt(st, p);
+}

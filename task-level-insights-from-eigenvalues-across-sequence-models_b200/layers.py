@@ -1,0 +1,359 @@
+"""Device-side mirrors of the reference's torch layers, driven by a reference-format state_dict.
+
+Only what the analysis path needs: parameter containers with the reference's attribute names (so the `get_eig_*`
+extractors can be handed either these objects or the reference's own modules) and a `__call__` that propagates the
+activations through one block with the eigb200 kernels.
+
+Reference: models/mamba.py (SSD :25-154, MambaBlock :301-340, Mamba :342-389), models/transformer.py
+(TransformerBlock :22-111, Transformer :113-161), models/attention.py (MHA :85-182), models/norm_attention.py
+(MHNA :160-258), models/common.py (GLU :50-58, MLP :33-48, TokenEmbeddings :117-176).
+Eval-mode semantics (dropout is the identity); see DESIGN.md for the init-pass dropout quirk.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class _Lin:
+    """nn.Linear-shaped parameter holder: .weight (N,K), .bias (N,) | None; callable through the eigb200 GEMM."""
+
+    def __init__(self, weight, bias=None):
+        self.weight = weight
+        self.bias = bias
+
+    def __call__(self, x, **kw):
+        out = ops.linear(x, self.weight, self.bias, **kw)
+        return out.reshape(x.shape[:-1] + (out.shape[-1],)) if out.shape[-1] == self.weight.shape[0] else out
+
+
+def _dev(sd: Dict[str, torch.Tensor], key: str, device, dtype=torch.float32) -> Optional[torch.Tensor]:
+    if key not in sd:
+        return None
+    t = sd[key]
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    return t.detach().to(device=device, dtype=dtype).contiguous()
+
+
+# ======================================================================================================================
+# Mamba-2
+# ======================================================================================================================
+
+class SSDParams(SimpleNamespace):
+    """Attribute names follow models/mamba.py:SSD so that get_eig_mamba2(x, layer) reads them unchanged."""
+
+
+class MambaBlockDev:
+    def __init__(self, sd, prefix, cfg, device):
+        D = cfg["hidden_dim"]
+        headdim = D // cfg["num_heads"]
+        d_inner = cfg["expansion"] * D
+        N = cfg["state_dim"]
+        self.prenorm = cfg["prenorm"]
+        m = SSDParams()
+        m.d_model, m.d_inner, m.d_state, m.ngroups, m.headdim = D, d_inner, N, 1, headdim
+        m.nheads = d_inner // headdim
+        m.in_proj = _Lin(_dev(sd, prefix + "mamba.in_proj.weight", device))
+        m.out_proj = _Lin(_dev(sd, prefix + "mamba.out_proj.weight", device))
+        m.dt_bias = _dev(sd, prefix + "mamba.dt_bias", device)
+        m.A_log = _dev(sd, prefix + "mamba.A_log", device)
+        m.D = _dev(sd, prefix + "mamba.D", device)
+        cw = _dev(sd, prefix + "mamba.conv1d.weight", device)
+        m.conv_w = cw.reshape(cw.shape[0], -1).contiguous() if cw is not None else None
+        m.conv_b = _dev(sd, prefix + "mamba.conv1d.bias", device)
+        m.use_conv = cw is not None
+        # the dt rows of in_proj: split order [x | B | C | dt] (models/mamba.py:62-63)
+        lo = d_inner + 2 * m.ngroups * N
+        m.W_dt = m.in_proj.weight[lo:lo + m.nheads].contiguous()
+        self.mamba = m
+        gw = _dev(sd, prefix + "glu.linear.weight", device)
+        self.glu = SimpleNamespace(linear=_Lin(gw, _dev(sd, prefix + "glu.linear.bias", device))) if gw is not None else None
+        self.norm = SimpleNamespace(weight=_dev(sd, prefix + "norm.weight", device), bias=_dev(sd, prefix + "norm.bias", device))
+        self.gemm_mode = cfg.get("_gemm_mode", "auto")
+
+    def __call__(self, x):
+        """MambaBlock.forward (models/mamba.py:328-340) with SSD.forward (:111-154) inlined."""
+        m = self.mamba
+        B, T, D = x.shape
+        skip = x
+        xn = ops.layernorm(x, self.norm.weight, self.norm.bias) if self.prenorm else x
+        d_in_proj = m.in_proj.weight.shape[0]
+        ldz = _pad4(d_in_proj)
+        z = ops.linear(xn, m.in_proj.weight, None, ldc=ldz, mode=self.gemm_mode)                  # (B*T, ldz) = [x | B | C | dt | pad]
+        y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
+        o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode)    # GELU(out_proj(y))  (:333)
+        if self.glu is not None:
+            out = ops.linear(o, self.glu.linear.weight, self.glu.linear.bias, epilogue="glu_residual",
+                             residual=skip.reshape(B * T, D), mode=self.gemm_mode)                 # GLU + skip (:335-337)
+        else:
+            out = ops.add(o, skip.reshape(B * T, D))
+        out = out.reshape(B, T, D)
+        if not self.prenorm:
+            out = ops.layernorm(out, self.norm.weight, self.norm.bias)
+        return out
+
+
+class TokenEmbeddingsDev:
+    def __init__(self, sd, prefix, device):
+        self.word = _dev(sd, prefix + "word_embeddings.weight", device)
+        self.pos = _dev(sd, prefix + "position_embeddings.weight", device)
+
+    def __call__(self, ids):
+        return ops.embedding(ids, self.word, self.pos)
+
+
+class LinearEncoderDev:
+    def __init__(self, sd, prefix, device):
+        self.lin = _Lin(_dev(sd, prefix + "weight", device), _dev(sd, prefix + "bias", device))
+
+    def __call__(self, x):
+        out = ops.linear(x.float(), self.lin.weight, self.lin.bias)
+        return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def _make_encoder(sd, device):
+    if "encoder.word_embeddings.weight" in sd:
+        return TokenEmbeddingsDev(sd, "encoder.", device)
+    return LinearEncoderDev(sd, "encoder.", device)
+
+
+class MambaDev:
+    """Mirror of models/mamba.py:Mamba for the analysis loop: .encoder, .blocks[i]."""
+
+    def __init__(self, cfg, state_dict, device="cuda"):
+        if cfg.get("version", "mamba2") != "mamba2":
+            raise RuntimeError("Non supported version")                               # models/mamba.py:313 (Mamba-1 is train-only)
+        self.cfg = dict(cfg)
+        self.encoder = _make_encoder(state_dict, device)
+        self.blocks = [MambaBlockDev(state_dict, "blocks.%d." % i, cfg, device) for i in range(cfg["num_layers"])]
+
+
+# ======================================================================================================================
+# Transformer (linear attention / normalised attention)
+# ======================================================================================================================
+
+class AttentionDev:
+    """MHA(lin_att=True, use_flash=False) or MHNA parameters + forward."""
+
+    def __init__(self, sd, prefix, cfg, device):
+        self.d_model = cfg["hidden_dim"]
+        self.d_qk = cfg["state_dim"]
+        self.num_heads = cfg["num_heads"]
+        self.head_dim = self.d_qk // self.num_heads
+        self.v_dim = self.d_model // self.num_heads
+        self.kind = cfg["attention_fn"]
+        self.conv_type = cfg.get("conv_type", "full")
+        if self.kind == "norm-attention":
+            self.Wvqkn = _Lin(_dev(sd, prefix + "Wvqkn.weight", device), _dev(sd, prefix + "Wvqkn.bias", device))
+            self.inner_attn = SimpleNamespace(offset=_dev(sd, prefix + "inner_attn.offset", device))
+            self.norm_fn = cfg["norm_fn"]
+            self.approx_fn = cfg["approx_fn"]
+            self.scale_B = cfg["scale_B"]
+            lo = self.d_model + 2 * self.d_qk
+            self.W_n = self.Wvqkn.weight[lo:lo + self.num_heads].contiguous()
+            self.b_n = self.Wvqkn.bias[lo:lo + self.num_heads].contiguous()
+        elif self.kind in ("lin-attention", "sm-attention"):
+            self.Wqkv = _Lin(_dev(sd, prefix + "Wqkv.weight", device), _dev(sd, prefix + "Wqkv.bias", device))
+            self.W_qk = self.Wqkv.weight[: 2 * self.d_qk].contiguous()
+            self.b_qk = self.Wqkv.bias[: 2 * self.d_qk].contiguous() if self.Wqkv.bias is not None else None
+        else:
+            raise RuntimeError("{0} is not a valid model option".format(self.kind))
+        self.out_proj = _Lin(_dev(sd, prefix + "out_proj.weight", device), _dev(sd, prefix + "out_proj.bias", device))
+        cw = _dev(sd, prefix + "conv1d.weight", device)
+        self.conv_w = cw.reshape(cw.shape[0], -1).contiguous() if cw is not None else None
+        self.conv_b = _dev(sd, prefix + "conv1d.bias", device)
+
+    def _conv(self, buf, ld, col0, ncols, B, T):
+        """conv+SiLU over columns [col0, col0+ncols) of buf (B*T, ld), in a fresh buffer that keeps the other columns."""
+        out = buf.clone() if ncols < buf.shape[1] else torch.empty_like(buf)
+        ops.conv_silu(buf[:, col0:], ld, self.conv_w, self.conv_b, B, T, ncols, out=out[:, col0:], ldo=ld)
+        return out
+
+    def forward_residual(self, xn, skip):
+        """out_proj(attention(xn)) + skip   (MHA.forward models/attention.py:149-182 / MHNA.forward norm_attention.py:230-258)."""
+        B, T, D = xn.shape
+        H, d, dv, dqk = self.num_heads, self.head_dim, self.v_dim, self.d_qk
+        if self.kind == "lin-attention":
+            ld = 2 * dqk + D
+            buf = ops.linear(xn, self.Wqkv.weight, self.Wqkv.bias)
+            if self.conv_w is not None:
+                buf = self._conv(buf, ld, 0, ld if self.conv_type == "full" else 2 * dqk, B, T)
+            ctx = ops.linattn_forward(buf, ld, 0, dqk, 2 * dqk, B, T, H, d, dv, phi_elu=True, normalise=True)
+        elif self.kind == "norm-attention":
+            ld = D + 2 * dqk + H
+            buf = ops.linear(xn, self.Wvqkn.weight, self.Wvqkn.bias)
+            gate = ops.normattn_gate(xn, self.W_n, self.b_n, self.inner_attn.offset, self.norm_fn)
+            if self.conv_w is not None:
+                if self.conv_type == "full":
+                    buf = self._conv(buf, ld, 0, D + 2 * dqk, B, T)
+                else:
+                    buf = self._conv(buf, ld, D, 2 * dqk, B, T)
+            kscale = 1.0 / math.sqrt(d) if self.scale_B else 1.0
+            ctx = ops.linattn_forward(buf, ld, D, D + dqk, 0, B, T, H, d, dv, gate=gate, phi_elu=(self.approx_fn == "elu"),
+                                      normalise=False, kscale=kscale)
+        else:
+            raise NotImplementedError("softmax attention layer forward is not on the eigb200 path yet")
+        out = ops.linear(ctx, self.out_proj.weight, self.out_proj.bias, epilogue="residual", residual=skip.reshape(B * T, D))
+        return out.reshape(B, T, D)
+
+
+class TransformerBlockDev:
+    def __init__(self, sd, prefix, cfg, device):
+        self.attention = AttentionDev(sd, prefix + "attention.", cfg, device)
+        self.norm = SimpleNamespace(weight=_dev(sd, prefix + "norm.weight", device), bias=_dev(sd, prefix + "norm.bias", device))
+        self.mixer_kind = cfg["mixer"]
+        self.use_gate = cfg.get("use_gate", False)
+        if self.use_gate:
+            self.Wz = _Lin(_dev(sd, prefix + "Wz.weight", device), _dev(sd, prefix + "Wz.bias", device))
+        if self.mixer_kind == "mlp":
+            self.mixer = SimpleNamespace(encoder=_Lin(_dev(sd, prefix + "mixer.encoder.weight", device), _dev(sd, prefix + "mixer.encoder.bias", device)),
+                                         decoder=_Lin(_dev(sd, prefix + "mixer.decoder.weight", device), _dev(sd, prefix + "mixer.decoder.bias", device)))
+        elif self.mixer_kind == "glu":
+            self.mixer = SimpleNamespace(linear=_Lin(_dev(sd, prefix + "mixer.linear.weight", device), _dev(sd, prefix + "mixer.linear.bias", device)))
+        elif self.mixer_kind == "none":
+            self.mixer = None
+        else:
+            raise RuntimeError("{0} mixer not implemented yet!".format(self.mixer_kind))     # models/transformer.py:76-77 ("hybrid" unsupported here)
+
+    def __call__(self, x):
+        """TransformerBlock.forward (models/transformer.py:90-111): one LayerNorm reused for both sub-blocks."""
+        B, T, D = x.shape
+        z = ops.linear(x, self.Wz.weight, self.Wz.bias).reshape(B, T, D) if self.use_gate else None
+        xn = ops.layernorm(x, self.norm.weight, self.norm.bias)
+        x = self.attention.forward_residual(xn, x)
+        y = ops.layernorm(x, self.norm.weight, self.norm.bias)
+        if self.mixer_kind == "none":                                                     # drop_skip (:73-75, :102-104)
+            return ops.mul_silu(y, z) if z is not None else y
+        x2 = x.reshape(B * T, D)
+        if self.mixer_kind == "glu":
+            out = ops.linear(y, self.mixer.linear.weight, self.mixer.linear.bias, epilogue="glu_residual", residual=x2)
+        else:
+            hmid = ops.linear(y, self.mixer.encoder.weight, self.mixer.encoder.bias, epilogue="gelu")
+            out = ops.linear(hmid, self.mixer.decoder.weight, self.mixer.decoder.bias, epilogue="residual", residual=x2)
+        out = out.reshape(B, T, D)
+        return ops.mul_silu(out, z) if z is not None else out
+
+
+class TransformerDev:
+    """Mirror of models/transformer.py:Transformer for the analysis loop: .encoder, .layers[i]."""
+
+    def __init__(self, cfg, state_dict, device="cuda"):
+        self.cfg = dict(cfg)
+        self.encoder = _make_encoder(state_dict, device)
+        self.layers = [TransformerBlockDev(state_dict, "layers.%d." % i, cfg, device) for i in range(cfg["num_layers"])]
+
+
+# ======================================================================================================================
+# initial parameters: the reference draws them from torch's CPU generator in constructor order (eval_eig.py:484-497)
+# ======================================================================================================================
+
+def init_mamba_state_dict(cfg, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """Parameters of models/mamba.py:Mamba(cfg) at construction, drawn in the reference's order so that
+    torch.manual_seed(seed) gives the same tensors (embedding; per block: in_proj, dt, A, conv1d, out_proj, GLU; decoder)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    D = cfg["hidden_dim"]; N = cfg["state_dim"]; k = cfg["conv_dim"]
+    headdim = D // cfg["num_heads"]; d_inner = cfg["expansion"] * D; H = d_inner // headdim; G = 1
+    sd = {}
+    if cfg["token_embedding"]:
+        sd["encoder.word_embeddings.weight"] = nn.Embedding(cfg["vocab_size"], D).weight.detach()
+    else:
+        enc = nn.Linear(cfg["input_dim"], D)
+        sd["encoder.weight"], sd["encoder.bias"] = enc.weight.detach(), enc.bias.detach()
+    for i in range(cfg["num_layers"]):
+        p = "blocks.%d." % i
+        sd[p + "mamba.in_proj.weight"] = nn.Linear(D, d_inner + 2 * G * N + H, bias=False).weight.detach()
+        dt = torch.exp(torch.rand(H) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))        # models/mamba.py:71-77
+        dt = torch.clamp(dt, min=1e-4)
+        sd[p + "mamba.dt_bias"] = dt + torch.log(-torch.expm1(-dt))
+        sd[p + "mamba.A_log"] = torch.log(torch.empty(H, dtype=torch.float32).uniform_(1, 16))     # :85-86
+        sd[p + "mamba.D"] = torch.ones(H)
+        if k > 0:
+            conv = nn.Conv1d(d_inner + 2 * G * N, d_inner + 2 * G * N, kernel_size=k, groups=d_inner + 2 * G * N, padding=k - 1)
+            sd[p + "mamba.conv1d.weight"], sd[p + "mamba.conv1d.bias"] = conv.weight.detach(), conv.bias.detach()
+        sd[p + "mamba.out_proj.weight"] = nn.Linear(d_inner, D, bias=False).weight.detach()
+        if cfg["glu"]:
+            glu = nn.Linear(D, 2 * D)
+            sd[p + "glu.linear.weight"], sd[p + "glu.linear.bias"] = glu.weight.detach(), glu.bias.detach()
+        sd[p + "norm.weight"], sd[p + "norm.bias"] = torch.ones(D), torch.zeros(D)
+    dec = nn.Linear(D, cfg["output_dim"])
+    sd["decoder.weight"], sd["decoder.bias"] = dec.weight.detach(), dec.bias.detach()
+    return sd
+
+
+def init_transformer_state_dict(cfg, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """Parameters of models/transformer.py:Transformer(cfg) at construction, in the reference's drawing order."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    D = cfg["hidden_dim"]; dqk = cfg["state_dim"]; H = cfg["num_heads"]
+    sd = {}
+    if cfg["embedding"]:
+        sd["encoder.word_embeddings.weight"] = nn.Embedding(cfg["vocab_size"], D).weight.detach()
+        if cfg["max_pos_embed"] > 0:
+            sd["encoder.position_embeddings.weight"] = nn.Embedding(cfg["max_pos_embed"], D).weight.detach()
+    else:
+        enc = nn.Linear(cfg["input_dim"], D)
+        sd["encoder.weight"], sd["encoder.bias"] = enc.weight.detach(), enc.bias.detach()
+    for i in range(cfg["num_layers"]):
+        p = "layers.%d." % i
+        kind = cfg["attention_fn"]
+        dim_conv = cfg.get("dim_conv", 0)
+        conv_type = cfg.get("conv_type", "full")
+        if kind == "norm-attention":
+            lin = nn.Linear(D, D + 2 * dqk + H)
+            sd[p + "attention.Wvqkn.weight"], sd[p + "attention.Wvqkn.bias"] = lin.weight.detach(), lin.bias.detach()
+            if cfg["offset"]:
+                if cfg["offset_init"] == "exp":
+                    sd[p + "attention.inner_attn.offset"] = torch.linspace(4, 9, H)               # norm_attention.py:52
+                elif cfg["offset_init"] == "uniform":
+                    if H == 1:
+                        off = torch.tensor([(14. - 8.) / 2])                                       # norm_attention.py:17-19
+                    else:
+                        x = torch.log(torch.expm1(torch.linspace(0.02, 0.1, H)))
+                        x = (x - x.min()) / (x.max() - x.min())
+                        off = x * abs(14. - 8.) + 8.
+                    sd[p + "attention.inner_attn.offset"] = off
+                else:
+                    raise RuntimeError("Invalid init option {0}".format(cfg["offset_init"]))
+        else:
+            lin = nn.Linear(D, 2 * dqk + D)
+            sd[p + "attention.Wqkv.weight"], sd[p + "attention.Wqkv.bias"] = lin.weight.detach(), lin.bias.detach()
+        op = nn.Linear(D, D)
+        sd[p + "attention.out_proj.weight"], sd[p + "attention.out_proj.bias"] = op.weight.detach(), op.bias.detach()
+        if dim_conv > 0:
+            cd = D + 2 * dqk if conv_type == "full" else 2 * dqk
+            conv = nn.Conv1d(cd, cd, kernel_size=dim_conv, groups=cd, padding=dim_conv - 1)
+            sd[p + "attention.conv1d.weight"], sd[p + "attention.conv1d.bias"] = conv.weight.detach(), conv.bias.detach()
+        if cfg.get("use_gate", False):
+            wz = nn.Linear(D, D)
+            nn.init.constant_(wz.bias, 1.0)
+            nn.init.xavier_uniform_(wz.weight, gain=0.1)
+            sd[p + "Wz.weight"], sd[p + "Wz.bias"] = wz.weight.detach(), wz.bias.detach()
+        if cfg["mixer"] == "mlp":
+            e = nn.Linear(D, cfg["mixer_dim"]); dcd = nn.Linear(cfg["mixer_dim"], D)
+            sd[p + "mixer.encoder.weight"], sd[p + "mixer.encoder.bias"] = e.weight.detach(), e.bias.detach()
+            sd[p + "mixer.decoder.weight"], sd[p + "mixer.decoder.bias"] = dcd.weight.detach(), dcd.bias.detach()
+        elif cfg["mixer"] == "glu":
+            gl = nn.Linear(D, 2 * D)
+            sd[p + "mixer.linear.weight"], sd[p + "mixer.linear.bias"] = gl.weight.detach(), gl.bias.detach()
+        sd[p + "norm.weight"], sd[p + "norm.bias"] = torch.ones(D), torch.zeros(D)
+    if cfg["classifier"]:
+        if cfg["mixer_dim"] != 0:
+            e = nn.Linear(D, cfg["mixer_dim"]); dcd = nn.Linear(cfg["mixer_dim"], cfg["output_dim"])
+            sd["classifier.encoder.weight"], sd["classifier.encoder.bias"] = e.weight.detach(), e.bias.detach()
+            sd["classifier.decoder.weight"], sd["classifier.decoder.bias"] = dcd.weight.detach(), dcd.bias.detach()
+    else:
+        sd["decoder.weight"] = nn.Linear(D, cfg["output_dim"], bias=False).weight.detach()
+    sd["norm.weight"], sd["norm.bias"] = torch.ones(D), torch.zeros(D)
+    return sd

@@ -103,7 +103,7 @@ def normattn_gate(x, W_n, b_n, offset, norm_fn: str):
     return n
 
 
-def ratio_hist(a, mode: int, thresholds=THRESHOLDS_RADIUS, want_out=True, counts=None, compare="float64"):
+def ratio_hist(a, mode: int, thresholds=THRESHOLDS_RADIUS, want_out=True, counts=None, compare="float64", out=None):
     """a (B,N,inner) f32|f64.  mode RATIO_NONE: plain threshold counts; ratio modes: eta (B,N-1,inner) f64 + counts."""
     a = _prep(a, name="a")
     if a.dtype not in (torch.float32, torch.float64):
@@ -111,9 +111,12 @@ def ratio_hist(a, mode: int, thresholds=THRESHOLDS_RADIUS, want_out=True, counts
     B, N = a.shape[0], a.shape[1]
     inner = int(np.prod(a.shape[2:])) if a.dim() > 2 else 1
     lib = _enter(a)
-    out = None
     if mode != L.RATIO_NONE and want_out:
-        out = torch.empty((B, N - 1) + tuple(a.shape[2:]), dtype=torch.float64, device=a.device)
+        if out is None:
+            out = torch.empty((B, N - 1) + tuple(a.shape[2:]), dtype=torch.float64, device=a.device)
+        assert out.is_contiguous() and out.dtype == torch.float64 and out.numel() == B * (N - 1) * inner
+    else:
+        out = None
     if counts is None:
         counts = new_counts(B, inner, a.device)
     thr, n = L.thresholds_arg(thresholds)
@@ -131,3 +134,219 @@ def count_moments(counts):
     s2 = torch.empty_like(s)
     L.check(lib.eigb200_count_moments(_stream(counts), _p(counts), B, inner, _p(s), _p(s2)), "eigb200_count_moments")
     return s, s2
+
+
+# ---- K1'': linear attention ---------------------------------------------------------------------------------------
+def linattn_nu(qk_buf, ld: int, B: int, T: int, H: int, d: int, k_offset: int):
+    """qk_buf: projection buffer (B*T, ld) f32 with q at column 0 and k at column `k_offset`.  -> nu (B,T,H) f64."""
+    qk_buf = _prep(qk_buf, torch.float32)
+    lib = _enter(qk_buf)
+    nu = torch.empty(B, T, H, dtype=torch.float64, device=qk_buf.device)
+    q_ptr = C.c_void_p(qk_buf.data_ptr())
+    k_ptr = C.c_void_p(qk_buf.data_ptr() + 4 * k_offset)
+    L.check(lib.eigb200_linattn_nu(_stream(qk_buf), q_ptr, k_ptr, ld, B, T, H, d, _p(nu)), "eigb200_linattn_nu")
+    return nu
+
+
+def linattn_forward(buf, ld, q_off, k_off, v_off, B, T, H, d, dv, gate=None, phi_elu=True, normalise=True, kscale=1.0):
+    """Causal linear attention over a projection buffer (B*T, ld); q/k/v live at the given column offsets."""
+    buf = _prep(buf, torch.float32)
+    lib = _enter(buf)
+    out = torch.empty(B, T, H * dv, dtype=torch.float32, device=buf.device)
+    base = buf.data_ptr()
+    gate = _prep(gate, torch.float32) if gate is not None else None
+    L.check(lib.eigb200_linattn_forward(_stream(buf), C.c_void_p(base + 4 * q_off), C.c_void_p(base + 4 * k_off),
+                                        C.c_void_p(base + 4 * v_off), ld, _p(gate), int(phi_elu), int(normalise), float(kscale),
+                                        _p(out), H * dv, B, T, H, d, dv), "eigb200_linattn_forward")
+    return out
+
+
+# ---- K2 scans -----------------------------------------------------------------------------------------------------
+def diag_scan(lam, Bu, reverse=False):
+    """lam (P,) complex64, Bu (B,T,P) complex64 -> h (B,T,P) complex64  (h_t = lam h_{t-1} + Bu_t)."""
+    lam = _prep(lam, torch.complex64); Bu = _prep(Bu, torch.complex64)
+    B, T, P = Bu.shape
+    lib = _enter(Bu)
+    h = torch.empty_like(Bu)
+    L.check(lib.eigb200_diag_scan(_stream(Bu), _p(torch.view_as_real(lam)), _p(torch.view_as_real(Bu)), _p(torch.view_as_real(h)),
+                                  B, T, P, int(reverse)), "eigb200_diag_scan")
+    return h
+
+
+def ssd_scan(x, dt, A, Bm, Cm, D=None, return_final_state=False):
+    """mamba_chunk_scan_combined semantics.  x (B,T,H,P), dt (B,T,H), A (H), Bm/Cm (B,T,G,N), D (H) -> y (B,T,H,P)."""
+    x = _prep(x, torch.float32); dt = _prep(dt, torch.float32); A = _prep(A, torch.float32)
+    Bm = _prep(Bm, torch.float32); Cm = _prep(Cm, torch.float32)
+    D = _prep(D, torch.float32) if D is not None else None
+    B, T, H, P = x.shape
+    G, N = Bm.shape[2], Bm.shape[3]
+    lib = _enter(x)
+    y = torch.empty_like(x)
+    fs = torch.empty(B, H, P, N, dtype=torch.float32, device=x.device) if return_final_state else None
+    L.check(lib.eigb200_ssd_scan(_stream(x), _p(x), H * P, _p(dt), _p(A), _p(Bm), _p(Cm), G * N, _p(D), _p(y), H * P, _p(fs),
+                                 B, T, H, P, G, N), "eigb200_ssd_scan")
+    return (y, fs) if return_final_state else y
+
+
+def mamba_conv_ssd(xbcdt, ldz, conv_w, conv_b, dt_bias, A_log, D, B, T, H, P, G, N, out=None):
+    """Fused conv+SiLU / softplus(dt) / SSD scan over the raw in_proj output (B*T, ldz) -> y (B,T,H*P)."""
+    xbcdt = _prep(xbcdt, torch.float32)
+    lib = _enter(xbcdt)
+    k = 0
+    if conv_w is not None:
+        conv_w = _prep(conv_w, torch.float32).reshape(conv_w.shape[0], -1)
+        conv_b = _prep(conv_b, torch.float32)
+        k = conv_w.shape[1]
+    y = out if out is not None else torch.empty(B, T, H * P, dtype=torch.float32, device=xbcdt.device)
+    L.check(lib.eigb200_mamba_conv_ssd(_stream(xbcdt), _p(xbcdt), ldz, _p(conv_w), _p(conv_b), k, _p(_prep(dt_bias, torch.float32)),
+                                       _p(_prep(A_log, torch.float32)), _p(_prep(D, torch.float32)), _p(y), H * P, B, T, H, P, G, N),
+            "eigb200_mamba_conv_ssd")
+    return y
+
+
+# ---- K4 + glue ----------------------------------------------------------------------------------------------------
+EPILOGUES = {"none": L.EPI_NONE, "gelu": L.EPI_GELU, "glu_residual": L.EPI_GLU_RESIDUAL, "residual": L.EPI_RESIDUAL}
+GEMM_MODES = {"auto": L.GEMM_AUTO, "simt": L.GEMM_SIMT_F32, "tc3": L.GEMM_TC_3XTF32, "tc1": L.GEMM_TC_TF32}
+_ws_cache = {}
+
+
+def linear_workspace(N, K, device):
+    lib = L.load()
+    nbytes = int(lib.eigb200_linear_workspace_bytes(N, K))
+    if nbytes == 0:
+        return None, 0
+    key = (N, K, str(device))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", out=None, ldc=None, workspace=None):
+    """a (..., K) with a.stride(-2) as the row stride -> epilogue(a W^T + bias).  weight (N,K) torch layout."""
+    assert a.is_cuda and a.dtype == torch.float32 and a.stride(-1) == 1
+    K = a.shape[-1]
+    M = a.numel() // K
+    a2 = a.reshape(M, K) if a.is_contiguous() else a
+    lda = a2.stride(0) if a2.dim() == 2 else K
+    weight = _prep(weight, torch.float32)
+    N = weight.shape[0]
+    assert weight.shape[1] == K
+    bias = _prep(bias, torch.float32) if bias is not None else None
+    nout = N // 2 if epilogue == "glu_residual" else N
+    lib = _enter(a)
+    if out is None:
+        ldc = ldc or nout
+        out = torch.empty(M, ldc, dtype=torch.float32, device=a.device)
+    else:
+        ldc = out.stride(-2)
+    ldr = 0
+    if residual is not None:
+        assert residual.is_cuda and residual.dtype == torch.float32 and residual.stride(-1) == 1
+        ldr = residual.stride(-2) if residual.dim() >= 2 else nout
+    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
+    L.check(lib.eigb200_linear(_stream(a), _p(a2), lda, _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
+                               EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb), "eigb200_linear")
+    return out
+
+
+def embedding(ids, word, pos=None):
+    ids = _prep(ids, torch.int64); word = _prep(word, torch.float32)
+    pos = _prep(pos, torch.float32) if pos is not None else None
+    B, T = ids.shape
+    V, D = word.shape
+    if pos is not None and pos.shape[0] < T:
+        raise L.Eigb200Error("embedding: sequence length %d exceeds max_position_embeddings %d" % (T, pos.shape[0]))
+    lib = _enter(ids)
+    out = torch.empty(B, T, D, dtype=torch.float32, device=ids.device)
+    L.check(lib.eigb200_embedding(_stream(ids), _p(ids), _p(word), _p(pos), _p(out), B, T, D, V), "eigb200_embedding")
+    return out
+
+
+def layernorm(x, w, b, eps=1e-5):
+    x = _prep(x, torch.float32)
+    D = x.shape[-1]
+    lib = _enter(x)
+    out = torch.empty_like(x)
+    L.check(lib.eigb200_layernorm(_stream(x), _p(x), _p(_prep(w, torch.float32)), _p(_prep(b, torch.float32)), float(eps), _p(out),
+                                  x.numel() // D, D), "eigb200_layernorm")
+    return out
+
+
+def conv_silu(x, ldx, w, b, B, T, Cn, out=None, ldo=None):
+    """x: buffer (B*T, ldx) whose first Cn columns are convolved; -> (B*T, ldo)."""
+    lib = _enter(x)
+    w = _prep(w, torch.float32).reshape(w.shape[0], -1); b = _prep(b, torch.float32)
+    if out is None:
+        ldo = ldo or Cn
+        out = torch.empty(B * T, ldo, dtype=torch.float32, device=x.device)
+    L.check(lib.eigb200_conv_silu(_stream(x), _p(x), ldx, _p(w), _p(b), w.shape[1], _p(out), ldo, B, T, Cn), "eigb200_conv_silu")
+    return out
+
+
+def add(a, b):
+    a = _prep(a, torch.float32); b = _prep(b, torch.float32)
+    lib = _enter(a)
+    out = torch.empty_like(a)
+    L.check(lib.eigb200_add(_stream(a), _p(a), _p(b), _p(out), a.numel()), "eigb200_add")
+    return out
+
+
+def mul_silu(y, z):
+    y = _prep(y, torch.float32); z = _prep(z, torch.float32)
+    lib = _enter(y)
+    out = torch.empty_like(y)
+    L.check(lib.eigb200_mul_silu(_stream(y), _p(y), _p(z), _p(out), y.numel()), "eigb200_mul_silu")
+    return out
+
+
+def gelu(x):
+    x = _prep(x, torch.float32)
+    lib = _enter(x)
+    out = torch.empty_like(x)
+    L.check(lib.eigb200_gelu(_stream(x), _p(x), _p(out), x.numel()), "eigb200_gelu")
+    return out
+
+
+def scale_cols(a, s):
+    a = _prep(a, torch.float32); s = _prep(s, torch.float32)
+    lib = _enter(a)
+    out = torch.empty_like(a)
+    cols = a.shape[-1]
+    L.check(lib.eigb200_scale_cols(_stream(a), _p(a), _p(s), _p(out), a.numel() // cols, cols), "eigb200_scale_cols")
+    return out
+
+
+SSM_KINDS = {"lru": 0, "s5_zoh": 1, "s5_bilinear": 2}
+
+
+def ssm_lambda(kind: str, p0, p1, p2=None):
+    """Parameter-only eigenvalues (P,) complex64 of LRU / S5 on the device."""
+    p0 = _prep(p0, torch.float32).reshape(-1); p1 = _prep(p1, torch.float32).reshape(-1)
+    p2 = _prep(p2, torch.float32).reshape(-1) if p2 is not None else None
+    lib = _enter(p0)
+    lam = torch.empty(p0.numel(), dtype=torch.complex64, device=p0.device)
+    L.check(lib.eigb200_ssm_lambda(_stream(p0), SSM_KINDS[kind], _p(p0), _p(p1), _p(p2), p0.numel(), _p(torch.view_as_real(lam))),
+            "eigb200_ssm_lambda")
+    return lam
+
+
+def dplr_abar(Lambda, Pv, Qv, step):
+    """(nmat,N) complex64 x3, step (nmat,) f32 -> Abar (nmat,N,N) complex64."""
+    Lambda = _prep(Lambda, torch.complex64); Pv = _prep(Pv, torch.complex64); Qv = _prep(Qv, torch.complex64)
+    step = _prep(step, torch.float32).reshape(-1)
+    nmat, N = Lambda.shape
+    lib = _enter(Lambda)
+    Ab = torch.empty(nmat, N, N, dtype=torch.complex64, device=Lambda.device)
+    L.check(lib.eigb200_dplr_abar(_stream(Lambda), _p(torch.view_as_real(Lambda)), _p(torch.view_as_real(Pv)), _p(torch.view_as_real(Qv)),
+                                  _p(step), nmat, N, _p(torch.view_as_real(Ab))), "eigb200_dplr_abar")
+    return Ab
+
+
+def eigvals_c64(A):
+    """np.linalg.eigvals for a batch (nmat,N,N) of complex64 matrices, N <= 64.  Returns (eig (nmat,N) complex64, info (nmat,) int32)."""
+    A = _prep(A, torch.complex64).clone()
+    nmat, N, _ = A.shape
+    lib = _enter(A)
+    ev = torch.empty(nmat, N, dtype=torch.complex64, device=A.device)
+    info = torch.empty(nmat, dtype=torch.int32, device=A.device)
+    L.check(lib.eigb200_eigvals_c64(_stream(A), _p(torch.view_as_real(A)), nmat, N, _p(torch.view_as_real(ev)), _p(info)),
+            "eigb200_eigvals_c64")
+    return ev, info

@@ -1,0 +1,126 @@
+"""GPU parity: block glue (embedding, LayerNorm, conv+SiLU, elementwise), the FFMA GEMM with its epilogues, linear attention."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import eigb200.ops as ops
+    return ops
+
+
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_embedding(ops):
+    rng = np.random.default_rng(0)
+    V, D, B, T = 100, 64, 5, 17
+    w = rng.normal(size=(V, D)).astype(np.float32); pos = rng.normal(size=(32, D)).astype(np.float32)
+    ids = rng.integers(0, V, (B, T))
+    np.testing.assert_array_equal(ops.embedding(dev(ids), dev(w)).cpu().numpy(), w[ids])
+    np.testing.assert_array_equal(ops.embedding(dev(ids), dev(w), dev(pos)).cpu().numpy(), w[ids] + pos[:T][None])
+
+
+@pytest.mark.parametrize("D", [32, 128, 512, 1000])
+def test_layernorm(ops, D):
+    rng = np.random.default_rng(D)
+    x = (rng.normal(size=(7, 19, D)) * 3 + 1).astype(np.float32)
+    w = rng.normal(size=D).astype(np.float32); b = rng.normal(size=D).astype(np.float32)
+    out = ops.layernorm(dev(x), dev(w), dev(b)).cpu().numpy()
+    ref = O.layer_norm(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64))
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 8])
+def test_conv_silu(ops, k):
+    rng = np.random.default_rng(k)
+    B, T, C, ld = 3, 150, 70, 96
+    buf = rng.normal(size=(B * T, ld)).astype(np.float32)
+    w = rng.normal(size=(C, k)).astype(np.float32); b = rng.normal(size=C).astype(np.float32)
+    out = ops.conv_silu(dev(buf), ld, dev(w), dev(b), B, T, C).cpu().numpy()
+    ref = O.causal_depthwise_conv_silu(buf.reshape(B, T, ld)[..., :C].astype(np.float64), w.astype(np.float64), b.astype(np.float64))
+    np.testing.assert_allclose(out.reshape(B, T, C), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_elementwise(ops):
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(1031,)).astype(np.float32) * 3; b = rng.normal(size=(1031,)).astype(np.float32) * 3
+    np.testing.assert_array_equal(ops.add(dev(a), dev(b)).cpu().numpy(), a + b)
+    np.testing.assert_allclose(ops.mul_silu(dev(a), dev(b)).cpu().numpy(), a * (b / (1 + np.exp(-b.astype(np.float64)))), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ops.gelu(dev(a)).cpu().numpy(), O.gelu_erf(a.astype(np.float64)), rtol=1e-5, atol=1e-7)
+    s = rng.normal(size=(8,)).astype(np.float32); m = rng.normal(size=(13, 8)).astype(np.float32)
+    np.testing.assert_array_equal(ops.scale_cols(dev(m), dev(s)).cpu().numpy(), m * s)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 161, 128), (1000, 128, 128), (257, 50, 32), (64, 96, 33), (5, 7, 3), (2048, 256, 128)])
+@pytest.mark.parametrize("epi", ["none", "gelu", "residual", "glu_residual"])
+def test_linear_simt(ops, M, N, K, epi):
+    if epi == "glu_residual" and N % 2:
+        N += 1
+    rng = np.random.default_rng(M + N + K)
+    a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    nout = N // 2 if epi == "glu_residual" else N
+    r = rng.normal(size=(M, nout)).astype(np.float32)
+    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r) if "residual" in epi else None, mode="simt").cpu().numpy()
+    z = a.astype(np.float64) @ w.astype(np.float64).T + bias
+    if epi == "gelu":
+        ref = O.gelu_erf(z)
+    elif epi == "residual":
+        ref = z + r
+    elif epi == "glu_residual":
+        ref = z[:, :nout] * O.sigmoid(z[:, nout:]) + r
+    else:
+        ref = z
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_linear_strided_output(ops):
+    rng = np.random.default_rng(5)
+    M, N, K = 100, 161, 128
+    a = rng.normal(size=(M, K)).astype(np.float32); w = rng.normal(size=(N, K)).astype(np.float32)
+    out = ops.linear(dev(a), dev(w), None, ldc=164, mode="simt").cpu().numpy()
+    assert out.shape == (M, 164)
+    np.testing.assert_allclose(out[:, :N], a.astype(np.float64) @ w.astype(np.float64).T, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("H,d,dv,normalise", [(2, 16, 16, True), (1, 64, 64, True), (4, 32, 64, False), (1, 128, 128, True), (8, 64, 64, False)])
+def test_linattn_forward(ops, H, d, dv, normalise):
+    rng = np.random.default_rng(d + dv)
+    B, T = 2, 45
+    ld = 2 * H * d + H * dv + 3
+    buf = rng.normal(size=(B * T, ld)).astype(np.float32)
+    gate = rng.uniform(0.1, 1.0, (B, T, H)).astype(np.float32)
+    out = ops.linattn_forward(dev(buf), ld, 0, H * d, 2 * H * d, B, T, H, d, dv, gate=None if normalise else dev(gate),
+                              phi_elu=True, normalise=normalise, kscale=1.0 if normalise else 0.25).cpu().numpy()
+    b3 = buf.reshape(B, T, ld).astype(np.float64)
+    q = O.elu(b3[..., :H * d].reshape(B, T, H, d)) + 1; k = O.elu(b3[..., H * d:2 * H * d].reshape(B, T, H, d)) + 1
+    v = b3[..., 2 * H * d:2 * H * d + H * dv].reshape(B, T, H, dv)
+    kv = np.cumsum(np.einsum("bthd,bthe->bthde", k * (1.0 if normalise else 0.25), v), axis=1)
+    num = np.einsum("bthd,bthde->bthe", q, kv)
+    if normalise:
+        ref = num / np.einsum("bthd,bthd->bth", q, np.cumsum(k, axis=1))[..., None]
+    else:
+        ref = num * gate[..., None]
+    np.testing.assert_allclose(out.reshape(B, T, H, dv), ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
+
+
+def test_linattn_nu_and_eta(ops):
+    from conftest import load_golden
+    g = load_golden("lin_softmax_extractor")
+    D, dqk, H = [int(v) for v in g["dims"]]
+    B, T, _ = g["x"].shape
+    qk = ops.linear(dev(g["x"]), dev(g["weight"][:2 * dqk]), dev(g["bias"][:2 * dqk]), mode="simt")
+    nu = ops.linattn_nu(qk, 2 * dqk, B, T, H, dqk // H, dqk)
+    eta, counts = ops.ratio_hist(nu, 2)
+    np.testing.assert_allclose(eta.cpu().numpy(), g["eta_lin"][..., 0], rtol=1e-5)
+    with np.errstate(invalid="ignore"):
+        exp = np.moveaxis(O.threshold_counts(eta.cpu().numpy(), O.THRESHOLDS_RADIUS, axis=1), 0, -1)
+    np.testing.assert_array_equal(counts.cpu().numpy()[..., :7], exp)

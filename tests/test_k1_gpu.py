@@ -22,6 +22,12 @@ def _dev(a, dtype=None):
     return t.to(dtype) if dtype is not None else t
 
 
+def _radius32(lam):
+    """float32 radius of a real float32 array the way the reference forms it (eval_eig.py:605-606)."""
+    lam = np.asarray(lam, np.float32)
+    return np.sqrt(np.power(lam, 2) + np.power(np.zeros_like(lam), 2))
+
+
 def _counts_from_values(vals, thr, compare="float64"):
     """Oracle bin counts (B,inner,nthr+1) of values (B,N,inner)."""
     with np.errstate(invalid="ignore"):
@@ -39,7 +45,7 @@ def test_mamba2_eig_golden(ops):
     assert_eig_close(lam, ref64, rtol=1e-5, what="lambda vs fp64 oracle")
     assert_eig_close(lam, g["lam"][..., 0], rtol=2e-5, what="lambda vs reference fp32 output")
     # bin counts are EXACT for the values the kernel produced
-    exp = _counts_from_values(lam, O.THRESHOLDS_RADIUS)
+    exp = _counts_from_values(_radius32(lam), O.THRESHOLDS_RADIUS)
     np.testing.assert_array_equal(counts[..., :7], exp)
     np.testing.assert_array_equal(counts[..., 7], lam.shape[1])
 
@@ -56,7 +62,7 @@ def test_mamba2_eig_shapes(ops, B, T, D, H):
     z = x.astype(np.float64) @ W.astype(np.float64).T + dt_bias
     ref = np.exp(O.softplus(z) * -np.exp(A_log.astype(np.float64)))
     assert_eig_close(lam, ref, rtol=1e-5)
-    np.testing.assert_array_equal(counts[..., :7], _counts_from_values(lam, O.THRESHOLDS_RADIUS))
+    np.testing.assert_array_equal(counts[..., :7], _counts_from_values(_radius32(lam), O.THRESHOLDS_RADIUS))
     np.testing.assert_array_equal(counts[..., 7], T)
     # statistics-only call (no eigenvalue array materialised) gives the same counts
     _, c2 = ops.mamba2_eig(_dev(x), _dev(W), _dev(dt_bias), _dev(A_log), want_lam=False)
@@ -77,7 +83,7 @@ def test_mamba2_eig_bf16_activations(ops):
     assert_eig_close(lam.cpu().numpy(), ref_r, rtol=1e-5)
     # ... and within the north-star's 1e-2 of the fp32-input result
     ref = np.exp(O.softplus(x.astype(np.float64) @ W.astype(np.float64).T + dt_bias) * -np.exp(A_log.astype(np.float64)))
-    np.testing.assert_allclose(lam.cpu().numpy(), ref, rtol=1e-2)
+    assert_eig_close(lam.cpu().numpy(), ref, rtol=1e-2, what="bf16 activations vs fp32-input truth")
 
 
 def test_edge_semantics_and_compare_modes(ops):
@@ -157,7 +163,7 @@ def test_full_size_properties_c2(ops):
     assert (counts[..., 7] == T).all()
     assert (counts[..., :7].sum(-1) >= T).all() and (counts[..., :7].sum(-1) <= T + 8).all()
     thr = torch.tensor(O.THRESHOLDS_RADIUS, device="cuda", dtype=torch.float64)
-    l64 = lam.double()
+    l64 = torch.sqrt(lam * lam).double()
     first = ((l64 >= 0) & (l64 <= thr[0])).sum(1)
     mid = ((l64 >= thr[1]) & (l64 <= thr[2])).sum(1)
     assert torch.equal(first.int(), counts[..., 0]) and torch.equal(mid.int(), counts[..., 2])

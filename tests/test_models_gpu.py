@@ -1,0 +1,134 @@
+"""GPU parity at model level: the reference's per-layer analysis loop (block forward -> extractor on the block OUTPUT)
+through eigb200.layers / eigb200.analysis against the golden vectors produced by the reference's own classes, and the
+LRU / S5 layer calls against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import golden_model, assert_eig_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eig():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import eigb200.analysis as A
+    import eigb200.layers as Ly
+    import eigb200.extractors as E
+    import eigb200.ssm as S
+    return A, Ly, E, S
+
+
+def _sd_torch(sd):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def test_mamba_model_pass_vs_reference(eig):
+    A, Ly, E, S = eig
+    sd, cfg, g = golden_model("model_mamba2")
+    model = Ly.MambaDev(cfg, _sd_torch(sd), "cuda")
+    X = torch.from_numpy(g["X"]).cuda()
+    # layer by layer: activations after every block, extractor through the drop-in signature
+    x = model.encoder(X)
+    np.testing.assert_array_equal(x.cpu().numpy(), g["act_0"])
+    for i, blk in enumerate(model.blocks):
+        x = blk(x)
+        ref = g["act_%d" % (i + 1)]
+        assert np.abs(x.cpu().numpy() - ref).max() <= 2e-5 * np.abs(ref).max(), "block %d" % i
+        lam = E.get_eig_mamba2(x, blk)
+        assert lam.shape == g["eig"][..., i:i + 1].shape and lam.dtype == np.float32
+        assert_eig_close(lam, g["eig"][..., i:i + 1], rtol=3e-5, what="layer %d lambda vs reference" % i)
+    # whole pass: eig layout and statistics
+    res = A.mamba_pass(model, X)
+    e = res.eig_host()
+    assert e.shape == g["eig"].shape and e.dtype == g["eig"].dtype
+    assert_eig_close(e, g["eig"], rtol=3e-5)
+    pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
+    assert pct.shape == g["percentage"].shape
+    assert np.abs(pct - g["percentage"]).max() <= 100.0 / e.shape[1] + 1e-9            # at most one value on the other side of an edge
+    # exact for our own values, via the drop-in threshold_analysis and the reference's radius expression
+    rad = np.sqrt(np.power(e.real, 2) + np.power(e.imag, 2))
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(pct, O.threshold_analysis(rad, O.THRESHOLDS_RADIUS))
+    np.testing.assert_array_equal(E.threshold_analysis(rad, O.THRESHOLDS_RADIUS, 3, 2, 8), pct)
+    ph = E.phase_percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 6)
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(ph, O.threshold_analysis(np.arctan2(e.imag, e.real) * 180 / np.pi, O.THRESHOLDS_PHASE))
+
+
+@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp"])
+def test_transformer_model_pass_vs_reference(eig, name):
+    A, Ly, E, S = eig
+    sd, cfg, g = golden_model(name)
+    model = Ly.TransformerDev(cfg, _sd_torch(sd), "cuda")
+    X = torch.from_numpy(g["X"]).cuda()
+    x = model.encoder(X)
+    np.testing.assert_allclose(x.cpu().numpy(), g["act_0"], rtol=0, atol=1e-6)
+    for i, layer in enumerate(model.layers):
+        x = layer(x)
+        ref = g["act_%d" % (i + 1)]
+        assert np.abs(x.cpu().numpy() - ref).max() <= 3e-5 * np.abs(ref).max(), "block %d" % i
+        if cfg["attention_fn"] == "lin-attention":
+            eta = E.get_eig_att_linear(x, layer, cfg["state_dim"], cfg["num_heads"], cfg["hidden_dim"])
+        else:
+            eta = E.get_eig_att_norm(x, layer, cfg["state_dim"], cfg["num_heads"], cfg["hidden_dim"], cfg)
+        r = g["eig"][..., i:i + 1]
+        assert eta.shape == r.shape and eta.dtype == np.float64
+        fin = np.isfinite(r)
+        np.testing.assert_allclose(eta[fin], r[fin], rtol=3e-4)
+    res = A.transformer_pass(model, X, cfg)
+    e = res.eig_host()
+    fin = np.isfinite(g["eig"])
+    np.testing.assert_allclose(e[fin], g["eig"][fin], rtol=3e-4)
+    pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(pct, O.threshold_analysis(e, O.THRESHOLDS_RADIUS))
+        ph = E.phase_percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 6)
+        np.testing.assert_array_equal(ph, O.threshold_analysis(0 * e, O.THRESHOLDS_PHASE))
+    assert np.abs(pct - g["percentage"]).max() <= 100.0 / e.shape[1] + 1e-9
+    np.testing.assert_array_equal(ph, g["percentage_phase"])
+
+
+def _lru_params(rng, P, H):
+    lam = np.sqrt(rng.uniform(0.9 ** 2, 0.999 ** 2, P)); nu_log = np.log(-np.log(lam)); theta_log = np.log(6.28 * rng.uniform(size=P))
+    return dict(nu_log=nu_log.astype(np.float32), theta_log=theta_log.astype(np.float32),
+                gamma_log=np.log(np.sqrt(1 - lam ** 2)).astype(np.float32),
+                B_re=(rng.normal(size=(P, H)) / np.sqrt(2 * H)).astype(np.float32), B_im=(rng.normal(size=(P, H)) / np.sqrt(2 * H)).astype(np.float32),
+                C_re=(rng.normal(size=(H, P)) / np.sqrt(P)).astype(np.float32), C_im=(rng.normal(size=(H, P)) / np.sqrt(P)).astype(np.float32),
+                D=rng.normal(size=H).astype(np.float32))
+
+
+def test_lru_layer_call(eig):
+    A, Ly, E, S = eig
+    rng = np.random.default_rng(0)
+    P, H, B, T = 64, 32, 3, 200
+    prm = _lru_params(rng, P, H)
+    u = rng.normal(size=(B, T, H)).astype(np.float32)
+    y, h = S.lru_forward(prm, u, return_states=True)
+    yr, hr, _ = O.lru_forward(prm, u)
+    scale = np.abs(hr).max(axis=1, keepdims=True)
+    assert (np.abs(h.cpu().numpy() - hr) <= 1e-5 * scale).all()
+    assert np.abs(y.cpu().numpy() - yr).max() <= 1e-5 * np.abs(yr).max()
+
+
+@pytest.mark.parametrize("disc,bidir", [("zoh", False), ("bilinear", False), ("zoh", True)])
+def test_s5_layer_call(eig, disc, bidir):
+    A, Ly, E, S = eig
+    rng = np.random.default_rng(1)
+    P, H, B, T = 32, 24, 2, 150
+    prm = dict(Lambda_re=(-np.abs(rng.normal(0.5, 0.2, P))).astype(np.float32), Lambda_im=rng.normal(0, 6, P).astype(np.float32),
+               B=rng.normal(size=(P, H, 2)).astype(np.float32) / np.sqrt(H), D=rng.normal(size=H).astype(np.float32),
+               log_step=rng.uniform(np.log(1e-3), np.log(1e-1), (P, 1)).astype(np.float32))
+    if bidir:
+        prm["C1"] = rng.normal(size=(H, P, 2)).astype(np.float32); prm["C2"] = rng.normal(size=(H, P, 2)).astype(np.float32)
+    else:
+        prm["C"] = rng.normal(size=(H, P, 2)).astype(np.float32)
+    u = rng.normal(size=(B, T, H)).astype(np.float32)
+    y, h = S.s5_forward(prm, u, discretization=disc, conj_sym=True, bidirectional=bidir, return_states=True)
+    yr, hr, _ = O.s5_forward(prm, u, discretization=disc, conj_sym=True, bidirectional=bidir)
+    scale = np.abs(hr).max(axis=1, keepdims=True)
+    assert (np.abs(h.cpu().numpy() - hr) <= 2e-5 * scale).all()
+    assert np.abs(y.cpu().numpy() - yr).max() <= 2e-5 * np.abs(yr).max()
