@@ -65,16 +65,18 @@ int         eigb200_zero_i32(void* stream, int32_t* d_buf, size_t n);
  * output (:605-618, :335-362).  lambda[b,t,h] = exp(softplus(x[b,t,:] . W_dt[h,:] + dt_bias[h]) * -exp(A_log[h])).
  *   d_x      (B,T,D) float32 (x_dtype EIGB200_F32) or bfloat16 (EIGB200_BF16), D % 4 == 0 (bf16: D % 8 == 0), 16-byte aligned
  *   d_W_dt   (H,D)   float32: rows [d_inner + 2*ngroups*d_state, +nheads) of in_proj.weight (models/mamba.py:62-64)
- *   d_lam    (B,T,H) float32 out, may be NULL (statistics only)
+ *   d_lam    float32 out, may be NULL (statistics only); entry (b,t,h) is written at d_lam[((b*T + t)*H + h) * lam_stride], so
+ *            lam_stride = 1 gives a dense (B,T,H) array and lam_stride = L with d_lam offset by the layer index writes straight
+ *            into the reference's (B,T,H,L) layout (np.concatenate(..., axis=-1), eval_eig.py:524-526)
  *   d_counts (B,H,8) int32 accumulated, may be NULL */
 int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
                        const float* d_W_dt, const float* d_dt_bias, const float* d_A_log, int H,
-                       float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+                       float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
 
 /* get_eig_mamba2_LTI (analysis/eval_eig.py:192-205): lambda[h] = exp(beta[h] * -softplus(A[h])), broadcast over (B,T).
  * d_lam (B,T,H) may be NULL; d_counts (B,H,8) accumulated. */
 int eigb200_mamba2_lti_eig(void* stream, const float* d_A, const float* d_beta, int64_t B, int64_t T, int H,
-                           float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+                           float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
 
 /* ---- K1': normalised-attention gate  n[b,t,h] = exp(-norm_fn(x . W_n[h] + b_n[h] (+ offset[h])))  in float32 --------
  * First half of get_eig_att_norm (analysis/eval_eig.py:154-163); W_n/b_n are rows [D + 2*d_qk, +H) of Wvqkn
@@ -104,10 +106,11 @@ int eigb200_softmax_eta(void* stream, const double* d_nu, const float* d_m, int6
  * a: (B,N,inner) of `dtype` (EIGB200_F32 / EIGB200_F64).  mode NONE: v = a[b,n,i] (N values per (b,i));
  * NEXT_OVER_CUR: v = z(a[b,n+1,i]) / z(a[b,n,i]); CUR_OVER_NEXT: v = z(a[b,n,i]) / z(a[b,n+1,i])  (N-1 values),
  * z(u) = 2e-23 if u == 0 else u (analysis/eval_eig.py:127, :167), computed in float64.
- * d_out: values written as float64 (ratio modes) -- (B,N-1,inner), may be NULL.   d_counts (B,inner,8) accumulated.
+ * d_out: values written as float64 (ratio modes), may be NULL; entry (b,n,i) at d_out[((b*(N-1) + n)*inner + i) * out_stride]
+ * (out_stride = 1: dense (B,N-1,inner)).   d_counts (B,inner,8) accumulated.
  * With mode NONE this is threshold_analysis itself (analysis/eval_eig.py:335-362) for a (B,N,H*L) array. */
 int eigb200_ratio_hist(void* stream, const void* d_a, int dtype, int mode, int64_t B, int64_t N, int64_t inner,
-                       double* d_out, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+                       double* d_out, int64_t out_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
 
 /* Batch moments of the bin counts: sum_b c and sum_b c^2 (int64) -- the only cross-sample (and cross-GPU) quantities
  * behind np.mean / np.std over the batch axis (analysis/eval_eig.py:620-623, :677-680).  d_counts (B,inner,8);

@@ -11,7 +11,7 @@ import math
 import numpy as np
 
 __all__ = [
-    "softplus", "elu", "norm_fn_apply",
+    "softplus", "elu", "sigmoid", "norm_fn_apply",
     "mamba2_dt_rows", "mamba2_eig", "mamba2_lti_eig", "normattn_rows", "normattn_eta",
     "linattn_qk", "linattn_eta_quadratic", "linattn_eta_prefix", "softmax_eta_quadratic", "softmax_eta_closed",
     "THRESHOLDS_RADIUS", "THRESHOLDS_PHASE", "threshold_counts", "threshold_analysis", "threshold_analysis_ssm",
@@ -20,7 +20,7 @@ __all__ = [
     "make_hippo", "make_nplr_hippo", "make_dplr_hippo", "discrete_dplr_abar", "s4_eigvals", "dplr_exact_spectrum",
     "ssd_scan_sequential", "ssd_scan_chunked", "layer_norm", "causal_depthwise_conv_silu", "gelu_erf", "glu",
     "ssd_mixer_forward", "mamba_block_forward", "token_embedding", "linattn_forward", "normattn_forward",
-    "transformer_block_forward", "mamba_eval_pass", "transformer_eval_pass",
+    "transformer_block_forward", "mamba_eval_pass", "transformer_eval_pass", "mamba_eval_pass_torch_cpu",
 ]
 
 # --------------------------------------------------------------------------------------------------
@@ -717,3 +717,53 @@ def transformer_eval_pass(ids_or_x, state_dict, cfg, dtype=np.float64, eta_dtype
                                      p.get("attention.inner_attn.offset") if cfg.get("offset", False) else None,
                                      cfg["norm_fn"], cfg["d_model"], cfg["d_qk"], cfg["num_heads"], eta_dtype))
     return np.concatenate(etas, axis=-1), x
+
+
+# --------------------------------------------------------------------------------------------------
+# torch-CPU fp32 port of one Mamba analysis pass -- the TIMED CPU BASELINE (bench.py cpu_baseline / --impl reference)
+# --------------------------------------------------------------------------------------------------
+
+def mamba_eval_pass_torch_cpu(ids, state_dict, cfg, chunk=64):
+    """The reference's per-layer loop for the Mamba branch (eval_eig.py:575-618) the way it runs on a host without CUDA:
+    torch fp32 on all cores for the block forward (F.layer_norm, F.linear, F.conv1d, chunked SSD in place of the
+    CUDA-only mamba_ssm Triton kernel), get_eig_mamba2's projection/softplus/exp, `.numpy()` per layer, np.concatenate,
+    then the radius and the threshold statistics in NumPy.  Returns (eig (B,T,H,L) f32, percentage (7,B,H,L), phase pct)."""
+    import torch
+    import torch.nn.functional as F
+    sd = {k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v))) for k, v in state_dict.items()}
+    di, G, N, H, hd = cfg["d_inner"], cfg["ngroups"], cfg["d_state"], cfg["nheads"], cfg["headdim"]
+    with torch.no_grad():
+        ids = torch.as_tensor(ids)
+        x = F.embedding(ids, sd["encoder.word_embeddings.weight"])
+        Bsz, T, D = x.shape
+        eig = None
+        for i in range(cfg["num_layers"]):
+            p = "blocks.%d." % i
+            skip = x
+            xn = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"]) if cfg.get("prenorm", True) else x
+            z = F.linear(xn, sd[p + "mamba.in_proj.weight"])
+            xBC, dt = z[..., : di + 2 * G * N], z[..., di + 2 * G * N:]
+            dt = F.softplus(dt + sd[p + "mamba.dt_bias"])
+            if p + "mamba.conv1d.weight" in sd:
+                w = sd[p + "mamba.conv1d.weight"]
+                k = w.shape[-1]
+                xBC = F.silu(F.conv1d(xBC.transpose(1, 2), w, sd[p + "mamba.conv1d.bias"], padding=k - 1, groups=w.shape[0]).transpose(1, 2))[:, :T]
+            xs, Bm, Cm = xBC[..., :di], xBC[..., di:di + G * N], xBC[..., di + G * N:]
+            y = ssd_scan_chunked(xs.reshape(Bsz, T, H, hd), dt, -torch.exp(sd[p + "mamba.A_log"]), Bm.reshape(Bsz, T, G, N),
+                                 Cm.reshape(Bsz, T, G, N), sd[p + "mamba.D"], chunk=chunk).reshape(Bsz, T, di)
+            o = F.gelu(F.linear(y, sd[p + "mamba.out_proj.weight"]))
+            if p + "glu.linear.weight" in sd:
+                g = F.linear(o, sd[p + "glu.linear.weight"], sd[p + "glu.linear.bias"])
+                o = g[..., :D] * torch.sigmoid(g[..., D:])
+            x = o + skip
+            if not cfg.get("prenorm", True):
+                x = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"])
+            # get_eig_mamba2 (eval_eig.py:176-190): the whole in_proj again on the block output
+            zz = F.linear(x, sd[p + "mamba.in_proj.weight"])
+            lam = torch.exp(F.softplus(zz[..., di + 2 * G * N:] + sd[p + "mamba.dt_bias"]) * -torch.exp(sd[p + "mamba.A_log"]))
+            lam = np.expand_dims(lam.numpy(), axis=-1)
+            eig = lam if eig is None else np.concatenate((eig, lam), axis=-1)
+    rad = np.sqrt(np.power(eig.real, 2) + np.power(eig.imag, 2))
+    pct = threshold_analysis(rad, THRESHOLDS_RADIUS)
+    ph = threshold_analysis(np.arctan2(eig.imag, eig.real) * 180 / np.pi, THRESHOLDS_PHASE)
+    return eig, pct, ph

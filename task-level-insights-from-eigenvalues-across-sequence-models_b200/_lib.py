@@ -27,13 +27,13 @@ SIGNATURES = {
     "eigb200_device_info": [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "eigb200_set_device": [_i],
     "eigb200_zero_i32": [_vp, _vp, _sz],
-    "eigb200_mamba2_eig": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _dp, _i, _i],
-    "eigb200_mamba2_lti_eig": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _dp, _i, _i],
+    "eigb200_mamba2_eig": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _dp, _i, _i],
+    "eigb200_mamba2_lti_eig": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_normattn_gate": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _i, _vp],
     "eigb200_linattn_nu": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "eigb200_softmax_nu": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "eigb200_softmax_eta": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _dp, _i],
-    "eigb200_ratio_hist": [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _vp, _dp, _i, _i],
+    "eigb200_ratio_hist": [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_count_moments": [_vp, _vp, _i64, _i64, _vp, _vp],
     "eigb200_diag_scan": [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i],
     "eigb200_ssd_scan": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i],

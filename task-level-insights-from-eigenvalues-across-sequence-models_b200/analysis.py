@@ -35,16 +35,21 @@ thresholds_phase = E.THRESHOLDS_PHASE
 # ----------------------------------------------------------------------------------------------------------------------
 
 class PassResult:
-    """eig: device tensor (L, B, T', H) or None; counts: (L, B, H, 8) int32 device tensor; n_per_seq = T'."""
+    """eig: device tensor (B, T', H, L) -- already the reference's layout (np.concatenate along the last axis,
+    eval_eig.py:524-526), each layer's kernel writes its own l-column -- or None; counts: (L, B, H, 8) int32 device tensor;
+    n_per_seq = T'."""
 
     def __init__(self, eig, counts, n_per_seq, x_last):
         self.eig, self.counts, self.n_per_seq, self.x_last = eig, counts, n_per_seq, x_last
 
-    def eig_host(self):
-        """(B, T', H, L) numpy, the reference's layout (np.concatenate along the last axis, eval_eig.py:524-526)."""
+    def eig_host(self, pinned_out=None):
+        """One device->host copy; no host-side permutation."""
         if self.eig is None:
             return None
-        return np.ascontiguousarray(self.eig.permute(1, 2, 3, 0).cpu().numpy())
+        if pinned_out is not None:
+            pinned_out.copy_(self.eig, non_blocking=True)
+            return pinned_out
+        return self.eig.cpu().numpy()
 
 
 def mamba_pass(model: "Ly.MambaDev", X, pseudoLTI=False, want_eig=True, compare="float64") -> PassResult:
@@ -53,16 +58,15 @@ def mamba_pass(model: "Ly.MambaDev", X, pseudoLTI=False, want_eig=True, compare=
     B, T, _ = x.shape
     H = model.blocks[0].mamba.nheads
     nl = len(model.blocks)
-    eig = torch.empty(nl, B, T, H, dtype=torch.float32, device=x.device) if want_eig else None
+    eig = torch.empty(B, T, H, nl, dtype=torch.float32, device=x.device) if want_eig else None
     counts = torch.zeros(nl, B, H, ops.NSLOT, dtype=torch.int32, device=x.device)
     for i, blk in enumerate(model.blocks):
         x = blk(x)
+        out_i = eig[..., i] if want_eig else None
         if pseudoLTI:
-            lam, _ = E.get_eig_mamba2_LTI_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare)
-            if want_eig:
-                eig[i].copy_(lam)
+            E.get_eig_mamba2_LTI_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=out_i)
         else:
-            E.get_eig_mamba2_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=eig[i] if want_eig else None)
+            E.get_eig_mamba2_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=out_i)
     return PassResult(eig, counts, T, x)
 
 
@@ -72,7 +76,7 @@ def transformer_pass(model: "Ly.TransformerDev", X, cfg, want_eig=True, compare=
     B, T, _ = x.shape
     H, dqk, dm = cfg["num_heads"], cfg["state_dim"], cfg["hidden_dim"]
     nl = len(model.layers)
-    eig = torch.empty(nl, B, T - 1, H, dtype=torch.float64, device=x.device) if want_eig else None
+    eig = torch.empty(B, T - 1, H, nl, dtype=torch.float64, device=x.device) if want_eig else None
     counts = torch.zeros(nl, B, H, ops.NSLOT, dtype=torch.int32, device=x.device)
     fn = cfg["attention_fn"]
     for i, layer in enumerate(model.layers):
@@ -81,11 +85,11 @@ def transformer_pass(model: "Ly.TransformerDev", X, cfg, want_eig=True, compare=
             att = layer.attention
             qk = ops.linear(x, att.W_qk, att.b_qk)
             nu = ops.linattn_nu(qk, 2 * dqk, B, T, H, att.head_dim, dqk)
-            ops.ratio_hist(nu, L.RATIO_CUR_OVER_NEXT, want_out=want_eig, counts=counts[i], compare=compare, out=eig[i] if want_eig else None)
+            ops.ratio_hist(nu, L.RATIO_CUR_OVER_NEXT, want_out=want_eig, counts=counts[i], compare=compare, out=eig[..., i] if want_eig else None)
         elif fn == "norm-attention":
             att = layer.attention
             n = ops.normattn_gate(x, att.W_n, att.b_n, att.inner_attn.offset if cfg["offset"] else None, cfg["norm_fn"])
-            ops.ratio_hist(n, L.RATIO_NEXT_OVER_CUR, want_out=want_eig, counts=counts[i], compare=compare, out=eig[i] if want_eig else None)
+            ops.ratio_hist(n, L.RATIO_NEXT_OVER_CUR, want_out=want_eig, counts=counts[i], compare=compare, out=eig[..., i] if want_eig else None)
         elif fn == "sm-attention":
             raise NotImplementedError("sm-attention analysis is SURVEY 8f row f3 (next); not on the eigb200 path in this build")
         else:
@@ -251,7 +255,7 @@ def eval_eig(args, conf_args, wandb_config, data_config, loader, path_file, perf
             counts = D.allreduce_counts(res.counts, batch_size, lo, batch_axis=1)          # the one exchange step
             eig = res.eig
             if eig is not None and world > 1:
-                eig = D.gather_batch(eig, batch_size, lo, batch_axis=1)
+                eig = D.gather_batch(eig, batch_size, lo, batch_axis=0)
             res.eig, res.counts = eig, counts
             return res
 

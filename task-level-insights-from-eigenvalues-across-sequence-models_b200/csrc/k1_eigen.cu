@@ -22,7 +22,7 @@ enum { K1_EPI_MAMBA2 = 0, K1_EPI_NORMGATE = 1 };
 
 struct K1Params {
   const void* x; const float* W; const float* p0; const float* p1; const float* p2;   // W (H,D); per-head vectors
-  float* out; int* counts;
+  float* out; int64_t out_stride; int* counts;
   int T, D, H, rows_per_warp, norm_fn;
   EdgesF e;
 };
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p
         const float raw = (dot + bias_only) + offs_only;
         val = expf(-norm_fn_apply(p.norm_fn, raw));
       }
-      if (p.out) p.out[((size_t)b * T + row) * H + hg] = val;
+      if (p.out) p.out[(((size_t)b * T + row) * H + hg) * p.out_stride] = val;
       if (EPI == K1_EPI_MAMBA2) {
         // the reference bins the float32 radius sqrt(fl(re^2) + fl(im^2)) of the real lambda (eval_eig.py:605-606)
         bin_f32(sqrtf(__fmul_rn(val, val)), p.e, cnt);
@@ -198,14 +198,14 @@ static int launch_k1(cudaStream_t st, const K1Params& p, int64_t B) {
 }
 
 // ---- LTI: parameter-only eigenvalues broadcast over (B,T) ------------------------------------------------------
-__global__ void k1_lti_kernel(const float* A, const float* beta, int64_t BT, int T, int H, float* lam, int* counts, EdgesF e) {
+__global__ void k1_lti_kernel(const float* A, const float* beta, int64_t BT, int T, int H, float* lam, int64_t lam_stride, int* counts, EdgesF e) {
   // one thread per head computes lambda and its bins once; the broadcast store is a plain grid-stride fill
   __shared__ float lam_s[256];
   for (int h = threadIdx.x; h < H; h += blockDim.x) lam_s[h] = expf(beta[h] * -softplus_f(A[h]));
   __syncthreads();
   if (lam) {
     const int64_t n = BT * H;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) lam[i] = lam_s[i % H];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) lam[i * lam_stride] = lam_s[i % H];
   }
   if (counts) {
     const int64_t Bn = BT / T;
@@ -225,7 +225,7 @@ __global__ void k1_lti_kernel(const float* A, const float* beta, int64_t BT, int
 
 // ---- ratios + bins over a (B,N,inner) array -------------------------------------------------------------------------
 struct RatioParams {
-  const void* a; double* out; int* counts;
+  const void* a; double* out; int64_t out_stride; int* counts;
   int64_t N, inner; int mode; int chunk;             // chunk = values of n handled per CTA
   EdgesF ef; EdgesD ed; int cmp_f32_on_f32;
 };
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) ratio_hist_kernel(const RatioParams p) {
         if (u0 == 0.0) u0 = 2e-23;
         if (u1 == 0.0) u1 = 2e-23;
         v = p.mode == EIGB200_RATIO_NEXT_OVER_CUR ? u1 / u0 : u0 / u1;
-        if (p.out) p.out[(size_t)b * Nout * inner + e] = v;
+        if (p.out) p.out[((size_t)b * Nout * inner + e) * p.out_stride] = v;
       }
       int c[EIGB_NCNT];
 #pragma unroll
@@ -315,15 +315,16 @@ extern "C" int eigb200_zero_i32(void* stream, int32_t* d_buf, size_t n) {
 
 extern "C" int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
                                   const float* d_W_dt, const float* d_dt_bias, const float* d_A_log, int H,
-                                  float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+                                  float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
   EIGB_CHECK_ARG(d_x && d_W_dt && d_dt_bias && d_A_log, "mamba2_eig: null input pointer");
+  EIGB_CHECK_ARG(!d_lam || lam_stride >= 1, "mamba2_eig: lam_stride must be >= 1");
   EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && H > 0, "mamba2_eig: bad shape B=%lld T=%lld D=%d H=%d", (long long)B, (long long)T, D, H);
   EIGB_CHECK_ARG(x_dtype == EIGB200_F32 || x_dtype == EIGB200_BF16, "mamba2_eig: x_dtype must be F32 or BF16");
   EIGB_CHECK_ARG(D % (x_dtype == EIGB200_BF16 ? 8 : 4) == 0, "mamba2_eig: D=%d must be a multiple of %d (128-bit rows)", D, x_dtype == EIGB200_BF16 ? 8 : 4);
   EIGB_CHECK_ARG(((uintptr_t)d_x & 15) == 0, "mamba2_eig: x must be 16-byte aligned");
   EIGB_CHECK_ARG(T < (1LL << 31), "mamba2_eig: T too large");
   K1Params p{};
-  p.x = d_x; p.W = d_W_dt; p.p0 = d_dt_bias; p.p1 = d_A_log; p.p2 = nullptr; p.out = d_lam; p.counts = d_counts;
+  p.x = d_x; p.W = d_W_dt; p.p0 = d_dt_bias; p.p1 = d_A_log; p.p2 = nullptr; p.out = d_lam; p.out_stride = lam_stride; p.counts = d_counts;
   p.T = (int)T; p.D = D; p.H = H; p.norm_fn = 0;
   if (d_counts) { int rc = make_edges_f(thresholds, nthr, compare_mode, &p.e); if (rc) return rc; }
   else { double one = 1.0; make_edges_f(&one, 1, 0, &p.e); }
@@ -341,7 +342,7 @@ extern "C" int eigb200_normattn_gate(void* stream, const void* d_x, int x_dtype,
   EIGB_CHECK_ARG(D % (x_dtype == EIGB200_BF16 ? 8 : 4) == 0, "normattn_gate: D=%d must be a multiple of %d", D, x_dtype == EIGB200_BF16 ? 8 : 4);
   EIGB_CHECK_ARG(((uintptr_t)d_x & 15) == 0, "normattn_gate: x must be 16-byte aligned");
   K1Params p{};
-  p.x = d_x; p.W = d_W_n; p.p0 = d_b_n; p.p1 = nullptr; p.p2 = d_offset; p.out = d_n; p.counts = nullptr;
+  p.x = d_x; p.W = d_W_n; p.p0 = d_b_n; p.p1 = nullptr; p.p2 = d_offset; p.out = d_n; p.out_stride = 1; p.counts = nullptr;
   p.T = (int)T; p.D = D; p.H = H; p.norm_fn = norm_fn;
   double one = 1.0; make_edges_f(&one, 1, 0, &p.e);
   return x_dtype == EIGB200_BF16 ? launch_k1<true, K1_EPI_NORMGATE>((cudaStream_t)stream, p, B)
@@ -349,27 +350,29 @@ extern "C" int eigb200_normattn_gate(void* stream, const void* d_x, int x_dtype,
 }
 
 extern "C" int eigb200_mamba2_lti_eig(void* stream, const float* d_A, const float* d_beta, int64_t B, int64_t T, int H,
-                                      float* d_lam, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+                                      float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
   EIGB_CHECK_ARG(d_A && d_beta, "mamba2_lti_eig: null pointer");
+  EIGB_CHECK_ARG(!d_lam || lam_stride >= 1, "mamba2_lti_eig: lam_stride must be >= 1");
   EIGB_CHECK_ARG(B > 0 && T > 0 && H > 0 && H <= 256, "mamba2_lti_eig: bad shape (H <= 256)");
   EdgesF e; double one = 1.0;
   if (d_counts) { int rc = make_edges_f(thresholds, nthr, compare_mode, &e); if (rc) return rc; } else make_edges_f(&one, 1, 0, &e);
   const int64_t n = B * T * H;
   int grid = (int)((n + 255) / 256); if (grid > num_sms() * 8) grid = num_sms() * 8; if (grid < 1) grid = 1;
-  k1_lti_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_A, d_beta, B * T, (int)T, H, d_lam, d_counts, e);
+  k1_lti_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_A, d_beta, B * T, (int)T, H, d_lam, lam_stride, d_counts, e);
   EIGB_LAUNCH_CHECK("k1_lti_kernel");
   return EIGB200_OK;
 }
 
 extern "C" int eigb200_ratio_hist(void* stream, const void* d_a, int dtype, int mode, int64_t B, int64_t N, int64_t inner,
-                                  double* d_out, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+                                  double* d_out, int64_t out_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
   EIGB_CHECK_ARG(d_a, "ratio_hist: null input");
+  EIGB_CHECK_ARG(!d_out || out_stride >= 1, "ratio_hist: out_stride must be >= 1");
   EIGB_CHECK_ARG(dtype == EIGB200_F32 || dtype == EIGB200_F64, "ratio_hist: dtype must be F32 or F64");
   EIGB_CHECK_ARG(mode >= EIGB200_RATIO_NONE && mode <= EIGB200_RATIO_CUR_OVER_NEXT, "ratio_hist: bad mode %d", mode);
   EIGB_CHECK_ARG(B > 0 && inner > 0 && N > (mode == EIGB200_RATIO_NONE ? 0 : 1), "ratio_hist: bad shape");
   EIGB_CHECK_ARG(B <= 65535, "ratio_hist: batch exceeds 65535; split the call");
   RatioParams p{};
-  p.a = d_a; p.out = d_out; p.counts = d_counts; p.N = N; p.inner = inner; p.mode = mode;
+  p.a = d_a; p.out = d_out; p.out_stride = out_stride; p.counts = d_counts; p.N = N; p.inner = inner; p.mode = mode;
   int rc = make_edges_d(thresholds, nthr, &p.ed); if (rc) return rc;
   rc = make_edges_f(thresholds, nthr, compare_mode, &p.ef); if (rc) return rc;
   if (dtype == EIGB200_F32 && mode == EIGB200_RATIO_NONE && compare_mode == EIGB200_CMP_F64) { /* ef already encodes the f64 compare */ }

@@ -57,11 +57,11 @@ def get_eig_mamba2(x, layer):
     return np.expand_dims(lam.cpu().numpy(), axis=-1)
 
 
-def get_eig_mamba2_LTI_device(x, layer, want_eig=True, counts=None, compare="float64"):
+def get_eig_mamba2_LTI_device(x, layer, want_eig=True, counts=None, compare="float64", lam_out=None):
     m = layer.mamba
     x = _cuda(x)
     B, T, _ = x.shape
-    return ops.mamba2_lti_eig(_cuda(_w(m.A)), _cuda(_w(m.beta)), B, T, want_lam=want_eig, counts=counts, compare=compare)
+    return ops.mamba2_lti_eig(_cuda(_w(m.A)), _cuda(_w(m.beta)), B, T, want_lam=want_eig, counts=counts, compare=compare, lam_out=lam_out)
 
 
 def get_eig_mamba2_LTI(x, layer):

@@ -50,6 +50,38 @@ def _xdtype(x):
     raise L.Eigb200Error("activations must be float32 or bfloat16, got %s" % x.dtype)
 
 
+LAUNCHES = {"n": 0}          # C-ABI compute calls enqueued through this module (bench.py reports it as gpu_launches)
+PROFILE = None               # set to a list to record (name, start_event, end_event) per call (bench.py roofline leg)
+
+
+def _call(lib, name, stream, *args):
+    """One C-ABI call: enqueue on `stream`, raise on a non-zero status, count it, optionally bracket it with CUDA events."""
+    fn = getattr(lib, name)
+    if PROFILE is not None:
+        ext = torch.cuda.ExternalStream(stream.value) if stream.value else torch.cuda.default_stream()
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record(ext)
+        rc = fn(stream, *args)
+        s1.record(ext)
+        PROFILE.append((name, s0, s1))
+    else:
+        rc = fn(stream, *args)
+    L.check(rc, name)
+    LAUNCHES["n"] += 1
+
+
+def _uniform_stride(t: torch.Tensor, shape) -> int:
+    """Element stride s such that entry with row-major index i over `shape` lives at t.data_ptr() + i*s; raises otherwise."""
+    assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+    s = t.stride(-1)
+    expect = s
+    for dim in range(t.dim() - 1, -1, -1):
+        if t.shape[dim] != 1 and t.stride(dim) != expect:
+            raise L.Eigb200Error("output view is not uniformly strided: shape %s strides %s" % (tuple(t.shape), t.stride()))
+        expect *= t.shape[dim]
+    return s
+
+
 def new_counts(B: int, inner: int, device) -> torch.Tensor:
     return torch.zeros(B, inner, NSLOT, dtype=torch.int32, device=device)
 
@@ -63,27 +95,31 @@ def mamba2_eig(x, W_dt, dt_bias, A_log, thresholds: Sequence[float] = THRESHOLDS
     H = W_dt.shape[0]
     lib = _enter(x)
     lam = None
+    stride = 1
     if want_lam:
         lam = lam_out if lam_out is not None else torch.empty(B, T, H, dtype=torch.float32, device=x.device)
-        assert lam.is_contiguous() and lam.numel() == B * T * H and lam.dtype == torch.float32
+        assert lam.dtype == torch.float32
+        stride = _uniform_stride(lam, (B, T, H))
     if want_counts and counts is None:
         counts = new_counts(B, H, x.device)
     thr, n = L.thresholds_arg(thresholds)
-    L.check(lib.eigb200_mamba2_eig(_stream(x), _p(x), _xdtype(x), B, T, D, _p(W_dt), _p(dt_bias), _p(A_log), H,
-                                   _p(lam), _p(counts if want_counts else None), thr, n, _cmp(compare)), "eigb200_mamba2_eig")
+    _call(lib, "eigb200_mamba2_eig", _stream(x), _p(x), _xdtype(x), B, T, D, _p(W_dt), _p(dt_bias), _p(A_log), H,
+                                   _p(lam), stride, _p(counts if want_counts else None), thr, n, _cmp(compare))
     return lam, (counts if want_counts else None)
 
 
-def mamba2_lti_eig(A, beta, B, T, thresholds=THRESHOLDS_RADIUS, want_lam=True, counts=None, compare="float64"):
+def mamba2_lti_eig(A, beta, B, T, thresholds=THRESHOLDS_RADIUS, want_lam=True, counts=None, compare="float64", lam_out=None):
     A = _prep(A, torch.float32); beta = _prep(beta, torch.float32)
     H = A.shape[0]
     lib = _enter(A)
-    lam = torch.empty(B, T, H, dtype=torch.float32, device=A.device) if want_lam else None
+    lam, stride = None, 1
+    if want_lam:
+        lam = lam_out if lam_out is not None else torch.empty(B, T, H, dtype=torch.float32, device=A.device)
+        stride = _uniform_stride(lam, (B, T, H))
     if counts is None:
         counts = new_counts(B, H, A.device)
     thr, n = L.thresholds_arg(thresholds)
-    L.check(lib.eigb200_mamba2_lti_eig(_stream(A), _p(A), _p(beta), B, T, H, _p(lam), _p(counts), thr, n, _cmp(compare)),
-            "eigb200_mamba2_lti_eig")
+    _call(lib, "eigb200_mamba2_lti_eig", _stream(A), _p(A), _p(beta), B, T, H, _p(lam), stride, _p(counts), thr, n, _cmp(compare))
     return lam, counts
 
 
@@ -98,8 +134,8 @@ def normattn_gate(x, W_n, b_n, offset, norm_fn: str):
     H = W_n.shape[0]
     lib = _enter(x)
     n = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
-    L.check(lib.eigb200_normattn_gate(_stream(x), _p(x), _xdtype(x), B, T, D, _p(W_n), _p(b_n), _p(offset), H,
-                                      L.NORM_FN[norm_fn], _p(n)), "eigb200_normattn_gate")
+    _call(lib, "eigb200_normattn_gate", _stream(x), _p(x), _xdtype(x), B, T, D, _p(W_n), _p(b_n), _p(offset), H,
+                                      L.NORM_FN[norm_fn], _p(n))
     return n
 
 
@@ -111,17 +147,19 @@ def ratio_hist(a, mode: int, thresholds=THRESHOLDS_RADIUS, want_out=True, counts
     B, N = a.shape[0], a.shape[1]
     inner = int(np.prod(a.shape[2:])) if a.dim() > 2 else 1
     lib = _enter(a)
+    ostride = 1
     if mode != L.RATIO_NONE and want_out:
         if out is None:
             out = torch.empty((B, N - 1) + tuple(a.shape[2:]), dtype=torch.float64, device=a.device)
-        assert out.is_contiguous() and out.dtype == torch.float64 and out.numel() == B * (N - 1) * inner
+        assert out.dtype == torch.float64 and out.numel() == B * (N - 1) * inner
+        ostride = _uniform_stride(out, tuple(out.shape))
     else:
         out = None
     if counts is None:
         counts = new_counts(B, inner, a.device)
     thr, n = L.thresholds_arg(thresholds)
-    L.check(lib.eigb200_ratio_hist(_stream(a), _p(a), L.F32 if a.dtype == torch.float32 else L.F64, mode, B, N, inner,
-                                   _p(out), _p(counts), thr, n, _cmp(compare)), "eigb200_ratio_hist")
+    _call(lib, "eigb200_ratio_hist", _stream(a), _p(a), L.F32 if a.dtype == torch.float32 else L.F64, mode, B, N, inner,
+                                   _p(out), ostride, _p(counts), thr, n, _cmp(compare))
     return out, counts
 
 
@@ -132,7 +170,7 @@ def count_moments(counts):
     lib = _enter(counts)
     s = torch.empty(inner, NSLOT, dtype=torch.int64, device=counts.device)
     s2 = torch.empty_like(s)
-    L.check(lib.eigb200_count_moments(_stream(counts), _p(counts), B, inner, _p(s), _p(s2)), "eigb200_count_moments")
+    _call(lib, "eigb200_count_moments", _stream(counts), _p(counts), B, inner, _p(s), _p(s2))
     return s, s2
 
 
@@ -144,7 +182,7 @@ def linattn_nu(qk_buf, ld: int, B: int, T: int, H: int, d: int, k_offset: int):
     nu = torch.empty(B, T, H, dtype=torch.float64, device=qk_buf.device)
     q_ptr = C.c_void_p(qk_buf.data_ptr())
     k_ptr = C.c_void_p(qk_buf.data_ptr() + 4 * k_offset)
-    L.check(lib.eigb200_linattn_nu(_stream(qk_buf), q_ptr, k_ptr, ld, B, T, H, d, _p(nu)), "eigb200_linattn_nu")
+    _call(lib, "eigb200_linattn_nu", _stream(qk_buf), q_ptr, k_ptr, ld, B, T, H, d, _p(nu))
     return nu
 
 
@@ -155,9 +193,9 @@ def linattn_forward(buf, ld, q_off, k_off, v_off, B, T, H, d, dv, gate=None, phi
     out = torch.empty(B, T, H * dv, dtype=torch.float32, device=buf.device)
     base = buf.data_ptr()
     gate = _prep(gate, torch.float32) if gate is not None else None
-    L.check(lib.eigb200_linattn_forward(_stream(buf), C.c_void_p(base + 4 * q_off), C.c_void_p(base + 4 * k_off),
+    _call(lib, "eigb200_linattn_forward", _stream(buf), C.c_void_p(base + 4 * q_off), C.c_void_p(base + 4 * k_off),
                                         C.c_void_p(base + 4 * v_off), ld, _p(gate), int(phi_elu), int(normalise), float(kscale),
-                                        _p(out), H * dv, B, T, H, d, dv), "eigb200_linattn_forward")
+                                        _p(out), H * dv, B, T, H, d, dv)
     return out
 
 
@@ -168,8 +206,8 @@ def diag_scan(lam, Bu, reverse=False):
     B, T, P = Bu.shape
     lib = _enter(Bu)
     h = torch.empty_like(Bu)
-    L.check(lib.eigb200_diag_scan(_stream(Bu), _p(torch.view_as_real(lam)), _p(torch.view_as_real(Bu)), _p(torch.view_as_real(h)),
-                                  B, T, P, int(reverse)), "eigb200_diag_scan")
+    _call(lib, "eigb200_diag_scan", _stream(Bu), _p(torch.view_as_real(lam)), _p(torch.view_as_real(Bu)), _p(torch.view_as_real(h)),
+                                  B, T, P, int(reverse))
     return h
 
 
@@ -183,8 +221,8 @@ def ssd_scan(x, dt, A, Bm, Cm, D=None, return_final_state=False):
     lib = _enter(x)
     y = torch.empty_like(x)
     fs = torch.empty(B, H, P, N, dtype=torch.float32, device=x.device) if return_final_state else None
-    L.check(lib.eigb200_ssd_scan(_stream(x), _p(x), H * P, _p(dt), _p(A), _p(Bm), _p(Cm), G * N, _p(D), _p(y), H * P, _p(fs),
-                                 B, T, H, P, G, N), "eigb200_ssd_scan")
+    _call(lib, "eigb200_ssd_scan", _stream(x), _p(x), H * P, _p(dt), _p(A), _p(Bm), _p(Cm), G * N, _p(D), _p(y), H * P, _p(fs),
+                                 B, T, H, P, G, N)
     return (y, fs) if return_final_state else y
 
 
@@ -198,9 +236,8 @@ def mamba_conv_ssd(xbcdt, ldz, conv_w, conv_b, dt_bias, A_log, D, B, T, H, P, G,
         conv_b = _prep(conv_b, torch.float32)
         k = conv_w.shape[1]
     y = out if out is not None else torch.empty(B, T, H * P, dtype=torch.float32, device=xbcdt.device)
-    L.check(lib.eigb200_mamba_conv_ssd(_stream(xbcdt), _p(xbcdt), ldz, _p(conv_w), _p(conv_b), k, _p(_prep(dt_bias, torch.float32)),
-                                       _p(_prep(A_log, torch.float32)), _p(_prep(D, torch.float32)), _p(y), H * P, B, T, H, P, G, N),
-            "eigb200_mamba_conv_ssd")
+    _call(lib, "eigb200_mamba_conv_ssd", _stream(xbcdt), _p(xbcdt), ldz, _p(conv_w), _p(conv_b), k, _p(_prep(dt_bias, torch.float32)),
+                                       _p(_prep(A_log, torch.float32)), _p(_prep(D, torch.float32)), _p(y), H * P, B, T, H, P, G, N)
     return y
 
 
@@ -242,8 +279,8 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
         assert residual.is_cuda and residual.dtype == torch.float32 and residual.stride(-1) == 1
         ldr = residual.stride(-2) if residual.dim() >= 2 else nout
     ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
-    L.check(lib.eigb200_linear(_stream(a), _p(a2), lda, _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
-                               EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb), "eigb200_linear")
+    _call(lib, "eigb200_linear", _stream(a), _p(a2), lda, _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
+                               EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb)
     return out
 
 
@@ -256,7 +293,7 @@ def embedding(ids, word, pos=None):
         raise L.Eigb200Error("embedding: sequence length %d exceeds max_position_embeddings %d" % (T, pos.shape[0]))
     lib = _enter(ids)
     out = torch.empty(B, T, D, dtype=torch.float32, device=ids.device)
-    L.check(lib.eigb200_embedding(_stream(ids), _p(ids), _p(word), _p(pos), _p(out), B, T, D, V), "eigb200_embedding")
+    _call(lib, "eigb200_embedding", _stream(ids), _p(ids), _p(word), _p(pos), _p(out), B, T, D, V)
     return out
 
 
@@ -265,8 +302,8 @@ def layernorm(x, w, b, eps=1e-5):
     D = x.shape[-1]
     lib = _enter(x)
     out = torch.empty_like(x)
-    L.check(lib.eigb200_layernorm(_stream(x), _p(x), _p(_prep(w, torch.float32)), _p(_prep(b, torch.float32)), float(eps), _p(out),
-                                  x.numel() // D, D), "eigb200_layernorm")
+    _call(lib, "eigb200_layernorm", _stream(x), _p(x), _p(_prep(w, torch.float32)), _p(_prep(b, torch.float32)), float(eps), _p(out),
+                                  x.numel() // D, D)
     return out
 
 
@@ -277,7 +314,7 @@ def conv_silu(x, ldx, w, b, B, T, Cn, out=None, ldo=None):
     if out is None:
         ldo = ldo or Cn
         out = torch.empty(B * T, ldo, dtype=torch.float32, device=x.device)
-    L.check(lib.eigb200_conv_silu(_stream(x), _p(x), ldx, _p(w), _p(b), w.shape[1], _p(out), ldo, B, T, Cn), "eigb200_conv_silu")
+    _call(lib, "eigb200_conv_silu", _stream(x), _p(x), ldx, _p(w), _p(b), w.shape[1], _p(out), ldo, B, T, Cn)
     return out
 
 
@@ -285,7 +322,7 @@ def add(a, b):
     a = _prep(a, torch.float32); b = _prep(b, torch.float32)
     lib = _enter(a)
     out = torch.empty_like(a)
-    L.check(lib.eigb200_add(_stream(a), _p(a), _p(b), _p(out), a.numel()), "eigb200_add")
+    _call(lib, "eigb200_add", _stream(a), _p(a), _p(b), _p(out), a.numel())
     return out
 
 
@@ -293,7 +330,7 @@ def mul_silu(y, z):
     y = _prep(y, torch.float32); z = _prep(z, torch.float32)
     lib = _enter(y)
     out = torch.empty_like(y)
-    L.check(lib.eigb200_mul_silu(_stream(y), _p(y), _p(z), _p(out), y.numel()), "eigb200_mul_silu")
+    _call(lib, "eigb200_mul_silu", _stream(y), _p(y), _p(z), _p(out), y.numel())
     return out
 
 
@@ -301,7 +338,7 @@ def gelu(x):
     x = _prep(x, torch.float32)
     lib = _enter(x)
     out = torch.empty_like(x)
-    L.check(lib.eigb200_gelu(_stream(x), _p(x), _p(out), x.numel()), "eigb200_gelu")
+    _call(lib, "eigb200_gelu", _stream(x), _p(x), _p(out), x.numel())
     return out
 
 
@@ -310,7 +347,7 @@ def scale_cols(a, s):
     lib = _enter(a)
     out = torch.empty_like(a)
     cols = a.shape[-1]
-    L.check(lib.eigb200_scale_cols(_stream(a), _p(a), _p(s), _p(out), a.numel() // cols, cols), "eigb200_scale_cols")
+    _call(lib, "eigb200_scale_cols", _stream(a), _p(a), _p(s), _p(out), a.numel() // cols, cols)
     return out
 
 
@@ -323,8 +360,7 @@ def ssm_lambda(kind: str, p0, p1, p2=None):
     p2 = _prep(p2, torch.float32).reshape(-1) if p2 is not None else None
     lib = _enter(p0)
     lam = torch.empty(p0.numel(), dtype=torch.complex64, device=p0.device)
-    L.check(lib.eigb200_ssm_lambda(_stream(p0), SSM_KINDS[kind], _p(p0), _p(p1), _p(p2), p0.numel(), _p(torch.view_as_real(lam))),
-            "eigb200_ssm_lambda")
+    _call(lib, "eigb200_ssm_lambda", _stream(p0), SSM_KINDS[kind], _p(p0), _p(p1), _p(p2), p0.numel(), _p(torch.view_as_real(lam)))
     return lam
 
 
@@ -335,8 +371,8 @@ def dplr_abar(Lambda, Pv, Qv, step):
     nmat, N = Lambda.shape
     lib = _enter(Lambda)
     Ab = torch.empty(nmat, N, N, dtype=torch.complex64, device=Lambda.device)
-    L.check(lib.eigb200_dplr_abar(_stream(Lambda), _p(torch.view_as_real(Lambda)), _p(torch.view_as_real(Pv)), _p(torch.view_as_real(Qv)),
-                                  _p(step), nmat, N, _p(torch.view_as_real(Ab))), "eigb200_dplr_abar")
+    _call(lib, "eigb200_dplr_abar", _stream(Lambda), _p(torch.view_as_real(Lambda)), _p(torch.view_as_real(Pv)), _p(torch.view_as_real(Qv)),
+                                  _p(step), nmat, N, _p(torch.view_as_real(Ab)))
     return Ab
 
 
@@ -347,6 +383,5 @@ def eigvals_c64(A):
     lib = _enter(A)
     ev = torch.empty(nmat, N, dtype=torch.complex64, device=A.device)
     info = torch.empty(nmat, dtype=torch.int32, device=A.device)
-    L.check(lib.eigb200_eigvals_c64(_stream(A), _p(torch.view_as_real(A)), nmat, N, _p(torch.view_as_real(ev)), _p(info)),
-            "eigb200_eigvals_c64")
+    _call(lib, "eigb200_eigvals_c64", _stream(A), _p(torch.view_as_real(A)), nmat, N, _p(torch.view_as_real(ev)), _p(info))
     return ev, info

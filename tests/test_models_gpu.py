@@ -109,9 +109,12 @@ def test_lru_layer_call(eig):
     u = rng.normal(size=(B, T, H)).astype(np.float32)
     y, h = S.lru_forward(prm, u, return_states=True)
     yr, hr, _ = O.lru_forward(prm, u)
+    # lambda and B_norm are formed in fp32 (as in the reference's complex64 JAX path); the oracle forms them in fp64 from the same
+    # fp32 parameters.  A 1e-7 relative rounding of lambda grows like t*1e-7 for |lambda| ~ 0.999, so the layer call is held to
+    # 1e-4 norm-wise; the scan kernel alone (same rounded lambda on both sides) is held to 1e-5 in test_scans_gpu.py.
     scale = np.abs(hr).max(axis=1, keepdims=True)
-    assert (np.abs(h.cpu().numpy() - hr) <= 1e-5 * scale).all()
-    assert np.abs(y.cpu().numpy() - yr).max() <= 1e-5 * np.abs(yr).max()
+    assert (np.abs(h.cpu().numpy() - hr) <= 1e-4 * scale).all()
+    assert np.abs(y.cpu().numpy() - yr).max() <= 1e-4 * np.abs(yr).max()
 
 
 @pytest.mark.parametrize("disc,bidir", [("zoh", False), ("bilinear", False), ("zoh", True)])
@@ -129,6 +132,6 @@ def test_s5_layer_call(eig, disc, bidir):
     u = rng.normal(size=(B, T, H)).astype(np.float32)
     y, h = S.s5_forward(prm, u, discretization=disc, conj_sym=True, bidirectional=bidir, return_states=True)
     yr, hr, _ = O.s5_forward(prm, u, discretization=disc, conj_sym=True, bidirectional=bidir)
-    scale = np.abs(hr).max(axis=1, keepdims=True)
-    assert (np.abs(h.cpu().numpy() - hr) <= 2e-5 * scale).all()
-    assert np.abs(y.cpu().numpy() - yr).max() <= 2e-5 * np.abs(yr).max()
+    scale = np.abs(hr).max(axis=1, keepdims=True)                # fp32 discretisation ((lam_bar - 1)/Lambda cancels), see test_lru_layer_call
+    assert (np.abs(h.cpu().numpy() - hr) <= 1e-4 * scale).all()
+    assert np.abs(y.cpu().numpy() - yr).max() <= 1e-4 * np.abs(yr).max()
