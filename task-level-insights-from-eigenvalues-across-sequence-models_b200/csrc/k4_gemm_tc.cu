@@ -17,7 +17,8 @@
 //     GLU gate / residual in registers and store 128-bit vectors;
 //   * N wider than one CTA's slice is split across `nsplit` CTAs that walk the same row tiles together (the second read of the A tile
 //     is an L2 hit).  For the GLU epilogue a CTA's slice is [BG value columns | their BG gate columns].
-// Warp roles (320 threads): warps 0-3 epilogue (TMEM lane quarters 0-3), warps 4-7 converters, warp 8 TMA producer, warp 9 MMA issuer.
+// Warp roles (448 threads): warps 0-7 epilogue (TMEM lane quarter = warp % 4, even / odd 32-column groups = warp / 4), warps 8-11 converters,
+// warp 12 TMA producer, warp 13 MMA issuer.
 #include "gemm_tc.cuh"
 #include <cuda.h>
 
@@ -26,7 +27,7 @@ namespace eigb200 {
 constexpr int TC_BM = 128;                 // rows per tile (UMMA M)
 constexpr int TC_KC = 32;                  // fp32 columns per K-chunk = one 128-byte swizzle row
 constexpr int TC_CHUNK_BYTES = TC_BM * TC_KC * 4;          // 16 KB
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
@@ -117,6 +118,28 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// 8x8 transpose of float4 items inside each group of 8 lanes.  In: lane (8g+i) holds, for its accumulator row 8g+i, the eight
+// float4 column quads q = 0..7 of a 32-column group.  Out: the same lane holds quad q = i of rows 8g+j, j = 0..7 -- so that for
+// every j the 8 lanes of a group cover one row's 128 contiguous bytes and a warp store instruction writes 4 full lines.
+__device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if ((q & s) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = v[4 * q + e], hi = v[4 * (q | s) + e];
+          const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, s);
+          v[4 * q + e] = up ? recv : lo;
+          v[4 * (q | s) + e] = up ? hi : recv;
+        }
+      }
+    }
+  }
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start address >> 4 in bits [0,14); LBO (unused for swizzled K-major) = 1 in [16,30); SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46);
 // descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
@@ -179,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   auto bar_dempty = [&](int j) { return bars + 8u * (3 + 3 * TC_MAX_STAGES + j); };   // accumulator j drained
   const uint32_t tmem_slot = bars + 8u * (5 + 3 * TC_MAX_STAGES);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));     // [bn] bias of this CTA's slice
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
@@ -187,17 +211,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_conv(s), 128); mbar_init(bar_empty(s), 1); }
-    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), 128); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), 256); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, tmem_cols);
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
+  if (threadIdx.x < 128) {                                            // bias of the slice, in accumulator-column order
+    constexpr bool GLU_ = EPI == EIGB200_EPI_GLU_RESIDUAL;
+    const int nout_ = GLU_ ? p.N / 2 : p.N;
+    for (int c = threadIdx.x; c < bn; c += 128) {
+      int n;
+      if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
+      else { n = split * bn + c; if (n >= p.N) n = -1; }
+      bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+    }
+  }
+  if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 12 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
@@ -218,9 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===================================== converters: raw fp32 -> tf32 hi (in place) + tf32 lo ==============================
-    const int ct = threadIdx.x - 128;                               // 0..127
+    const int ct = threadIdx.x - 256;                               // 0..127
     int s = 0; uint32_t ph = 0;
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
       for (int c = 0; c < kch; ++c) {
@@ -251,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ===================================== MMA issuer ======================================
     const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
     mbar_wait(bar_w, 0);
@@ -285,77 +319,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
       if (++j == 2) { j = 0; dph ^= 1; }
     }
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // ===================================== epilogue ======================================
     constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
     const int nout = GLU ? p.N / 2 : p.N;
     const int cols_out = GLU ? p.bg : bn;                            // output columns produced by this CTA
     const int n_cta0 = split * cols_out;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    const int gi = lane & 7, gg = lane >> 3;                         // after the transpose: column quad gi of rows 8*gg + jj
+    const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
     int j = 0; uint32_t dph = 0;
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      mbar_wait(bar_dfull(j), dph);
-      tc_fence_after();
-      const int64_t m = tile * TC_BM + warp * 32 + lane;
-      const bool row_ok = m < p.M;
+      const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
       const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
-      for (int cg = 0; cg < cols_out; cg += 32) {
+      bool waited = false, arrived = false;
+      for (int cg = 32 * half; cg < cols_out; cg += 64) {
+        const int ccol = cg + 4 * gi;                                // column inside the CTA slice (transposed layout)
+        const int n = n_cta0 + ccol;
+        const bool col_ok = ccol < cols_out && n < nout;
+        const bool full = n + 3 < nout;
+        // residual rows of this group: issued first so that their DRAM latency hides behind the TMEM load, the math and the transpose
+        float4 rr[8];
+        if (use_r) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            rr[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && full && row0 + jj < p.M) rr[jj] = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + (row0 + jj) * p.ldr + n));
+          }
+        }
+        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
         float v[32];
         tmem_ld_32x32(d_tmem + cg, v);
         if (GLU) {
           float g[32];
           tmem_ld_32x32(d_tmem + p.bg + cg, g);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int n = n_cta0 + cg + i;
-            if (n < nout) {
-              float vv = v[i], gg = g[i];
-              if (p.bias) { vv += __ldg(p.bias + n); gg += __ldg(p.bias + nout + n); }
-              v[i] = vv * sigmoid_f(gg);
-            }
-          }
+          for (int i = 0; i < 32; ++i) v[i] = (v[i] + bias_s[cg + i]) * sigmoid_fast_f(g[i] + bias_s[p.bg + cg + i]);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int n = n_cta0 + cg + i;
-            if (n < nout) {
-              float vv = v[i];
-              if (p.bias) vv += __ldg(p.bias + n);
-              if (EPI == EIGB200_EPI_GELU) vv = gelu_f(vv);
-              v[i] = vv;
-            }
+            float vv = v[i] + bias_s[cg + i];
+            if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
+            v[i] = vv;
           }
         }
-        if (cg + 32 >= cols_out) {                                   // all TMEM reads of this accumulator are done: release it early
+        if (cg + 64 >= cols_out) {                                   // this warp's last TMEM read of the accumulator: release it early
           tc_fence_before();
           mbar_arrive(bar_dempty(j));
+          arrived = true;
         }
-        if (row_ok) {
-          const int n0 = n_cta0 + cg;
-          float* crow = p.C + m * p.ldc + n0;
-          const float* rrow = (p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL)) ? p.R + m * p.ldr + n0 : nullptr;
+        transpose8x8_f4(v, lane);
+        if (col_ok) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int n = n0 + 4 * q;
-            if (n + 3 < nout) {
-              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              if (rrow) { const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + 4 * q)); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-              *reinterpret_cast<float4*>(crow + 4 * q) = o;
-            } else {
+          for (int jj = 0; jj < 8; ++jj) {
+            const int64_t mrow = row0 + jj;
+            if (mrow < p.M) {
+              float* cptr = p.C + mrow * p.ldc + n;
+              if (full) {
+                float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                if (use_r) { o.x += rr[jj].x; o.y += rr[jj].y; o.z += rr[jj].z; o.w += rr[jj].w; }
+                *reinterpret_cast<float4*>(cptr) = o;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n + e < nout) crow[4 * q + e] = v[4 * q + e] + (rrow ? rrow[4 * q + e] : 0.f);
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < nout) cptr[e] = v[4 * jj + e] + (use_r ? p.R[mrow * p.ldr + n + e] : 0.f);
+              }
             }
           }
         }
       }
+      if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
+      if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
       if (++j == 2) { j = 0; dph ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if (warp == 13) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -404,7 +446,7 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   const bool glu = epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const int nout = glu ? N / 2 : N;
   const int per_col_bytes = pl.kpad * 4 * 2 * (glu ? 2 : 1);         // hi+lo bytes per OUTPUT column
-  const int max_w_bytes = TC_SMEM_LIMIT - 2048 - 2 * 2 * TC_CHUNK_BYTES;   // keep room for >= 2 stages
+  const int max_w_bytes = TC_SMEM_LIMIT - 2560 - 2 * 2 * TC_CHUNK_BYTES;   // keep room for >= 2 stages
   int max_cols = max_w_bytes / per_col_bytes;
   const int cap = glu ? 64 : 128;
   if (max_cols > cap) max_cols = cap;
@@ -417,11 +459,11 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   pl.bg = cols;
   pl.bn = glu ? 2 * cols : cols;
   const size_t wbytes = (size_t)2 * pl.kchunks * pl.bn * 128;
-  int nst = (int)((TC_SMEM_LIMIT - 2048 - (long)wbytes) / (2 * TC_CHUNK_BYTES));
+  int nst = (int)((TC_SMEM_LIMIT - 2560 - (long)wbytes) / (2 * TC_CHUNK_BYTES));
   if (nst > TC_MAX_STAGES) nst = TC_MAX_STAGES;
   if (nst < 2) return pl;
   pl.nstages = nst;
-  pl.smem = wbytes + (size_t)nst * 2 * TC_CHUNK_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+  pl.smem = wbytes + (size_t)nst * 2 * TC_CHUNK_BYTES + 1024 /*alignment*/ + 1024 /*barriers + bias*/;
   pl.ok = true;
   return pl;
 }

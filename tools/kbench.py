@@ -77,7 +77,8 @@ def case_linear(M, N, K, epi, mode):
     a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     nout = N // 2 if epi == "glu_residual" else N
     ldc = (nout + 3) // 4 * 4
-    r = torch.randn(M, nout, device="cuda") if "residual" in epi else None
+    r = torch.randn(M, nout, device="cuda") if ("residual" in epi and not epi.endswith("_nores")) else None
+    epi = epi.replace("_nores", "")
     out = torch.empty(M, ldc, device="cuda")
     ws, _ = ops.linear_workspace(N, K, "cuda")
     def fn():
@@ -104,6 +105,12 @@ CASES = {
     "lin_out_tc1": lambda: case_linear(M_C2, 128, 128, "gelu", "tc1"),
     "lin_out_simt": lambda: case_linear(M_C2, 128, 128, "gelu", "simt"),
     "lin_small_tc3": lambda: case_linear(65536, 128, 128, "gelu", "tc3"),
+    "lin_glu_mid_tc3": lambda: case_linear(524288, 256, 128, "glu_residual", "tc3"),
+    "lin_glu_nores_tc3": lambda: case_linear(M_C2, 256, 128, "glu_residual_nores", "tc3"),
+    "lin_out_none_tc3": lambda: case_linear(M_C2, 128, 128, "none", "tc3"),
+    "lin_n96_none_tc3": lambda: case_linear(M_C2, 96, 128, "none", "tc3"),
+    "lin_n96_gelu_tc3": lambda: case_linear(M_C2, 96, 128, "gelu", "tc3"),
+    "lin_n64_none_tc3": lambda: case_linear(M_C2, 64, 128, "none", "tc3"),
     "k1_c2": lambda: case_k1(4096, 512, 128, 1),
     "k1_c2_nolam": lambda: case_k1(4096, 512, 128, 1, want_lam=False),
     "k1_c2_bf16": lambda: case_k1(4096, 512, 128, 1, torch.bfloat16),
