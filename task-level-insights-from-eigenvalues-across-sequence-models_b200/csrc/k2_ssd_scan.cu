@@ -16,6 +16,8 @@
 // then the serial phase runs TC steps out of shared memory (broadcast LDS.128 for B_t/C_t).  Several CTAs per SM overlap
 // one CTA's staging with another's recurrence.
 #include "common.cuh"
+#include <type_traits>
+#include <stdlib.h>
 
 namespace eigb200 {
 
@@ -161,12 +163,272 @@ __global__ void __launch_bounds__(SSD_THREADS) ssd_scan_kernel(const SsdParams p
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// v2: whole state row per thread (N <= 16), CPT channels per thread, x streamed through registers.
+//
+// The HBM-bound regime of the north star (d_state 16).  Differences from the generic kernel above:
+//   * the per-channel operand x never touches shared memory: every thread loads its own CPT adjacent channels straight from
+//     global memory U tokens ahead (a warp reads 32*CPT*4 contiguous bytes per token), so the only shared-memory traffic of the
+//     serial phase is the broadcast read of B_t, C_t (2N floats) and (dt_t, exp(dt_t A));
+//   * CPT = 2 halves those broadcast LDS per channel-token and doubles the independent FMA chains per thread (2N);
+//   * the raw B/C rows of the NEXT chunk are fetched into registers before the serial phase of the current chunk and only then
+//     convolved into the second shared-memory buffer: one __syncthreads per 32 tokens on the critical path;
+//   * y is accumulated in 4 partial sums (no 16-deep dependent FMA chain) and SiLU uses ex2/rcp approximations.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int SSD2_TC = 32;
+
+__device__ __forceinline__ float silu_fast_f(float z) { return z * sigmoid_fast_f(z); }
+
+template <int N, int CPT, int NT, int U, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ssd_scan_v2_kernel(const SsdParams p) {
+  constexpr int TC = SSD2_TC;                                      // U = x prefetch distance (tokens)
+  constexpr int PC = NT * CPT;                                     // channels per CTA
+  constexpr int RAW_ROWS = TC + SSD_HIST;
+  constexpr int RAW_F4 = RAW_ROWS * 2 * N / 4;                     // float4s of raw [B|C] rows per chunk
+  constexpr int RAW_PER_T = (RAW_F4 + NT - 1) / NT;
+  __shared__ __align__(16) float raw_s[RAW_ROWS][2 * N];           // raw B | C rows (history + chunk)
+  __shared__ __align__(16) float bc_s[2][TC][2 * N];               // conv'd B | C, double buffered
+  __shared__ __align__(8) float2 dd_s[2][TC];                      // (dt, exp(dt A))
+
+  const int P = p.P;
+  const int b = blockIdx.z, h = blockIdx.y, pblk = blockIdx.x;
+  const int g = h / (p.H / p.G);
+  const int tid = threadIdx.x;
+  const int pch = pblk * PC + tid * CPT;                           // first channel of this thread within the head
+  const bool pvalid = pch < P;                                     // P % CPT == 0 is guaranteed by the launcher
+  const int HP = p.H * P, GN = p.G * N;
+  const bool conv = p.fused && p.kconv > 0;
+  const float Ah = p.fused ? -expf(p.A[h]) : p.A[h];
+  const float Dh = p.D ? p.D[h] : 0.f;
+  const float dtb = p.fused ? p.dt_bias[h] : 0.f;
+
+  float cw[CPT][4], cb[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    cw[c][0] = cw[c][1] = cw[c][2] = 0.f; cw[c][3] = 1.f; cb[c] = 0.f;
+    if (conv && pvalid) {
+      const int ch = h * P + pch + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cw[c][j] = (j >= 4 - p.kconv) ? p.conv_w[(size_t)ch * p.kconv + j - (4 - p.kconv)] : 0.f;
+      cb[c] = p.conv_b[ch];
+    }
+  }
+  // conv taps of the B and C channels handled by this thread in the prep phase: element e = tid + k*NT of a [TC][2N] chunk has
+  // column (tid + k*NT) % 2N -- fixed per k when NT % 2N == 0, which holds for NT in {32,64} and N <= 16
+  constexpr int PREP_PER_T = TC * 2 * N / NT;
+  static_assert((TC * 2 * N) % NT == 0 && NT % (2 * N) == 0, "prep mapping");
+  const int bc_col = tid % (2 * N);
+  float bw[4] = {0.f, 0.f, 0.f, 1.f}, bbias = 0.f;
+  if (conv) {
+    const int ch = HP + (bc_col < N ? g * N + bc_col : GN + g * N + (bc_col - N));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bw[j] = (j >= 4 - p.kconv) ? p.conv_w[(size_t)ch * p.kconv + j - (4 - p.kconv)] : 0.f;
+    bbias = p.conv_b[ch];
+  }
+
+  float s[CPT][N];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c)
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[c][i] = 0.f;
+  float win[CPT][3];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) win[c][0] = win[c][1] = win[c][2] = 0.f;
+
+  const size_t rowbase = (size_t)b * p.T;
+  const float* xg = p.x + (size_t)h * P + pch;
+  float* yg = p.y + (size_t)h * P + pch;
+  const float* bgp = p.Bm + (size_t)g * N;
+  const float* cgp = p.Cm + (size_t)g * N;
+
+  // ---- raw [B|C] rows of a chunk: global -> registers (issued early) -> shared -------------------------------------------
+  float4 rawreg[RAW_PER_T];
+  auto raw_fetch = [&](int64_t t0) {
+#pragma unroll
+    for (int k = 0; k < RAW_PER_T; ++k) {
+      const int e = tid + k * NT;
+      rawreg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < RAW_F4) {
+        const int r = e / (2 * N / 4), q = e - r * (2 * N / 4);    // row, float4 within the [B|C] row
+        const int64_t t = t0 - SSD_HIST + r;
+        if (t >= 0 && t < p.T) {
+          const float* src = (q < N / 4) ? bgp + (rowbase + t) * p.ldbc + 4 * q : cgp + (rowbase + t) * p.ldbc + 4 * (q - N / 4);
+          rawreg[k] = __ldg(reinterpret_cast<const float4*>(src));
+        }
+      }
+    }
+  };
+  auto raw_commit = [&]() {
+#pragma unroll
+    for (int k = 0; k < RAW_PER_T; ++k) {
+      const int e = tid + k * NT;
+      if (e < RAW_F4) reinterpret_cast<float4*>(&raw_s[0][0])[e] = rawreg[k];
+    }
+  };
+  float dtreg = 0.f;
+  auto dt_fetch = [&](int64_t t0) {
+    if (tid < TC && t0 + tid < p.T) dtreg = __ldg(p.dt + (rowbase + t0 + tid) * p.lddt + h);
+  };
+  // conv + SiLU of raw_s into bc_s[buf], and (dt, decay) into dd_s[buf]
+  auto prep = [&](int buf, int tc) {
+#pragma unroll
+    for (int k = 0; k < PREP_PER_T; ++k) {
+      const int e = tid + k * NT;
+      const int r = e / (2 * N);                                   // token within the chunk; column is bc_col
+      float v;
+      if (conv) {
+        v = fmaf(bw[3], raw_s[r + 3][bc_col], fmaf(bw[2], raw_s[r + 2][bc_col], fmaf(bw[1], raw_s[r + 1][bc_col], fmaf(bw[0], raw_s[r][bc_col], bbias))));
+        v = silu_fast_f(v);
+      } else v = raw_s[r + 3][bc_col];
+      bc_s[buf][r][bc_col] = v;
+    }
+    if (tid < tc) {
+      const float d = p.fused ? softplus_f(dtreg + dtb) : dtreg;
+      dd_s[buf][tid] = make_float2(d, expf(d * Ah));
+    }
+  };
+
+  // ---- x pipeline: U tokens ahead in registers ---------------------------------------------------------------------------
+  using xvec = typename std::conditional<CPT == 2, float2, float>::type;
+  xvec xq[U];
+  auto x_fetch = [&](int64_t t) -> xvec {
+    xvec v;
+    if constexpr (CPT == 2) v = make_float2(0.f, 0.f); else v = 0.f;
+    if (pvalid && t < p.T) {
+      if constexpr (CPT == 2) v = ldg_stream_f2(reinterpret_cast<const float2*>(xg + (rowbase + t) * p.ldx));
+      else v = __ldg(xg + (rowbase + t) * p.ldx);
+    }
+    return v;
+  };
+#pragma unroll
+  for (int u = 0; u < U; ++u) xq[u] = x_fetch(u);
+
+  // prologue: chunk 0 operands
+  raw_fetch(0); dt_fetch(0);
+  raw_commit();
+  __syncthreads();
+  prep(0, (int)min((int64_t)TC, p.T));
+  __syncthreads();
+
+  int buf = 0;
+  for (int64_t t0 = 0; t0 < p.T; t0 += TC, buf ^= 1) {
+    const int tc = (int)min((int64_t)TC, p.T - t0);
+    const bool more = t0 + TC < p.T;
+    if (more) { raw_fetch(t0 + TC); dt_fetch(t0 + TC); }            // next chunk's shared operands: in flight during the serial phase
+    // ---- serial phase over the chunk, U tokens per trip -------------------------------------------------------------------
+    for (int tt0 = 0; tt0 < tc; tt0 += U) {
+      xvec xc_raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { xc_raw[u] = xq[u]; xq[u] = x_fetch(t0 + tt0 + U + u); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int tt = tt0 + u;
+        if (tt < tc) {
+          const float2 dd = dd_s[buf][tt];
+          float xin[CPT], xcv[CPT], uu[CPT], acc[CPT][4];
+          if constexpr (CPT == 2) { xin[0] = xc_raw[u].x; xin[1] = xc_raw[u].y; } else xin[0] = xc_raw[u];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            float xv = xin[c];
+            if (conv) {
+              xv = fmaf(cw[c][3], xin[c], fmaf(cw[c][2], win[c][2], fmaf(cw[c][1], win[c][1], fmaf(cw[c][0], win[c][0], cb[c]))));
+              xv = silu_fast_f(xv);
+            }
+            win[c][0] = win[c][1]; win[c][1] = win[c][2]; win[c][2] = xin[c];
+            xcv[c] = xv; uu[c] = xv * dd.x;
+            acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+          }
+          const float4* B4 = reinterpret_cast<const float4*>(&bc_s[buf][tt][0]);
+          const float4* C4 = reinterpret_cast<const float4*>(&bc_s[buf][tt][N]);
+#pragma unroll
+          for (int q = 0; q < N / 4; ++q) {
+            const float4 bv = B4[q], cv = C4[q];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              s[c][4 * q + 0] = fmaf(dd.y, s[c][4 * q + 0], uu[c] * bv.x); acc[c][0] = fmaf(cv.x, s[c][4 * q + 0], acc[c][0]);
+              s[c][4 * q + 1] = fmaf(dd.y, s[c][4 * q + 1], uu[c] * bv.y); acc[c][1] = fmaf(cv.y, s[c][4 * q + 1], acc[c][1]);
+              s[c][4 * q + 2] = fmaf(dd.y, s[c][4 * q + 2], uu[c] * bv.z); acc[c][2] = fmaf(cv.z, s[c][4 * q + 2], acc[c][2]);
+              s[c][4 * q + 3] = fmaf(dd.y, s[c][4 * q + 3], uu[c] * bv.w); acc[c][3] = fmaf(cv.w, s[c][4 * q + 3], acc[c][3]);
+            }
+          }
+          if (pvalid) {
+            float* yp = yg + (rowbase + t0 + tt) * p.ldy;
+            const float y0 = fmaf(Dh, xcv[0], (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]));
+            if constexpr (CPT == 2) {
+              const float y1 = fmaf(Dh, xcv[1], (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]));
+              *reinterpret_cast<float2*>(yp) = make_float2(y0, y1);
+            } else *yp = y0;
+          }
+        }
+      }
+    }
+    // ---- hand over to the next chunk ---------------------------------------------------------------------------------------
+    if (more) {
+      raw_commit();                                                // raw_s was last read by prep() of this chunk, before the serial phase
+      __syncthreads();
+      prep(buf ^ 1, (int)min((int64_t)TC, p.T - (t0 + TC)));
+      __syncthreads();
+    }
+  }
+  if (p.final_state && pvalid) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      float* fs = p.final_state + (((size_t)b * p.H + h) * P + pch + c) * N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) fs[i] = s[c][i];
+    }
+  }
+}
+
+template <int N, int CPT, int NT, int U = 8, int MINB = 1>
+static int launch_ssd_v2(cudaStream_t st, const SsdParams& p, int64_t B) {
+  dim3 grid((p.P + NT * CPT - 1) / (NT * CPT), p.H, (unsigned)B);
+  ssd_scan_v2_kernel<N, CPT, NT, U, MINB><<<grid, NT, 0, st>>>(p);
+  EIGB_LAUNCH_CHECK("ssd_scan_v2_kernel");
+  return EIGB200_OK;
+}
+
+// v2 needs: whole state row per thread, 16-byte aligned [B|C] rows, 8-byte aligned channel pairs
+static bool ssd_v2_ok(const SsdParams& p, int* cpt) {
+  if (!(p.N == 16 || p.N == 8 || p.N == 4)) return false;
+  if (p.ldbc % 4 != 0 || ((uintptr_t)p.Bm & 15) || ((uintptr_t)p.Cm & 15)) return false;
+  const bool pair = (p.P % 2 == 0) && (p.ldx % 2 == 0) && (p.ldy % 2 == 0) && (((uintptr_t)p.x & 7) == 0) && (((uintptr_t)p.y & 7) == 0);
+  *cpt = pair ? 2 : 1;
+  return true;
+}
+
 static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
   EIGB_CHECK_ARG(B > 0 && p.T > 0 && p.H > 0 && p.P > 0 && p.G > 0 && p.N > 0, "ssd_scan: bad shape");
   EIGB_CHECK_ARG(p.H % p.G == 0, "ssd_scan: nheads %d not divisible by ngroups %d", p.H, p.G);
   EIGB_CHECK_ARG(p.N % 4 == 0, "ssd_scan: d_state %d must be a multiple of 4", p.N);
   EIGB_CHECK_ARG(p.kconv >= 0 && p.kconv <= 4, "ssd_scan: conv kernel size %d not in 0..4", p.kconv);
   EIGB_CHECK_ARG(B <= 65535 && p.H <= 65535, "ssd_scan: batch/heads exceed grid limits");
+  {
+    int cpt = 1;
+    if (ssd_v2_ok(p, &cpt)) {
+      const bool wide = p.P >= 128;                                 // 64 threads cover 128 channels at CPT = 2
+      if (const char* var = getenv("EIGB200_SSD_VARIANT")) {        // tuning hook (tools/kbench.py); N = 16 only
+        if (p.N == 16 && p.P % 2 == 0 && cpt == 2) {
+          switch (atoi(var)) {
+            case 1: return launch_ssd_v2<16, 2, 64, 4, 1>(st, p, B);
+            case 2: return launch_ssd_v2<16, 2, 64, 8, 6>(st, p, B);
+            case 3: return launch_ssd_v2<16, 2, 64, 4, 6>(st, p, B);
+            case 4: return launch_ssd_v2<16, 1, 64, 8, 1>(st, p, B);
+            case 5: return launch_ssd_v2<16, 1, 128, 8, 1>(st, p, B);
+            case 6: return launch_ssd_v2<16, 1, 128, 4, 4>(st, p, B);
+            case 7: return launch_ssd_v2<16, 2, 64, 2, 8>(st, p, B);
+            default: break;
+          }
+        }
+      }
+#define SSD2_CASE(N_)                                                                                                       \
+      case N_:   /* U = 2, >= 8 CTAs/SM: measured best at C2 (occupancy beats prefetch depth, profiles/kbench_r1.md) */        \
+        if (cpt == 2) return wide ? launch_ssd_v2<N_, 2, 64, 2, 8>(st, p, B) : launch_ssd_v2<N_, 2, 32, 2, 8>(st, p, B);        \
+        return wide ? launch_ssd_v2<N_, 1, 64, 4, 8>(st, p, B) : launch_ssd_v2<N_, 1, 32, 4, 8>(st, p, B);
+      switch (p.N) { SSD2_CASE(16) SSD2_CASE(8) SSD2_CASE(4) default: break; }
+#undef SSD2_CASE
+    }
+  }
   // state slice per thread: the largest of 16/8/4 that divides N with N/NS a power of two <= 32
   int ns = 0;
   for (int c : {16, 8, 4}) {

@@ -125,14 +125,23 @@ def main():
     ap.add_argument("cases", nargs="*", default=["k1_c2"])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--ssd-variants", default=None, help="comma list of EIGB200_SSD_VARIANT values to sweep for ssd_* cases")
     a = ap.parse_args()
     peak, kind = peak_gbs()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     out = []
+    sweep = []
     for name in a.cases:
+        if a.ssd_variants and name.startswith("ssd_"):
+            sweep += [(name, v) for v in a.ssd_variants.split(",")]
+        else:
+            sweep.append((name, None))
+    for name, variant in sweep:
+        if variant is not None:
+            os.environ["EIGB200_SSD_VARIANT"] = variant
         fn, nbytes, units = CASES[name]()
         med, best = time_fn(fn, a.iters, flush=flush if nbytes < (512 << 20) else None)
-        rec = {"case": name, "ms_median": med, "ms_best": best, "alg_bytes": nbytes, "GBps": nbytes / med / 1e6,
+        rec = {"case": name if variant is None else "%s[v%s]" % (name, variant), "ms_median": med, "ms_best": best, "alg_bytes": nbytes, "GBps": nbytes / med / 1e6,
                "frac_of_%s_peak" % kind: nbytes / med / 1e6 / peak, "units_per_s": units / med * 1e3}
         if name.startswith("lin_"):
             rec["TFLOPs_fp32_equiv"] = units / med / 1e9
