@@ -6,5 +6,3 @@ using namespace eigb200;
 
 extern "C" int eigb200_softmax_nu(void*, const float*, const float*, int64_t, int64_t, int64_t, int, int, double*, float*) { EIGB_STUB("eigb200_softmax_nu"); }
 extern "C" int eigb200_softmax_eta(void*, const double*, const float*, int64_t, int64_t, int, double*, int32_t*, const double*, int) { EIGB_STUB("eigb200_softmax_eta"); }
-extern "C" int eigb200_dplr_abar(void*, const float*, const float*, const float*, const float*, int64_t, int, float*) { EIGB_STUB("eigb200_dplr_abar"); }
-extern "C" int eigb200_eigvals_c64(void*, float*, int64_t, int, float*, int32_t*) { EIGB_STUB("eigb200_eigvals_c64"); }

@@ -54,7 +54,7 @@ def test_elementwise(ops):
     a = rng.normal(size=(1031,)).astype(np.float32) * 3; b = rng.normal(size=(1031,)).astype(np.float32) * 3
     np.testing.assert_array_equal(ops.add(dev(a), dev(b)).cpu().numpy(), a + b)
     np.testing.assert_allclose(ops.mul_silu(dev(a), dev(b)).cpu().numpy(), a * (b / (1 + np.exp(-b.astype(np.float64)))), rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(ops.gelu(dev(a)).cpu().numpy(), O.gelu_erf(a.astype(np.float64)), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ops.gelu(dev(a)).cpu().numpy(), O.gelu_erf(a.astype(np.float64)), rtol=1e-5, atol=1e-6)
     s = rng.normal(size=(8,)).astype(np.float32); m = rng.normal(size=(13, 8)).astype(np.float32)
     np.testing.assert_array_equal(ops.scale_cols(dev(m), dev(s)).cpu().numpy(), m * s)
 

@@ -1,0 +1,119 @@
+"""GPU parity: K3 -- S4 DPLR discretisation and the batched small-N nonsymmetric eigensolver.
+
+Parity definition (DESIGN.md "K3"): (i) A-bar element-wise within 1e-5 of the reference's discrete_DPLR output;
+(ii) on THE SAME input matrix the eigenvalues match np.linalg.eigvals (which computes in complex128 on the complex64 input and casts
+back, exactly what analysis/eval_eig.py:296 does) to rel 1e-5 after matching, including the non-normal HiPPO matrices;
+(iii) backward error sigma_min(A - lambda I) <= 1e-6 ||A||.  Eigenvalues of a GPU-built A-bar versus the reference's A-bar differ by
+cond * 1e-7 and are REPORTED, not asserted."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import eigb200.ops as ops
+    return ops
+
+
+def _match(ev, ref):
+    """greedy nearest matching; returns max relative distance"""
+    ev = list(np.asarray(ev, np.complex128)); worst = 0.0
+    for x in np.asarray(ref, np.complex128):
+        j = int(np.argmin([abs(x - y) for y in ev]))
+        worst = max(worst, abs(x - ev[j]) / max(abs(x), 1e-30))
+        ev.pop(j)
+    return worst
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 16, 33, 64])
+def test_eigvals_random_batches(ops, n):
+    rng = np.random.default_rng(n)
+    nb = 40
+    A = (rng.normal(size=(nb, n, n)) + 1j * rng.normal(size=(nb, n, n))).astype(np.complex64)
+    A[1] *= np.exp(rng.normal(0, 3, n))[None, :].astype(np.float32)                     # badly scaled columns
+    A[2] = np.triu(A[2]) + np.diag(np.full(max(n - 1, 0), 1e-3), -1).astype(np.complex64)    # nearly triangular
+    A[3] = np.diag(rng.normal(size=n)).astype(np.complex64)                             # already diagonal
+    ev, info = ops.eigvals_c64(torch.from_numpy(A).cuda())
+    assert int(info.abs().max()) == 0
+    ev = ev.cpu().numpy()
+    assert ev.dtype == np.complex64 and ev.shape == (nb, n)
+    for b in range(nb):
+        ref = np.linalg.eigvals(A[b])                     # complex128 internally, complex64 out -- the reference's call
+        assert _match(ev[b], ref) <= (1e-4 if b == 1 else 1e-5), (b, _match(ev[b], ref))
+
+
+def test_dplr_abar_and_reference_eigs(ops):
+    g = load_golden("hippo_s4")
+    report = []
+    for N in (8, 16, 64):
+        for l in (0, 1):
+            lay = {k: g["s4_N%d_l%d_%s" % (N, l, k)] for k in ["Lambda_re", "Lambda_im", "P", "log_step"]}
+            idx = 1
+            Lam = (np.minimum(lay["Lambda_re"][:, idx], np.float32(-1e-4)) + 1j * lay["Lambda_im"][:, idx]).astype(np.complex64)
+            Pv = lay["P"][:, idx].astype(np.complex64)
+            step = np.exp(lay["log_step"][0, idx]).astype(np.float32)
+            Ab = ops.dplr_abar(torch.from_numpy(Lam[None]).cuda(), torch.from_numpy(Pv[None]).cuda(), torch.from_numpy(Pv[None]).cuda(),
+                               torch.tensor([step]).cuda())[0].cpu().numpy()
+            ref_Ab = g["s4_N%d_l%d_Abar" % (N, l)]
+            assert np.abs(Ab - ref_Ab).max() <= 1e-5 * np.abs(ref_Ab).max()                      # (i)
+            # (ii) same matrix in, same eigenvalues out -- including the ill-conditioned HiPPO case
+            # (the golden A-bar is complex128 because numpy-as-jnp promotes jnp.eye to float64; the real JAX reference holds it in
+            #  complex64, so the matrix handed to both solvers is its complex64 rounding)
+            A64 = ref_Ab.astype(np.complex64)
+            ev, info = ops.eigvals_c64(torch.from_numpy(A64[None]).cuda())
+            assert int(info[0]) == 0
+            assert _match(ev[0].cpu().numpy(), np.linalg.eigvals(A64)) <= 1e-5
+            ref_ev = g["s4_N%d_l%d_eig" % (N, l)][:, 0]
+            # (iii) backward error of the eigenvalues of the GPU-built matrix
+            ev2, _ = ops.eigvals_c64(torch.from_numpy(Ab[None]).cuda())
+            ev2 = ev2[0].cpu().numpy().astype(np.complex128)
+            nrm = np.linalg.norm(Ab.astype(np.complex128), 2)
+            be = max(np.linalg.svd(Ab.astype(np.complex128) - lam * np.eye(N), compute_uv=False)[-1] for lam in ev2) / nrm
+            assert be <= 1e-6
+            report.append((N, l, "built-vs-golden %.1e" % _match(ev2, ref_ev), "c64-rounded-golden-matrix-vs-golden %.1e" % _match(ev[0].cpu().numpy(), ref_ev)))
+    print("eigenvalues of the GPU-built A-bar vs the reference's (REPORTED, conditioning-limited):", report)
+
+
+def test_get_eigvals_ssm_s4_dropin(ops):
+    import eigb200.ssm as S
+    import eigb200.extractors as E
+    g = load_golden("hippo_s4")
+    for N in (8, 16, 64):
+        layers = [{k: g["s4_N%d_l%d_%s" % (N, l, k)] for k in ["Lambda_re", "Lambda_im", "P", "B", "C", "log_step"]} for l in (0, 1)]
+        out = np.concatenate([S.get_eigvals_ssm("s4", layers, l, 1, 64) for l in (0, 1)], axis=-1)
+        assert out.shape == (N, 2) and out.dtype == np.complex64
+        ref = np.concatenate([g["s4_N%d_l%d_eig" % (N, l)] for l in (0, 1)], axis=-1)
+        rad, ph = S.radius_phase(out)
+        rrad, rph = O.radius_phase(ref)
+        pct = E.threshold_analysis_ssm(rad, O.THRESHOLDS_RADIUS, 2)
+        np.testing.assert_array_equal(pct, O.threshold_analysis_ssm(rad, O.THRESHOLDS_RADIUS))    # binning exact for our values
+        ref_pct = O.threshold_analysis_ssm(rrad, O.THRESHOLDS_RADIUS)
+        print("S4 N=%d radius-bin percentages, ours vs reference (reported):" % N, np.round(pct.T, 1).tolist(), np.round(ref_pct.T, 1).tolist())
+        if N <= 16:
+            assert np.abs(pct - ref_pct).max() <= 100.0 / N + 1e-9
+
+
+def test_batched_all_features(ops):
+    import eigb200.ssm as S
+    rng = np.random.default_rng(3)
+    N, Hf, L = 64, 48, 2
+    Lam, P, _, _, _ = O.make_dplr_hippo(N)
+    layers = []
+    for _ in range(L):
+        layers.append(dict(Lambda_re=(np.repeat(Lam.real[:, None], Hf, 1) + 0.05 * rng.normal(size=(N, Hf))).astype(np.float32),
+                           Lambda_im=(np.repeat(Lam.imag[:, None], Hf, 1) + 0.05 * rng.normal(size=(N, Hf))).astype(np.float32),
+                           P=(np.repeat(P[:, None], Hf, 1) + 0.05 * rng.normal(size=(N, Hf))).astype(np.complex64),
+                           log_step=rng.uniform(np.log(1e-3), np.log(1e-1), (1, Hf)).astype(np.float32)))
+    ev, info, Ab = S.eigvals_s4_all_features(layers)
+    assert ev.shape == (L, Hf, N) and int(info.abs().max()) == 0
+    Abn = Ab.cpu().numpy(); evn = ev.cpu().numpy().reshape(L * Hf, N)
+    for m in (0, 17, L * Hf - 1):
+        assert _match(evn[m], np.linalg.eigvals(Abn[m])) <= 1e-5
