@@ -379,7 +379,36 @@ def crosscheck_ssd_against_hf():
          x=x.numpy(), dt=dt.numpy(), A=A.numpy(), Bm=Bm.numpy(), Cm=Cm.numpy(), D=D.numpy(), y_fla=y_fla)
 
 
+def gold_report_files():
+    """The text reports written by create_file_percentage / create_file_percentage_ssm (eval_eig.py:393-459), byte for byte."""
+    ns = extract("analysis/eval_eig.py", ["create_file_percentage", "create_file_percentage_ssm"], {"np": np})
+    rng = np.random.default_rng(21)
+    B, H, L = 8, 2, 3
+    pct = rng.uniform(0, 100, (7, B, H, L)); pct_i = rng.uniform(0, 100, (7, B, H, L))
+    thr = np.array([0.1, 0.5, 0.9, 1.0, 10, 100]); thp = np.array([1, 10, 45, 90, 180])
+    cwd = os.getcwd()
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            ns["create_file_percentage"](thr, pct, pct_i, pct.mean(1), pct_i.mean(1), pct.std(1), pct_i.std(1))
+            txt1 = open("percentage_file.txt").read()
+            ps = rng.uniform(0, 100, (7, L)); psi = rng.uniform(0, 100, (7, L)); pp = rng.uniform(0, 100, (6, L)); ppi = rng.uniform(0, 100, (6, L))
+            ns["create_file_percentage_ssm"](thr, thp, ps, psi, pp, ppi)
+            txt2 = open("percentage_file.txt").read()
+        finally:
+            os.chdir(cwd)
+    save("report_files", "analysis/eval_eig.py:393-459", pct=pct, pct_i=pct_i, ps=ps, psi=psi, pp=pp, ppi=ppi,
+         txt_torch=np.frombuffer(txt1.encode(), dtype=np.uint8), txt_ssm=np.frombuffer(txt2.encode(), dtype=np.uint8))
+
+
 if __name__ == "__main__":
+    if "--only-reports" in sys.argv:
+        MANIFEST.update(json.load(open(os.path.join(OUT, "MANIFEST.json"))))
+        gold_report_files()
+        with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
+            json.dump(MANIFEST, f, indent=1, sort_keys=True)
+        sys.exit(0)
     gold_thresholds()
     gold_mamba2_extractor()
     gold_norm_extractor()
@@ -388,6 +417,7 @@ if __name__ == "__main__":
     gold_hippo_s4()
     crosscheck_ssd_against_hf()
     gold_models()
+    gold_report_files()
     MANIFEST["_env"] = {"numpy": np.__version__, "torch": torch.__version__}
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
         json.dump(MANIFEST, f, indent=1, sort_keys=True)
