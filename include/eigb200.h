@@ -68,10 +68,14 @@ int         eigb200_zero_i32(void* stream, int32_t* d_buf, size_t n);
  *   d_lam    float32 out, may be NULL (statistics only); entry (b,t,h) is written at d_lam[((b*T + t)*H + h) * lam_stride], so
  *            lam_stride = 1 gives a dense (B,T,H) array and lam_stride = L with d_lam offset by the layer index writes straight
  *            into the reference's (B,T,H,L) layout (np.concatenate(..., axis=-1), eval_eig.py:524-526)
- *   d_counts (B,H,8) int32 accumulated, may be NULL */
+ *   d_counts (B,H,8) int32 accumulated, may be NULL
+ *   d_rowstats (B,T,2) float32 out, may be NULL: (mean, 1/sqrt(var + ln_eps)) of every row of x -- the LayerNorm statistics of the
+ *            NEXT block's prenorm (models/mamba.py:329-331), produced for free while x streams through the extractor and consumed by
+ *            eigb200_linear_ln so that the normalised activations never exist in HBM */
 int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
                        const float* d_W_dt, const float* d_dt_bias, const float* d_A_log, int H,
-                       float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode);
+                       float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode,
+                       float* d_rowstats, float ln_eps);
 
 /* get_eig_mamba2_LTI (analysis/eval_eig.py:192-205): lambda[h] = exp(beta[h] * -softplus(A[h])), broadcast over (B,T).
  * d_lam (B,T,H) may be NULL; d_counts (B,H,8) accumulated. */
@@ -164,6 +168,14 @@ int eigb200_eigvals_c64(void* stream, float* d_A, int64_t nmat, int N, float* d_
  *   mode: SIMT_F32 = fp32 FFMA; TC_3XTF32 = tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy); AUTO picks.
  *   d_workspace/workspace_bytes: eigb200_linear_workspace_bytes(N, K) bytes (split weights for the tensor-core path). */
 size_t eigb200_linear_workspace_bytes(int N, int K);
+/* eigb200_linear with nn.LayerNorm fused into the A operand: C = epilogue(LN(A) W^T + bias), LN(A)[m,k] = (A[m,k] - mean_m) * rstd_m *
+ * gamma[k] + beta[k] with d_ln_stats (M,2) = (mean, rstd) per row (from eigb200_mamba2_eig / eigb200_embedding / eigb200_rowstats).
+ * Tensor-core path only (same shape limits as eigb200_linear mode TC_3XTF32); EIGB200_EUNSUPPORTED otherwise. */
+int eigb200_linear_ln(void* stream, const float* d_A, int64_t lda, const float* d_ln_stats, const float* d_ln_gamma, const float* d_ln_beta,
+                      const float* d_W, const float* d_bias, float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
+                      int64_t M, int N, int K, int epilogue, void* d_workspace, size_t workspace_bytes);
+/* (mean, 1/sqrt(var + eps)) of every row of x (rows, D) -> d_stats (rows, 2). */
+int eigb200_rowstats(void* stream, const float* d_x, int64_t rows, int D, float eps, float* d_stats);
 int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
                    float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
                    int64_t M, int N, int K, int epilogue, int mode, void* d_workspace, size_t workspace_bytes);
@@ -171,6 +183,9 @@ int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W
 /* TokenEmbeddings.forward (models/common.py:160-176): out[b,t,:] = word[ids[b,t],:] (+ pos[t,:] if d_pos != NULL). ids int64. */
 int eigb200_embedding(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,
                       int64_t B, int64_t T, int D, int64_t vocab);
+/* same, also emitting the LayerNorm row statistics (mean, rstd) of the embedded rows into d_rowstats (B,T,2). */
+int eigb200_embedding_stats(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,
+                            int64_t B, int64_t T, int D, int64_t vocab, float* d_rowstats, float ln_eps);
 /* nn.LayerNorm over the last axis, eps inside the sqrt, biased variance (models/mamba.py:321; transformer.py:84). */
 int eigb200_layernorm(void* stream, const float* d_x, const float* d_w, const float* d_b, float eps, float* d_out, int64_t rows, int D);
 /* Depthwise causal conv1d (k taps, padding k-1, truncated to T) + SiLU over x (B,T,C) row stride ldx -> out row stride ldo

@@ -27,7 +27,7 @@ SIGNATURES = {
     "eigb200_device_info": [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "eigb200_set_device": [_i],
     "eigb200_zero_i32": [_vp, _vp, _sz],
-    "eigb200_mamba2_eig": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _dp, _i, _i],
+    "eigb200_mamba2_eig": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _dp, _i, _i, _vp, _f],
     "eigb200_mamba2_lti_eig": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_normattn_gate": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _i, _vp],
     "eigb200_linattn_nu": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
@@ -43,6 +43,9 @@ SIGNATURES = {
     "eigb200_linear_workspace_bytes": [_i, _i],
     "eigb200_linear": [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _sz],
     "eigb200_embedding": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64],
+    "eigb200_embedding_stats": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64, _vp, _f],
+    "eigb200_rowstats": [_vp, _vp, _i64, _i, _f, _vp],
+    "eigb200_linear_ln": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _sz],
     "eigb200_layernorm": [_vp, _vp, _vp, _vp, _f, _vp, _i64, _i],
     "eigb200_conv_silu": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _i64, _i64, _i64, _i],
     "eigb200_linattn_forward": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _f, _vp, _i64, _i64, _i64, _i, _i, _i],

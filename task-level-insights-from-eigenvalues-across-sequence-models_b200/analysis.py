@@ -54,19 +54,25 @@ class PassResult:
 
 def mamba_pass(model: "Ly.MambaDev", X, pseudoLTI=False, want_eig=True, compare="float64") -> PassResult:
     """eval_eig.py:501-526 / :575-600 for one batch on the current device."""
-    x = model.encoder(X)
+    # LayerNorm fusion: the kernel that PRODUCES a block's input also emits that row's (mean, rstd) -- the embedding for block 0,
+    # the extractor of block i for block i+1 -- and the in_proj GEMM normalises its A operand on the fly (eigb200_linear_ln).
+    fuse = (not pseudoLTI) and isinstance(model.encoder, Ly.TokenEmbeddingsDev) and all(b.fuses_layernorm() for b in model.blocks)
+    Bn, Tn = X.shape[0], X.shape[1]
+    stats = torch.empty(2, Bn, Tn, 2, dtype=torch.float32, device=X.device) if fuse else None
+    x = model.encoder(X, rowstats_out=stats[0]) if fuse else model.encoder(X)
     B, T, _ = x.shape
     H = model.blocks[0].mamba.nheads
     nl = len(model.blocks)
     eig = torch.empty(B, T, H, nl, dtype=torch.float32, device=x.device) if want_eig else None
     counts = torch.zeros(nl, B, H, ops.NSLOT, dtype=torch.int32, device=x.device)
     for i, blk in enumerate(model.blocks):
-        x = blk(x)
+        x = blk(x, stats[i & 1]) if fuse else blk(x)
         out_i = eig[..., i] if want_eig else None
         if pseudoLTI:
             E.get_eig_mamba2_LTI_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=out_i)
         else:
-            E.get_eig_mamba2_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=out_i)
+            E.get_eig_mamba2_device(x, blk, want_eig=want_eig, counts=counts[i], compare=compare, lam_out=out_i,
+                                    rowstats_out=stats[(i + 1) & 1] if (fuse and i + 1 < nl) else None)
     return PassResult(eig, counts, T, x)
 
 

@@ -12,7 +12,8 @@ namespace eigb200 {
 // ---- embedding: one warp per (b,t) row --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
                                                         const float* __restrict__ pos, float* __restrict__ out,
-                                                        int64_t rows, int64_t T, int D, int64_t vocab, int* __restrict__ err) {
+                                                        int64_t rows, int64_t T, int D, int64_t vocab, int* __restrict__ err,
+                                                        float2* __restrict__ rowstats, float ln_eps) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -23,11 +24,46 @@ __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restric
     const float4* w = reinterpret_cast<const float4*>(word + id * D);
     const float4* pp = pos ? reinterpret_cast<const float4*>(pos + (r % T) * D) : nullptr;
     float4* o = reinterpret_cast<float4*>(out + r * D);
+    float s1 = 0.f, s2 = 0.f;
+    const float shift = rowstats ? (__ldg(word + id * D) + (pos ? __ldg(pos + (r % T) * D) : 0.f)) : 0.f;
     for (int c = lane; c < nv; c += 32) {
       float4 v = __ldg(w + c);
       if (pp) { const float4 q = __ldg(pp + c); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
       o[c] = v;
+      if (rowstats) {
+        const float a = v.x - shift, bb = v.y - shift, cc = v.z - shift, d = v.w - shift;
+        s1 += (a + bb) + (cc + d); s2 += (a * a + bb * bb) + (cc * cc + d * d);
+      }
     }
+    if (rowstats) {
+#pragma unroll
+      for (int ofs = 16; ofs >= 1; ofs >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, ofs); s2 += __shfl_xor_sync(0xffffffffu, s2, ofs); }
+      if (lane == 0) {
+        const float md = s1 / (float)D;
+        rowstats[r] = make_float2(shift + md, rsqrtf(fmaxf(s2 / (float)D - md * md, 0.f) + ln_eps));
+      }
+    }
+  }
+}
+
+// (mean, rstd) of every row: one warp per row, shifted moments
+__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ x, int64_t rows, int D, float eps, float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = D >> 2;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+    const float shift = __ldg(x + r * D);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+      const float4 v = ldg_stream_f4(xr + c);
+      const float a = v.x - shift, bb = v.y - shift, cc = v.z - shift, d = v.w - shift;
+      s1 += (a + bb) + (cc + d); s2 += (a * a + bb * bb) + (cc * cc + d * d);
+    }
+#pragma unroll
+    for (int ofs = 16; ofs >= 1; ofs >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, ofs); s2 += __shfl_xor_sync(0xffffffffu, s2, ofs); }
+    if (lane == 0) { const float md = s1 / (float)D; stats[r] = make_float2(shift + md, rsqrtf(fmaxf(s2 / (float)D - md * md, 0.f) + eps)); }
   }
 }
 
@@ -153,8 +189,28 @@ extern "C" int eigb200_embedding(void* stream, const int64_t* d_ids, const float
   EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && D % 4 == 0 && vocab > 0, "embedding: bad shape (D %% 4 == 0 required)");
   const int64_t rows = B * T;
   int64_t g = (rows + 7) / 8; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
-  embedding_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_ids, d_word, d_pos, d_out, rows, T, D, vocab, nullptr);
+  embedding_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_ids, d_word, d_pos, d_out, rows, T, D, vocab, nullptr, nullptr, 0.f);
   EIGB_LAUNCH_CHECK("embedding_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_embedding_stats(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,
+                                       int64_t B, int64_t T, int D, int64_t vocab, float* d_rowstats, float ln_eps) {
+  EIGB_CHECK_ARG(d_ids && d_word && d_out && d_rowstats, "embedding_stats: null pointer");
+  EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && D % 4 == 0 && vocab > 0, "embedding_stats: bad shape (D %% 4 == 0 required)");
+  const int64_t rows = B * T;
+  int64_t g = (rows + 7) / 8; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
+  embedding_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_ids, d_word, d_pos, d_out, rows, T, D, vocab, nullptr,
+                                                                  reinterpret_cast<float2*>(d_rowstats), ln_eps);
+  EIGB_LAUNCH_CHECK("embedding_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_rowstats(void* stream, const float* d_x, int64_t rows, int D, float eps, float* d_stats) {
+  EIGB_CHECK_ARG(d_x && d_stats && rows > 0 && D > 0 && D % 4 == 0, "rowstats: bad arguments (D %% 4 == 0 required)");
+  int64_t g = (rows + 7) / 8; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
+  rowstats_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_x, rows, D, eps, reinterpret_cast<float2*>(d_stats));
+  EIGB_LAUNCH_CHECK("rowstats_kernel");
   return EIGB200_OK;
 }
 

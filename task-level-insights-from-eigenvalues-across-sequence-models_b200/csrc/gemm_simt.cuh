@@ -6,6 +6,8 @@ struct LinearParams {
   const float* A; int64_t lda; const float* W; const float* bias;
   float* C; int64_t ldc; const float* R; int64_t ldr;
   int64_t M; int N, K, epilogue;
+  // optional LayerNorm fused into the A operand (tensor-core path only): (mean, rstd) per row, gamma / beta per column
+  const float* ln_stats = nullptr; const float* ln_gamma = nullptr; const float* ln_beta = nullptr;
 };
 int launch_linear_simt(cudaStream_t st, const LinearParams& p);
 }  // namespace eigb200

@@ -23,6 +23,7 @@ enum { K1_EPI_MAMBA2 = 0, K1_EPI_NORMGATE = 1 };
 struct K1Params {
   const void* x; const float* W; const float* p0; const float* p1; const float* p2;   // W (H,D); per-head vectors
   float* out; int64_t out_stride; int* counts;
+  float2* rowstats; float ln_eps;                   // optional (mean, rstd) of every row of x: LayerNorm statistics for the next block
   int T, D, H, rows_per_warp, norm_fn;
   EdgesF e;
 };
@@ -102,18 +103,34 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p
   const int nvec = D / VEC;
   const float4* Ws4 = reinterpret_cast<const float4*>(Ws);
 
+  const bool want_stats = (EPI == K1_EPI_MAMBA2) && p.rowstats != nullptr && blockIdx.z == 0;
   for (int t = t0; t < t1; t += K1_R) {
     float acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    float s1[K1_R], s2[K1_R], shift[K1_R];            // shifted moments: sum(x - x_0), sum((x - x_0)^2)
+#pragma unroll
+    for (int r = 0; r < K1_R; ++r) { s1[r] = 0.f; s2[r] = 0.f; shift[r] = 0.f; }
     const char* rows[K1_R];
 #pragma unroll
     for (int r = 0; r < K1_R; ++r) rows[r] = xb + (size_t)min(t + r, t1 - 1) * row_bytes;   // clamp: tail rows re-read a valid row
+    if (want_stats) {                                   // shift = first element of the row (same broadcast load in every lane)
+#pragma unroll
+      for (int r = 0; r < K1_R; ++r)
+        shift[r] = BF16 ? __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(rows[r])) << 16)
+                        : __ldg(reinterpret_cast<const float*>(rows[r]));
+    }
 #pragma unroll 2
     for (int c = lane; c < nvec; c += 32) {
       float xv[K1_R][8];
 #pragma unroll
       for (int r = 0; r < K1_R; ++r) XLoad<BF16>::load(rows[r], c, xv[r]);
+      if (want_stats) {
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) { const float dlt = xv[r][e] - shift[r]; s1[r] += dlt; s2[r] = fmaf(dlt, dlt, s2[r]); }
+      }
 #pragma unroll
       for (int h = 0; h < HT; ++h) {
 #pragma unroll
@@ -132,6 +149,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p
       }
     }
     const float dot = transpose_reduce<NV>(acc, lane);
+    if (want_stats) {
+      const float m1 = transpose_reduce<K1_R>(s1, lane), m2 = transpose_reduce<K1_R>(s2, lane);
+      const int rr = lane >> 3;                          // K1_R = 4 partials: lanes 8r..8r+7 hold row r
+      const float sh = rr == 0 ? shift[0] : (rr == 1 ? shift[1] : (rr == 2 ? shift[2] : shift[3]));
+      if ((lane & 7) == 0 && t + rr < t1) {
+        const float invD = 1.f / (float)D;
+        const float md = m1 * invD;                      // mean - shift
+        const float var = fmaxf(m2 * invD - md * md, 0.f);
+        p.rowstats[(size_t)b * T + t + rr] = make_float2(sh + md, rsqrtf(var + p.ln_eps));
+      }
+    }
     const int row = t + r_own;
     if (lead && row < t1) {
       float val;
@@ -315,7 +343,8 @@ extern "C" int eigb200_zero_i32(void* stream, int32_t* d_buf, size_t n) {
 
 extern "C" int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, int64_t T, int D,
                                   const float* d_W_dt, const float* d_dt_bias, const float* d_A_log, int H,
-                                  float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode) {
+                                  float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode,
+                                  float* d_rowstats, float ln_eps) {
   EIGB_CHECK_ARG(d_x && d_W_dt && d_dt_bias && d_A_log, "mamba2_eig: null input pointer");
   EIGB_CHECK_ARG(!d_lam || lam_stride >= 1, "mamba2_eig: lam_stride must be >= 1");
   EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && H > 0, "mamba2_eig: bad shape B=%lld T=%lld D=%d H=%d", (long long)B, (long long)T, D, H);
@@ -325,6 +354,7 @@ extern "C" int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, in
   EIGB_CHECK_ARG(T < (1LL << 31), "mamba2_eig: T too large");
   K1Params p{};
   p.x = d_x; p.W = d_W_dt; p.p0 = d_dt_bias; p.p1 = d_A_log; p.p2 = nullptr; p.out = d_lam; p.out_stride = lam_stride; p.counts = d_counts;
+  p.rowstats = reinterpret_cast<float2*>(d_rowstats); p.ln_eps = ln_eps;
   p.T = (int)T; p.D = D; p.H = H; p.norm_fn = 0;
   if (d_counts) { int rc = make_edges_f(thresholds, nthr, compare_mode, &p.e); if (rc) return rc; }
   else { double one = 1.0; make_edges_f(&one, 1, 0, &p.e); }

@@ -21,6 +21,7 @@
 // warp 12 TMA producer, warp 13 MMA issuer.
 #include "gemm_tc.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace eigb200 {
 
@@ -33,10 +34,11 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
   const float* bias; float* C; int64_t ldc; const float* R; int64_t ldr;
+  const float2* ln_stats; const float* ln_gamma; const float* ln_beta;      // LayerNorm fused into the converter (nullable)
   int64_t M; int N, K, epilogue;
   int bn;            // columns per CTA (UMMA N), multiple of 32, <= 128
   int bg;            // GLU: value columns per CTA (bn = 2*bg); otherwise bn
-  int nsplit, kchunks, nstages, nterms, workers;
+  int nsplit, kchunks, nstages, nterms, workers, debug;
   int64_t ntiles;
 };
 
@@ -51,6 +53,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
 }
+// arrive that is data-dependent on `dep`: the values loaded from the buffer being released are in registers before the arrive issues
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar), "r"(dep) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
 }
@@ -62,6 +68,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+  // the polling loop lives inside the asm block, so the compiler inserts no reconvergence point after it: lanes may leave it on
+  // different iterations.  Every caller goes on to .sync.aligned instructions (tcgen05.ld / st / wait) or lane-0 election, which need
+  // the warp converged -- without this barrier single TMEM lanes (rows) were silently dropped by tcgen05.st.
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -110,6 +120,33 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// store 32 columns of 32-bit into TMEM: thread i of the warp writes columns [col, col+32) of lane (lane_base + i)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr),
+         "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+         "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+         "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+         "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+         "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+         "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+         "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+         "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (128 lanes = rows, 8 columns = the K step of tf32 values) is read from TMEM
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -178,6 +215,91 @@ __global__ void split_weights_kernel(const float* __restrict__ W, float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// epilogue (8 warps): TMEM accumulator -> registers -> bias / GELU / GLU gate -> shuffle transpose -> (+ residual) -> 128-byte coalesced stores
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int bn, uint32_t bar_dfull0, uint32_t bar_dempty0,
+                                            const float* bias_s, int worker, int split, int warp, int lane) {
+  auto bar_dfull = [&](int j) { return bar_dfull0 + 8u * j; };
+  auto bar_dempty = [&](int j) { return bar_dempty0 + 8u * j; };
+  {
+    constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
+    const int nout = GLU ? p.N / 2 : p.N;
+    const int cols_out = GLU ? p.bg : bn;                            // output columns produced by this CTA
+    const int n_cta0 = split * cols_out;
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    const int gi = lane & 7, gg = lane >> 3;                         // after the transpose: column quad gi of rows 8*gg + jj
+    const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
+    int j = 0; uint32_t dph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
+      bool waited = false, arrived = false;
+      for (int cg = 32 * half; cg < cols_out; cg += 64) {
+        const int ccol = cg + 4 * gi;                                // column inside the CTA slice (transposed layout)
+        const int n = n_cta0 + ccol;
+        const bool col_ok = ccol < cols_out && n < nout;
+        const bool full = n + 3 < nout;
+        // residual rows of this group: issued first so that their DRAM latency hides behind the TMEM load, the math and the transpose
+        float4 rr[8];
+        if ((p.debug & 4) && !waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
+        if (use_r) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            rr[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && full && row0 + jj < p.M) rr[jj] = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + (row0 + jj) * p.ldr + n));
+          }
+        }
+        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
+        float v[32];
+        tmem_ld_32x32(d_tmem + cg, v);
+        if (GLU) {
+          float g[32];
+          tmem_ld_32x32(d_tmem + p.bg + cg, g);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (v[i] + bias_s[cg + i]) * sigmoid_fast_f(g[i] + bias_s[p.bg + cg + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float vv = v[i] + bias_s[cg + i];
+            if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
+            v[i] = vv;
+          }
+        }
+        if (cg + 64 >= cols_out) {                                   // this warp's last TMEM read of the accumulator: release it early
+          tc_fence_before();
+          mbar_arrive(bar_dempty(j));
+          arrived = true;
+        }
+        transpose8x8_f4(v, lane);
+        if (col_ok) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int64_t mrow = row0 + jj;
+            if (mrow < p.M) {
+              float* cptr = p.C + mrow * p.ldc + n;
+              if (full) {
+                float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                if (use_r) { o.x += rr[jj].x; o.y += rr[jj].y; o.z += rr[jj].z; o.w += rr[jj].w; }
+                *reinterpret_cast<float4*>(cptr) = o;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < nout) cptr[e] = v[4 * jj + e] + (use_r ? p.R[mrow * p.ldr + n + e] : 0.f);
+              }
+            }
+          }
+        }
+      }
+      if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
+      if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
+      if (++j == 2) { j = 0; dph ^= 1; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------------------------------------------------------
 template <int EPI>
@@ -203,6 +325,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (5 + 3 * TC_MAX_STAGES);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));     // [bn] bias of this CTA's slice
+  float* ln_g_s = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));    // [kch*32] LayerNorm gamma, then beta
+  float* ln_b_s = ln_g_s + kch * TC_KC;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
@@ -222,6 +346,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
       else { n = split * bn + c; if (n >= p.N) n = -1; }
       bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+    }
+  }
+  if (p.ln_stats && threadIdx.x >= 128 && threadIdx.x < 256) {        // LayerNorm affine parameters, zero beyond K
+    for (int k = threadIdx.x - 128; k < kch * TC_KC; k += 128) {
+      ln_g_s[k] = k < p.K ? p.ln_gamma[k] : 0.f;
+      ln_b_s[k] = k < p.K ? p.ln_beta[k] : 0.f;
     }
   }
   if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
@@ -255,14 +385,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   } else if (warp >= 8 && warp < 12) {
     // ===================================== converters: raw fp32 -> tf32 hi (in place) + tf32 lo ==============================
     const int ct = threadIdx.x - 256;                               // 0..127
+    const bool ln = p.ln_stats != nullptr;
     int s = 0; uint32_t ph = 0;
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      // float4 #idx = i*128 + ct of a chunk is row idx>>3, physical 16-byte slot idx&7 = logical slot ^ (row & 7) (SWIZZLE_128B):
+      // this thread's 8 rows are the same for every chunk of the tile, so their LayerNorm statistics are fetched once per tile
+      float2 st[8];
+      if (ln) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t m = tile * TC_BM + ((i * 128 + ct) >> 3);
+          st[i] = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f);
+        }
+      }
       for (int c = 0; c < kch; ++c) {
         mbar_wait(bar_full(s), ph);
         uint8_t* hi_ptr = smem_raw + (stage0 + s * 2 * TC_CHUNK_BYTES - smem_u32(smem_raw));
         float4* h4 = reinterpret_cast<float4*>(hi_ptr);
         float4* l4 = reinterpret_cast<float4*>(hi_ptr + TC_CHUNK_BYTES);
-        if (p.nterms == 3) {
+        if (ln) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 128 + ct;
+            const int r = idx >> 3;
+            const int kcol = c * TC_KC + 4 * ((idx & 7) ^ (r & 7));
+            float4 a = h4[idx];
+            const float4 gm = *reinterpret_cast<const float4*>(ln_g_s + kcol), bt = *reinterpret_cast<const float4*>(ln_b_s + kcol);
+            a.x = fmaf((a.x - st[i].x) * st[i].y, gm.x, bt.x); a.y = fmaf((a.y - st[i].x) * st[i].y, gm.y, bt.y);
+            a.z = fmaf((a.z - st[i].x) * st[i].y, gm.z, bt.z); a.w = fmaf((a.w - st[i].x) * st[i].y, gm.w, bt.w);
+            float4 h, l;
+            h.x = to_tf32(a.x); h.y = to_tf32(a.y); h.z = to_tf32(a.z); h.w = to_tf32(a.w);
+            l.x = to_tf32(a.x - h.x); l.y = to_tf32(a.y - h.y); l.z = to_tf32(a.z - h.z); l.w = to_tf32(a.w - h.w);
+            h4[idx] = h; l4[idx] = l;
+          }
+        } else if (p.nterms == 3) {
 #pragma unroll
           for (int i = 0; i < TC_CHUNK_BYTES / 16 / 128; ++i) {      // 8 float4 per thread; the split is elementwise, layout agnostic
             const int idx = i * 128 + ct;
@@ -321,78 +477,199 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
   } else if (warp < 8) {
     // ===================================== epilogue ======================================
-    constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
-    const int nout = GLU ? p.N / 2 : p.N;
-    const int cols_out = GLU ? p.bg : bn;                            // output columns produced by this CTA
-    const int n_cta0 = split * cols_out;
-    const int quarter = warp & 3, half = warp >> 2;
-    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const int gi = lane & 7, gg = lane >> 3;                         // after the transpose: column quad gi of rows 8*gg + jj
-    const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
+    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// TS variant: the A operand lives in TMEM.
+// Shared memory then holds only the resident weight slice and a deep ring of RAW 16 KB chunks (TMA destinations): a converter thread
+// owns one row (= one TMEM lane), reads its 32 floats of the chunk from the swizzled tile, releases the ring slot immediately,
+// applies the optional LayerNorm, splits into tf32 hi / lo and writes both with tcgen05.st into one of TS_ASTAGES TMEM operand
+// stages (64 columns each); the MMA thread issues D += A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T with A read from TMEM.
+// Bytes in flight per SM: nstages x 16 KB (6-8 stages) instead of 3-4, and the ring slot turns around without waiting for the MMAs.
+// TMEM columns: [0, 2*bn) accumulators, then TS_ASTAGES x [hi 32 | lo 32].
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int TS_MAX_STAGES = 8;
+constexpr int TS_ASTAGES = 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapWhi,
+                  const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int bn = p.bn, kch = p.kchunks, nst = p.nstages;
+  const uint32_t w_chunk_bytes = (uint32_t)bn * 128u;
+  const uint32_t whi = base;
+  const uint32_t wlo = whi + kch * w_chunk_bytes;
+  const uint32_t stage0 = wlo + kch * w_chunk_bytes;                 // stage s: raw 16 KB chunk
+  const uint32_t bars = stage0 + nst * TC_CHUNK_BYTES;
+  const uint32_t bar_w = bars;
+  auto bar_full = [&](int s) { return bars + 8u * (1 + s); };                              // TMA landed the raw chunk
+  auto bar_free = [&](int s) { return bars + 8u * (1 + TS_MAX_STAGES + s); };              // converters have read it
+  auto bar_afull = [&](int t) { return bars + 8u * (1 + 2 * TS_MAX_STAGES + t); };         // TMEM operand stage written
+  auto bar_aempty = [&](int t) { return bars + 8u * (1 + 2 * TS_MAX_STAGES + TS_ASTAGES + t); };   // MMAs reading it retired
+  auto bar_dfull = [&](int j) { return bars + 8u * (1 + 2 * TS_MAX_STAGES + 2 * TS_ASTAGES + j); };
+  auto bar_dempty = [&](int j) { return bars + 8u * (3 + 2 * TS_MAX_STAGES + 2 * TS_ASTAGES + j); };
+  const uint32_t tmem_slot = bars + 8u * (5 + 2 * TS_MAX_STAGES + 2 * TS_ASTAGES);          // slot 29 -> byte 232 (< 256)
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
+  float* ln_g_s = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));
+  float* ln_b_s = ln_g_s + kch * TC_KC;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
+  const uint32_t a_col0 = (uint32_t)(2 * bn);                        // first TMEM column of the operand stages
+  const uint32_t need_cols = a_col0 + TS_ASTAGES * 64;
+  const uint32_t tmem_cols = need_cols <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_free(s), 128); }
+    for (int t = 0; t < TS_ASTAGES; ++t) { mbar_init(bar_afull(t), 128); mbar_init(bar_aempty(t), 1); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), 256); }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 128) {
+    constexpr bool GLU_ = EPI == EIGB200_EPI_GLU_RESIDUAL;
+    const int nout_ = GLU_ ? p.N / 2 : p.N;
+    for (int c = threadIdx.x; c < bn; c += 128) {
+      int n;
+      if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
+      else { n = split * bn + c; if (n >= p.N) n = -1; }
+      bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+    }
+  }
+  if (p.ln_stats && threadIdx.x >= 128 && threadIdx.x < 256) {
+    for (int k = threadIdx.x - 128; k < kch * TC_KC; k += 128) {
+      ln_g_s[k] = k < p.K ? p.ln_gamma[k] : 0.f;
+      ln_b_s[k] = k < p.K ? p.ln_beta[k] : 0.f;
+    }
+  }
+  if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 12 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 12) {
+    // ===================================== TMA producer ======================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
+      for (int c = 0; c < kch; ++c) {
+        tma_load_2d(&tmapWhi, bar_w, whi + c * w_chunk_bytes, c * TC_KC, split * bn);
+        tma_load_2d(&tmapWlo, bar_w, wlo + c * w_chunk_bytes, c * TC_KC, split * bn);
+      }
+    }
+    int s = 0; uint32_t ph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_free(s), ph ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar_full(s), TC_CHUNK_BYTES);
+          tma_load_2d(&tmapA, bar_full(s), stage0 + s * TC_CHUNK_BYTES, c * TC_KC, (int)(tile * TC_BM));
+        }
+        __syncwarp();
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ===================================== converters: one row (TMEM lane) per thread ======================================
+    const int r = threadIdx.x - 256;                                 // row of the tile = TMEM lane; warp % 4 == r / 32 (lane quarter)
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const bool ln = p.ln_stats != nullptr;
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const int sw = r & 7;
+    int s = 0; uint32_t ph = 0;
+    int t = 0; uint32_t aph = 0;
+    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+      float2 st = make_float2(0.f, 1.f);
+      if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); }
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_full(s), ph);
+        const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage0 + s * TC_CHUNK_BYTES + row_off - smem_u32(smem_raw)));
+        float a[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                                // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+          const float4 v = src[q ^ sw];
+          a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+        }
+        if (ln) {
+          const float* gs = ln_g_s + c * TC_KC; const float* bs = ln_b_s + c * TC_KC;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = fmaf((a[i] - st.x) * st.y, gs[i], bs[i]);
+        }
+        float hi[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hi[i] = to_tf32(a[i]);
+        if (p.debug & 16) __syncwarp();
+        if (p.debug & 8) fence_proxy_async();
+        if (!(p.debug & 1)) {                                        // the raw slot can be refilled: its values are in registers
+          uint32_t dep = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dep ^= __float_as_uint(hi[4 * q]);
+          mbar_arrive_after(bar_free(s), dep);
+        }
+        mbar_wait(bar_aempty(t), aph ^ 1);                           // MMAs that read this operand stage have retired
+        tc_fence_after();
+        const uint32_t acol = tmem_base + lane_sel + a_col0 + (uint32_t)t * 64u;
+        if (p.debug & 2) __syncwarp();
+        tmem_st_32x32(acol, hi);
+        if (p.nterms == 3) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = to_tf32(a[i] - hi[i]);
+          tmem_st_32x32(acol + 32u, a);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        if (p.debug & 1) mbar_arrive(bar_free(s));
+        mbar_arrive(bar_afull(t));
+        if (++s == nst) { s = 0; ph ^= 1; }
+        if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 13) {
+    // ===================================== MMA issuer ======================================
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+    mbar_wait(bar_w, 0);
+    int t = 0; uint32_t aph = 0;
     int j = 0; uint32_t dph = 0;
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
-      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
-      bool waited = false, arrived = false;
-      for (int cg = 32 * half; cg < cols_out; cg += 64) {
-        const int ccol = cg + 4 * gi;                                // column inside the CTA slice (transposed layout)
-        const int n = n_cta0 + ccol;
-        const bool col_ok = ccol < cols_out && n < nout;
-        const bool full = n + 3 < nout;
-        // residual rows of this group: issued first so that their DRAM latency hides behind the TMEM load, the math and the transpose
-        float4 rr[8];
-        if (use_r) {
+      mbar_wait(bar_dempty(j), dph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_afull(t), aph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)t * 64u, a_lo = a_hi + 32u;
+          const uint32_t b_hi = whi + c * w_chunk_bytes, b_lo = wlo + c * w_chunk_bytes;
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            rr[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && full && row0 + jj < p.M) rr[jj] = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + (row0 + jj) * p.ldr + n));
-          }
-        }
-        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
-        float v[32];
-        tmem_ld_32x32(d_tmem + cg, v);
-        if (GLU) {
-          float g[32];
-          tmem_ld_32x32(d_tmem + p.bg + cg, g);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (v[i] + bias_s[cg + i]) * sigmoid_fast_f(g[i] + bias_s[p.bg + cg + i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float vv = v[i] + bias_s[cg + i];
-            if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
-            v[i] = vv;
-          }
-        }
-        if (cg + 64 >= cols_out) {                                   // this warp's last TMEM read of the accumulator: release it early
-          tc_fence_before();
-          mbar_arrive(bar_dempty(j));
-          arrived = true;
-        }
-        transpose8x8_f4(v, lane);
-        if (col_ok) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int64_t mrow = row0 + jj;
-            if (mrow < p.M) {
-              float* cptr = p.C + mrow * p.ldc + n;
-              if (full) {
-                float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-                if (use_r) { o.x += rr[jj].x; o.y += rr[jj].y; o.z += rr[jj].z; o.w += rr[jj].w; }
-                *reinterpret_cast<float4*>(cptr) = o;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (n + e < nout) cptr[e] = v[4 * jj + e] + (use_r ? p.R[mrow * p.ldr + n + e] : 0.f);
-              }
+          for (int k = 0; k < TC_KC / 8; ++k) {
+            const uint64_t dbh = umma_desc_k_sw128(b_hi + k * 32), dbl = umma_desc_k_sw128(b_lo + k * 32);
+            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            if (p.nterms == 3) {
+              umma_tf32_ts(d_tmem, a_hi + 8u * k, dbl, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh, idesc, 1u);
             }
           }
+          umma_commit(bar_aempty(t));
+          if (c == kch - 1) umma_commit(bar_dfull(j));
         }
+        __syncwarp();
+        if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
       }
-      if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
-      if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
       if (++j == 2) { j = 0; dph ^= 1; }
     }
+  } else if (warp < 8) {
+    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
   }
 
   tc_fence_before();
@@ -434,11 +711,18 @@ static int make_tmap(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t
   return EIGB200_OK;
 }
 
-struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages; size_t smem; bool ok; };
+struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages; size_t smem; bool ok; bool ts; };
+
+static bool use_ts_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EIGB200_GEMM_VARIANT"); v = (e && e[0] == 't' && e[1] == 's') ? 1 : 0; }   // "ts" selects the TMEM-operand kernel (experimental)
+  return v == 1;
+}
 
 static TcPlan make_plan(int N, int K, int epilogue) {
   TcPlan pl{};
   pl.ok = false;
+  pl.ts = use_ts_variant();
   if (K % 4 != 0 || K <= 0) return pl;
   pl.kpad = (K + TC_KC - 1) / TC_KC * TC_KC;
   pl.kchunks = pl.kpad / TC_KC;
@@ -446,7 +730,8 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   const bool glu = epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const int nout = glu ? N / 2 : N;
   const int per_col_bytes = pl.kpad * 4 * 2 * (glu ? 2 : 1);         // hi+lo bytes per OUTPUT column
-  const int max_w_bytes = TC_SMEM_LIMIT - 2560 - 2 * 2 * TC_CHUNK_BYTES;   // keep room for >= 2 stages
+  const int stage_bytes = pl.ts ? TC_CHUNK_BYTES : 2 * TC_CHUNK_BYTES;
+  const int max_w_bytes = TC_SMEM_LIMIT - 2048 - 2 * pl.kpad * 4 - (pl.ts ? 4 : 2) * stage_bytes;   // keep room for the minimum ring
   int max_cols = max_w_bytes / per_col_bytes;
   const int cap = glu ? 64 : 128;
   if (max_cols > cap) max_cols = cap;
@@ -459,11 +744,11 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   pl.bg = cols;
   pl.bn = glu ? 2 * cols : cols;
   const size_t wbytes = (size_t)2 * pl.kchunks * pl.bn * 128;
-  int nst = (int)((TC_SMEM_LIMIT - 2560 - (long)wbytes) / (2 * TC_CHUNK_BYTES));
-  if (nst > TC_MAX_STAGES) nst = TC_MAX_STAGES;
+  int nst = (int)((TC_SMEM_LIMIT - 2048 - 2 * pl.kpad * 4 - (long)wbytes) / stage_bytes);
+  if (nst > (pl.ts ? TS_MAX_STAGES : TC_MAX_STAGES)) nst = pl.ts ? TS_MAX_STAGES : TC_MAX_STAGES;
   if (nst < 2) return pl;
   pl.nstages = nst;
-  pl.smem = wbytes + (size_t)nst * 2 * TC_CHUNK_BYTES + 1024 /*alignment*/ + 1024 /*barriers + bias*/;
+  pl.smem = wbytes + (size_t)nst * stage_bytes + 1024 /*alignment*/ + 1024 /*barriers + bias*/ + (size_t)2 * pl.kpad * 4 /*LayerNorm gamma, beta*/;
   pl.ok = true;
   return pl;
 }
@@ -507,9 +792,11 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
 
   TcParams p{};
+  p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats); p.ln_gamma = lp.ln_gamma; p.ln_beta = lp.ln_beta;
   p.bias = lp.bias; p.C = lp.C; p.ldc = lp.ldc; p.R = lp.R; p.ldr = lp.ldr; p.M = lp.M; p.N = lp.N; p.K = lp.K; p.epilogue = lp.epilogue;
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
+  { const char* e = getenv("EIGB200_TS_DEBUG"); p.debug = e ? atoi(e) : 0; }
   int workers = num_sms() / pl.nsplit;
   if (workers < 1) workers = 1;
   if ((int64_t)workers > p.ntiles) workers = (int)p.ntiles;
@@ -517,8 +804,13 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   dim3 grid(workers * pl.nsplit);
 #define TC_LAUNCH(EPI_)                                                                                                         \
   do {                                                                                                                          \
-    EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));           \
-    gemm_tc_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                                   \
+    if (pl.ts) {                                                                                                                \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));      \
+      gemm_tc_ts_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                              \
+    } else {                                                                                                                    \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));         \
+      gemm_tc_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                                 \
+    }                                                                                                                           \
   } while (0)
   switch (lp.epilogue) {
     case EIGB200_EPI_NONE: TC_LAUNCH(EIGB200_EPI_NONE); break;

@@ -26,3 +26,20 @@ extern "C" int eigb200_linear(void* stream, const float* d_A, int64_t lda, const
   if (tc_ok && M >= 1024) return launch_linear_tc(st, p, 3, d_workspace);
   return launch_linear_simt(st, p);
 }
+
+extern "C" int eigb200_linear_ln(void* stream, const float* d_A, int64_t lda, const float* d_ln_stats, const float* d_ln_gamma, const float* d_ln_beta,
+                                 const float* d_W, const float* d_bias, float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
+                                 int64_t M, int N, int K, int epilogue, void* d_workspace, size_t workspace_bytes) {
+  EIGB_CHECK_ARG(d_A && d_W && d_C && d_ln_stats && d_ln_gamma && d_ln_beta, "linear_ln: null pointer");
+  EIGB_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_ln: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  EIGB_CHECK_ARG(epilogue >= EIGB200_EPI_NONE && epilogue <= EIGB200_EPI_RESIDUAL, "linear_ln: unknown epilogue %d", epilogue);
+  EIGB_CHECK_ARG(epilogue != EIGB200_EPI_GLU_RESIDUAL || N % 2 == 0, "linear_ln: GLU epilogue needs an even N");
+  EIGB_CHECK_ARG(((uintptr_t)d_ln_stats & 7) == 0, "linear_ln: row statistics must be 8-byte aligned");
+  LinearParams p{d_A, lda, d_W, d_bias, d_C, ldc, d_R, ldr, M, N, K, epilogue};
+  p.ln_stats = d_ln_stats; p.ln_gamma = d_ln_gamma; p.ln_beta = d_ln_beta;
+  if (!(tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes(N, K))) {
+    set_error("linear_ln: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda);
+    return EIGB200_EUNSUPPORTED;
+  }
+  return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace);
+}

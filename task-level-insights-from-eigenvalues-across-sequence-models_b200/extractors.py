@@ -44,11 +44,11 @@ def _mamba_gate_rows(m):
     return _w(m.in_proj.weight)[lo:lo + m.nheads].contiguous()
 
 
-def get_eig_mamba2_device(x, layer, want_eig=True, counts=None, compare="float64", lam_out=None):
+def get_eig_mamba2_device(x, layer, want_eig=True, counts=None, compare="float64", lam_out=None, rowstats_out=None):
     m = layer.mamba
     x = _cuda(x)
     return ops.mamba2_eig(x, _cuda(_mamba_gate_rows(m)), _cuda(_w(m.dt_bias)), _cuda(_w(m.A_log)),
-                          want_lam=want_eig, counts=counts, compare=compare, lam_out=lam_out)
+                          want_lam=want_eig, counts=counts, compare=compare, lam_out=lam_out, rowstats_out=rowstats_out)
 
 
 def get_eig_mamba2(x, layer):

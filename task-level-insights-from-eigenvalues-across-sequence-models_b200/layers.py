@@ -82,15 +82,26 @@ class MambaBlockDev:
         self.norm = SimpleNamespace(weight=_dev(sd, prefix + "norm.weight", device), bias=_dev(sd, prefix + "norm.bias", device))
         self.gemm_mode = cfg.get("_gemm_mode", "auto")
 
-    def __call__(self, x):
-        """MambaBlock.forward (models/mamba.py:328-340) with SSD.forward (:111-154) inlined."""
+    def fuses_layernorm(self):
+        """True when the prenorm LayerNorm can ride inside the in_proj GEMM (row statistics supplied by the producer of x)."""
+        m = self.mamba
+        return (self.prenorm and self.gemm_mode in ("auto", "tc3") and m.d_model % 4 == 0 and
+                ops.linear_ln_supported(m.in_proj.weight.shape[0], m.d_model))
+
+    def __call__(self, x, stats=None):
+        """MambaBlock.forward (models/mamba.py:328-340) with SSD.forward (:111-154) inlined.
+        stats: optional (B,T,2) LayerNorm (mean, rstd) of x from the kernel that produced x (embedding / previous extractor);
+        with it the normalised activations are formed inside the in_proj GEMM and never written to HBM."""
         m = self.mamba
         B, T, D = x.shape
         skip = x
-        xn = ops.layernorm(x, self.norm.weight, self.norm.bias) if self.prenorm else x
         d_in_proj = m.in_proj.weight.shape[0]
         ldz = _pad4(d_in_proj)
-        z = ops.linear(xn, m.in_proj.weight, None, ldc=ldz, mode=self.gemm_mode)                  # (B*T, ldz) = [x | B | C | dt | pad]
+        if stats is not None and self.fuses_layernorm():
+            z = ops.linear_ln(x, stats, self.norm.weight, self.norm.bias, m.in_proj.weight, None, ldc=ldz)
+        else:
+            xn = ops.layernorm(x, self.norm.weight, self.norm.bias) if self.prenorm else x
+            z = ops.linear(xn, m.in_proj.weight, None, ldc=ldz, mode=self.gemm_mode)              # (B*T, ldz) = [x | B | C | dt | pad]
         y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
         o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode)    # GELU(out_proj(y))  (:333)
         if self.glu is not None:
@@ -109,8 +120,8 @@ class TokenEmbeddingsDev:
         self.word = _dev(sd, prefix + "word_embeddings.weight", device)
         self.pos = _dev(sd, prefix + "position_embeddings.weight", device)
 
-    def __call__(self, ids):
-        return ops.embedding(ids, self.word, self.pos)
+    def __call__(self, ids, rowstats_out=None):
+        return ops.embedding(ids, self.word, self.pos, rowstats_out=rowstats_out)
 
 
 class LinearEncoderDev:

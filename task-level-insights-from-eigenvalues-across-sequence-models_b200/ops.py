@@ -87,8 +87,10 @@ def new_counts(B: int, inner: int, device) -> torch.Tensor:
 
 
 def mamba2_eig(x, W_dt, dt_bias, A_log, thresholds: Sequence[float] = THRESHOLDS_RADIUS, want_lam=True,
-               counts: Optional[torch.Tensor] = None, want_counts=True, compare="float64", lam_out=None):
-    """K1.  x (B,T,D) f32|bf16 -> (lam (B,T,H) f32 | None, counts (B,H,8) int32 | None)."""
+               counts: Optional[torch.Tensor] = None, want_counts=True, compare="float64", lam_out=None,
+               rowstats_out: Optional[torch.Tensor] = None, ln_eps: float = 1e-5):
+    """K1.  x (B,T,D) f32|bf16 -> (lam (B,T,H) f32 | None, counts (B,H,8) int32 | None).
+    rowstats_out (B,T,2) f32: also emit the LayerNorm (mean, rstd) of every row of x for the next block (see linear_ln)."""
     x = _prep(x, name="x")
     B, T, D = x.shape
     W_dt = _prep(W_dt, torch.float32); dt_bias = _prep(dt_bias, torch.float32); A_log = _prep(A_log, torch.float32)
@@ -104,7 +106,8 @@ def mamba2_eig(x, W_dt, dt_bias, A_log, thresholds: Sequence[float] = THRESHOLDS
         counts = new_counts(B, H, x.device)
     thr, n = L.thresholds_arg(thresholds)
     _call(lib, "eigb200_mamba2_eig", _stream(x), _p(x), _xdtype(x), B, T, D, _p(W_dt), _p(dt_bias), _p(A_log), H,
-                                   _p(lam), stride, _p(counts if want_counts else None), thr, n, _cmp(compare))
+                                   _p(lam), stride, _p(counts if want_counts else None), thr, n, _cmp(compare),
+          _p(rowstats_out), float(ln_eps))
     return lam, (counts if want_counts else None)
 
 
@@ -284,7 +287,43 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     return out
 
 
-def embedding(ids, word, pos=None):
+def rowstats(x, eps=1e-5):
+    """(mean, rstd) of every row of x (..., D) -> (..., 2) float32."""
+    x = _prep(x, torch.float32)
+    D = x.shape[-1]
+    lib = _enter(x)
+    out = torch.empty(x.shape[:-1] + (2,), dtype=torch.float32, device=x.device)
+    _call(lib, "eigb200_rowstats", _stream(x), _p(x), x.numel() // D, D, float(eps), _p(out))
+    return out
+
+
+def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residual=None, out=None, ldc=None, workspace=None):
+    """epilogue(LayerNorm(a) W^T + bias) with the normalisation applied inside the GEMM's A-operand stage (tensor-core path)."""
+    assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()
+    K = a.shape[-1]
+    M = a.numel() // K
+    weight = _prep(weight, torch.float32)
+    N = weight.shape[0]
+    bias = _prep(bias, torch.float32) if bias is not None else None
+    nout = N // 2 if epilogue == "glu_residual" else N
+    lib = _enter(a)
+    if out is None:
+        ldc = ldc or nout
+        out = torch.empty(M, ldc, dtype=torch.float32, device=a.device)
+    else:
+        ldc = out.stride(-2)
+    ldr = residual.stride(-2) if residual is not None else 0
+    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
+    _call(lib, "eigb200_linear_ln", _stream(a), _p(a), K, _p(_prep(stats, torch.float32)), _p(_prep(gamma, torch.float32)),
+          _p(_prep(beta, torch.float32)), _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K, EPILOGUES[epilogue], _p(ws), wsb)
+    return out
+
+
+def linear_ln_supported(N, K):
+    return int(L.load().eigb200_linear_workspace_bytes(N, K)) > 0
+
+
+def embedding(ids, word, pos=None, rowstats_out=None, ln_eps=1e-5):
     ids = _prep(ids, torch.int64); word = _prep(word, torch.float32)
     pos = _prep(pos, torch.float32) if pos is not None else None
     B, T = ids.shape
@@ -293,7 +332,10 @@ def embedding(ids, word, pos=None):
         raise L.Eigb200Error("embedding: sequence length %d exceeds max_position_embeddings %d" % (T, pos.shape[0]))
     lib = _enter(ids)
     out = torch.empty(B, T, D, dtype=torch.float32, device=ids.device)
-    _call(lib, "eigb200_embedding", _stream(ids), _p(ids), _p(word), _p(pos), _p(out), B, T, D, V)
+    if rowstats_out is not None:
+        _call(lib, "eigb200_embedding_stats", _stream(ids), _p(ids), _p(word), _p(pos), _p(out), B, T, D, V, _p(rowstats_out), float(ln_eps))
+    else:
+        _call(lib, "eigb200_embedding", _stream(ids), _p(ids), _p(word), _p(pos), _p(out), B, T, D, V)
     return out
 
 

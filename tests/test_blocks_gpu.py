@@ -167,3 +167,51 @@ def test_linear_tcgen05_plain_tf32_is_coarser(ops):
     e1 = np.abs(ops.linear(dev(a), dev(w), None, mode="tc1").cpu().numpy() - ref).max()
     e3 = np.abs(ops.linear(dev(a), dev(w), None, mode="tc3").cpu().numpy() - ref).max()
     assert e1 < 5e-3 and e3 < 2e-5 and e3 < e1 / 20
+
+
+# ---- LayerNorm fused into the GEMM A operand: statistics from the producer kernels ------------------------------------------
+def _ln_stats_ref(x, eps=1e-5):
+    x = x.astype(np.float64)
+    mu = x.mean(-1); var = ((x - mu[..., None]) ** 2).mean(-1)
+    return mu, 1.0 / np.sqrt(var + eps)
+
+
+@pytest.mark.parametrize("D", [32, 64, 128, 512])
+def test_rowstats_sources_agree(ops, D):
+    rng = np.random.default_rng(D)
+    B, T, H = 3, 50, 2
+    x = (rng.normal(size=(B, T, D)) * rng.uniform(0.1, 3, (B, T, 1)) + rng.normal(0, 5, (B, T, 1))).astype(np.float32)   # large means: cancellation test
+    mu, rstd = _ln_stats_ref(x)
+    st = ops.rowstats(dev(x)).cpu().numpy()
+    np.testing.assert_allclose(st[..., 0], mu, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(st[..., 1], rstd, rtol=2e-5)
+    # the K1 extractor emits the same statistics while it streams x
+    W = rng.normal(size=(H, D)).astype(np.float32) * 0.1
+    out = torch.empty(B, T, 2, device="cuda")
+    ops.mamba2_eig(dev(x), dev(W), dev(np.zeros(H, np.float32)), dev(np.zeros(H, np.float32)), rowstats_out=out)
+    np.testing.assert_allclose(out.cpu().numpy()[..., 0], mu, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out.cpu().numpy()[..., 1], rstd, rtol=2e-5)
+    # ... and so does the embedding
+    V = 40
+    word = (rng.normal(size=(V, D)) + 3).astype(np.float32); pos = rng.normal(size=(T, D)).astype(np.float32)
+    ids = rng.integers(0, V, (B, T))
+    est = torch.empty(B, T, 2, device="cuda")
+    e = ops.embedding(dev(ids), dev(word), dev(pos), rowstats_out=est).cpu().numpy()
+    mu2, rstd2 = _ln_stats_ref(e)
+    np.testing.assert_allclose(est.cpu().numpy()[..., 0], mu2, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(est.cpu().numpy()[..., 1], rstd2, rtol=2e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 161, 128), (1000, 50, 32), (3000, 384, 128), (700, 96, 64)])
+def test_linear_ln_fused(ops, M, N, K):
+    rng = np.random.default_rng(M + N)
+    a = (rng.normal(size=(M, K)) * 2 + rng.normal(0, 1, (M, 1))).astype(np.float32)
+    w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    gamma = rng.normal(1, 0.3, K).astype(np.float32); beta = rng.normal(0, 0.3, K).astype(np.float32)
+    st = ops.rowstats(dev(a))
+    ldc = (N + 3) // 4 * 4
+    out = ops.linear_ln(dev(a), st, dev(gamma), dev(beta), dev(w), None, ldc=ldc).cpu().numpy()
+    ref = O.layer_norm(a.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64)) @ w.astype(np.float64).T
+    np.testing.assert_allclose(out[:, :N], ref, rtol=2e-5, atol=2e-5)
+    unfused = ops.linear(ops.layernorm(dev(a), dev(gamma), dev(beta)), dev(w), None, mode="tc3", ldc=ldc).cpu().numpy()
+    assert np.abs(out[:, :N] - unfused[:, :N]).max() <= 2e-5

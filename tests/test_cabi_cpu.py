@@ -36,7 +36,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
 
 def test_version_and_error_plumbing(lib):
     assert lib.eigb200_version() == 100
-    rc = lib.eigb200_mamba2_eig(None, None, 0, 1, 1, 4, None, None, None, 1, None, 1, None, None, 0, 0)
+    rc = lib.eigb200_mamba2_eig(None, None, 0, 1, 1, 4, None, None, None, 1, None, 1, None, None, 0, 0, None, 0.0)
     assert rc == -1 and b"null" in lib.eigb200_last_error()
 
 
