@@ -55,7 +55,7 @@ __device__ __forceinline__ float norm_fn_apply(int fn, float z) {
   }
 }
 
-template <int HT, bool BF16, int EPI>
+template <int HT, bool BF16, int EPI, bool STATS>
 __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p) {
   constexpr int VEC = XLoad<BF16>::VEC;
   constexpr int NV = K1_R * HT;                       // partial sums per lane
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p
   const int nvec = D / VEC;
   const float4* Ws4 = reinterpret_cast<const float4*>(Ws);
 
-  const bool want_stats = (EPI == K1_EPI_MAMBA2) && p.rowstats != nullptr && blockIdx.z == 0;
+  const bool want_stats = STATS && blockIdx.z == 0;   // compile-time off for the plain extractor: no extra registers in its hot loop
   for (int t = t0; t < t1; t += K1_R) {
     float acc[NV];
 #pragma unroll
@@ -213,14 +213,20 @@ static int launch_k1(cudaStream_t st, const K1Params& p, int64_t B) {
   dim3 grid(ctas_per_seq, (unsigned)B, hgroups), block(K1_WARPS * 32);
   EIGB_CHECK_ARG(B <= 65535, "k1: batch %lld exceeds grid.y limit 65535; split the call", (long long)B);
   const size_t smem = (size_t)ht * p.D * sizeof(float);
+  const bool stats = (EPI == K1_EPI_MAMBA2) && p.rowstats != nullptr;
+#define K1_LAUNCH(HT_, ST_)                                                                                       \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      EIGB_CUDA(cudaFuncSetAttribute(k1_gate_kernel<HT_, BF16, EPI, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k1_gate_kernel<HT_, BF16, EPI, ST_><<<grid, block, smem, st>>>(q);                                            \
+  } while (0)
 #define K1_CASE(HT_)                                                                                              \
   case HT_: {                                                                                                     \
-    if (smem > 48 * 1024)                                                                                         \
-      EIGB_CUDA(cudaFuncSetAttribute(k1_gate_kernel<HT_, BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k1_gate_kernel<HT_, BF16, EPI><<<grid, block, smem, st>>>(q);                                                 \
+    if (stats) K1_LAUNCH(HT_, (EPI == K1_EPI_MAMBA2)); else K1_LAUNCH(HT_, false);                                \
   } break;
   switch (ht) { K1_CASE(1) K1_CASE(2) K1_CASE(4) K1_CASE(8) default: set_error("k1: bad head tile"); return EIGB200_EINVAL; }
 #undef K1_CASE
+#undef K1_LAUNCH
   EIGB_LAUNCH_CHECK("k1_gate_kernel");
   return EIGB200_OK;
 }

@@ -34,11 +34,14 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
   const float* bias; float* C; int64_t ldc; const float* R; int64_t ldr;
-  const float2* ln_stats; const float* ln_gamma; const float* ln_beta;      // LayerNorm fused into the converter (nullable)
+  const float2* ln_stats;                                                   // LayerNorm (mean, rstd) per row applied by the converter (nullable)
   int64_t M; int N, K, epilogue;
   int bn;            // columns per CTA (UMMA N), multiple of 32, <= 128
   int bg;            // GLU: value columns per CTA (bn = 2*bg); otherwise bn
-  int nsplit, kchunks, nstages, nterms, workers, debug;
+  int nsplit, kchunks, nstages, nterms, workers;
+  int zero;          // always 0; a run-time value the compilers cannot fold (mbar_arrive_after)
+  int direct;        // epilogue stores rows straight from the accumulator layout with 256-bit accesses (needs 32-byte aligned rows)
+  int store_cols;    // columns of C that may be written: N rounded up to 8 when the row pitch leaves room (pad columns receive zeros)
   int64_t ntiles;
 };
 
@@ -53,9 +56,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
 }
-// arrive that is data-dependent on `dep`: the values loaded from the buffer being released are in registers before the arrive issues
-__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar), "r"(dep) : "memory");
+// Arrive that is DATA-dependent on `dep`: the barrier address is bar + (dep & zero) with `zero` a kernel parameter that is 0 at run time, so
+// neither nvcc nor ptxas can fold the dependency away and the arrive cannot issue before the registers that feed `dep` -- the values loaded
+// from the buffer being released -- have landed.  (An asm operand that the template does not reference creates no dependency in the PTX:
+// with it the arrive overtook the last LDS of the chunk and TMA refilled the slot under the reader.)
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, uint32_t zero) {
+  mbar_arrive(bar + (dep & zero));
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
@@ -155,6 +161,18 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// Converter split a = hi + lo for the 3xTF32 product.  hi = a rounded to tf32 (nearest, ties away: integer add of half a tf32 ulp, then
+// mask -- the same result as cvt.rna.tf32.f32 for finite a, in 2 ALU operations instead of the ~5 the cvt expands to); lo = a - hi is
+// exact in fp32 and is handed to the tensor core unrounded: kind::tf32 reads the top 19 bits of the container, so lo is truncated to
+// tf32 by the hardware (|error| <= 2^-21 |a|, sign of lo, i.e. unbiased), the same order as the dropped a_lo * w_lo term.
+__device__ __forceinline__ void split_tf32(float a, float& h, float& l) {
+  h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+  l = a - h;
+}
+__device__ __forceinline__ void split_tf32_4(const float4 a, float4& h, float4& l) {
+  split_tf32(a.x, h.x, l.x); split_tf32(a.y, h.y, l.y); split_tf32(a.z, h.z, l.z); split_tf32(a.w, h.w, l.w);
+}
+
 // 8x8 transpose of float4 items inside each group of 8 lanes.  In: lane (8g+i) holds, for its accumulator row 8g+i, the eight
 // float4 column quads q = 0..7 of a 32-column group.  Out: the same lane holds quad q = i of rows 8g+j, j = 0..7 -- so that for
 // every j the 8 lanes of a group cover one row's 128 contiguous bytes and a warp store instruction writes 4 full lines.
@@ -177,6 +195,16 @@ __device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
   }
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread
+__device__ __forceinline__ void stg_v8(float* ptr, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ldg_stream_v8(const float* ptr, float* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start address >> 4 in bits [0,14); LBO (unused for swizzled K-major) = 1 in [16,30); SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46);
 // descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
@@ -192,8 +220,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
 // ---------------------------------------------------------------------------------------------------------------------------
 // weight preparation: split W (N,K) into tf32 hi / lo in the per-split row order the CTAs consume, zero padded
 // ---------------------------------------------------------------------------------------------------------------------------
+// With a fused LayerNorm the affine part is folded into the weights: LN(a) W^T = ((a - mu) rstd) (W diag(gamma))^T + W beta, so the
+// converter only applies the per-row (mu, rstd) and the bias vector becomes bias + W beta (ln_bias_kernel).
 __global__ void split_weights_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo,
-                                     int N, int K, int kpad, int bn, int bg, int nsplit, int glu) {
+                                     int N, int K, int kpad, int bn, int bg, int nsplit, int glu, const float* __restrict__ gamma) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = nsplit * bn * kpad;
   if (idx >= total) return;
@@ -208,10 +238,22 @@ __global__ void split_weights_kernel(const float* __restrict__ W, float* __restr
     n = split * bn + local;
   }
   float w = 0.f;
-  if (n >= 0 && n < N && k < K) w = W[(size_t)n * K + k];
+  if (n >= 0 && n < N && k < K) w = W[(size_t)n * K + k] * (gamma ? gamma[k] : 1.f);
   const float h = to_tf32(w);
   hi[idx] = h;
   lo[idx] = to_tf32(w - h);
+}
+
+// bias2[n] = bias[n] + sum_k W[n,k] beta[k]: one warp per output column
+__global__ void ln_bias_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ beta,
+                               float* __restrict__ bias2, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(W[(size_t)n * K + k], beta[k], acc);
+#pragma unroll
+  for (int ofs = 16; ofs >= 1; ofs >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, ofs);
+  if (lane == 0) bias2[n] = acc + (bias ? bias[n] : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -232,6 +274,66 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     const int gi = lane & 7, gg = lane >> 3;                         // after the transpose: column quad gi of rows 8*gg + jj
     const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
     int j = 0; uint32_t dph = 0;
+    if (p.direct) {
+      // Direct path: lane i keeps accumulator row (quarter*32 + i); its 32 columns of a group are 128 contiguous bytes of the C row, written
+      // as four 256-bit stores (full 32-byte sectors, so no read-modify-write in L2) -- no register transpose, no address math per quad.
+      for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+        const int64_t mrow = tile * TC_BM + quarter * 32 + lane;
+        const bool row_ok = mrow < p.M;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
+        bool waited = false, arrived = false;
+        for (int cg = 32 * half; cg < cols_out; cg += 64) {
+          const int n0 = n_cta0 + cg;
+          float rr[32];
+          if (use_r) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (row_ok && n0 + 8 * q + 8 <= nout) ldg_stream_v8(p.R + mrow * p.ldr + n0 + 8 * q, rr + 8 * q);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rr[8 * q + e] = (row_ok && n0 + 8 * q + e < nout) ? p.R[mrow * p.ldr + n0 + 8 * q + e] : 0.f;
+              }
+            }
+          }
+          if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
+          float v[32];
+          tmem_ld_32x32(d_tmem + cg, v);
+          if (GLU) {
+            float g[32];
+            tmem_ld_32x32(d_tmem + p.bg + cg, g);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] + bias_s[cg + i]) * sigmoid_fast_f(g[i] + bias_s[p.bg + cg + i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float vv = v[i] + bias_s[cg + i];
+              if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
+              v[i] = vv;
+            }
+          }
+          if (cg + 64 >= cols_out) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
+          if (use_r) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += rr[i];
+          }
+          if (row_ok) {
+            float* cptr = p.C + mrow * p.ldc + n0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n0 + 8 * q + 8 <= p.store_cols) stg_v8(cptr + 8 * q, v + 8 * q);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (n0 + 8 * q + e < nout) cptr[8 * q + e] = v[8 * q + e];
+              }
+            }
+          }
+        }
+        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
+        if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
+        if (++j == 2) { j = 0; dph ^= 1; }
+      }
+      return;
+    }
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
       const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
       const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
@@ -243,7 +345,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         const bool full = n + 3 < nout;
         // residual rows of this group: issued first so that their DRAM latency hides behind the TMEM load, the math and the transpose
         float4 rr[8];
-        if ((p.debug & 4) && !waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
         if (use_r) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -325,8 +426,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (5 + 3 * TC_MAX_STAGES);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));     // [bn] bias of this CTA's slice
-  float* ln_g_s = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));    // [kch*32] LayerNorm gamma, then beta
-  float* ln_b_s = ln_g_s + kch * TC_KC;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
@@ -346,12 +445,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
       else { n = split * bn + c; if (n >= p.N) n = -1; }
       bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
-    }
-  }
-  if (p.ln_stats && threadIdx.x >= 128 && threadIdx.x < 256) {        // LayerNorm affine parameters, zero beyond K
-    for (int k = threadIdx.x - 128; k < kch * TC_KC; k += 128) {
-      ln_g_s[k] = k < p.K ? p.ln_gamma[k] : 0.f;
-      ln_b_s[k] = k < p.K ? p.ln_beta[k] : 0.f;
     }
   }
   if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
@@ -396,6 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         for (int i = 0; i < 8; ++i) {
           const int64_t m = tile * TC_BM + ((i * 128 + ct) >> 3);
           st[i] = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f);
+          st[i].x = -st[i].x * st[i].y;                               // (a - mu) rstd = fma(a, rstd, -mu rstd)
         }
       }
       for (int c = 0; c < kch; ++c) {
@@ -407,15 +501,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int idx = i * 128 + ct;
-            const int r = idx >> 3;
-            const int kcol = c * TC_KC + 4 * ((idx & 7) ^ (r & 7));
             float4 a = h4[idx];
-            const float4 gm = *reinterpret_cast<const float4*>(ln_g_s + kcol), bt = *reinterpret_cast<const float4*>(ln_b_s + kcol);
-            a.x = fmaf((a.x - st[i].x) * st[i].y, gm.x, bt.x); a.y = fmaf((a.y - st[i].x) * st[i].y, gm.y, bt.y);
-            a.z = fmaf((a.z - st[i].x) * st[i].y, gm.z, bt.z); a.w = fmaf((a.w - st[i].x) * st[i].y, gm.w, bt.w);
+            a.x = fmaf(a.x, st[i].y, st[i].x); a.y = fmaf(a.y, st[i].y, st[i].x);
+            a.z = fmaf(a.z, st[i].y, st[i].x); a.w = fmaf(a.w, st[i].y, st[i].x);
             float4 h, l;
-            h.x = to_tf32(a.x); h.y = to_tf32(a.y); h.z = to_tf32(a.z); h.w = to_tf32(a.w);
-            l.x = to_tf32(a.x - h.x); l.y = to_tf32(a.y - h.y); l.z = to_tf32(a.z - h.z); l.w = to_tf32(a.w - h.w);
+            split_tf32_4(a, h, l);
             h4[idx] = h; l4[idx] = l;
           }
         } else if (p.nterms == 3) {
@@ -424,8 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const int idx = i * 128 + ct;
             const float4 a = h4[idx];
             float4 h, l;
-            h.x = to_tf32(a.x); h.y = to_tf32(a.y); h.z = to_tf32(a.z); h.w = to_tf32(a.w);
-            l.x = to_tf32(a.x - h.x); l.y = to_tf32(a.y - h.y); l.z = to_tf32(a.z - h.z); l.w = to_tf32(a.w - h.w);
+            split_tf32_4(a, h, l);
             h4[idx] = h; l4[idx] = l;
           }
         } else {
@@ -520,8 +609,6 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const uint32_t tmem_slot = bars + 8u * (5 + 2 * TS_MAX_STAGES + 2 * TS_ASTAGES);          // slot 29 -> byte 232 (< 256)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
-  float* ln_g_s = reinterpret_cast<float*>(smem_raw + (bars + 1024u - smem_u32(smem_raw)));
-  float* ln_b_s = ln_g_s + kch * TC_KC;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
@@ -544,12 +631,6 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
       else { n = split * bn + c; if (n >= p.N) n = -1; }
       bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
-    }
-  }
-  if (p.ln_stats && threadIdx.x >= 128 && threadIdx.x < 256) {
-    for (int k = threadIdx.x - 128; k < kch * TC_KC; k += 128) {
-      ln_g_s[k] = k < p.K ? p.ln_gamma[k] : 0.f;
-      ln_b_s[k] = k < p.K ? p.ln_beta[k] : 0.f;
     }
   }
   if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
@@ -591,7 +672,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     int t = 0; uint32_t aph = 0;
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
       float2 st = make_float2(0.f, 1.f);
-      if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); }
+      if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); st.x = -st.x * st.y; }
       for (int c = 0; c < kch; ++c) {
         mbar_wait(bar_full(s), ph);
         const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage0 + s * TC_CHUNK_BYTES + row_off - smem_u32(smem_raw)));
@@ -602,34 +683,29 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
         }
         if (ln) {
-          const float* gs = ln_g_s + c * TC_KC; const float* bs = ln_b_s + c * TC_KC;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = fmaf((a[i] - st.x) * st.y, gs[i], bs[i]);
+          for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], st.y, st.x);
         }
         float hi[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) hi[i] = to_tf32(a[i]);
-        if (p.debug & 16) __syncwarp();
-        if (p.debug & 8) fence_proxy_async();
-        if (!(p.debug & 1)) {                                        // the raw slot can be refilled: its values are in registers
+        for (int i = 0; i < 32; ++i) hi[i] = __uint_as_float((__float_as_uint(a[i]) + 0x1000u) & 0xffffe000u);
+        {                                                            // the raw slot can be refilled: its values are in registers
           uint32_t dep = 0;
 #pragma unroll
           for (int q = 0; q < 8; ++q) dep ^= __float_as_uint(hi[4 * q]);
-          mbar_arrive_after(bar_free(s), dep);
+          mbar_arrive_after(bar_free(s), dep, (uint32_t)p.zero);
         }
         mbar_wait(bar_aempty(t), aph ^ 1);                           // MMAs that read this operand stage have retired
         tc_fence_after();
         const uint32_t acol = tmem_base + lane_sel + a_col0 + (uint32_t)t * 64u;
-        if (p.debug & 2) __syncwarp();
         tmem_st_32x32(acol, hi);
         if (p.nterms == 3) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = to_tf32(a[i] - hi[i]);
+          for (int i = 0; i < 32; ++i) a[i] = a[i] - hi[i];
           tmem_st_32x32(acol + 32u, a);
         }
         tmem_st_wait();
         tc_fence_before();
-        if (p.debug & 1) mbar_arrive(bar_free(s));
         mbar_arrive(bar_afull(t));
         if (++s == nst) { s = 0; ph ^= 1; }
         if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
@@ -731,7 +807,7 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   const int nout = glu ? N / 2 : N;
   const int per_col_bytes = pl.kpad * 4 * 2 * (glu ? 2 : 1);         // hi+lo bytes per OUTPUT column
   const int stage_bytes = pl.ts ? TC_CHUNK_BYTES : 2 * TC_CHUNK_BYTES;
-  const int max_w_bytes = TC_SMEM_LIMIT - 2048 - 2 * pl.kpad * 4 - (pl.ts ? 4 : 2) * stage_bytes;   // keep room for the minimum ring
+  const int max_w_bytes = TC_SMEM_LIMIT - 2048 - (pl.ts ? 4 : 2) * stage_bytes;   // keep room for the minimum ring
   int max_cols = max_w_bytes / per_col_bytes;
   const int cap = glu ? 64 : 128;
   if (max_cols > cap) max_cols = cap;
@@ -744,11 +820,11 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   pl.bg = cols;
   pl.bn = glu ? 2 * cols : cols;
   const size_t wbytes = (size_t)2 * pl.kchunks * pl.bn * 128;
-  int nst = (int)((TC_SMEM_LIMIT - 2048 - 2 * pl.kpad * 4 - (long)wbytes) / stage_bytes);
+  int nst = (int)((TC_SMEM_LIMIT - 2048 - (long)wbytes) / stage_bytes);
   if (nst > (pl.ts ? TS_MAX_STAGES : TC_MAX_STAGES)) nst = pl.ts ? TS_MAX_STAGES : TC_MAX_STAGES;
   if (nst < 2) return pl;
   pl.nstages = nst;
-  pl.smem = wbytes + (size_t)nst * stage_bytes + 1024 /*alignment*/ + 1024 /*barriers + bias*/ + (size_t)2 * pl.kpad * 4 /*LayerNorm gamma, beta*/;
+  pl.smem = wbytes + (size_t)nst * stage_bytes + 1024 /*alignment*/ + 1024 /*barriers + bias*/;
   pl.ok = true;
   return pl;
 }
@@ -760,7 +836,7 @@ size_t tc_workspace_bytes(int N, int K) {
     if (epi == EIGB200_EPI_GLU_RESIDUAL && N % 2) continue;
     TcPlan pl = make_plan(N, K, epi);
     if (!pl.ok) continue;
-    const size_t b = (size_t)2 * pl.nsplit * pl.bn * pl.kpad * sizeof(float);
+    const size_t b = (size_t)2 * pl.nsplit * pl.bn * pl.kpad * sizeof(float) + (size_t)((N + 3) / 4 * 4) * sizeof(float);   // + folded LayerNorm bias
     if (b > best) best = b;
   }
   return best;
@@ -782,8 +858,16 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   float* w_lo = w_hi + wrows * pl.kpad;
   {
     const int total = (int)(wrows * pl.kpad);
-    split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kpad, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0);
+    split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kpad, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0,
+                                                              lp.ln_stats ? lp.ln_gamma : nullptr);
     EIGB_LAUNCH_CHECK("split_weights_kernel");
+  }
+  const float* bias_eff = lp.bias;
+  if (lp.ln_stats) {                                                 // bias + W beta, behind the split weights in the workspace
+    float* bias2 = w_lo + wrows * pl.kpad;
+    ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
+    EIGB_LAUNCH_CHECK("ln_bias_kernel");
+    bias_eff = bias2;
   }
   CUtensorMap tA, tWh, tWl;
   int rc;
@@ -792,11 +876,20 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
 
   TcParams p{};
-  p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats); p.ln_gamma = lp.ln_gamma; p.ln_beta = lp.ln_beta;
-  p.bias = lp.bias; p.C = lp.C; p.ldc = lp.ldc; p.R = lp.R; p.ldr = lp.ldr; p.M = lp.M; p.N = lp.N; p.K = lp.K; p.epilogue = lp.epilogue;
+  p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats);
+  p.bias = bias_eff; p.C = lp.C; p.ldc = lp.ldc; p.R = lp.R; p.ldr = lp.ldr; p.M = lp.M; p.N = lp.N; p.K = lp.K; p.epilogue = lp.epilogue;
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
-  { const char* e = getenv("EIGB200_TS_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  p.zero = 0;
+  {
+    static int want_direct = -1;
+    if (want_direct < 0) { const char* e = getenv("EIGB200_GEMM_STORE"); want_direct = (e && e[0] == 't') ? 0 : 1; }   // "transpose" selects the shuffle path
+    const int nout = glu ? lp.N / 2 : lp.N;
+    const bool al = (((uintptr_t)lp.C & 31) == 0) && lp.ldc % 8 == 0 && (!lp.R || ((((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0));
+    p.direct = (want_direct && al) ? 1 : 0;
+    const int n8 = (nout + 7) / 8 * 8;
+    p.store_cols = (int64_t)n8 <= lp.ldc ? n8 : nout / 8 * 8;
+  }
   int workers = num_sms() / pl.nsplit;
   if (workers < 1) workers = 1;
   if ((int64_t)workers > p.ntiles) workers = (int)p.ntiles;

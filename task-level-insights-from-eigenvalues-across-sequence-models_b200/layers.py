@@ -25,6 +25,11 @@ def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def _pad8(n: int) -> int:
+    """Row pitch of GEMM outputs: a multiple of 8 floats keeps every row 32-byte aligned for the 256-bit epilogue stores."""
+    return (n + 7) // 8 * 8
+
+
 class _Lin:
     """nn.Linear-shaped parameter holder: .weight (N,K), .bias (N,) | None; callable through the eigb200 GEMM."""
 
@@ -96,7 +101,7 @@ class MambaBlockDev:
         B, T, D = x.shape
         skip = x
         d_in_proj = m.in_proj.weight.shape[0]
-        ldz = _pad4(d_in_proj)
+        ldz = _pad8(d_in_proj)
         if stats is not None and self.fuses_layernorm():
             z = ops.linear_ln(x, stats, self.norm.weight, self.norm.bias, m.in_proj.weight, None, ldc=ldz)
         else:
