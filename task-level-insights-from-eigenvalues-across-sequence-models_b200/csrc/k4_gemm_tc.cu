@@ -28,7 +28,12 @@ namespace eigb200 {
 constexpr int TC_BM = 128;                 // rows per tile (UMMA M)
 constexpr int TC_KC = 32;                  // fp32 columns per K-chunk = one 128-byte swizzle row
 constexpr int TC_CHUNK_BYTES = TC_BM * TC_KC * 4;          // 16 KB
-constexpr int TC_THREADS = 448;
+constexpr int TC_EPI_WARPS = 16;           // epilogue warps: TMEM lane quarter = warp % 4, 32-column group = warp / 4 (+ TC_EPI_GROUPS per trip)
+constexpr int TC_EPI_GROUPS = TC_EPI_WARPS / 4;
+constexpr int TC_CONV_WARP0 = TC_EPI_WARPS;                  // 4 converter warps
+constexpr int TC_TMA_WARP = TC_EPI_WARPS + 4;
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + 5;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 6) * 32;
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
@@ -39,9 +44,8 @@ struct TcParams {
   int bn;            // columns per CTA (UMMA N), multiple of 32, <= 128
   int bg;            // GLU: value columns per CTA (bn = 2*bg); otherwise bn
   int nsplit, kchunks, nstages, nterms, workers;
+  int r_v8;          // residual rows are 32-byte aligned: add them in the accumulator layout with 256-bit loads
   int zero;          // always 0; a run-time value the compilers cannot fold (mbar_arrive_after)
-  int direct;        // epilogue stores rows straight from the accumulator layout with 256-bit accesses (needs 32-byte aligned rows)
-  int store_cols;    // columns of C that may be written: N rounded up to 8 when the row pitch leaves room (pad columns receive zeros)
   int64_t ntiles;
 };
 
@@ -195,11 +199,7 @@ __device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
   }
 }
 
-// 256-bit global accesses (sm_100): one full 32-byte sector per thread
-__device__ __forceinline__ void stg_v8(float* ptr, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-}
+// 256-bit streaming load (sm_100): one full 32-byte sector per thread
 __device__ __forceinline__ void ldg_stream_v8(const float* ptr, float* v) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
@@ -217,6 +217,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// GLU column order inside a CTA slice (bn = 2*bg accumulator columns): 32-column accumulator group k holds the VALUE columns of output
+// columns [16k, 16k+16) of the slice in its first half and their GATE columns in its second half, so ONE tcgen05.ld hands a warp both
+// factors of 16 finished output columns and every accumulator group is independent work for an epilogue warp.
+__host__ __device__ __forceinline__ int glu_weight_row(int local, int split, int bg, int nout) {
+  const int c = split * bg + (local >> 5) * 16 + (local & 15);
+  if (c >= nout) return -1;
+  return (local & 16) ? nout + c : c;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // weight preparation: split W (N,K) into tf32 hi / lo in the per-split row order the CTAs consume, zero padded
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -230,10 +239,8 @@ __global__ void split_weights_kernel(const float* __restrict__ W, float* __restr
   const int k = idx % kpad, row = idx / kpad;
   const int split = row / bn, local = row - split * bn;
   int n;
-  if (glu) {                                             // CTA slice = [bg value columns | their bg gate columns]
-    const int nout = N / 2;
-    const int c = split * bg + (local < bg ? local : local - bg);
-    n = c < nout ? (local < bg ? c : nout + c) : -1;
+  if (glu) {                                             // CTA slice: value / gate columns interleaved in groups of 16 (glu_weight_row)
+    n = glu_weight_row(local, split, bg, N / 2);
   } else {
     n = split * bn + local;
   }
@@ -259,119 +266,125 @@ __global__ void ln_bias_kernel(const float* __restrict__ W, const float* __restr
 // ---------------------------------------------------------------------------------------------------------------------------
 // epilogue (8 warps): TMEM accumulator -> registers -> bias / GELU / GLU gate -> shuffle transpose -> (+ residual) -> 128-byte coalesced stores
 // ---------------------------------------------------------------------------------------------------------------------------
+// 4x4 transpose of float4 items inside each group of 4 lanes: lane 4g+i holds the four quads of its row 4g+i; on return it holds quad i of
+// rows 4g+j, j = 0..3 (4 lanes cover 64 contiguous bytes of one row).
+__device__ __forceinline__ void transpose4x4_f4(float (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 2; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if ((q & s) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = v[4 * q + e], hi = v[4 * (q | s) + e];
+          const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, s);
+          v[4 * q + e] = up ? recv : lo;
+          v[4 * (q | s) + e] = up ? hi : recv;
+        }
+      }
+    }
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int bn, uint32_t bar_dfull0, uint32_t bar_dempty0,
                                             const float* bias_s, int worker, int split, int warp, int lane) {
   auto bar_dfull = [&](int j) { return bar_dfull0 + 8u * j; };
   auto bar_dempty = [&](int j) { return bar_dempty0 + 8u * j; };
-  {
-    constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
-    const int nout = GLU ? p.N / 2 : p.N;
-    const int cols_out = GLU ? p.bg : bn;                            // output columns produced by this CTA
-    const int n_cta0 = split * cols_out;
-    const int quarter = warp & 3, half = warp >> 2;
-    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const int gi = lane & 7, gg = lane >> 3;                         // after the transpose: column quad gi of rows 8*gg + jj
-    const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
-    int j = 0; uint32_t dph = 0;
-    if (p.direct) {
-      // Direct path: lane i keeps accumulator row (quarter*32 + i); its 32 columns of a group are 128 contiguous bytes of the C row, written
-      // as four 256-bit stores (full 32-byte sectors, so no read-modify-write in L2) -- no register transpose, no address math per quad.
-      for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-        const int64_t mrow = tile * TC_BM + quarter * 32 + lane;
-        const bool row_ok = mrow < p.M;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
-        bool waited = false, arrived = false;
-        for (int cg = 32 * half; cg < cols_out; cg += 64) {
-          const int n0 = n_cta0 + cg;
-          float rr[32];
-          if (use_r) {
+  constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
+  const int nout = GLU ? p.N / 2 : p.N;
+  const int cols_out = GLU ? p.bg : bn;                              // output columns produced by this CTA
+  const int n_cta0 = split * cols_out;
+  const int quarter = warp & 3, grp = warp >> 2;                     // TMEM lane quarter; first 32-column accumulator group of this warp
+  const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+  const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
+  const bool r_own = use_r && p.r_v8;                                // residual added in the accumulator layout with 256-bit loads
+  int j = 0; uint32_t dph = 0;
+  for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+    const int64_t own_row = tile * TC_BM + quarter * 32 + lane;      // accumulator layout: lane = row
+    const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
+    bool waited = false, arrived = false;
+    for (int cg = 32 * grp; cg < bn; cg += 32 * TC_EPI_GROUPS) {
+      const bool last = cg + 32 * TC_EPI_GROUPS >= bn;               // this warp's last TMEM read of the accumulator: release it early
+      if (GLU) {
+        const int oc = n_cta0 + (cg >> 1);                           // first of the 16 output columns of this group
+        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
+        float a[32];
+        tmem_ld_32x32(d_tmem + cg, a);
+        if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
+        float v[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (row_ok && n0 + 8 * q + 8 <= nout) ldg_stream_v8(p.R + mrow * p.ldr + n0 + 8 * q, rr + 8 * q);
-              else {
+        for (int i = 0; i < 16; ++i) v[i] = (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
+        if (r_own) {
+          const float* rptr = p.R + own_row * p.ldr + oc;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) rr[8 * q + e] = (row_ok && n0 + 8 * q + e < nout) ? p.R[mrow * p.ldr + n0 + 8 * q + e] : 0.f;
-              }
+          for (int q = 0; q < 2; ++q) {
+            float rr[8];
+            if (own_row < p.M && oc + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[e] = (own_row < p.M && oc + 8 * q + e < nout) ? __ldg(rptr + 8 * q + e) : 0.f;
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * q + e] += rr[e];
           }
-          if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
-          float v[32];
-          tmem_ld_32x32(d_tmem + cg, v);
-          if (GLU) {
-            float g[32];
-            tmem_ld_32x32(d_tmem + p.bg + cg, g);
+        }
+        transpose4x4_f4(v, lane);
+        const int n = oc + 4 * (lane & 3);
+        const int64_t row0 = tile * TC_BM + quarter * 32 + (lane & ~3);
+        if (n < nout) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (v[i] + bias_s[cg + i]) * sigmoid_fast_f(g[i] + bias_s[p.bg + cg + i]);
-          } else {
+          for (int jj = 0; jj < 4; ++jj) {
+            const int64_t mrow = row0 + jj;
+            if (mrow < p.M) {
+              float* cptr = p.C + mrow * p.ldc + n;
+              if (n + 3 < nout) {
+                float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                if (use_r && !p.r_v8) {
+                  const float4 r4 = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + mrow * p.ldr + n));
+                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                }
+                *reinterpret_cast<float4*>(cptr) = o;
+              } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float vv = v[i] + bias_s[cg + i];
-              if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
-              v[i] = vv;
-            }
-          }
-          if (cg + 64 >= cols_out) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
-          if (use_r) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += rr[i];
-          }
-          if (row_ok) {
-            float* cptr = p.C + mrow * p.ldc + n0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (n0 + 8 * q + 8 <= p.store_cols) stg_v8(cptr + 8 * q, v + 8 * q);
-              else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (n0 + 8 * q + e < nout) cptr[8 * q + e] = v[8 * q + e];
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < nout) cptr[e] = v[4 * jj + e] + ((use_r && !p.r_v8) ? p.R[mrow * p.ldr + n + e] : 0.f);
               }
             }
           }
         }
-        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
-        if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
-        if (++j == 2) { j = 0; dph ^= 1; }
-      }
-      return;
-    }
-    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
-      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
-      bool waited = false, arrived = false;
-      for (int cg = 32 * half; cg < cols_out; cg += 64) {
-        const int ccol = cg + 4 * gi;                                // column inside the CTA slice (transposed layout)
-        const int n = n_cta0 + ccol;
-        const bool col_ok = ccol < cols_out && n < nout;
+      } else {
+        const int gi = lane & 7, gg = lane >> 3;                     // after the transpose: column quad gi of rows 8*gg + jj
+        const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
+        const int n = n_cta0 + cg + 4 * gi;
+        const bool col_ok = n < nout;
         const bool full = n + 3 < nout;
-        // residual rows of this group: issued first so that their DRAM latency hides behind the TMEM load, the math and the transpose
-        float4 rr[8];
-        if (use_r) {
+        const float* rptr = p.R + own_row * p.ldr + n_cta0 + cg;
+        float rr[32];
+        if (r_own) {                                                 // prefetch behind the accumulator wait
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            rr[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && full && row0 + jj < p.M) rr[jj] = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + (row0 + jj) * p.ldr + n));
+          for (int q = 0; q < 4; ++q) {
+            if (own_row < p.M && n_cta0 + cg + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr + 8 * q);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[8 * q + e] = (own_row < p.M && n_cta0 + cg + 8 * q + e < nout) ? __ldg(rptr + 8 * q + e) : 0.f;
+            }
           }
         }
         if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
         float v[32];
         tmem_ld_32x32(d_tmem + cg, v);
-        if (GLU) {
-          float g[32];
-          tmem_ld_32x32(d_tmem + p.bg + cg, g);
+        if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (v[i] + bias_s[cg + i]) * sigmoid_fast_f(g[i] + bias_s[p.bg + cg + i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float vv = v[i] + bias_s[cg + i];
-            if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
-            v[i] = vv;
-          }
+        for (int i = 0; i < 32; ++i) {
+          float vv = v[i] + bias_s[cg + i];
+          if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
+          v[i] = vv;
         }
-        if (cg + 64 >= cols_out) {                                   // this warp's last TMEM read of the accumulator: release it early
-          tc_fence_before();
-          mbar_arrive(bar_dempty(j));
-          arrived = true;
+        if (r_own) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += rr[i];
         }
         transpose8x8_f4(v, lane);
         if (col_ok) {
@@ -382,21 +395,24 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
               float* cptr = p.C + mrow * p.ldc + n;
               if (full) {
                 float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-                if (use_r) { o.x += rr[jj].x; o.y += rr[jj].y; o.z += rr[jj].z; o.w += rr[jj].w; }
+                if (use_r && !p.r_v8) {
+                  const float4 r4 = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + mrow * p.ldr + n));
+                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                }
                 *reinterpret_cast<float4*>(cptr) = o;
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  if (n + e < nout) cptr[e] = v[4 * jj + e] + (use_r ? p.R[mrow * p.ldr + n + e] : 0.f);
+                  if (n + e < nout) cptr[e] = v[4 * jj + e] + ((use_r && !p.r_v8) ? p.R[mrow * p.ldr + n + e] : 0.f);
               }
             }
           }
         }
       }
-      if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
-      if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
-      if (++j == 2) { j = 0; dph ^= 1; }
     }
+    if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
+    if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
+    if (++j == 2) { j = 0; dph ^= 1; }
   }
 }
 
@@ -434,7 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_conv(s), 128); mbar_init(bar_empty(s), 1); }
-    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), 256); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), TC_EPI_WARPS * 32); }
     fence_barrier_init();
   }
   if (threadIdx.x < 128) {                                            // bias of the slice, in accumulator-column order
@@ -442,19 +458,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     const int nout_ = GLU_ ? p.N / 2 : p.N;
     for (int c = threadIdx.x; c < bn; c += 128) {
       int n;
-      if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
+      if (GLU_) n = glu_weight_row(c, split, p.bg, nout_);
       else { n = split * bn + c; if (n >= p.N) n = -1; }
       bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
     }
   }
-  if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
-  if (warp == 12 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
+  if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TC_TMA_WARP && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 12) {
+  if (warp == TC_TMA_WARP) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
@@ -475,9 +491,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= TC_CONV_WARP0 && warp < TC_CONV_WARP0 + 4) {
     // ===================================== converters: raw fp32 -> tf32 hi (in place) + tf32 lo ==============================
-    const int ct = threadIdx.x - 256;                               // 0..127
+    const int ct = threadIdx.x - TC_CONV_WARP0 * 32;                               // 0..127
     const bool ln = p.ln_stats != nullptr;
     int s = 0; uint32_t ph = 0;
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
@@ -530,7 +546,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA issuer ======================================
     const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
     mbar_wait(bar_w, 0);
@@ -564,14 +580,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
       if (++j == 2) { j = 0; dph ^= 1; }
     }
-  } else if (warp < 8) {
+  } else if (warp < TC_EPI_WARPS) {
     // ===================================== epilogue ======================================
     tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if (warp == TC_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 
@@ -620,7 +636,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     mbar_init(bar_w, 1);
     for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_free(s), 128); }
     for (int t = 0; t < TS_ASTAGES; ++t) { mbar_init(bar_afull(t), 128); mbar_init(bar_aempty(t), 1); }
-    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), 256); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), TC_EPI_WARPS * 32); }
     fence_barrier_init();
   }
   if (threadIdx.x < 128) {
@@ -628,19 +644,19 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int nout_ = GLU_ ? p.N / 2 : p.N;
     for (int c = threadIdx.x; c < bn; c += 128) {
       int n;
-      if (GLU_) { const int cc = split * p.bg + (c < p.bg ? c : c - p.bg); n = cc < nout_ ? (c < p.bg ? cc : nout_ + cc) : -1; }
+      if (GLU_) n = glu_weight_row(c, split, p.bg, nout_);
       else { n = split * bn + c; if (n >= p.N) n = -1; }
       bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
     }
   }
-  if (warp == 13) tmem_alloc(tmem_slot, tmem_cols);
-  if (warp == 12 && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
+  if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TC_TMA_WARP && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 12) {
+  if (warp == TC_TMA_WARP) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
@@ -661,9 +677,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= TC_CONV_WARP0 && warp < TC_CONV_WARP0 + 4) {
     // ===================================== converters: one row (TMEM lane) per thread ======================================
-    const int r = threadIdx.x - 256;                                 // row of the tile = TMEM lane; warp % 4 == r / 32 (lane quarter)
+    const int r = threadIdx.x - TC_CONV_WARP0 * 32;                                 // row of the tile = TMEM lane; warp % 4 == r / 32 (lane quarter)
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const bool ln = p.ln_stats != nullptr;
     const uint32_t row_off = (uint32_t)r * 128u;
@@ -711,7 +727,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA issuer ======================================
     const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
     mbar_wait(bar_w, 0);
@@ -744,13 +760,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
       if (++j == 2) { j = 0; dph ^= 1; }
     }
-  } else if (warp < 8) {
+  } else if (warp < TC_EPI_WARPS) {
     tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if (warp == TC_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -791,7 +807,7 @@ struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages; size_t smem; bool ok
 
 static bool use_ts_variant() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("EIGB200_GEMM_VARIANT"); v = (e && e[0] == 't' && e[1] == 's') ? 1 : 0; }   // "ts" selects the TMEM-operand kernel (experimental)
+  if (v < 0) { const char* e = getenv("EIGB200_GEMM_VARIANT"); v = (e && e[0] == 's' && e[1] == 's') ? 0 : 1; }   // default: TMEM-operand kernel; "ss" selects the smem-operand kernel
   return v == 1;
 }
 
@@ -881,15 +897,7 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
   p.zero = 0;
-  {
-    static int want_direct = -1;
-    if (want_direct < 0) { const char* e = getenv("EIGB200_GEMM_STORE"); want_direct = (e && e[0] == 't') ? 0 : 1; }   // "transpose" selects the shuffle path
-    const int nout = glu ? lp.N / 2 : lp.N;
-    const bool al = (((uintptr_t)lp.C & 31) == 0) && lp.ldc % 8 == 0 && (!lp.R || ((((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0));
-    p.direct = (want_direct && al) ? 1 : 0;
-    const int n8 = (nout + 7) / 8 * 8;
-    p.store_cols = (int64_t)n8 <= lp.ldc ? n8 : nout / 8 * 8;
-  }
+  p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
   int workers = num_sms() / pl.nsplit;
   if (workers < 1) workers = 1;
   if ((int64_t)workers > p.ntiles) workers = (int)p.ntiles;
