@@ -83,6 +83,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // the warp converged -- without this barrier single TMEM lanes (rows) were silently dropped by tcgen05.st.
   __syncwarp();
 }
+// spin on the barrier from a single elected thread (no warp re-convergence: the caller is the only active lane of its warp)
+__device__ __forceinline__ void mbar_wait_one(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+// elect.sync: true in exactly one lane of the (converged) warp.  Code guarded by it is a single-thread region for the compiler, so the
+// operands of UTCHMMA / UTMALDG are trivially warp-uniform -- with `lane == 0` instead it wrapped every tcgen05.mma in an ELECT/BRA.U.ANY
+// waterfall loop and the issue rate, not the tensor pipe, paced the kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -472,25 +490,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
   if (warp == TC_TMA_WARP) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
       for (int c = 0; c < kch; ++c) {
         tma_load_2d(&tmapWhi, bar_w, whi + c * w_chunk_bytes, c * TC_KC, split * bn);
         tma_load_2d(&tmapWlo, bar_w, wlo + c * w_chunk_bytes, c * TC_KC, split * bn);
       }
-    }
-    int s = 0; uint32_t ph = 0;
-    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      for (int c = 0; c < kch; ++c) {
-        mbar_wait(bar_empty(s), ph ^ 1);
-        if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+        for (int c = 0; c < kch; ++c) {
+          mbar_wait_one(bar_empty(s), ph ^ 1);
           mbar_arrive_expect_tx(bar_full(s), TC_CHUNK_BYTES);
           tma_load_2d(&tmapA, bar_full(s), stage0 + s * 2 * TC_CHUNK_BYTES, c * TC_KC, (int)(tile * TC_BM));
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= TC_CONV_WARP0 && warp < TC_CONV_WARP0 + 4) {
     // ===================================== converters: raw fp32 -> tf32 hi (in place) + tf32 lo ==============================
     const int ct = threadIdx.x - TC_CONV_WARP0 * 32;                               // 0..127
@@ -548,38 +564,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
   } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA issuer ======================================
-    const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
-    mbar_wait(bar_w, 0);
-    int s = 0; uint32_t ph = 0;
-    int j = 0; uint32_t dph = 0;
-    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      mbar_wait(bar_dempty(j), dph ^ 1);                            // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
-      for (int c = 0; c < kch; ++c) {
-        mbar_wait(bar_conv(s), ph);
+    if (elect_one()) {                                               // ONE thread runs the whole issue loop
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+      const bool three = p.nterms == 3;
+      mbar_wait_one(bar_w, 0);
+      int s = 0; uint32_t ph = 0;
+      int j = 0; uint32_t dph = 0;
+      for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+        mbar_wait_one(bar_dempty(j), dph ^ 1);                      // epilogue has drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = stage0 + s * 2 * TC_CHUNK_BYTES, a_lo = a_hi + TC_CHUNK_BYTES;
-          const uint32_t b_hi = whi + c * w_chunk_bytes, b_lo = wlo + c * w_chunk_bytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
+        for (int c = 0; c < kch; ++c) {
+          mbar_wait_one(bar_conv(s), ph);
+          tc_fence_after();
+          const uint32_t a_hi = stage0 + s * 2 * TC_CHUNK_BYTES;
+          const uint64_t dah0 = umma_desc_k_sw128(a_hi), dal0 = umma_desc_k_sw128(a_hi + TC_CHUNK_BYTES);
+          const uint64_t dbh0 = umma_desc_k_sw128(whi + c * w_chunk_bytes), dbl0 = umma_desc_k_sw128(wlo + c * w_chunk_bytes);
 #pragma unroll
-          for (int k = 0; k < TC_KC / 8; ++k) {                      // UMMA K = 8 tf32 = 32 bytes along the swizzled row
-            const uint64_t dah = umma_desc_k_sw128(a_hi + k * 32), dal = umma_desc_k_sw128(a_lo + k * 32);
-            const uint64_t dbh = umma_desc_k_sw128(b_hi + k * 32), dbl = umma_desc_k_sw128(b_lo + k * 32);
-            umma_tf32(d_tmem, dah, dbh, idesc, (c > 0 || k > 0) ? 1u : 0u);
-            if (p.nterms == 3) {
-              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-              umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+          for (int k = 0; k < TC_KC / 8; ++k) {                      // UMMA K = 8 tf32 = 32 bytes along the swizzled row = +2 in the address field
+            umma_tf32(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            if (three) {
+              umma_tf32(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
+              umma_tf32(d_tmem, dal0 + 2u * k, dbh0 + 2u * k, idesc, 1u);
             }
           }
           umma_commit(bar_empty(s));                                 // stage reusable once these MMAs retire
           if (c == kch - 1) umma_commit(bar_dfull(j));               // accumulator complete
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == nst) { s = 0; ph ^= 1; }
+        if (++j == 2) { j = 0; dph ^= 1; }
       }
-      if (++j == 2) { j = 0; dph ^= 1; }
     }
+    __syncwarp();
   } else if (warp < TC_EPI_WARPS) {
     // ===================================== epilogue ======================================
     tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
@@ -658,25 +674,23 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
   if (warp == TC_TMA_WARP) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
       for (int c = 0; c < kch; ++c) {
         tma_load_2d(&tmapWhi, bar_w, whi + c * w_chunk_bytes, c * TC_KC, split * bn);
         tma_load_2d(&tmapWlo, bar_w, wlo + c * w_chunk_bytes, c * TC_KC, split * bn);
       }
-    }
-    int s = 0; uint32_t ph = 0;
-    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      for (int c = 0; c < kch; ++c) {
-        mbar_wait(bar_free(s), ph ^ 1);
-        if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+        for (int c = 0; c < kch; ++c) {
+          mbar_wait_one(bar_free(s), ph ^ 1);
           mbar_arrive_expect_tx(bar_full(s), TC_CHUNK_BYTES);
           tma_load_2d(&tmapA, bar_full(s), stage0 + s * TC_CHUNK_BYTES, c * TC_KC, (int)(tile * TC_BM));
+          if (++s == nst) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == nst) { s = 0; ph ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= TC_CONV_WARP0 && warp < TC_CONV_WARP0 + 4) {
     // ===================================== converters: one row (TMEM lane) per thread ======================================
     const int r = threadIdx.x - TC_CONV_WARP0 * 32;                                 // row of the tile = TMEM lane; warp % 4 == r / 32 (lane quarter)
@@ -729,37 +743,37 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
   } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA issuer ======================================
-    const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
-    mbar_wait(bar_w, 0);
-    int t = 0; uint32_t aph = 0;
-    int j = 0; uint32_t dph = 0;
-    for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      mbar_wait(bar_dempty(j), dph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
-      for (int c = 0; c < kch; ++c) {
-        mbar_wait(bar_afull(t), aph);
+    if (elect_one()) {                                               // ONE thread runs the whole issue loop
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+      const bool three = p.nterms == 3;
+      mbar_wait_one(bar_w, 0);
+      int t = 0; uint32_t aph = 0;
+      int j = 0; uint32_t dph = 0;
+      for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
+        mbar_wait_one(bar_dempty(j), dph ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
+        for (int c = 0; c < kch; ++c) {
+          mbar_wait_one(bar_afull(t), aph);
+          tc_fence_after();
           const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)t * 64u, a_lo = a_hi + 32u;
-          const uint32_t b_hi = whi + c * w_chunk_bytes, b_lo = wlo + c * w_chunk_bytes;
+          const uint64_t dbh0 = umma_desc_k_sw128(whi + c * w_chunk_bytes), dbl0 = umma_desc_k_sw128(wlo + c * w_chunk_bytes);
 #pragma unroll
-          for (int k = 0; k < TC_KC / 8; ++k) {
-            const uint64_t dbh = umma_desc_k_sw128(b_hi + k * 32), dbl = umma_desc_k_sw128(b_lo + k * 32);
-            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbh, idesc, (c > 0 || k > 0) ? 1u : 0u);
-            if (p.nterms == 3) {
-              umma_tf32_ts(d_tmem, a_hi + 8u * k, dbl, idesc, 1u);
-              umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh, idesc, 1u);
+          for (int k = 0; k < TC_KC / 8; ++k) {                      // +32 bytes along the swizzled row = +2 in the descriptor's address field
+            umma_tf32_ts(d_tmem, a_hi + 8u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            if (three) {
+              umma_tf32_ts(d_tmem, a_hi + 8u * k, dbl0 + 2u * k, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_lo + 8u * k, dbh0 + 2u * k, idesc, 1u);
             }
           }
           umma_commit(bar_aempty(t));
           if (c == kch - 1) umma_commit(bar_dfull(j));
+          if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
         }
-        __syncwarp();
-        if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
+        if (++j == 2) { j = 0; dph ^= 1; }
       }
-      if (++j == 2) { j = 0; dph ^= 1; }
     }
+    __syncwarp();
   } else if (warp < TC_EPI_WARPS) {
     tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
   }
