@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeigb200.so")
+LIB_PATH = os.environ.get("EIGB200_LIB") or os.path.join(HERE, "libeigb200.so")   # EIGB200_LIB: A/B-test another build of the same ABI
 
 NSLOT = 8
 OK, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3

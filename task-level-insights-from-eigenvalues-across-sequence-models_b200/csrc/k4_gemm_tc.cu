@@ -327,6 +327,18 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
       const bool last = cg + 32 * TC_EPI_GROUPS >= bn;               // this warp's last TMEM read of the accumulator: release it early
       if (GLU) {
         const int oc = n_cta0 + (cg >> 1);                           // first of the 16 output columns of this group
+        float rr[16];
+        if (r_own) {                                                 // residual prefetch: its DRAM latency hides behind the accumulator wait
+          const float* rptr = p.R + own_row * p.ldr + oc;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (own_row < p.M && oc + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr + 8 * q);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[8 * q + e] = (own_row < p.M && oc + 8 * q + e < nout) ? __ldg(rptr + 8 * q + e) : 0.f;
+            }
+          }
+        }
         if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
         float a[32];
         tmem_ld_32x32(d_tmem + cg, a);
@@ -335,18 +347,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
         if (r_own) {
-          const float* rptr = p.R + own_row * p.ldr + oc;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float rr[8];
-            if (own_row < p.M && oc + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr);
-            else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) rr[e] = (own_row < p.M && oc + 8 * q + e < nout) ? __ldg(rptr + 8 * q + e) : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[8 * q + e] += rr[e];
-          }
+          for (int i = 0; i < 16; ++i) v[i] += rr[i];
         }
         transpose4x4_f4(v, lane);
         const int n = oc + 4 * (lane & 3);
