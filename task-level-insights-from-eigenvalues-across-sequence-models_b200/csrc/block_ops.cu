@@ -9,27 +9,33 @@
 
 namespace eigb200 {
 
-// ---- embedding: one warp per (b,t) row --------------------------------------------------------------------------
+// ---- embedding: LPR lanes per (b,t) row (8 for D <= 256: a warp gathers 4 rows per trip, 32 otherwise) ------------------------------
+template <int LPR>
 __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
                                                         const float* __restrict__ pos, float* __restrict__ out,
                                                         int64_t rows, int64_t T, int D, int64_t vocab, int* __restrict__ err,
                                                         float2* __restrict__ rowstats, float ln_eps) {
+  constexpr int RPW = 32 / LPR;                                       // rows per warp trip
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int nv = D >> 2;
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    int64_t id = ids[r];
-    if (id < 0 || id >= vocab) { if (lane == 0 && err) atomicExch(err, 1); id = 0; }
+  for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+    const int64_t r = r0 + sub;
+    const bool ok = r < rows;
+    const int64_t rc = ok ? r : rows - 1;
+    int64_t id = ids[rc];
+    if (id < 0 || id >= vocab) { if (err) *err = 1; id = 0; }
     const float4* w = reinterpret_cast<const float4*>(word + id * D);
-    const float4* pp = pos ? reinterpret_cast<const float4*>(pos + (r % T) * D) : nullptr;
-    float4* o = reinterpret_cast<float4*>(out + r * D);
+    const float4* pp = pos ? reinterpret_cast<const float4*>(pos + (rc % T) * D) : nullptr;
+    float4* o = reinterpret_cast<float4*>(out + rc * D);
     float s1 = 0.f, s2 = 0.f;
-    const float shift = rowstats ? (__ldg(word + id * D) + (pos ? __ldg(pos + (r % T) * D) : 0.f)) : 0.f;
-    for (int c = lane; c < nv; c += 32) {
+    const float shift = rowstats ? (__ldg(word + id * D) + (pos ? __ldg(pos + (rc % T) * D) : 0.f)) : 0.f;
+    for (int c = l; c < nv; c += LPR) {
       float4 v = __ldg(w + c);
       if (pp) { const float4 q = __ldg(pp + c); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-      o[c] = v;
+      if (ok) stg_stream_f4(o + c, v);
       if (rowstats) {
         const float a = v.x - shift, bb = v.y - shift, cc = v.z - shift, d = v.w - shift;
         s1 += (a + bb) + (cc + d); s2 += (a * a + bb * bb) + (cc * cc + d * d);
@@ -37,13 +43,22 @@ __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restric
     }
     if (rowstats) {
 #pragma unroll
-      for (int ofs = 16; ofs >= 1; ofs >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, ofs); s2 += __shfl_xor_sync(0xffffffffu, s2, ofs); }
-      if (lane == 0) {
+      for (int ofs = LPR / 2; ofs >= 1; ofs >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, ofs); s2 += __shfl_xor_sync(0xffffffffu, s2, ofs); }
+      if (l == 0 && ok) {
         const float md = s1 / (float)D;
         rowstats[r] = make_float2(shift + md, rsqrtf(fmaxf(s2 / (float)D - md * md, 0.f) + ln_eps));
       }
     }
   }
+}
+
+static void launch_embedding(cudaStream_t st, const int64_t* ids, const float* word, const float* pos, float* out, int64_t rows, int64_t T, int D,
+                             int64_t vocab, float2* rowstats, float ln_eps) {
+  const int lpr = D <= 256 ? 8 : 32;
+  const int64_t rows_per_cta = 8 * (32 / lpr);
+  int64_t g = (rows + rows_per_cta - 1) / rows_per_cta; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
+  if (lpr == 8) embedding_kernel<8><<<(unsigned)g, 256, 0, st>>>(ids, word, pos, out, rows, T, D, vocab, nullptr, rowstats, ln_eps);
+  else embedding_kernel<32><<<(unsigned)g, 256, 0, st>>>(ids, word, pos, out, rows, T, D, vocab, nullptr, rowstats, ln_eps);
 }
 
 // (mean, rstd) of every row: one warp per row, shifted moments
@@ -187,9 +202,7 @@ extern "C" int eigb200_embedding(void* stream, const int64_t* d_ids, const float
                                  int64_t B, int64_t T, int D, int64_t vocab) {
   EIGB_CHECK_ARG(d_ids && d_word && d_out, "embedding: null pointer");
   EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && D % 4 == 0 && vocab > 0, "embedding: bad shape (D %% 4 == 0 required)");
-  const int64_t rows = B * T;
-  int64_t g = (rows + 7) / 8; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
-  embedding_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_ids, d_word, d_pos, d_out, rows, T, D, vocab, nullptr, nullptr, 0.f);
+  launch_embedding((cudaStream_t)stream, d_ids, d_word, d_pos, d_out, B * T, T, D, vocab, nullptr, 0.f);
   EIGB_LAUNCH_CHECK("embedding_kernel");
   return EIGB200_OK;
 }
@@ -198,10 +211,7 @@ extern "C" int eigb200_embedding_stats(void* stream, const int64_t* d_ids, const
                                        int64_t B, int64_t T, int D, int64_t vocab, float* d_rowstats, float ln_eps) {
   EIGB_CHECK_ARG(d_ids && d_word && d_out && d_rowstats, "embedding_stats: null pointer");
   EIGB_CHECK_ARG(B > 0 && T > 0 && D > 0 && D % 4 == 0 && vocab > 0, "embedding_stats: bad shape (D %% 4 == 0 required)");
-  const int64_t rows = B * T;
-  int64_t g = (rows + 7) / 8; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
-  embedding_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_ids, d_word, d_pos, d_out, rows, T, D, vocab, nullptr,
-                                                                  reinterpret_cast<float2*>(d_rowstats), ln_eps);
+  launch_embedding((cudaStream_t)stream, d_ids, d_word, d_pos, d_out, B * T, T, D, vocab, reinterpret_cast<float2*>(d_rowstats), ln_eps);
   EIGB_LAUNCH_CHECK("embedding_kernel");
   return EIGB200_OK;
 }

@@ -194,6 +194,121 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_gate_kernel(const K1Params p
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Small-H, small-D specialisation of the Mamba-2 extractor (BASELINE C2: D = 128, H = 1): 8 lanes share a row.
+// Lane l of an 8-lane group loads the float4s l, l+8, l+16, ... of its row (a warp instruction reads 4 rows x 128 contiguous bytes), keeps
+// its slice of the H gate rows of W in REGISTERS (no shared-memory traffic in the loop) and the three per-row sums -- the gate dot product and,
+// for the LayerNorm statistics of the next block, sum(x - x0) and sum((x - x0)^2) -- are reduced with 3 xor-shuffles each inside the group
+// (9 shuffles per 4 rows instead of 18 with the warp-per-4-rows butterfly).  Two row groups (8 rows) are in flight per trip.
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int HT, int NF4, bool STATS>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_row8_kernel(const K1Params p) {
+  __shared__ int hist[HT][EIGB200_NSLOT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int D = p.D, T = p.T, H = p.H;
+  const int g = lane >> 3, l = lane & 7;
+  if (threadIdx.x < HT * EIGB200_NSLOT) (&hist[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+
+  float4 w[HT][NF4];
+#pragma unroll
+  for (int h = 0; h < HT; ++h)
+#pragma unroll
+    for (int j = 0; j < NF4; ++j)
+      w[h][j] = (h < H) ? __ldg(reinterpret_cast<const float4*>(p.W + (size_t)h * D) + l + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // after the butterfly every lane of the group holds the full sums: lane l < H finishes head l
+  const bool fin = l < H;
+  const float e0 = fin ? p.p0[l] : 0.f;                               // dt_bias
+  const float e1 = fin ? -expf(p.p1[l]) : 0.f;                        // A = -exp(A_log)
+  int cnt[EIGB_NCNT];
+#pragma unroll
+  for (int j = 0; j < EIGB_NCNT; ++j) cnt[j] = 0;
+
+  const int wid = blockIdx.x * K1_WARPS + warp;
+  const int t0 = wid * p.rows_per_warp;
+  const int t1 = min(T, t0 + p.rows_per_warp);
+  const float4* xb = reinterpret_cast<const float4*>(p.x) + (size_t)b * T * (D / 4);
+  constexpr int U = 2;                                                // row groups per trip
+  for (int t = t0; t < t1; t += 4 * U) {
+    float4 xv[U][NF4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int row = min(t + 4 * u + g, t1 - 1);                     // clamp: tail lanes re-read a valid row
+      const float4* xr = xb + (size_t)row * (D / 4) + l;
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) xv[u][j] = ldg_stream_f4(xr + 8 * j);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int row = t + 4 * u + g;
+      float acc[HT], s1 = 0.f, s2 = 0.f, shift = 0.f;
+#pragma unroll
+      for (int h = 0; h < HT; ++h) acc[h] = 0.f;
+      if (STATS) shift = __shfl_sync(0xffffffffu, xv[u][0].x, lane & ~7);   // first element of the row
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) {
+        const float4 v = xv[u][j];
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          float a = acc[h];
+          a = fmaf(v.x, w[h][j].x, a); a = fmaf(v.y, w[h][j].y, a); a = fmaf(v.z, w[h][j].z, a); a = fmaf(v.w, w[h][j].w, a);
+          acc[h] = a;
+        }
+        if (STATS) {
+          const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+        }
+      }
+#pragma unroll
+      for (int ofs = 4; ofs >= 1; ofs >>= 1) {
+#pragma unroll
+        for (int h = 0; h < HT; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], ofs);
+        if (STATS) { s1 += __shfl_xor_sync(0xffffffffu, s1, ofs); s2 += __shfl_xor_sync(0xffffffffu, s2, ofs); }
+      }
+      if (row < t1) {
+        if (STATS && l == 7) {                                        // a lane that finishes no head
+          const float invD = 1.f / (float)D;
+          const float md = s1 * invD;                                 // mean - shift
+          const float var = fmaxf(s2 * invD - md * md, 0.f);
+          p.rowstats[(size_t)b * T + row] = make_float2(shift + md, rsqrtf(var + p.ln_eps));
+        }
+        if (fin) {
+          float dot = acc[0];
+#pragma unroll
+          for (int h = 1; h < HT; ++h) dot = (l == h) ? acc[h] : dot;
+          const float dt = softplus_f(dot + e0);
+          const float val = expf(dt * e1);
+          if (p.out) p.out[(((size_t)b * T + row) * H + l) * p.out_stride] = val;
+          bin_f32(sqrtf(__fmul_rn(val, val)), p.e, cnt);             // eval_eig.py:605-606: float32 radius sqrt(fl(re^2))
+          cnt[8] += (val == val) ? 1 : 0;
+        }
+      }
+    }
+  }
+  if (p.counts) {
+    if (fin) {
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j)
+        if (cnt[j]) atomicAdd(&hist[l][slot_of(j, p.e.nb)], cnt[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < HT * EIGB200_NSLOT) {
+      const int h = threadIdx.x / EIGB200_NSLOT, sl = threadIdx.x % EIGB200_NSLOT;
+      const int v = hist[h][sl];
+      if (v && h < H) atomicAdd(&p.counts[((size_t)b * H + h) * EIGB200_NSLOT + sl], v);
+    }
+  }
+}
+
+template <int HT, int NF4>
+static void launch_row8(cudaStream_t st, const K1Params& q, dim3 grid, dim3 block) {
+  if (q.rowstats) k1_row8_kernel<HT, NF4, true><<<grid, block, 0, st>>>(q);
+  else k1_row8_kernel<HT, NF4, false><<<grid, block, 0, st>>>(q);
+}
+
 template <bool BF16, int EPI>
 static int launch_k1(cudaStream_t st, const K1Params& p, int64_t B) {
   int ht = 1;
@@ -212,6 +327,20 @@ static int launch_k1(cudaStream_t st, const K1Params& p, int64_t B) {
   ctas_per_seq = (p.T + rpw * K1_WARPS - 1) / (rpw * K1_WARPS);
   dim3 grid(ctas_per_seq, (unsigned)B, hgroups), block(K1_WARPS * 32);
   EIGB_CHECK_ARG(B <= 65535, "k1: batch %lld exceeds grid.y limit 65535; split the call", (long long)B);
+  if (EPI == K1_EPI_MAMBA2 && !BF16 && p.H <= 2 && p.D % 32 == 0 && p.D <= 256 && (p.D & (p.D - 1)) == 0) {
+    // 8-lanes-per-row specialisation (fp32, H <= 2, D in {32,64,128,256}); rows per warp rounded to whole trips of 8 rows
+    rpw = (rpw + 7) / 8 * 8;
+    q.rows_per_warp = rpw;
+    grid.x = (p.T + rpw * K1_WARPS - 1) / (rpw * K1_WARPS);
+    const int nf4 = p.D / 32;
+#define K1_ROW8(HT_)                                                                                               \
+    switch (nf4) { case 1: launch_row8<HT_, 1>(st, q, grid, block); break; case 2: launch_row8<HT_, 2>(st, q, grid, block); break;      \
+                   case 4: launch_row8<HT_, 4>(st, q, grid, block); break; default: launch_row8<HT_, 8>(st, q, grid, block); break; }
+    if (p.H == 1) { K1_ROW8(1) } else { K1_ROW8(2) }
+#undef K1_ROW8
+    EIGB_LAUNCH_CHECK("k1_row8_kernel");
+    return EIGB200_OK;
+  }
   const size_t smem = (size_t)ht * p.D * sizeof(float);
   const bool stats = (EPI == K1_EPI_MAMBA2) && p.rowstats != nullptr;
 #define K1_LAUNCH(HT_, ST_)                                                                                       \

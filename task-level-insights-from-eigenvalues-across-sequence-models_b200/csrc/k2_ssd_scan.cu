@@ -289,13 +289,14 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v2_kernel(const SsdParams p
   };
 
   // ---- x pipeline: U tokens ahead in registers ---------------------------------------------------------------------------
-  using xvec = typename std::conditional<CPT == 2, float2, float>::type;
+  using xvec = typename std::conditional<CPT == 4, float4, typename std::conditional<CPT == 2, float2, float>::type>::type;
   xvec xq[U];
   auto x_fetch = [&](int64_t t) -> xvec {
     xvec v;
-    if constexpr (CPT == 2) v = make_float2(0.f, 0.f); else v = 0.f;
+    if constexpr (CPT == 4) v = make_float4(0.f, 0.f, 0.f, 0.f); else if constexpr (CPT == 2) v = make_float2(0.f, 0.f); else v = 0.f;
     if (pvalid && t < p.T) {
-      if constexpr (CPT == 2) v = ldg_stream_f2(reinterpret_cast<const float2*>(xg + (rowbase + t) * p.ldx));
+      if constexpr (CPT == 4) v = ldg_stream_f4(reinterpret_cast<const float4*>(xg + (rowbase + t) * p.ldx));
+      else if constexpr (CPT == 2) v = ldg_stream_f2(reinterpret_cast<const float2*>(xg + (rowbase + t) * p.ldx));
       else v = __ldg(xg + (rowbase + t) * p.ldx);
     }
     return v;
@@ -326,7 +327,8 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v2_kernel(const SsdParams p
         if (tt < tc) {
           const float2 dd = dd_s[buf][tt];
           float xin[CPT], xcv[CPT], uu[CPT], acc[CPT][4];
-          if constexpr (CPT == 2) { xin[0] = xc_raw[u].x; xin[1] = xc_raw[u].y; } else xin[0] = xc_raw[u];
+          if constexpr (CPT == 4) { xin[0] = xc_raw[u].x; xin[1] = xc_raw[u].y; xin[2] = xc_raw[u].z; xin[3] = xc_raw[u].w; }
+          else if constexpr (CPT == 2) { xin[0] = xc_raw[u].x; xin[1] = xc_raw[u].y; } else xin[0] = xc_raw[u];
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
             float xv = xin[c];
@@ -353,11 +355,12 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v2_kernel(const SsdParams p
           }
           if (pvalid) {
             float* yp = yg + (rowbase + t0 + tt) * p.ldy;
-            const float y0 = fmaf(Dh, xcv[0], (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]));
-            if constexpr (CPT == 2) {
-              const float y1 = fmaf(Dh, xcv[1], (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]));
-              *reinterpret_cast<float2*>(yp) = make_float2(y0, y1);
-            } else *yp = y0;
+            float yv[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) yv[c] = fmaf(Dh, xcv[c], (acc[c][0] + acc[c][1]) + (acc[c][2] + acc[c][3]));
+            if constexpr (CPT == 4) *reinterpret_cast<float4*>(yp) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            else if constexpr (CPT == 2) *reinterpret_cast<float2*>(yp) = make_float2(yv[0], yv[1]);
+            else *yp = yv[0];
           }
         }
       }
@@ -417,6 +420,10 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
             case 5: return launch_ssd_v2<16, 1, 128, 8, 1>(st, p, B);
             case 6: return launch_ssd_v2<16, 1, 128, 4, 4>(st, p, B);
             case 7: return launch_ssd_v2<16, 2, 64, 2, 8>(st, p, B);
+            case 8: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 2, 8>(st, p, B); break;
+            case 9: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 4, 4>(st, p, B); break;
+            case 10: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 2, 12>(st, p, B); break;
+            case 11: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 1, 12>(st, p, B); break;
             default: break;
           }
         }

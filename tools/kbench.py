@@ -50,6 +50,26 @@ def case_k1(B, T, D, H, dtype=torch.float32, want_lam=True):
     return fn, nbytes, B * T * H
 
 
+def case_k1_stats(B, T, D, H):
+    x = torch.randn(B, T, D, device="cuda")
+    W = torch.randn(H, D, device="cuda") * 0.3
+    dtb = torch.full((H,), -1.0, device="cuda"); Al = torch.zeros(H, device="cuda")
+    counts = ops.new_counts(B, H, "cuda")
+    lam = torch.empty(B, T, H, device="cuda"); st = torch.empty(B, T, 2, device="cuda")
+    def fn():
+        ops.mamba2_eig(x, W, dtb, Al, counts=counts, lam_out=lam, rowstats_out=st)
+    return fn, x.numel() * 4 + B * T * H * 4 + B * T * 8, B * T * H
+
+
+def case_embed(B, T, D, V, stats=True):
+    ids = torch.randint(0, V, (B, T), device="cuda")
+    word = torch.randn(V, D, device="cuda"); pos = torch.randn(T, D, device="cuda")
+    st = torch.empty(B, T, 2, device="cuda") if stats else None
+    def fn():
+        ops.embedding(ids, word, pos, rowstats_out=st)
+    return fn, B * T * (8 + D * 4 + (8 if stats else 0)), B * T
+
+
 def case_normgate(B, T, D, H):
     x = torch.randn(B, T, D, device="cuda")
     W = torch.randn(H, D, device="cuda") * 0.3
@@ -112,6 +132,9 @@ CASES = {
     "lin_n96_gelu_tc3": lambda: case_linear(M_C2, 96, 128, "gelu", "tc3"),
     "lin_n64_none_tc3": lambda: case_linear(M_C2, 64, 128, "none", "tc3"),
     "k1_c2": lambda: case_k1(4096, 512, 128, 1),
+    "k1_c2_stats": lambda: case_k1_stats(4096, 512, 128, 1),
+    "emb_c2": lambda: case_embed(4096, 512, 128, 8192),
+    "emb_c2_nostats": lambda: case_embed(4096, 512, 128, 8192, stats=False),
     "k1_c2_nolam": lambda: case_k1(4096, 512, 128, 1, want_lam=False),
     "k1_c2_bf16": lambda: case_k1(4096, 512, 128, 1, torch.bfloat16),
     "k1_c5": lambda: case_k1(1024, 1024, 512, 8),
