@@ -105,6 +105,12 @@ int eigb200_softmax_nu(void* stream, const float* d_q, const float* d_k, int64_t
                        double* d_nu, float* d_m);
 int eigb200_softmax_eta(void* stream, const double* d_nu, const float* d_m, int64_t B, int64_t T, int H,
                         double* d_eta, int32_t* d_counts, const double* thresholds, int nthr);
+/* SelfAttention.forward (models/attention.py:14-35), causal softmax attention in float32 without the (B,H,T,T) score tensor:
+ * out[b,t,h,:] = sum_{s<=t} softmax_s(q_t . (k_s * scale)) v_s.  q/k/v live in one projection buffer with row stride ld (element (b,t,h,i) of q at
+ * d_q[(b*T+t)*ld + h*d + i], v at d_v[(b*T+t)*ld + h*dv + i]); out row stride ldo.  The reference's additive -10000 mask equals an exact mask
+ * unless a row's scores fall below about -9900.  dv in {16,32,64,128}. */
+int eigb200_softmax_attn_forward(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld, float scale,
+                                 float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv);
 
 /* ---- ratios + threshold statistics ----------------------------------------------------------------------------------
  * a: (B,N,inner) of `dtype` (EIGB200_F32 / EIGB200_F64).  mode NONE: v = a[b,n,i] (N values per (b,i));

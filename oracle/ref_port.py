@@ -13,7 +13,7 @@ import numpy as np
 __all__ = [
     "softplus", "elu", "sigmoid", "norm_fn_apply",
     "mamba2_dt_rows", "mamba2_eig", "mamba2_lti_eig", "normattn_rows", "normattn_eta",
-    "linattn_qk", "linattn_eta_quadratic", "linattn_eta_prefix", "softmax_eta_quadratic", "softmax_eta_closed",
+    "linattn_qk", "linattn_eta_quadratic", "linattn_eta_prefix", "softmax_eta_quadratic", "softmax_eta_closed", "smattn_forward",
     "THRESHOLDS_RADIUS", "THRESHOLDS_PHASE", "threshold_counts", "threshold_analysis", "threshold_analysis_ssm",
     "radius_phase", "batch_mean_std", "batch_mean_std_from_counts",
     "lru_lambda", "s5_lambda", "diag_scan", "lru_forward", "s5_discretize", "s5_forward",
@@ -609,6 +609,31 @@ def linattn_forward(x, p, cfg, dtype=np.float64):
     return out.reshape(Bsz, T, D) @ np.asarray(p["out_proj.weight"], dtype).T + np.asarray(p["out_proj.bias"], dtype)
 
 
+def smattn_forward(x, p, cfg, dtype=np.float64):
+    """MHA.forward with SelfAttention (models/attention.py:14-35, :149-182), the "naive" path: k scaled by 1/sqrt(d) before the
+    product, additive -10000 causal mask, softmax over keys, P V, out_proj.  (use_flash=True rounds q,k,v to fp16 first.)"""
+    x = np.asarray(x, dtype)
+    D, dqk, H = cfg["d_model"], cfg["d_qk"], cfg["num_heads"]
+    qkv = x @ np.asarray(p["Wqkv.weight"], dtype).T + np.asarray(p["Wqkv.bias"], dtype)
+    if "conv1d.weight" in p:
+        if cfg.get("conv_type", "full") == "full":
+            qkv = causal_depthwise_conv_silu(qkv, p["conv1d.weight"], p["conv1d.bias"])
+        else:
+            qk_ = causal_depthwise_conv_silu(qkv[..., : 2 * dqk], p["conv1d.weight"], p["conv1d.bias"])
+            qkv = np.concatenate([qk_, qkv[..., 2 * dqk:]], axis=-1)
+    Bsz, T, _ = x.shape
+    d, dv = dqk // H, D // H
+    q = qkv[..., :dqk].reshape(Bsz, T, H, d)
+    k = qkv[..., dqk:2 * dqk].reshape(Bsz, T, H, d)
+    v = qkv[..., 2 * dqk:].reshape(Bsz, T, H, dv)
+    sc = np.einsum("bthd,bshd->bhts", q, k * dtype(1.0 / math.sqrt(d))) + np.triu(np.full((T, T), -10000.0, dtype), 1)
+    sc = sc - sc.max(axis=-1, keepdims=True)
+    pr = np.exp(sc)
+    pr = pr / pr.sum(axis=-1, keepdims=True)
+    out = np.einsum("bhts,bshd->bthd", pr, v)
+    return out.reshape(Bsz, T, D) @ np.asarray(p["out_proj.weight"], dtype).T + np.asarray(p["out_proj.bias"], dtype)
+
+
 def normattn_forward(x, p, cfg, dtype=np.float64):
     """MHNA.forward -> SelfNormAttention (models/norm_attention.py:61-89, :230-258), O(T) form."""
     x = np.asarray(x, dtype)
@@ -655,6 +680,8 @@ def transformer_block_forward(x, p, cfg, dtype=np.float64):
         a = linattn_forward(xn, ap, cfg, dtype)
     elif cfg["attention_fn"] == "norm-attention":
         a = normattn_forward(xn, ap, cfg, dtype)
+    elif cfg["attention_fn"] == "sm-attention":
+        a = smattn_forward(xn, ap, cfg, dtype)
     else:
         raise NotImplementedError(cfg["attention_fn"])
     x = a + skip
@@ -712,6 +739,9 @@ def transformer_eval_pass(ids_or_x, state_dict, cfg, dtype=np.float64, eta_dtype
         if cfg["attention_fn"] == "lin-attention":
             q, k = linattn_qk(x, p["attention.Wqkv.weight"], p["attention.Wqkv.bias"], cfg["d_qk"], cfg["num_heads"], eta_dtype)
             etas.append(linattn_eta_prefix(q, k, eta_dtype))
+        elif cfg["attention_fn"] == "sm-attention":
+            q, k = linattn_qk(x, p["attention.Wqkv.weight"], p["attention.Wqkv.bias"], cfg["d_qk"], cfg["num_heads"], eta_dtype)
+            etas.append(softmax_eta_closed(q, k, eta_dtype))
         else:
             etas.append(normattn_eta(x, p["attention.Wvqkn.weight"], p["attention.Wvqkn.bias"],
                                      p.get("attention.inner_attn.offset") if cfg.get("offset", False) else None,

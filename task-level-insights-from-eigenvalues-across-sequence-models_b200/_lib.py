@@ -33,6 +33,7 @@ SIGNATURES = {
     "eigb200_linattn_nu": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],
     "eigb200_softmax_nu": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "eigb200_softmax_eta": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _vp, _dp, _i],
+    "eigb200_softmax_attn_forward": [_vp, _vp, _vp, _vp, _i64, _f, _vp, _i64, _i64, _i64, _i, _i, _i],
     "eigb200_ratio_hist": [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_count_moments": [_vp, _vp, _i64, _i64, _vp, _vp],
     "eigb200_diag_scan": [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i],

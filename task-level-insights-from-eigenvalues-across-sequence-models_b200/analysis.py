@@ -97,7 +97,12 @@ def transformer_pass(model: "Ly.TransformerDev", X, cfg, want_eig=True, compare=
             n = ops.normattn_gate(x, att.W_n, att.b_n, att.inner_attn.offset if cfg["offset"] else None, cfg["norm_fn"])
             ops.ratio_hist(n, L.RATIO_NEXT_OVER_CUR, want_out=want_eig, counts=counts[i], compare=compare, out=eig[..., i] if want_eig else None)
         elif fn == "sm-attention":
-            raise NotImplementedError("sm-attention analysis is SURVEY 8f row f3 (next); not on the eigb200 path in this build")
+            att = layer.attention
+            qk = ops.linear(x, att.W_qk, att.b_qk)
+            nu, m = ops.softmax_nu(qk, 2 * dqk, B, T, H, att.head_dim, dqk)
+            eta, _ = ops.softmax_eta(nu, m, want_out=want_eig, counts=counts[i])
+            if want_eig:
+                eig[..., i].copy_(eta)
         else:
             raise RuntimeError("{0} is not a valid model option".format(fn))
     return PassResult(eig, counts, T - 1, x)

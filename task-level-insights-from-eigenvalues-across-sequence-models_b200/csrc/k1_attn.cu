@@ -134,6 +134,157 @@ __global__ void __launch_bounds__(LA_THREADS) linattn_forward_kernel(const LinAt
   }
 }
 
+
+// ---- softmax attention: normaliser of get_eig_att_softmax and the layer forward, both streaming over key tiles -------------------------------
+// Reference: analysis/eval_eig.py:43-95 (the (B,T,T,H) score tensor, its multiplicative mask and the row maximum that therefore includes the
+// masked zeros) and SelfAttention.forward, models/attention.py:14-35 (k scaled by 1/sqrt(d) BEFORE the product, additive -10000 mask, softmax).
+// A CTA owns SM_TQ query rows of one (b,h); 4 threads share a row and take the keys s = j, j+4, ... of every 32-key tile.  Two passes over the
+// key tiles: the row maximum first, then the sums with the FINAL maximum -- the reference subtracts it in float32 and exponentiates in float64,
+// which an online rescaling would not reproduce.  Scores are recomputed, not stored: O(T) memory.
+constexpr int SM_TQ = 32, SM_TK = 32, SM_THREADS = 128;
+
+__device__ __forceinline__ float sm_dot(const float* __restrict__ qr, const float* __restrict__ kr, int d) {
+  float acc = 0.f;
+  for (int c = 0; c < d; ++c) acc = fmaf(qr[c], kr[c], acc);
+  return acc;
+}
+
+__global__ void __launch_bounds__(SM_THREADS) softmax_nu_kernel(const float* __restrict__ q, const float* __restrict__ k, int64_t ld,
+                                                                int64_t T, int H, int d, double* __restrict__ nu, float* __restrict__ m) {
+  extern __shared__ __align__(16) float sm[];
+  const int dp = d + 1;                                            // +1: rows of a tile fall in different banks
+  float* qs = sm;                                                  // [SM_TQ][dp]
+  float* ks = qs + SM_TQ * dp;                                     // [SM_TK][dp]
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, r = tid >> 2, j = tid & 3;
+  const int64_t t = (int64_t)qt * SM_TQ + r;
+  const float* qb = q + ((size_t)b * T) * ld + (size_t)h * d;
+  const float* kb = k + ((size_t)b * T) * ld + (size_t)h * d;
+  for (int i = tid; i < SM_TQ * d; i += SM_THREADS) {
+    const int rr = i / d, c = i - rr * d;
+    const int64_t tt = (int64_t)qt * SM_TQ + rr;
+    qs[rr * dp + c] = tt < T ? __ldg(qb + tt * ld + c) : 0.f;
+  }
+  float mx = -INFINITY;
+  double sum = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int kt = 0; kt <= qt; ++kt) {
+      __syncthreads();
+      for (int i = tid; i < SM_TK * d; i += SM_THREADS) {
+        const int rr = i / d, c = i - rr * d;
+        const int64_t ss = (int64_t)kt * SM_TK + rr;
+        ks[rr * dp + c] = ss < T ? __ldg(kb + ss * ld + c) : 0.f;
+      }
+      __syncthreads();
+      if (t < T) {
+        for (int s = j; s < SM_TK; s += 4) {
+          const int64_t sg = (int64_t)kt * SM_TK + s;
+          if (sg <= t) {
+            const float dot = sm_dot(qs + r * dp, ks + s * dp, d);
+            if (pass == 0) mx = fmaxf(mx, dot);
+            else sum += exp((double)(dot - mx));                   // float32 difference, float64 exponential (eval_eig.py:72-77)
+          }
+        }
+      }
+    }
+    if (pass == 0) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      if (t < T - 1) mx = fmaxf(mx, 0.f);                          // the masked (zeroed) scores take part in torch.max (eval_eig.py:58-62)
+    }
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  if (t < T && j == 0) {
+    const size_t o = ((size_t)b * T + t) * H + h;
+    nu[o] = sum + (double)(T - 1 - t);                             // every masked position contributes exp(0 - 0) = 1
+    m[o] = mx;
+  }
+}
+
+// layer forward: out[t,:] = sum_{s<=t} softmax_s(q_t . (k_s * scale)) v_s.  Pass 0: row maximum and denominator (online), pass 1: P V.
+template <int DV>
+__global__ void __launch_bounds__(SM_THREADS) softmax_attn_forward_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                                          int64_t ld, float scale, float* __restrict__ out, int64_t ldo,
+                                                                          int64_t T, int H, int d) {
+  extern __shared__ __align__(16) float sm[];
+  const int dp = d + 1;
+  float* qs = sm;                                                  // [SM_TQ][dp]
+  float* ks = qs + SM_TQ * dp;                                     // [SM_TK][dp]   k * scale
+  float* vs = ks + SM_TK * dp;                                     // [SM_TK][DV]
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, r = tid >> 2, j = tid & 3;
+  const int64_t t = (int64_t)qt * SM_TQ + r;
+  const float* qb = q + ((size_t)b * T) * ld + (size_t)h * d;
+  const float* kb = k + ((size_t)b * T) * ld + (size_t)h * d;
+  const float* vb = v + ((size_t)b * T) * ld + (size_t)h * DV;
+  for (int i = tid; i < SM_TQ * d; i += SM_THREADS) {
+    const int rr = i / d, c = i - rr * d;
+    const int64_t tt = (int64_t)qt * SM_TQ + rr;
+    qs[rr * dp + c] = tt < T ? __ldg(qb + tt * ld + c) : 0.f;
+  }
+  float mx = -INFINITY, den = 0.f;
+  float acc[DV];
+#pragma unroll
+  for (int c = 0; c < DV; ++c) acc[c] = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int kt = 0; kt <= qt; ++kt) {
+      __syncthreads();
+      for (int i = tid; i < SM_TK * d; i += SM_THREADS) {
+        const int rr = i / d, c = i - rr * d;
+        const int64_t ss = (int64_t)kt * SM_TK + rr;
+        ks[rr * dp + c] = ss < T ? __ldg(kb + ss * ld + c) * scale : 0.f;
+      }
+      if (pass == 1) {
+        for (int i = tid; i < SM_TK * DV; i += SM_THREADS) {
+          const int rr = i / DV, c = i - rr * DV;
+          const int64_t ss = (int64_t)kt * SM_TK + rr;
+          vs[i] = ss < T ? __ldg(vb + ss * ld + c) : 0.f;
+        }
+      }
+      __syncthreads();
+      if (t < T) {
+        for (int s = j; s < SM_TK; s += 4) {
+          const int64_t sg = (int64_t)kt * SM_TK + s;
+          if (sg <= t) {
+            const float dot = sm_dot(qs + r * dp, ks + s * dp, d);
+            if (pass == 0) {
+              const float nm = fmaxf(mx, dot);
+              den = den * expf(mx - nm) + expf(dot - nm);
+              mx = nm;
+            } else {
+              const float pw = expf(dot - mx) * den;               // den holds 1 / sum in pass 1
+#pragma unroll
+              for (int c = 0; c < DV; ++c) acc[c] = fmaf(pw, vs[s * DV + c], acc[c]);
+            }
+          }
+        }
+      }
+    }
+    if (pass == 0) {                                               // combine the 4 partial (max, denominator) pairs of the row
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o), od = __shfl_xor_sync(0xffffffffu, den, o);
+        const float nm = fmaxf(mx, om);
+        den = (mx == -INFINITY ? 0.f : den * expf(mx - nm)) + (om == -INFINITY ? 0.f : od * expf(om - nm));
+        mx = nm;
+      }
+      den = 1.f / den;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < DV; ++c) {
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+    acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+  }
+  if (t < T) {
+    float* op = out + ((size_t)b * T + t) * ldo + (size_t)h * DV;
+#pragma unroll
+    for (int c = 0; c < DV; ++c)
+      if ((c & 3) == j) op[c] = acc[c];                            // the 4 lanes of the row write interleaved columns
+  }
+}
+
 }  // namespace eigb200
 
 using namespace eigb200;
@@ -168,5 +319,37 @@ extern "C" int eigb200_linattn_forward(void* stream, const float* d_q, const flo
   switch (ri) { LA_CASE(1) LA_CASE(2) LA_CASE(4) LA_CASE(8) LA_CASE(16) LA_CASE(32) LA_CASE(64) default: break; }
 #undef LA_CASE
   EIGB_LAUNCH_CHECK("linattn_forward_kernel");
+  return EIGB200_OK;
+}
+
+
+extern "C" int eigb200_softmax_nu(void* stream, const float* d_q, const float* d_k, int64_t ld, int64_t B, int64_t T, int H, int d,
+                                  double* d_nu, float* d_m) {
+  EIGB_CHECK_ARG(d_q && d_k && d_nu && d_m, "softmax_nu: null pointer");
+  EIGB_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && H > 0 && H <= 65535 && d > 0, "softmax_nu: bad shape");
+  const size_t smem = sizeof(float) * (size_t)(SM_TQ + SM_TK) * (d + 1);
+  EIGB_CHECK_ARG(smem <= 200 * 1024, "softmax_nu: head dim %d too large", d);
+  if (smem > 48 * 1024) EIGB_CUDA(cudaFuncSetAttribute(softmax_nu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((T + SM_TQ - 1) / SM_TQ), H, (unsigned)B);
+  softmax_nu_kernel<<<grid, SM_THREADS, smem, (cudaStream_t)stream>>>(d_q, d_k, ld, T, H, d, d_nu, d_m);
+  EIGB_LAUNCH_CHECK("softmax_nu_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_softmax_attn_forward(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld, float scale,
+                                            float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv) {
+  EIGB_CHECK_ARG(d_q && d_k && d_v && d_out, "softmax_attn_forward: null pointer");
+  EIGB_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && H > 0 && H <= 65535 && d > 0, "softmax_attn_forward: bad shape");
+  EIGB_CHECK_ARG(dv == 16 || dv == 32 || dv == 64 || dv == 128, "softmax_attn_forward: value head dim %d must be 16, 32, 64 or 128", dv);
+  const size_t smem = sizeof(float) * ((size_t)(SM_TQ + SM_TK) * (d + 1) + (size_t)SM_TK * dv);
+  EIGB_CHECK_ARG(smem <= 200 * 1024, "softmax_attn_forward: head dims %d/%d too large", d, dv);
+  dim3 grid((unsigned)((T + SM_TQ - 1) / SM_TQ), H, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SMF_CASE(DV_) case DV_: \
+    if (smem > 48 * 1024) EIGB_CUDA(cudaFuncSetAttribute(softmax_attn_forward_kernel<DV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    softmax_attn_forward_kernel<DV_><<<grid, SM_THREADS, smem, st>>>(d_q, d_k, d_v, ld, scale, d_out, ldo, T, H, d); break;
+  switch (dv) { SMF_CASE(16) SMF_CASE(32) SMF_CASE(64) SMF_CASE(128) default: break; }
+#undef SMF_CASE
+  EIGB_LAUNCH_CHECK("softmax_attn_forward_kernel");
   return EIGB200_OK;
 }

@@ -390,6 +390,7 @@ __global__ void k1_lti_kernel(const float* A, const float* beta, int64_t BT, int
 struct RatioParams {
   const void* a; double* out; int64_t out_stride; int* counts;
   int64_t N, inner; int mode; int chunk;             // chunk = values of n handled per CTA
+  const float* mscale;                               // softmax eta: v *= exp(double(mscale[n] - mscale[n+1])) (eval_eig.py:83-88), no zero guard
   EdgesF ef; EdgesD ed; int cmp_f32_on_f32;
 };
 
@@ -419,9 +420,15 @@ __global__ void __launch_bounds__(256) ratio_hist_kernel(const RatioParams p) {
         v = (double)a[e]; vf = (float)a[e];
       } else {
         double u0 = (double)a[e], u1 = (double)a[e + inner];
-        if (u0 == 0.0) u0 = 2e-23;
-        if (u1 == 0.0) u1 = 2e-23;
+        if (!p.mscale) {
+          if (u0 == 0.0) u0 = 2e-23;
+          if (u1 == 0.0) u1 = 2e-23;
+        }
         v = p.mode == EIGB200_RATIO_NEXT_OVER_CUR ? u1 / u0 : u0 / u1;
+        if (p.mscale) {                                  // different row maxima: rescale by exp(m_t - m_{t+1}), difference formed in float32
+          const float* ms = p.mscale + (size_t)b * p.N * inner;
+          v *= exp((double)(ms[e] - ms[e + inner]));
+        }
         if (p.out) p.out[((size_t)b * Nout * inner + e) * p.out_stride] = v;
       }
       int c[EIGB_NCNT];
@@ -553,6 +560,28 @@ extern "C" int eigb200_ratio_hist(void* stream, const void* d_a, int dtype, int 
   const size_t smem = inner <= 256 ? (size_t)inner * EIGB200_NSLOT * sizeof(int) : 0;
   if (dtype == EIGB200_F32) ratio_hist_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   else ratio_hist_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  EIGB_LAUNCH_CHECK("ratio_hist_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_softmax_eta(void* stream, const double* d_nu, const float* d_m, int64_t B, int64_t T, int H,
+                                   double* d_eta, int32_t* d_counts, const double* thresholds, int nthr) {
+  EIGB_CHECK_ARG(d_nu && d_m, "softmax_eta: null input");
+  EIGB_CHECK_ARG(B > 0 && B <= 65535 && T > 1 && H > 0, "softmax_eta: bad shape (T >= 2)");
+  RatioParams p{};
+  p.a = d_nu; p.out = d_eta; p.out_stride = 1; p.counts = d_counts; p.N = T; p.inner = H; p.mode = EIGB200_RATIO_CUR_OVER_NEXT; p.mscale = d_m;
+  int rc = make_edges_d(thresholds, nthr, &p.ed); if (rc) return rc;
+  rc = make_edges_f(thresholds, nthr, EIGB200_CMP_F64, &p.ef); if (rc) return rc;
+  const int64_t Nout = T - 1;
+  int64_t per_seq = ((int64_t)num_sms() * 8 + B - 1) / B;
+  const int64_t max_ps = (Nout * H + 2047) / 2048;
+  if (per_seq > max_ps) per_seq = max_ps;
+  if (per_seq < 1) per_seq = 1;
+  p.chunk = (int)((Nout + per_seq - 1) / per_seq);
+  per_seq = (Nout + p.chunk - 1) / p.chunk;
+  dim3 grid((unsigned)per_seq, (unsigned)B);
+  const size_t smem = H <= 256 ? (size_t)H * EIGB200_NSLOT * sizeof(int) : 0;
+  ratio_hist_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   EIGB_LAUNCH_CHECK("ratio_hist_kernel");
   return EIGB200_OK;
 }

@@ -117,9 +117,25 @@ def get_eig_att_linear(x, layer, d_qk, num_heads, d_model):
     return np.expand_dims(eta.cpu().numpy(), axis=-1)
 
 
+def get_eig_att_softmax_device(x, layer, d_qk, num_heads, d_model, want_eig=True, counts=None, compare="float64"):
+    att = layer.attention
+    x = _cuda(x)
+    B, T, _ = x.shape
+    W_qk = getattr(att, "W_qk", None)
+    if W_qk is None:
+        W_qk = _w(att.Wqkv.weight)[: 2 * d_qk].contiguous()                                       # eval_eig.py:46-48
+        b_qk = _w(att.Wqkv.bias)[: 2 * d_qk].contiguous() if att.Wqkv.bias is not None else None
+    else:
+        b_qk = att.b_qk
+    qk = ops.linear(x, _cuda(W_qk), _cuda(b_qk) if b_qk is not None else None)                    # (B*T, 2*d_qk): [q (h d) | k (h d)]
+    nu, m = ops.softmax_nu(qk, 2 * d_qk, B, T, num_heads, att.head_dim, d_qk)
+    return ops.softmax_eta(nu, m, want_out=want_eig, counts=counts)
+
+
 def get_eig_att_softmax(x, layer, d_qk, num_heads, d_model):
-    """analysis/eval_eig.py:43-95 -- SURVEY 8f row f3 ("next"); not on the eigb200 path in this build."""
-    raise NotImplementedError("softmax-attention extractor: eigb200_softmax_nu is not implemented in this build")
+    """analysis/eval_eig.py:43-95 in O(T) memory (no (B,T,T,H) tensors), reproducing the multiplicative-mask row maximum.  -> (B,T-1,H,1) float64."""
+    eta, _ = get_eig_att_softmax_device(x, layer, d_qk, num_heads, d_model)
+    return np.expand_dims(eta.cpu().numpy(), axis=-1)
 
 
 # ---- threshold statistics ---------------------------------------------------------------------------------------------------

@@ -218,8 +218,15 @@ class AttentionDev:
             kscale = 1.0 / math.sqrt(d) if self.scale_B else 1.0
             ctx = ops.linattn_forward(buf, ld, D, D + dqk, 0, B, T, H, d, dv, gate=gate, phi_elu=(self.approx_fn == "elu"),
                                       normalise=False, kscale=kscale)
+        elif self.kind == "sm-attention":
+            # SelfAttention.forward (models/attention.py:14-35), the float32 "naive" path; with use_flash the reference rounds q,k,v to fp16 first
+            ld = 2 * dqk + D
+            buf = ops.linear(xn, self.Wqkv.weight, self.Wqkv.bias)
+            if self.conv_w is not None:
+                buf = self._conv(buf, ld, 0, ld if self.conv_type == "full" else 2 * dqk, B, T)
+            ctx = ops.softmax_attn_forward(buf, ld, 0, dqk, 2 * dqk, B, T, H, d, dv, 1.0 / math.sqrt(d))
         else:
-            raise NotImplementedError("softmax attention layer forward is not on the eigb200 path yet")
+            raise RuntimeError("{0} is not a valid model option".format(self.kind))
         out = ops.linear(ctx, self.out_proj.weight, self.out_proj.bias, epilogue="residual", residual=skip.reshape(B * T, D))
         return out.reshape(B, T, D)
 

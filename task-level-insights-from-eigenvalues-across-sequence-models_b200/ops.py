@@ -189,6 +189,42 @@ def linattn_nu(qk_buf, ld: int, B: int, T: int, H: int, d: int, k_offset: int):
     return nu
 
 
+def softmax_nu(qk_buf, ld: int, B: int, T: int, H: int, d: int, k_offset: int):
+    """Softmax-attention normaliser with the reference's masking quirk.  -> (nu (B,T,H) f64, m (B,T,H) f32)."""
+    qk_buf = _prep(qk_buf, torch.float32)
+    lib = _enter(qk_buf)
+    nu = torch.empty(B, T, H, dtype=torch.float64, device=qk_buf.device)
+    m = torch.empty(B, T, H, dtype=torch.float32, device=qk_buf.device)
+    q_ptr = C.c_void_p(qk_buf.data_ptr())
+    k_ptr = C.c_void_p(qk_buf.data_ptr() + 4 * k_offset)
+    _call(lib, "eigb200_softmax_nu", _stream(qk_buf), q_ptr, k_ptr, ld, B, T, H, d, _p(nu), _p(m))
+    return nu, m
+
+
+def softmax_eta(nu, m, thresholds=THRESHOLDS_RADIUS, want_out=True, counts=None):
+    """eta_t = nu_t / nu_{t+1} * exp(m_t - m_{t+1}) (B,T-1,H) f64 and its threshold counts (B,H,8)."""
+    nu = _prep(nu, torch.float64); m = _prep(m, torch.float32)
+    B, T, H = nu.shape
+    lib = _enter(nu)
+    out = torch.empty(B, T - 1, H, dtype=torch.float64, device=nu.device) if want_out else None
+    if counts is None:
+        counts = new_counts(B, H, nu.device)
+    thr, n = L.thresholds_arg(thresholds)
+    _call(lib, "eigb200_softmax_eta", _stream(nu), _p(nu), _p(m), B, T, H, _p(out), _p(counts), thr, n)
+    return out, counts
+
+
+def softmax_attn_forward(buf, ld, q_off, k_off, v_off, B, T, H, d, dv, scale):
+    """Causal softmax attention over a projection buffer (B*T, ld); q/k/v at the given column offsets.  -> (B,T,H*dv)."""
+    buf = _prep(buf, torch.float32)
+    lib = _enter(buf)
+    out = torch.empty(B, T, H * dv, dtype=torch.float32, device=buf.device)
+    base = buf.data_ptr()
+    _call(lib, "eigb200_softmax_attn_forward", _stream(buf), C.c_void_p(base + 4 * q_off), C.c_void_p(base + 4 * k_off), C.c_void_p(base + 4 * v_off),
+          ld, float(scale), _p(out), H * dv, B, T, H, d, dv)
+    return out
+
+
 def linattn_forward(buf, ld, q_off, k_off, v_off, B, T, H, d, dv, gate=None, phi_elu=True, normalise=True, kscale=1.0):
     """Causal linear attention over a projection buffer (B*T, ld); q/k/v live at the given column offsets."""
     buf = _prep(buf, torch.float32)

@@ -294,8 +294,14 @@ def reference_layer_loop(model, layers, X, extractor):
     return eig, acts
 
 
-def gold_models():
+def gold_models(only=None):
     ns = load_reference_models()
+    if only is None:
+        _gold_mamba_model(ns)
+    _gold_transformer_models(ns, only)
+
+
+def _gold_mamba_model(ns):
     # ---- Mamba-2 (models/mamba.py) ----
     torch.manual_seed(1919)
     cfg = dict(version="mamba2", num_layers=3, input_dim=1, output_dim=64, hidden_dim=32, num_heads=2, state_dim=8,
@@ -316,7 +322,10 @@ def gold_models():
                                                         np.array([0.1, 0.5, 0.9, 1.0, 10, 100]), 3, 2, 8)
     save("model_mamba2", "models/mamba.py:25-154,301-389 + analysis/eval_eig.py:501-526 (SSD kernel := fla naive recurrence)", **arrays)
 
-    # ---- Transformer, linear attention (C1-like) and normalised attention ----
+
+
+def _gold_transformer_models(ns, only=None):
+    # ---- Transformer, linear attention (C1-like), normalised attention and softmax attention ----
     base = dict(input_dim=1, output_dim=64, num_layers=2, hidden_dim=32, embedding=True, vocab_size=64, max_pos_embed=24,
                 pooling="none", dual=False, classifier=False, mixer_dim=64, norm="layer", dropout=0.0, state_dim=32,
                 num_heads=2, att_dropout=0.0, use_flash=False)
@@ -328,8 +337,11 @@ def gold_models():
         "model_normattn_exp": dict(base, attention_fn="norm-attention", mixer="none", mode="attention", norm_fn="exp",
                                    approx_fn="none", scale_B=True, offset=False, offset_init="uniform", learn_A=False, dim_conv=0,
                                    max_pos_embed=0),
+        "model_smattn": dict(base, attention_fn="sm-attention", mixer="mlp"),
     }
     for name, c in variants.items():
+        if only is not None and name not in only:
+            continue
         torch.manual_seed(1919)
         model = ns["Transformer"](dict(c)).eval()
         model.encoder.device = "cpu"          # TokenEmbeddings hard-codes device='cuda' for position ids (common.py:126)
@@ -337,6 +349,8 @@ def gold_models():
         dqk, H, D = c["state_dim"], c["num_heads"], c["hidden_dim"]
         if c["attention_fn"] == "lin-attention":
             ext = lambda x, layer: EV["get_eig_att_linear"](x, layer, dqk, H, D)
+        elif c["attention_fn"] == "sm-attention":
+            ext = lambda x, layer: EV["get_eig_att_softmax"](x, layer, dqk, H, D)
         else:
             ext = lambda x, layer, c=c: EV["get_eig_att_norm"](x, layer, dqk, H, D, c)
         with torch.no_grad(), np.errstate(all="ignore"):
@@ -403,6 +417,12 @@ def gold_report_files():
 
 
 if __name__ == "__main__":
+    if "--only-smattn" in sys.argv:                 # add the softmax-attention model without touching the other vectors
+        MANIFEST.update(json.load(open(os.path.join(OUT, "MANIFEST.json"))))
+        gold_models(only=["model_smattn"])
+        with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
+            json.dump(MANIFEST, f, indent=1, sort_keys=True)
+        sys.exit(0)
     if "--only-reports" in sys.argv:
         MANIFEST.update(json.load(open(os.path.join(OUT, "MANIFEST.json"))))
         gold_report_files()

@@ -126,6 +126,57 @@ def test_linattn_nu_and_eta(ops):
     np.testing.assert_array_equal(counts.cpu().numpy()[..., :7], exp)
 
 
+def test_softmax_nu_and_eta_golden(ops):
+    """get_eig_att_softmax (eval_eig.py:43-95) against the vector produced by executing the reference function."""
+    from conftest import load_golden
+    g = load_golden("lin_softmax_extractor")
+    D, dqk, H = [int(v) for v in g["dims"]]
+    B, T, _ = g["x"].shape
+    qk = ops.linear(dev(g["x"]), dev(g["weight"][:2 * dqk]), dev(g["bias"][:2 * dqk]), mode="simt")
+    nu, m = ops.softmax_nu(qk, 2 * dqk, B, T, H, dqk // H, dqk)
+    eta, counts = ops.softmax_eta(nu, m)
+    np.testing.assert_allclose(eta.cpu().numpy(), g["eta_sm"][..., 0], rtol=1e-4)     # fp32 score rounding order differs from cuBLAS / einsum
+    with np.errstate(invalid="ignore"):
+        exp = np.moveaxis(O.threshold_counts(eta.cpu().numpy(), O.THRESHOLDS_RADIUS, axis=1), 0, -1)
+    np.testing.assert_array_equal(counts.cpu().numpy()[..., :7], exp)
+
+
+@pytest.mark.parametrize("B,T,H,d,scale", [(2, 70, 2, 16, 1.0), (1, 33, 1, 64, 3.0), (3, 129, 4, 8, 0.3), (2, 2, 1, 4, 1.0)])
+def test_softmax_nu_matches_quadratic_and_closed_forms(ops, B, T, H, d, scale):
+    """Ragged T (tile tails), several heads, large logits (scale 3: row maxima far from 0) and the T = 2 minimum."""
+    rng = np.random.default_rng(T * 7 + d)
+    q = (rng.normal(size=(B, T, H, d)) * scale).astype(np.float32); k = (rng.normal(size=(B, T, H, d)) * scale).astype(np.float32)
+    buf = np.concatenate([q.reshape(B * T, H * d), k.reshape(B * T, H * d)], axis=1)
+    nu, m = ops.softmax_nu(dev(buf), 2 * H * d, B, T, H, d, H * d)
+    eta, _ = ops.softmax_eta(nu, m)
+    ref_q = O.softmax_eta_quadratic(q, k)[..., 0]; ref_c = O.softmax_eta_closed(q, k)[..., 0]
+    np.testing.assert_allclose(ref_c, ref_q, rtol=1e-4)
+    np.testing.assert_allclose(eta.cpu().numpy(), ref_q, rtol=2e-4)
+    # the row maximum is an actual score (or the masked zero), so it is reproduced to fp32 rounding of the dot product
+    s = np.einsum("bthd,bshd->btsh", q.astype(np.float64), k.astype(np.float64))
+    mask = np.tril(np.ones((T, T)))[None, :, :, None]
+    mref = (s * mask).max(axis=2)
+    np.testing.assert_allclose(m.cpu().numpy(), mref, rtol=1e-5, atol=1e-5 * np.abs(s).max())
+    assert (nu.cpu().numpy() >= 1.0 - 1e-6).all()
+
+
+@pytest.mark.parametrize("B,T,H,d,dv", [(2, 70, 2, 16, 16), (1, 129, 1, 64, 64), (2, 33, 4, 8, 32)])
+def test_softmax_attn_forward(ops, B, T, H, d, dv):
+    """SelfAttention.forward (models/attention.py:14-35): k scaled before the product, additive -10000 causal mask, softmax, P V."""
+    rng = np.random.default_rng(T + dv)
+    ld = 2 * H * d + H * dv
+    buf = rng.normal(size=(B * T, ld)).astype(np.float32)
+    scale = 1.0 / np.sqrt(d)
+    out = ops.softmax_attn_forward(dev(buf), ld, 0, H * d, 2 * H * d, B, T, H, d, dv, scale).cpu().numpy().reshape(B, T, H, dv)
+    b3 = buf.reshape(B, T, ld).astype(np.float64)
+    q = b3[..., :H * d].reshape(B, T, H, d); k = b3[..., H * d:2 * H * d].reshape(B, T, H, d); v = b3[..., 2 * H * d:].reshape(B, T, H, dv)
+    sc = np.einsum("bthd,bshd->bhts", q, k * scale) + np.triu(np.full((T, T), -10000.0), 1)
+    sc = sc - sc.max(axis=-1, keepdims=True)
+    pr = np.exp(sc); pr /= pr.sum(axis=-1, keepdims=True)
+    ref = np.einsum("bhts,bshd->bthd", pr, v)
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-6 * np.abs(ref).max() + 1e-6)
+
+
 # ---- K4 on the tensor cores ------------------------------------------------------------------------------------------
 def _lin_ref(a, w, bias, epi, r):
     z = a.astype(np.float64) @ w.astype(np.float64).T + (bias if bias is not None else 0)

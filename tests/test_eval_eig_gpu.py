@@ -68,7 +68,7 @@ def test_eval_eig_mamba_end_to_end(A, tmp_path, monkeypatch):
     assert open(tmp_path / "percentage_file.txt").read().startswith("threshold radius: [  0.1   0.5   0.9   1.   10.  100. ]")
 
 
-@pytest.mark.parametrize("name", ["model_linattn", "model_normattn"])
+@pytest.mark.parametrize("name", ["model_linattn", "model_normattn", "model_smattn"])
 def test_eval_eig_transformer_end_to_end(A, tmp_path, monkeypatch, name):
     sd, cfg, g = golden_model(name)
     ckpt = str(tmp_path / "tf.pth")

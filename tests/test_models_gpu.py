@@ -59,7 +59,7 @@ def test_mamba_model_pass_vs_reference(eig):
         np.testing.assert_array_equal(ph, O.threshold_analysis(np.arctan2(e.imag, e.real) * 180 / np.pi, O.THRESHOLDS_PHASE))
 
 
-@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp"])
+@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp", "model_smattn"])
 def test_transformer_model_pass_vs_reference(eig, name):
     A, Ly, E, S = eig
     sd, cfg, g = golden_model(name)
@@ -73,6 +73,8 @@ def test_transformer_model_pass_vs_reference(eig, name):
         assert np.abs(x.cpu().numpy() - ref).max() <= 3e-5 * np.abs(ref).max(), "block %d" % i
         if cfg["attention_fn"] == "lin-attention":
             eta = E.get_eig_att_linear(x, layer, cfg["state_dim"], cfg["num_heads"], cfg["hidden_dim"])
+        elif cfg["attention_fn"] == "sm-attention":
+            eta = E.get_eig_att_softmax(x, layer, cfg["state_dim"], cfg["num_heads"], cfg["hidden_dim"])
         else:
             eta = E.get_eig_att_norm(x, layer, cfg["state_dim"], cfg["num_heads"], cfg["hidden_dim"], cfg)
         r = g["eig"][..., i:i + 1]
