@@ -143,7 +143,8 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     return {"workload": "C2 mamba2-mqar: T=512 d_model=128 heads=1 d_state=16 conv=4 glu prenorm layers=4 vocab=8192",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "seq_len": SEQ_LEN, "parallelism": "batch-sharded x%d" % world,
-            "l2": "inputs larger than L2 (activations 1.07 GB per layer per GPU)", "gemm": args.gemm}
+            "l2": "inputs larger than L2 (activations 1.07 GB per layer per GPU)", "gemm": args.gemm,
+            "launch": "cuda-graph replay" if args.graph else "eager"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -175,15 +176,20 @@ def run_eigb200(args, rank, local, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph = A.MambaPassGraph(model, X, want_eig=True) if args.graph else None
+
+    def run_pass(Xd):
+        return graph.run(Xd) if graph is not None else A.mamba_pass(model, Xd, want_eig=True)
+
     def step_resident():
-        res = A.mamba_pass(model, X, want_eig=True)
+        res = run_pass(None) if graph is not None else A.mamba_pass(model, X, want_eig=True)
         if world > 1:
             D.allreduce_moments(*ops.count_moments(res.counts.reshape(nl * Bsz, H, ops.NSLOT)))     # the one exchange step (statistics only)
         return res
 
     def step_e2e():
         Xd = X_host.to(dev, non_blocking=True)
-        res = A.mamba_pass(model, Xd, want_eig=True)
+        res = run_pass(Xd)
         eig_host.copy_(res.eig, non_blocking=True)
         counts_host.copy_(res.counts, non_blocking=True)
         if world > 1:
@@ -221,7 +227,7 @@ def run_eigb200(args, rank, local, world):
 
     # ---- per-kernel durations (CUDA events around every C-ABI call of one more step) -> roofline of the dominant kernel --
     ops.PROFILE = []
-    step_resident()
+    A.mamba_pass(model, X, want_eig=True)                          # eager (not the graph): one event pair per C-ABI call
     torch.cuda.synchronize()
     per = {}
     for name, s0, s1 in ops.PROFILE:
@@ -238,31 +244,38 @@ def run_eigb200(args, rank, local, world):
     pk = peaks()
     D_, N_ = cfg["hidden_dim"], cfg["state_dim"]
     d_in = D_ + 2 * N_ + H
+    ldz = (d_in + 7) // 8 * 8                                    # in_proj rows are padded to 32 bytes (layers._pad8)
     tokens = Bsz * T
-    alg = {"eigb200_mamba2_eig": tokens * (D_ * 4 + 4 * H), "eigb200_mamba_conv_ssd": tokens * (d_in + D_) * 4,
-           "eigb200_layernorm": tokens * 2 * D_ * 4, "eigb200_embedding": tokens * (8 + D_ * 4)}
-    # the three nn.Linear per layer: (K + Nout) floats per row (+ residual row for the GLU), and their 3xTF32 / FFMA flops
-    lin_bytes = [tokens * (D_ + d_in) * 4, tokens * 2 * D_ * 4, tokens * 3 * D_ * 4]
-    lin_flops = [2.0 * tokens * D_ * d_in, 2.0 * tokens * D_ * D_, 2.0 * tokens * D_ * 2 * D_]
+    # ALGORITHMIC bytes per launch of every C-ABI call of the step: operands read once, results written once, fp32.
+    # GEMMs are recorded per shape: all three are memory-bound at K = 128 (36-64 fp32 flop per byte, below the tensor ridge), so their
+    # roofline is HBM; the fp32-equivalent tensor rate is reported next to it.
+    alg = {"eigb200_mamba2_eig": tokens * (D_ * 4 + 4 * H + 8), "eigb200_mamba_conv_ssd": tokens * (d_in + D_) * 4,
+           "eigb200_layernorm": tokens * 2 * D_ * 4, "eigb200_embedding": tokens * (8 + D_ * 4), "eigb200_embedding_stats": tokens * (8 + D_ * 4 + 8),
+           "eigb200_linear_ln[N%d K%d none]" % (d_in, D_): tokens * (D_ + d_in) * 4 + tokens * 8,
+           "eigb200_linear[N%d K%d none]" % (d_in, D_): tokens * (D_ + d_in) * 4,
+           "eigb200_linear[N%d K%d gelu]" % (D_, D_): tokens * 2 * D_ * 4,
+           "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): tokens * 3 * D_ * 4}
+    flops = {"eigb200_linear_ln[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in, "eigb200_linear[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in,
+             "eigb200_linear[N%d K%d gelu]" % (D_, D_): 2.0 * tokens * D_ * D_, "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_}
     totals = {k: sum(v) for k, v in per.items()}
     step_total = sum(totals.values())
     dom = max(totals, key=totals.get)
     dom_avg_ms = totals[dom] / len(per[dom])
-    if dom == "eigb200_linear":
-        nlin = len(per[dom])
-        flops = sum(lin_flops) * nl / nlin                       # fp32-equivalent flops per launch (averaged over the 3 shapes)
-        achieved = flops / (dom_avg_ms * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-                "traffic": None, "peak_kind": pk["kind"] + " bf16 sustained", "share_of_step": totals[dom] / step_total,
-                "hbm_GBps": sum(lin_bytes) * nl / nlin / (dom_avg_ms * 1e-3) / 1e9}
-    else:
-        achieved = alg[dom] / (dom_avg_ms * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                "traffic": None, "peak_kind": pk["kind"] + " copy", "share_of_step": totals[dom] / step_total}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per launch from the committed ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    achieved = alg.get(dom, 0) / (dom_avg_ms * 1e-3) / 1e9
+    roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+            "traffic": traffic, "peak_kind": pk["kind"] + " copy (MEASURED_PEAKS.json hbm_gbs)", "share_of_step": totals[dom] / step_total,
+            "algorithmic_bytes_per_launch": alg.get(dom), "avg_launch_ms": dom_avg_ms}
+    if dom in flops:
+        roof["fp32_equiv_TFLOPs"] = flops[dom] / (dom_avg_ms * 1e-3) / 1e12
     kernels = {k: {"launches_per_step": len(v), "ms_per_step": sum(v)} for k, v in per.items()}
     for k in kernels:
         if k in alg:
             kernels[k]["GBps_alg"] = alg[k] * len(per[k]) / (kernels[k]["ms_per_step"] * 1e-3) / 1e9
+            kernels[k]["frac_of_hbm_peak"] = kernels[k]["GBps_alg"] / pk["hbm"]
 
     value = n_eig * world * args.steps / (ms * 1e-3)
     e2e_val = n_eig * world * args.steps / (e2e_ms * 1e-3)
@@ -293,6 +306,7 @@ def main():
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc3", "tc1"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="sequences in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "eigb200":
         args.warmup = 3                                            # timing rule: W >= 3
@@ -305,6 +319,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the eigb200 path has no CPU fallback (use --impl reference for the host baseline)")
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("EIGB200_NCCL_DEBUG", "WARN")   # NCCL_DEBUG=VERSION prints to stdout: keep it to the ONE JSON line
         import eigb200.dist as D
         D.init_from_env("nccl")
     try:

@@ -695,6 +695,13 @@ def transformer_block_forward(x, p, cfg, dtype=np.float64):
     elif mixer == "mlp":
         y = gelu_erf(y @ np.asarray(p["mixer.encoder.weight"], dtype).T + np.asarray(p["mixer.encoder.bias"], dtype))
         y = y @ np.asarray(p["mixer.decoder.weight"], dtype).T + np.asarray(p["mixer.decoder.bias"], dtype)
+    elif mixer == "hybrid":                                        # LAMBDA, models/common.py:60-84
+        xz = y @ np.asarray(p["mixer.encoder.weight"], dtype).T + np.asarray(p["mixer.encoder.bias"], dtype)
+        a = sigmoid(np.asarray(p["mixer.alpha"], dtype).reshape(()))
+        Dm = xz.shape[-1] // 2
+        g = xz[..., :Dm] * sigmoid(xz[..., Dm:])
+        m = gelu_erf(xz) @ np.asarray(p["mixer.decoder.weight"], dtype).T + np.asarray(p["mixer.decoder.bias"], dtype)
+        y = a * g + (1 - a) * m
     else:
         raise NotImplementedError(mixer)
     return (x + y) * silu(z) if z is not None else x + y

@@ -244,10 +244,20 @@ class TransformerBlockDev:
                                          decoder=_Lin(_dev(sd, prefix + "mixer.decoder.weight", device), _dev(sd, prefix + "mixer.decoder.bias", device)))
         elif self.mixer_kind == "glu":
             self.mixer = SimpleNamespace(linear=_Lin(_dev(sd, prefix + "mixer.linear.weight", device), _dev(sd, prefix + "mixer.linear.bias", device)))
+        elif self.mixer_kind == "hybrid":
+            # LAMBDA (models/common.py:60-84): a * glu(xz) + (1 - a) * decoder(gelu(xz)), xz = encoder(y), a = sigmoid(alpha).  The scalar blend is
+            # folded into the weights once: value rows of the encoder scaled by a (GLU epilogue then yields a * glu), decoder scaled by 1 - a.
+            enc_w, enc_b = _dev(sd, prefix + "mixer.encoder.weight", device), _dev(sd, prefix + "mixer.encoder.bias", device)
+            dec_w, dec_b = _dev(sd, prefix + "mixer.decoder.weight", device), _dev(sd, prefix + "mixer.decoder.bias", device)
+            a = torch.sigmoid(_dev(sd, prefix + "mixer.alpha", device).reshape(()))
+            Dm = enc_w.shape[1]
+            sc = torch.cat([a.expand(Dm), torch.ones(Dm, device=enc_w.device)])
+            self.mixer = SimpleNamespace(encoder=_Lin(enc_w, enc_b), glu_scaled=_Lin((enc_w * sc[:, None]).contiguous(), (enc_b * sc).contiguous()),
+                                         decoder_scaled=_Lin((dec_w * (1 - a)).contiguous(), (dec_b * (1 - a)).contiguous()))
         elif self.mixer_kind == "none":
             self.mixer = None
         else:
-            raise RuntimeError("{0} mixer not implemented yet!".format(self.mixer_kind))     # models/transformer.py:76-77 ("hybrid" unsupported here)
+            raise RuntimeError("{0} mixer not implemented yet!".format(self.mixer_kind))     # models/transformer.py:76-77
 
     def __call__(self, x):
         """TransformerBlock.forward (models/transformer.py:90-111): one LayerNorm reused for both sub-blocks."""
@@ -261,6 +271,10 @@ class TransformerBlockDev:
         x2 = x.reshape(B * T, D)
         if self.mixer_kind == "glu":
             out = ops.linear(y, self.mixer.linear.weight, self.mixer.linear.bias, epilogue="glu_residual", residual=x2)
+        elif self.mixer_kind == "hybrid":
+            part = ops.linear(y, self.mixer.glu_scaled.weight, self.mixer.glu_scaled.bias, epilogue="glu_residual", residual=x2)   # x + a * glu(xz)
+            hmid = ops.linear(y, self.mixer.encoder.weight, self.mixer.encoder.bias, epilogue="gelu")                             # gelu(xz)
+            out = ops.linear(hmid, self.mixer.decoder_scaled.weight, self.mixer.decoder_scaled.bias, epilogue="residual", residual=part)
         else:
             hmid = ops.linear(y, self.mixer.encoder.weight, self.mixer.encoder.bias, epilogue="gelu")
             out = ops.linear(hmid, self.mixer.decoder.weight, self.mixer.decoder.bias, epilogue="residual", residual=x2)
@@ -370,6 +384,11 @@ def init_transformer_state_dict(cfg, seed: Optional[int] = None) -> Dict[str, to
         elif cfg["mixer"] == "glu":
             gl = nn.Linear(D, 2 * D)
             sd[p + "mixer.linear.weight"], sd[p + "mixer.linear.bias"] = gl.weight.detach(), gl.bias.detach()
+        elif cfg["mixer"] == "hybrid":                                                              # LAMBDA(hidden_dim, init=0.2), transformer.py:75-77
+            e = nn.Linear(D, 2 * D); dcd = nn.Linear(2 * D, D)
+            sd[p + "mixer.alpha"] = torch.ones(1) * (-math.log(1 / 0.2 - 1))
+            sd[p + "mixer.encoder.weight"], sd[p + "mixer.encoder.bias"] = e.weight.detach(), e.bias.detach()
+            sd[p + "mixer.decoder.weight"], sd[p + "mixer.decoder.bias"] = dcd.weight.detach(), dcd.bias.detach()
         sd[p + "norm.weight"], sd[p + "norm.bias"] = torch.ones(D), torch.zeros(D)
     if cfg["classifier"]:
         if cfg["mixer_dim"] != 0:

@@ -54,16 +54,21 @@ LAUNCHES = {"n": 0}          # C-ABI compute calls enqueued through this module 
 PROFILE = None               # set to a list to record (name, start_event, end_event) per call (bench.py roofline leg)
 
 
-def _call(lib, name, stream, *args):
-    """One C-ABI call: enqueue on `stream`, raise on a non-zero status, count it, optionally bracket it with CUDA events."""
+def _call(lib, name, stream, *args, tag=None):
+    """One C-ABI call: enqueue on `stream`, raise on a non-zero status, count it, optionally bracket it with CUDA events
+    (recorded under `name` or `name[tag]`, e.g. the GEMM shape, so that bench.py can attribute time to ONE kernel configuration)."""
     fn = getattr(lib, name)
+    if PROFILE is not None and tag:
+        name_rec = "%s[%s]" % (name, tag)
+    else:
+        name_rec = name
     if PROFILE is not None:
         ext = torch.cuda.ExternalStream(stream.value) if stream.value else torch.cuda.default_stream()
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
         s0.record(ext)
         rc = fn(stream, *args)
         s1.record(ext)
-        PROFILE.append((name, s0, s1))
+        PROFILE.append((name_rec, s0, s1))
     else:
         rc = fn(stream, *args)
     L.check(rc, name)
@@ -319,7 +324,7 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
         ldr = residual.stride(-2) if residual.dim() >= 2 else nout
     ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
     _call(lib, "eigb200_linear", _stream(a), _p(a2), lda, _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
-                               EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb)
+                               EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb, tag="N%d K%d %s" % (N, K, epilogue))
     return out
 
 
@@ -351,7 +356,8 @@ def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residua
     ldr = residual.stride(-2) if residual is not None else 0
     ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
     _call(lib, "eigb200_linear_ln", _stream(a), _p(a), K, _p(_prep(stats, torch.float32)), _p(_prep(gamma, torch.float32)),
-          _p(_prep(beta, torch.float32)), _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K, EPILOGUES[epilogue], _p(ws), wsb)
+          _p(_prep(beta, torch.float32)), _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K, EPILOGUES[epilogue], _p(ws), wsb,
+          tag="N%d K%d %s" % (N, K, epilogue))
     return out
 
 

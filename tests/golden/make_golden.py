@@ -338,6 +338,7 @@ def _gold_transformer_models(ns, only=None):
                                    approx_fn="none", scale_B=True, offset=False, offset_init="uniform", learn_A=False, dim_conv=0,
                                    max_pos_embed=0),
         "model_smattn": dict(base, attention_fn="sm-attention", mixer="mlp"),
+        "model_linattn_hybrid": dict(base, attention_fn="lin-attention", mixer="hybrid"),
     }
     for name, c in variants.items():
         if only is not None and name not in only:
@@ -417,9 +418,9 @@ def gold_report_files():
 
 
 if __name__ == "__main__":
-    if "--only-smattn" in sys.argv:                 # add the softmax-attention model without touching the other vectors
+    if "--only-models" in sys.argv:                 # (re)generate the named transformer models without touching the other vectors
         MANIFEST.update(json.load(open(os.path.join(OUT, "MANIFEST.json"))))
-        gold_models(only=["model_smattn"])
+        gold_models(only=sys.argv[sys.argv.index("--only-models") + 1].split(","))
         with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
             json.dump(MANIFEST, f, indent=1, sort_keys=True)
         sys.exit(0)

@@ -117,3 +117,18 @@ def test_eval_eig_ssm_branch(A, tmp_path, monkeypatch, kind):
     np.testing.assert_array_equal(pct, O.threshold_analysis_ssm(rad, O.THRESHOLDS_RADIUS))
     np.testing.assert_array_equal(pct_ph, O.threshold_analysis_ssm(ph, O.THRESHOLDS_PHASE))
     assert open(tmp_path / "percentage_file.txt").read().startswith("threshold radius:")
+
+
+def test_mamba_pass_graph_replay_matches_eager(A):
+    """The CUDA-graph replay of a pass gives bit-identical eigenvalues and counts to the eager launches, also for a new batch."""
+    import eigb200.layers as Ly
+    sd, cfg, g = golden_model("model_mamba2")
+    model = Ly.MambaDev(cfg, {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, "cuda")
+    X = torch.from_numpy(g["X"]).cuda()
+    gp = A.MambaPassGraph(model, X)
+    for Xb in (X, torch.flip(X, dims=[0]), X.roll(3, dims=1)):
+        ref = A.mamba_pass(model, Xb)
+        res = gp.run(Xb)
+        torch.cuda.synchronize()
+        assert torch.equal(res.eig, ref.eig) and torch.equal(res.counts, ref.counts)
+    assert gp.launches_per_run > 0

@@ -59,7 +59,7 @@ def test_mamba_model_pass_vs_reference(eig):
         np.testing.assert_array_equal(ph, O.threshold_analysis(np.arctan2(e.imag, e.real) * 180 / np.pi, O.THRESHOLDS_PHASE))
 
 
-@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp", "model_smattn"])
+@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp", "model_smattn", "model_linattn_hybrid"])
 def test_transformer_model_pass_vs_reference(eig, name):
     A, Ly, E, S = eig
     sd, cfg, g = golden_model(name)

@@ -143,7 +143,7 @@ def _tf_cfg(cfg):
     return c
 
 
-@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp", "model_smattn"])
+@pytest.mark.parametrize("name", ["model_linattn", "model_linattn_glu_conv", "model_normattn", "model_normattn_exp", "model_smattn", "model_linattn_hybrid"])
 def test_transformer_model_pass(name):
     sd, cfg, g = golden_model(name)
     eig, x = O.transformer_eval_pass(g["X"], sd, _tf_cfg(cfg), np.float64)
