@@ -383,6 +383,236 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v2_kernel(const SsdParams p
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// v3: v2 with the per-token bookkeeping strength-reduced (the v2 loop issued ~98 instructions per channel-token for 48 FMA-pipe operations):
+//   * two channels per thread, 4 tokens per group: the conv window and the x pipeline are indexed statically inside the unrolled group (history
+//     rotates once per 4 tokens, not per token), x / y are addressed with running pointers, and every chunk whose tokens and prefetches are all
+//     in range runs a guard-free copy of the loop (GUARD = false); only the last chunk of a sequence takes the predicated copy;
+//   * the raw [B|C] rows of the next chunk go global -> shared with cp.async (zero-fill for rows outside the sequence) instead of through
+//     20 registers held across the serial phase;
+//   * x is prefetched one whole group (4 tokens) ahead.
+// Same arithmetic, same order of operations as v2 (bit-identical results).
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int N, int NT, int MINB, bool CONV>
+__global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p) {
+  constexpr int TC = SSD2_TC, GT = 4;                              // tokens per chunk / per unrolled group
+  constexpr int RAW_ROWS = TC + SSD_HIST;
+  constexpr int F4_PER_ROW = 2 * N / 4;
+  constexpr int RAW_F4 = RAW_ROWS * F4_PER_ROW;
+  constexpr int RAW_PER_T = (RAW_F4 + NT - 1) / NT;
+  constexpr int PREP_PER_T = TC * 2 * N / NT;
+  static_assert((TC * 2 * N) % NT == 0 && NT % (2 * N) == 0 && TC % GT == 0, "prep / group mapping");
+  __shared__ __align__(16) float raw_s[RAW_ROWS][2 * N];
+  __shared__ __align__(16) float bc_s[2][TC][2 * N];
+  __shared__ __align__(8) float2 dd_s[2][TC];
+
+  const int P = p.P;
+  const int b = blockIdx.z, h = blockIdx.y, pblk = blockIdx.x;
+  const int g = h / (p.H / p.G);
+  const int tid = threadIdx.x;
+  const int pch = pblk * (NT * 2) + tid * 2;                       // P % (2 NT) == 0: every thread owns two valid channels
+  const int HP = p.H * P, GN = p.G * N;
+  constexpr bool conv = CONV;                                      // compile-time: no per-token branch around the window FMAs
+  const float Ah = p.fused ? -expf(p.A[h]) : p.A[h];
+  const float Dh = p.D ? p.D[h] : 0.f;
+  const float dtb = p.fused ? p.dt_bias[h] : 0.f;
+  const int64_t T = p.T;
+
+  float cw[2][4], cb[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    cw[c][0] = cw[c][1] = cw[c][2] = 0.f; cw[c][3] = 1.f; cb[c] = 0.f;
+    if (conv) {
+      const int ch = h * P + pch + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cw[c][j] = (j >= 4 - p.kconv) ? p.conv_w[(size_t)ch * p.kconv + j - (4 - p.kconv)] : 0.f;
+      cb[c] = p.conv_b[ch];
+    }
+  }
+  const int bc_col = tid % (2 * N);
+  float bw[4] = {0.f, 0.f, 0.f, 1.f}, bbias = 0.f;
+  if (conv) {
+    const int ch = HP + (bc_col < N ? g * N + bc_col : GN + g * N + (bc_col - N));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bw[j] = (j >= 4 - p.kconv) ? p.conv_w[(size_t)ch * p.kconv + j - (4 - p.kconv)] : 0.f;
+    bbias = p.conv_b[ch];
+  }
+
+  float s[2][N];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[c][i] = 0.f;
+  float2 hist[3];                                                  // raw x of the 3 tokens before the current group (.x / .y = the two channels)
+  hist[0] = hist[1] = hist[2] = make_float2(0.f, 0.f);
+
+  const size_t rowbase = (size_t)b * p.T;
+  const size_t ldx = (size_t)p.ldx, ldy = (size_t)p.ldy;
+  const float* xpre = p.x + rowbase * ldx + (size_t)h * P + pch;   // next token to prefetch
+  float* yptr = p.y + rowbase * ldy + (size_t)h * P + pch;         // next token to store
+  const float* bgp = p.Bm + (size_t)g * N;
+  const float* cgp = p.Cm + (size_t)g * N;
+
+  auto raw_async = [&](int64_t t0) {                               // rows [t0-3, t0+TC) of [B|C] -> raw_s, zero-filled outside the sequence
+#pragma unroll
+    for (int k = 0; k < RAW_PER_T; ++k) {
+      const int e = tid + k * NT;
+      if (e < RAW_F4) {
+        const int r = e / F4_PER_ROW, q = e - r * F4_PER_ROW;
+        const int64_t t = t0 - SSD_HIST + r;
+        const bool ok = t >= 0 && t < T;
+        const int64_t tc_ = ok ? t : 0;
+        const float* src = (q < N / 4) ? bgp + (rowbase + tc_) * p.ldbc + 4 * q : cgp + (rowbase + tc_) * p.ldbc + 4 * (q - N / 4);
+        cp_async_16_zfill(reinterpret_cast<float4*>(&raw_s[0][0]) + e, src, ok);
+      }
+    }
+  };
+  float dtreg = 0.f;
+  auto dt_fetch = [&](int64_t t0) {
+    if (tid < TC && t0 + tid < T) dtreg = __ldg(p.dt + (rowbase + t0 + tid) * p.lddt + h);
+  };
+  auto prep = [&](int buf, int tc) {
+#pragma unroll
+    for (int k = 0; k < PREP_PER_T; ++k) {
+      const int e = tid + k * NT;
+      const int r = e / (2 * N);
+      float v;
+      if (conv) {
+        v = fmaf(bw[3], raw_s[r + 3][bc_col], fmaf(bw[2], raw_s[r + 2][bc_col], fmaf(bw[1], raw_s[r + 1][bc_col], fmaf(bw[0], raw_s[r][bc_col], bbias))));
+        v = silu_fast_f(v);
+      } else v = raw_s[r + 3][bc_col];
+      bc_s[buf][r][bc_col] = v;
+    }
+    if (tid < tc) {
+      const float d = p.fused ? softplus_f(dtreg + dtb) : dtreg;
+      dd_s[buf][tid] = make_float2(d, expf(d * Ah));
+    }
+  };
+
+  // one token: conv + SiLU of the two x channels, state update, output
+  auto token = [&](int buf, int tt, float2 x0, float2 xm1, float2 xm2, float2 xm3, float* yp) {
+    const float2 dd = dd_s[buf][tt];
+    const float xin[2] = {x0.x, x0.y}, a1[2] = {xm1.x, xm1.y}, a2[2] = {xm2.x, xm2.y}, a3[2] = {xm3.x, xm3.y};
+    float xcv[2], uu[2], acc[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float xv = xin[c];
+      if (conv) {
+        xv = fmaf(cw[c][3], xin[c], fmaf(cw[c][2], a1[c], fmaf(cw[c][1], a2[c], fmaf(cw[c][0], a3[c], cb[c]))));
+        xv = silu_fast_f(xv);
+      }
+      xcv[c] = xv; uu[c] = xv * dd.x;
+      acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    }
+    const float4* B4 = reinterpret_cast<const float4*>(&bc_s[buf][tt][0]);
+    const float4* C4 = reinterpret_cast<const float4*>(&bc_s[buf][tt][N]);
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 bv = B4[q], cv = C4[q];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        s[c][4 * q + 0] = fmaf(dd.y, s[c][4 * q + 0], uu[c] * bv.x); acc[c][0] = fmaf(cv.x, s[c][4 * q + 0], acc[c][0]);
+        s[c][4 * q + 1] = fmaf(dd.y, s[c][4 * q + 1], uu[c] * bv.y); acc[c][1] = fmaf(cv.y, s[c][4 * q + 1], acc[c][1]);
+        s[c][4 * q + 2] = fmaf(dd.y, s[c][4 * q + 2], uu[c] * bv.z); acc[c][2] = fmaf(cv.z, s[c][4 * q + 2], acc[c][2]);
+        s[c][4 * q + 3] = fmaf(dd.y, s[c][4 * q + 3], uu[c] * bv.w); acc[c][3] = fmaf(cv.w, s[c][4 * q + 3], acc[c][3]);
+      }
+    }
+    const float y0 = fmaf(Dh, xcv[0], (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]));
+    const float y1 = fmaf(Dh, xcv[1], (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]));
+    *reinterpret_cast<float2*>(yp) = make_float2(y0, y1);
+  };
+
+  // x pipeline: the GT tokens of the current group in registers, the next group in flight
+  float2 xcur[GT];
+#pragma unroll
+  for (int j = 0; j < GT; ++j) xcur[j] = (j < T) ? ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx)) : make_float2(0.f, 0.f);
+  xpre += GT * ldx;
+
+  raw_async(0); dt_fetch(0);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  prep(0, (int)min((int64_t)TC, T));
+  __syncthreads();
+
+  int buf = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += TC, buf ^= 1) {
+    const int tc = (int)min((int64_t)TC, T - t0);
+    const bool more = t0 + TC < T;
+    if (more) { raw_async(t0 + TC); dt_fetch(t0 + TC); }           // next chunk's shared operands: in flight during the serial phase
+    if (t0 + TC + GT <= T) {
+      // ---- guard-free serial phase: every token of the chunk and every prefetch is inside the sequence --------------------------
+#pragma unroll 1
+      for (int gi = 0; gi < TC / GT; ++gi) {
+        float2 xn[GT];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) xn[j] = ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx));
+        xpre += GT * ldx;
+        token(buf, gi * GT + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
+        token(buf, gi * GT + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
+        token(buf, gi * GT + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
+        token(buf, gi * GT + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
+        yptr += GT * ldy;
+        hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) xcur[j] = xn[j];
+      }
+    } else {
+      // ---- last chunk(s): predicated copy ------------------------------------------------------------------------------------------
+#pragma unroll 1
+      for (int gi = 0; gi < TC / GT; ++gi) {
+        const int64_t tn = t0 + (int64_t)(gi + 1) * GT;             // first token of the next group
+        float2 xn[GT];
+#pragma unroll
+        for (int j = 0; j < GT; ++j)
+          xn[j] = (tn + j < T) ? ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx)) : make_float2(0.f, 0.f);
+        xpre += GT * ldx;
+        const int tt = gi * GT;
+        if (tt + 0 < tc) token(buf, tt + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
+        if (tt + 1 < tc) token(buf, tt + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
+        if (tt + 2 < tc) token(buf, tt + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
+        if (tt + 3 < tc) token(buf, tt + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
+        yptr += GT * ldy;
+        hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) xcur[j] = xn[j];
+      }
+    }
+    if (more) {
+      cp_async_commit_wait_all();                                  // raw_s was last read by prep() of this chunk, before the serial phase
+      __syncthreads();
+      prep(buf ^ 1, (int)min((int64_t)TC, T - (t0 + TC)));
+      __syncthreads();
+    }
+  }
+  if (p.final_state) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float* fs = p.final_state + (((size_t)b * p.H + h) * P + pch + c) * N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) fs[i] = s[c][i];
+    }
+  }
+}
+
+template <int N, int NT, int MINB>
+static int launch_ssd_v3(cudaStream_t st, const SsdParams& p, int64_t B) {
+  dim3 grid(p.P / (NT * 2), p.H, (unsigned)B);
+  if (p.fused && p.kconv > 0) ssd_scan_v3_kernel<N, NT, MINB, true><<<grid, NT, 0, st>>>(p);
+  else ssd_scan_v3_kernel<N, NT, MINB, false><<<grid, NT, 0, st>>>(p);
+  EIGB_LAUNCH_CHECK("ssd_scan_v3_kernel");
+  return EIGB200_OK;
+}
+
 template <int N, int CPT, int NT, int U = 8, int MINB = 1>
 static int launch_ssd_v2(cudaStream_t st, const SsdParams& p, int64_t B) {
   dim3 grid((p.P + NT * CPT - 1) / (NT * CPT), p.H, (unsigned)B);
@@ -413,6 +643,7 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
       if (const char* var = getenv("EIGB200_SSD_VARIANT")) {        // tuning hook (tools/kbench.py); N = 16 only
         if (p.N == 16 && p.P % 2 == 0 && cpt == 2) {
           switch (atoi(var)) {
+            case 30: return launch_ssd_v2<16, 2, 64, 2, 8>(st, p, B);                  // the previous default
             case 1: return launch_ssd_v2<16, 2, 64, 4, 1>(st, p, B);
             case 2: return launch_ssd_v2<16, 2, 64, 8, 6>(st, p, B);
             case 3: return launch_ssd_v2<16, 2, 64, 4, 6>(st, p, B);
@@ -420,6 +651,10 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
             case 5: return launch_ssd_v2<16, 1, 128, 8, 1>(st, p, B);
             case 6: return launch_ssd_v2<16, 1, 128, 4, 4>(st, p, B);
             case 7: return launch_ssd_v2<16, 2, 64, 2, 8>(st, p, B);
+            case 20: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 8>(st, p, B); break;
+            case 21: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 6>(st, p, B); break;
+            case 22: if (p.P % 64 == 0) return launch_ssd_v3<16, 32, 12>(st, p, B); break;
+            case 23: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 7>(st, p, B); break;
             case 8: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 2, 8>(st, p, B); break;
             case 9: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 4, 4>(st, p, B); break;
             case 10: if (p.P % 4 == 0 && p.ldx % 4 == 0 && p.ldy % 4 == 0) return launch_ssd_v2<16, 4, 32, 2, 12>(st, p, B); break;
@@ -429,7 +664,9 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
         }
       }
 #define SSD2_CASE(N_)                                                                                                       \
-      case N_:   /* U = 2, >= 8 CTAs/SM: measured best at C2 (occupancy beats prefetch depth, profiles/kbench_r1.md) */        \
+      case N_:   /* v3 (strength-reduced loop) when the channels tile exactly; else v2 with U = 2, >= 8 CTAs/SM */                \
+        if (cpt == 2 && p.P % 128 == 0) return launch_ssd_v3<N_, 64, 8>(st, p, B);                                              \
+        if (cpt == 2 && p.P % 64 == 0) return launch_ssd_v3<N_, 32, 8>(st, p, B);                                               \
         if (cpt == 2) return wide ? launch_ssd_v2<N_, 2, 64, 2, 8>(st, p, B) : launch_ssd_v2<N_, 2, 32, 2, 8>(st, p, B);        \
         return wide ? launch_ssd_v2<N_, 1, 64, 4, 8>(st, p, B) : launch_ssd_v2<N_, 1, 32, 4, 8>(st, p, B);
       switch (p.N) { SSD2_CASE(16) SSD2_CASE(8) SSD2_CASE(4) default: break; }

@@ -79,7 +79,8 @@ def test_ssd_scan_golden(ops):
     assert np.abs(y - g["y_fla"]).max() <= 2e-5 * np.abs(ref).max()          # third-party (fla) output
 
 
-@pytest.mark.parametrize("B,T,H,P,G,N", [(3, 70, 1, 128, 1, 16), (2, 33, 4, 16, 2, 8), (2, 40, 2, 64, 1, 128), (1, 96, 8, 8, 1, 64), (2, 20, 3, 20, 1, 4)])
+@pytest.mark.parametrize("B,T,H,P,G,N", [(3, 70, 1, 128, 1, 16), (2, 33, 4, 16, 2, 8), (2, 40, 2, 64, 1, 128), (1, 96, 8, 8, 1, 64), (2, 20, 3, 20, 1, 4),
+                                          (2, 512, 2, 128, 1, 16), (1, 37, 1, 64, 1, 8), (2, 3, 1, 256, 1, 16), (1, 64, 2, 64, 2, 4), (1, 100, 1, 128, 1, 16)])
 def test_ssd_scan_shapes(ops, B, T, H, P, G, N):
     rng = np.random.default_rng(T + N)
     x = rng.normal(size=(B, T, H, P)).astype(np.float32)
@@ -94,10 +95,11 @@ def test_ssd_scan_shapes(ops, B, T, H, P, G, N):
     assert np.abs(fs.cpu().numpy() - st).max() <= 1e-5 * np.abs(st).max() + 1e-7
 
 
+@pytest.mark.parametrize("P,T", [(32, 75), (128, 75), (128, 256), (64, 33)])
 @pytest.mark.parametrize("kconv", [4, 2, 0])
-def test_mamba_conv_ssd_fused(ops, kconv):
+def test_mamba_conv_ssd_fused(ops, kconv, P, T):
     rng = np.random.default_rng(kconv)
-    B, T, H, P, G, N = 3, 75, 2, 32, 1, 16
+    B, H, G, N = 3, 2, 1, 16
     C_ = H * P + 2 * G * N
     ldz = (C_ + H + 3) // 4 * 4
     z = rng.normal(size=(B, T, ldz)).astype(np.float32)
