@@ -533,9 +533,12 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
   };
 
   // x pipeline: the GT tokens of the current group in registers, the next group in flight
-  float2 xcur[GT];
+  float2 xcur[GT], xnx[GT];                                        // current group, next group; the group after that is loaded inside the loop
 #pragma unroll
   for (int j = 0; j < GT; ++j) xcur[j] = (j < T) ? ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx)) : make_float2(0.f, 0.f);
+  xpre += GT * ldx;
+#pragma unroll
+  for (int j = 0; j < GT; ++j) xnx[j] = (GT + j < T) ? ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx)) : make_float2(0.f, 0.f);
   xpre += GT * ldx;
 
   raw_async(0); dt_fetch(0);
@@ -549,13 +552,13 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
     const int tc = (int)min((int64_t)TC, T - t0);
     const bool more = t0 + TC < T;
     if (more) { raw_async(t0 + TC); dt_fetch(t0 + TC); }           // next chunk's shared operands: in flight during the serial phase
-    if (t0 + TC + GT <= T) {
+    if (t0 + TC + 2 * GT <= T) {
       // ---- guard-free serial phase: every token of the chunk and every prefetch is inside the sequence --------------------------
 #pragma unroll 1
       for (int gi = 0; gi < TC / GT; ++gi) {
         float2 xn[GT];
 #pragma unroll
-        for (int j = 0; j < GT; ++j) xn[j] = ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx));
+        for (int j = 0; j < GT; ++j) xn[j] = ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx));   // two groups (8 tokens) ahead
         xpre += GT * ldx;
         token(buf, gi * GT + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
         token(buf, gi * GT + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
@@ -564,13 +567,13 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
         yptr += GT * ldy;
         hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
 #pragma unroll
-        for (int j = 0; j < GT; ++j) xcur[j] = xn[j];
+        for (int j = 0; j < GT; ++j) { xcur[j] = xnx[j]; xnx[j] = xn[j]; }
       }
     } else {
       // ---- last chunk(s): predicated copy ------------------------------------------------------------------------------------------
 #pragma unroll 1
       for (int gi = 0; gi < TC / GT; ++gi) {
-        const int64_t tn = t0 + (int64_t)(gi + 1) * GT;             // first token of the next group
+        const int64_t tn = t0 + (int64_t)(gi + 2) * GT;             // first token of the group being prefetched
         float2 xn[GT];
 #pragma unroll
         for (int j = 0; j < GT; ++j)
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
         yptr += GT * ldy;
         hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
 #pragma unroll
-        for (int j = 0; j < GT; ++j) xcur[j] = xn[j];
+        for (int j = 0; j < GT; ++j) { xcur[j] = xnx[j]; xnx[j] = xn[j]; }
       }
     }
     if (more) {
