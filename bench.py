@@ -13,7 +13,8 @@ block's output (analysis/eval_eig.py:575-618).  One "eigenvalue" = one element o
 
 value   : whole-job eigenvalues/s with the token ids already resident in HBM (CUDA events, max over ranks).
 e2e     : the same through the public API with HOST buffers: pinned token ids -> device, the pass, eigenvalue array + bin counts ->
-          pinned host memory, inside the timed region, every step.
+          pinned host memory, inside the timed region, every step.  Two batches are in flight (two captured passes, uploads and downloads on
+          their own streams), so the PCIe transfers of one step overlap the kernels of the next; `--no-graph` runs it strictly serially.
 roofline: dominant kernel of the step, algorithmic bytes / its event-timed duration, against MEASURED_PEAKS.json.
 """
 from __future__ import annotations
@@ -133,7 +134,7 @@ def run_reference(args, rank, world):
     eps, sec = cpu_pass_eigs_per_s(cfg, sample_b, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": eps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), launch="host threads (torch CPU)"),
             "cpu_baseline": {"value": eps, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d sequences x T=%d x %d layers per step (throughput is batch-linear)" % (sample_b, SEQ_LEN, cfg["num_layers"])},
             "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -215,14 +216,57 @@ def run_eigb200(args, rank, local, world):
     launches = ops.LAUNCHES["n"]
 
     # ---- end to end with host buffers ----------------------------------------------------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # Every step copies ITS token ids from pinned host memory and brings ITS eigenvalue array + bin counts back to pinned host memory.  With the
+    # graph path two batches are in flight (two captured passes with their own static buffers, copies on a second stream), so the PCIe
+    # transfers of step i overlap the kernels of step i+1; --no-graph runs the strictly serial copy -> pass -> copy -> sync loop.
+    if graph is not None:
+        graphs = [graph, A.MambaPassGraph(model, X, want_eig=True)]
+        eig_hosts = [eig_host, torch.empty_like(eig_host).pin_memory()]
+        cnt_hosts = [counts_host, torch.empty_like(counts_host).pin_memory()]
+        h2d_stream = torch.cuda.Stream(); d2h_stream = torch.cuda.Stream()   # separate queues: an upload must not wait behind the previous download
+        main = torch.cuda.current_stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]; ev_done = [torch.cuda.Event() for _ in range(2)]; ev_out = [torch.cuda.Event() for _ in range(2)]
+        started = [False, False]
+
+        def e2e_pipelined(nsteps):
+            for i in range(nsteps):
+                k = i & 1
+                gk = graphs[k]
+                with torch.cuda.stream(h2d_stream):
+                    if started[k]:
+                        h2d_stream.wait_event(ev_done[k])        # the previous pass on these buffers has read its input
+                    gk.X.copy_(X_host, non_blocking=True)        # H2D of this step's token ids
+                    ev_in[k].record(h2d_stream)
+                main.wait_event(ev_in[k])
+                if started[k]:
+                    main.wait_event(ev_out[k])                   # the previous results of these buffers are on the host
+                res = gk.run(None)
+                if world > 1:
+                    D.allreduce_moments(*ops.count_moments(res.counts.reshape(nl * Bsz, H, ops.NSLOT)))
+                ev_done[k].record(main)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(ev_done[k])
+                    eig_hosts[k].copy_(res.eig, non_blocking=True)   # D2H of this step's results
+                    cnt_hosts[k].copy_(res.counts, non_blocking=True)
+                    ev_out[k].record(d2h_stream)
+                started[k] = True
+            torch.cuda.synchronize()
+
+        e2e_pipelined(max(2, args.warmup // 2))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_pipelined(args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    else:
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
     clocks = clocks_summary(proc, f, clk_path, local) if rank == 0 else None
 
     # ---- per-kernel durations (CUDA events around every C-ABI call of one more step) -> roofline of the dominant kernel --
@@ -283,7 +327,8 @@ def run_eigb200(args, rank, local, world):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": X_host.numel() * 8,
-                    "d2h_bytes_per_step": eig_host.numel() * 4 + counts_host.numel() * 4},
+                    "d2h_bytes_per_step": eig_host.numel() * 4 + counts_host.numel() * 4,
+                    "mode": "2 batches in flight (uploads and downloads on their own streams)" if args.graph else "serial copy-pass-copy"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
             "alg_bytes_per_eig": 2696, "e2e_path_frac_of_hbm": (2696.0 * n_eig / (ms / args.steps * 1e-3) / 1e9) / pk["hbm"]}
     if not args.no_cpu_baseline and world == 1:

@@ -183,6 +183,20 @@ extern "C" int eigb200_diag_scan(void* stream, const float* d_lam, const float* 
     return EIGB200_OK;
   }
   float* ws = nullptr;
+  {
+    // the chunk states come from the device's stream-ordered pool; keep freed blocks cached across synchronisation points (the default
+    // release threshold of 0 hands them back to the driver at every sync, which turns the next call's allocation into a cudaMalloc)
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    EIGB_CUDA(cudaGetDevice(&dev));
+    if (pool_ready_dev != dev) {
+      cudaMemPool_t pool;
+      EIGB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = 256ull << 20;
+      EIGB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      pool_ready_dev = dev;
+    }
+  }
   EIGB_CUDA(cudaMallocAsync((void**)&ws, (size_t)B * nchunks * P * 2 * sizeof(float), st));
   dim3 grid(gx, nchunks);
   if (cpt == 2) diag_scan_kernel<2, 1><<<grid, 128, 0, st>>>(d_lam, d_Bu, d_h, ws, B, T, P, chunk_len, nchunks, reverse);

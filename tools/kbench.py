@@ -70,6 +70,29 @@ def case_embed(B, T, D, V, stats=True):
     return fn, B * T * (8 + D * 4 + (8 if stats else 0)), B * T
 
 
+def case_diag(B, T, P):
+    """C3 (LRU / S5 on ListOps-shaped input): h_t = lam h_{t-1} + Bu_t over complex64, 16 B per state update."""
+    lam = torch.polar(torch.empty(P, device="cuda").uniform_(0.9, 0.999), torch.empty(P, device="cuda").uniform_(0, 6.28))
+    Bu = torch.view_as_complex(torch.randn(B, T, P, 2, device="cuda"))
+    def fn():
+        ops.diag_scan(lam, Bu)
+    return fn, B * T * P * 16, B * T * P
+
+
+def case_k3(nmat, N):
+    """C4 (S4 DPLR, N = 64): discretise + dense nonsymmetric eigenvalues, one warp per matrix.  Reported as matrices/s (latency / FP64 bound)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    Lam = torch.from_numpy((-0.5 + 1j * np.pi * np.arange(N))[None].repeat(nmat, 0).astype(np.complex64)).cuda()
+    Lam = Lam + torch.view_as_complex(torch.randn(nmat, N, 2, device="cuda") * 0.05)
+    Pv = torch.view_as_complex(torch.randn(nmat, N, 2, device="cuda") * 0.5)
+    step = torch.exp(torch.empty(nmat, device="cuda").uniform_(-6.9, -2.3))
+    def fn():
+        Ab = ops.dplr_abar(Lam, Pv, Pv, step)
+        ops.eigvals_c64(Ab)
+    return fn, nmat * (4 * N * 8 + N * 8), nmat
+
+
 def case_normgate(B, T, D, H):
     x = torch.randn(B, T, D, device="cuda")
     W = torch.randn(H, D, device="cuda") * 0.3
@@ -131,6 +154,8 @@ CASES = {
     "lin_n96_none_tc3": lambda: case_linear(M_C2, 96, 128, "none", "tc3"),
     "lin_n96_gelu_tc3": lambda: case_linear(M_C2, 96, 128, "gelu", "tc3"),
     "lin_n64_none_tc3": lambda: case_linear(M_C2, 64, 128, "none", "tc3"),
+    "diag_c3": lambda: case_diag(128, 2048, 256),
+    "k3_c4": lambda: case_k3(3072, 64),
     "k1_c2": lambda: case_k1(4096, 512, 128, 1),
     "k1_c2_stats": lambda: case_k1_stats(4096, 512, 128, 1),
     "emb_c2": lambda: case_embed(4096, 512, 128, 8192),
