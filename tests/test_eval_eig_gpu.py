@@ -132,3 +132,42 @@ def test_mamba_pass_graph_replay_matches_eager(A):
         torch.cuda.synchronize()
         assert torch.equal(res.eig, ref.eig) and torch.equal(res.counts, ref.counts)
     assert gp.launches_per_run > 0
+
+
+def test_full_size_pass_properties_c2(A):
+    """BASELINE config C2 model (T=512, d_model=128, d_state=16, 4 layers) at 1024 sequences: properties of the WHOLE pass that need no CPU
+    reference -- sequences are independent (permutation equivariance, which is what makes batch sharding across GPUs exact), bin counts are a
+    checksum of the eigenvalue array, the graph replay equals the eager pass, and a sample of sequences matches the fp64 oracle."""
+    import eigb200.layers as Ly
+    import eigb200.ops as ops
+    import eigb200.extractors as E
+    cfg = dict(layer="mamba", version="mamba2", num_layers=4, num_heads=1, input_dim=1, output_dim=8192, hidden_dim=128, state_dim=16,
+               conv_dim=4, expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none",
+               token_embedding=True, vocab_size=8192)
+    sd = Ly.init_mamba_state_dict(cfg, 1919)
+    model = Ly.MambaDev(cfg, sd, "cuda")
+    B, T, L = 1024, 512, 4
+    g = torch.Generator().manual_seed(5)
+    X = torch.randint(0, 8192, (B, T), generator=g).cuda()
+    res = A.mamba_pass(model, X)
+    eig, counts = res.eig.clone(), res.counts.clone()
+    assert eig.shape == (B, T, 1, L) and counts.shape == (L, B, 1, ops.NSLOT)
+    assert bool(((eig > 0) & (eig < 1)).all())                                        # lambda = exp(dt A), dt > 0, A < 0
+    # (1) permutation equivariance, bitwise
+    perm = torch.randperm(B, generator=g).cuda()
+    res_p = A.mamba_pass(model, X[perm])
+    assert torch.equal(res_p.eig, eig[perm]) and torch.equal(res_p.counts, counts[:, perm])
+    # (2) the counts are the histogram of the eigenvalues the pass wrote
+    assert bool((counts[..., 7] == T).all()) and bool((counts[..., :7].sum(-1) >= T).all())
+    rad = torch.sqrt(eig * eig)                                                       # (B,T,1,L) float32 radius as eval_eig.py:605-606
+    chk = E.threshold_counts_device(rad.reshape(B, T, L), O.THRESHOLDS_RADIUS)        # (B, L, 8)
+    assert torch.equal(chk[..., :7].permute(1, 0, 2), counts[:, :, 0, :7])
+    # (3) CUDA-graph replay == eager
+    gp = A.MambaPassGraph(model, X)
+    r2 = gp.run(X)
+    torch.cuda.synchronize()
+    assert torch.equal(r2.eig, eig) and torch.equal(r2.counts, counts)
+    # (4) a sample of sequences against the fp64 oracle of the whole pass
+    idx = [0, 511, 1023]
+    ref, _ = O.mamba_eval_pass(X[idx].cpu().numpy(), {k: v.numpy() for k, v in sd.items()}, _mamba_ocfg(cfg), np.float64)
+    assert_eig_close(eig[idx].cpu().numpy(), ref, rtol=3e-5)
