@@ -621,7 +621,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 constexpr int TS_MAX_STAGES = 8;
 constexpr int TS_ASTAGES = 4;
 
-template <int EPI>
+template <int EPI, bool DEFER>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapWhi,
                   const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
@@ -702,6 +702,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int sw = r & 7;
     int s = 0; uint32_t ph = 0;
     int t = 0; uint32_t aph = 0;
+    int t_pending = -1;                                              // operand stage whose tcgen05.st are issued but not yet published
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
       float2 st = make_float2(0.f, 1.f);
       if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); st.x = -st.x * st.y; }
@@ -713,6 +714,11 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         for (int q = 0; q < 8; ++q) {                                // logical 16-byte slot q sits at physical slot q ^ (row & 7)
           const float4 v = src[q ^ sw];
           a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+        }
+        if (DEFER && t_pending >= 0) {                               // publish the PREVIOUS chunk while this chunk's shared-memory loads are in flight
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_afull(t_pending));
         }
         if (ln) {
 #pragma unroll
@@ -736,13 +742,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           for (int i = 0; i < 32; ++i) a[i] = a[i] - hi[i];
           tmem_st_32x32(acol + 32u, a);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(bar_afull(t));
+        if (DEFER) t_pending = t;                                    // publish behind the next chunk's loads (converter-bound shapes)
+        else { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar_afull(t)); }
         if (++s == nst) { s = 0; ph ^= 1; }
         if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
       }
     }
+    if (DEFER && t_pending >= 0) { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar_afull(t_pending)); }
   } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA issuer ======================================
     if (elect_one()) {                                               // ONE thread runs the whole issue loop
@@ -913,6 +919,10 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
   p.zero = 0;
+  // TMEM-operand converter: DEFER publishes a chunk after the next chunk's shared-memory loads were issued.  Measured: +10 % on the converter-bound
+  // N-split shape (bn = 96, in_proj), -6 % on the tensor-bound GLU shape (bn = 128) where the MMA wants its operand at once; a run-time flag
+  // instead of the template parameter costs both shapes 3 % (the converter loop is latency-critical), hence two instantiations.
+  const bool defer = pl.bn < 128;
   p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
   int workers = num_sms() / pl.nsplit;
   if (workers < 1) workers = 1;
@@ -921,9 +931,12 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   dim3 grid(workers * pl.nsplit);
 #define TC_LAUNCH(EPI_)                                                                                                         \
   do {                                                                                                                          \
-    if (pl.ts) {                                                                                                                \
-      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));      \
-      gemm_tc_ts_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                              \
+    if (pl.ts && defer) {                                                                                                       \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+      gemm_tc_ts_kernel<EPI_, true><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                        \
+    } else if (pl.ts) {                                                                                                         \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+      gemm_tc_ts_kernel<EPI_, false><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                       \
     } else {                                                                                                                    \
       EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));         \
       gemm_tc_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                                 \
