@@ -703,9 +703,12 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     int s = 0; uint32_t ph = 0;
     int t = 0; uint32_t aph = 0;
     int t_pending = -1;                                              // operand stage whose tcgen05.st are issued but not yet published
+    float2 st_next = make_float2(0.f, 1.f);                          // LayerNorm (mean, rstd) of this thread's row, fetched one tile ahead
+    if (ln) { const int64_t m = (int64_t)worker * TC_BM + r; if (m < p.M) st_next = __ldg(p.ln_stats + m); }
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      float2 st = make_float2(0.f, 1.f);
-      if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); st.x = -st.x * st.y; }
+      float2 st = st_next;
+      st.x = -st.x * st.y;                                           // (a - mean) rstd = fma(a, rstd, -mean rstd)
+      if (ln) { const int64_t m = (tile + p.workers) * TC_BM + r; if (m < p.M) st_next = __ldg(p.ln_stats + m); }
       for (int c = 0; c < kch; ++c) {
         mbar_wait(bar_full(s), ph);
         const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage0 + s * TC_CHUNK_BYTES + row_off - smem_u32(smem_raw)));
