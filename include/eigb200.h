@@ -174,6 +174,9 @@ int eigb200_eigvals_c64(void* stream, float* d_A, int64_t nmat, int N, float* d_
  *   mode: SIMT_F32 = fp32 FFMA; TC_3XTF32 = tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy); AUTO picks.
  *   d_workspace/workspace_bytes: eigb200_linear_workspace_bytes(N, K) bytes (split weights for the tensor-core path). */
 size_t eigb200_linear_workspace_bytes(int N, int K);
+/* workspace for ANY shape the tensor-core path takes: equals the above when the weight slice stays resident in shared memory (K <= 256); for larger
+ * K the streamed-operand kernel additionally keeps a tf32 hi/lo copy of A (2 * M * round_up(K,32) floats) there. */
+size_t eigb200_linear_workspace_bytes_m(int64_t M, int N, int K);
 /* eigb200_linear with nn.LayerNorm fused into the A operand: C = epilogue(LN(A) W^T + bias), LN(A)[m,k] = (A[m,k] - mean_m) * rstd_m *
  * gamma[k] + beta[k] with d_ln_stats (M,2) = (mean, rstd) per row (from eigb200_mamba2_eig / eigb200_embedding / eigb200_rowstats).
  * Tensor-core path only (same shape limits as eigb200_linear mode TC_3XTF32); EIGB200_EUNSUPPORTED otherwise. */

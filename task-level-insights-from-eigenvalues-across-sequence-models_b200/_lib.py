@@ -42,6 +42,7 @@ SIGNATURES = {
     "eigb200_dplr_abar": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "eigb200_eigvals_c64": [_vp, _vp, _i64, _i, _vp, _vp],
     "eigb200_linear_workspace_bytes": [_i, _i],
+    "eigb200_linear_workspace_bytes_m": [_i64, _i, _i],
     "eigb200_linear": [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _sz],
     "eigb200_embedding": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64],
     "eigb200_embedding_stats": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64, _vp, _f],
@@ -56,7 +57,7 @@ SIGNATURES = {
     "eigb200_scale_cols": [_vp, _vp, _vp, _vp, _i64, _i],
     "eigb200_ssm_lambda": [_vp, _i, _vp, _vp, _vp, _i, _vp],
 }
-_RESTYPES = {"eigb200_last_error": C.c_char_p, "eigb200_linear_workspace_bytes": C.c_size_t}
+_RESTYPES = {"eigb200_last_error": C.c_char_p, "eigb200_linear_workspace_bytes": C.c_size_t, "eigb200_linear_workspace_bytes_m": C.c_size_t}
 
 
 class Eigb200Error(RuntimeError):

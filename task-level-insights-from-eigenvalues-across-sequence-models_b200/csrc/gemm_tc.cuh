@@ -2,7 +2,8 @@
 #pragma once
 #include "gemm_simt.cuh"
 namespace eigb200 {
-size_t tc_workspace_bytes(int N, int K);
+size_t tc_workspace_bytes(int N, int K);                 // resident-weight kernels only (K <= 256)
+size_t tc_workspace_bytes_m(int64_t M, int N, int K);    // any supported shape: adds the split copy of A the streamed-operand kernel needs
 bool tc_supported(const LinearParams& p);
 // nsplit = 3: 3xTF32 error-compensated (fp32-level accuracy); nsplit = 1: plain TF32.
 int launch_linear_tc(cudaStream_t st, const LinearParams& p, int nsplit, void* workspace);

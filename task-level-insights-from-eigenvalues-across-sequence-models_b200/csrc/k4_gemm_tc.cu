@@ -436,6 +436,149 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
   }
 }
 
+// Epilogue of the streamed-operand kernel (a separate copy: the resident-weight kernels are sensitive to any change of their epilogue's code
+// generation -- folding the two behind a template flag cost them 10 %): the CTA walks (row tile, N tile) pairs blockIdx.x, + gridDim.x, ... with the N tile fastest; bias_s points
+// at the whole bias vector in accumulator-column order in GLOBAL memory (p.nsplit * bn entries).
+template <int EPI, bool STREAM = true>
+__device__ __forceinline__ void tc_epilogue_stream(const TcParams& p, uint32_t tmem_base, int bn, uint32_t bar_dfull0, uint32_t bar_dempty0,
+                                            const float* bias_s, int worker, int split, int warp, int lane) {
+  auto bar_dfull = [&](int j) { return bar_dfull0 + 8u * j; };
+  auto bar_dempty = [&](int j) { return bar_dempty0 + 8u * j; };
+  constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
+  const int nout = GLU ? p.N / 2 : p.N;
+  const int cols_out = GLU ? p.bg : bn;                              // output columns produced by this CTA
+  int n_cta0 = split * cols_out;
+  const int quarter = warp & 3, grp = warp >> 2;                     // TMEM lane quarter; first 32-column accumulator group of this warp
+  const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+  const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
+  const bool r_own = use_r && p.r_v8;                                // residual added in the accumulator layout with 256-bit loads
+  int j = 0; uint32_t dph = 0;
+  const int64_t it_end = STREAM ? p.ntiles * p.nsplit : p.ntiles;
+  const int64_t it_step = STREAM ? (int64_t)gridDim.x : (int64_t)p.workers;
+  const float* bias0 = bias_s;
+  for (int64_t it = STREAM ? (int64_t)blockIdx.x : (int64_t)worker; it < it_end; it += it_step) {
+    const int64_t tile = STREAM ? it / p.nsplit : it;
+    if (STREAM) {
+      const int sp = (int)(it - tile * p.nsplit);
+      n_cta0 = sp * cols_out;
+      bias_s = bias0 + (size_t)sp * bn;
+    }
+    const int64_t own_row = tile * TC_BM + quarter * 32 + lane;      // accumulator layout: lane = row
+    const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn) + lane_sel;
+    bool waited = false, arrived = false;
+    for (int cg = 32 * grp; cg < bn; cg += 32 * TC_EPI_GROUPS) {
+      const bool last = cg + 32 * TC_EPI_GROUPS >= bn;               // this warp's last TMEM read of the accumulator: release it early
+      if (GLU) {
+        const int oc = n_cta0 + (cg >> 1);                           // first of the 16 output columns of this group
+        float rr[16];
+        if (r_own) {                                                 // residual prefetch: its DRAM latency hides behind the accumulator wait
+          const float* rptr = p.R + own_row * p.ldr + oc;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (own_row < p.M && oc + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr + 8 * q);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[8 * q + e] = (own_row < p.M && oc + 8 * q + e < nout) ? __ldg(rptr + 8 * q + e) : 0.f;
+            }
+          }
+        }
+        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
+        float a[32];
+        tmem_ld_32x32(d_tmem + cg, a);
+        if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
+        if (r_own) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += rr[i];
+        }
+        transpose4x4_f4(v, lane);
+        const int n = oc + 4 * (lane & 3);
+        const int64_t row0 = tile * TC_BM + quarter * 32 + (lane & ~3);
+        if (n < nout) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int64_t mrow = row0 + jj;
+            if (mrow < p.M) {
+              float* cptr = p.C + mrow * p.ldc + n;
+              if (n + 3 < nout) {
+                float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                if (use_r && !p.r_v8) {
+                  const float4 r4 = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + mrow * p.ldr + n));
+                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                }
+                *reinterpret_cast<float4*>(cptr) = o;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < nout) cptr[e] = v[4 * jj + e] + ((use_r && !p.r_v8) ? p.R[mrow * p.ldr + n + e] : 0.f);
+              }
+            }
+          }
+        }
+      } else {
+        const int gi = lane & 7, gg = lane >> 3;                     // after the transpose: column quad gi of rows 8*gg + jj
+        const int64_t row0 = tile * TC_BM + quarter * 32 + 8 * gg;
+        const int n = n_cta0 + cg + 4 * gi;
+        const bool col_ok = n < nout;
+        const bool full = n + 3 < nout;
+        const float* rptr = p.R + own_row * p.ldr + n_cta0 + cg;
+        float rr[32];
+        if (r_own) {                                                 // prefetch behind the accumulator wait
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (own_row < p.M && n_cta0 + cg + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr + 8 * q);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[8 * q + e] = (own_row < p.M && n_cta0 + cg + 8 * q + e < nout) ? __ldg(rptr + 8 * q + e) : 0.f;
+            }
+          }
+        }
+        if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); waited = true; }
+        float v[32];
+        tmem_ld_32x32(d_tmem + cg, v);
+        if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float vv = v[i] + bias_s[cg + i];
+          if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
+          v[i] = vv;
+        }
+        if (r_own) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += rr[i];
+        }
+        transpose8x8_f4(v, lane);
+        if (col_ok) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int64_t mrow = row0 + jj;
+            if (mrow < p.M) {
+              float* cptr = p.C + mrow * p.ldc + n;
+              if (full) {
+                float4 o = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                if (use_r && !p.r_v8) {
+                  const float4 r4 = ldg_stream_f4(reinterpret_cast<const float4*>(p.R + mrow * p.ldr + n));
+                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                }
+                *reinterpret_cast<float4*>(cptr) = o;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < nout) cptr[e] = v[4 * jj + e] + ((use_r && !p.r_v8) ? p.R[mrow * p.ldr + n + e] : 0.f);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (!waited) { mbar_wait(bar_dfull(j), dph); tc_fence_after(); }
+    if (!arrived) { tc_fence_before(); mbar_arrive(bar_dempty(j)); }
+    if (++j == 2) { j = 0; dph ^= 1; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // the GEMM kernel
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -703,12 +846,12 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     int s = 0; uint32_t ph = 0;
     int t = 0; uint32_t aph = 0;
     int t_pending = -1;                                              // operand stage whose tcgen05.st are issued but not yet published
-    float2 st_next = make_float2(0.f, 1.f);                          // LayerNorm (mean, rstd) of this thread's row, fetched one tile ahead
-    if (ln) { const int64_t m = (int64_t)worker * TC_BM + r; if (m < p.M) st_next = __ldg(p.ln_stats + m); }
     for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
-      float2 st = st_next;
-      st.x = -st.x * st.y;                                           // (a - mean) rstd = fma(a, rstd, -mean rstd)
-      if (ln) { const int64_t m = (tile + p.workers) * TC_BM + r; if (m < p.M) st_next = __ldg(p.ln_stats + m); }
+      // NOTE: this loop is latency-critical and its performance follows ptxas' schedule: prefetching the statistics one tile ahead, making
+      // `ln` a template parameter or forcing the publish ahead of the split with a data dependency were each measured 10-18 % SLOWER on the
+      // plain N-split shapes (A/B on the same GPU), for a 2 % gain on the LayerNorm shape.
+      float2 st = make_float2(0.f, 1.f);
+      if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); st.x = -st.x * st.y; }
       for (int c = 0; c < kch; ++c) {
         mbar_wait(bar_full(s), ph);
         const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage0 + s * TC_CHUNK_BYTES + row_off - smem_u32(smem_raw)));
@@ -795,6 +938,142 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// Streamed-operand variant for the shapes the resident-weight kernels cannot take (K > 256 or a weight slice that does not fit shared memory:
+// the LM-sized layers of BASELINE C5, d_model 512).  There the GEMM is compute-bound (2 N K / (K + N) flop per byte > 500), so the classic
+// pipeline is the right shape: A is split ONCE into tf32 hi / lo in global memory (split_a_kernel, which also applies the LayerNorm row
+// statistics), and a ring of stages [A_hi | A_lo | W_hi | W_lo] x 32 K-columns is filled by one TMA thread; one thread issues the 12
+// tcgen05.mma per stage (both operands from shared memory); the 16 epilogue warps are the same as above.  CTAs walk (row tile, N tile) pairs with
+// the N tile fastest, so the A tile of a row block is re-read from L2.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void split_a_kernel(const float* __restrict__ A, int64_t lda, const float2* __restrict__ stats, float* __restrict__ hi, float* __restrict__ lo,
+                               int64_t M, int K, int kpad) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;             // one float4 of the padded (M, kpad) array
+  const int kq = kpad >> 2;
+  if (idx >= M * kq) return;
+  const int64_t m = idx / kq;
+  const int k = (int)(idx - m * kq) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < K) {                                                                     // K % 4 == 0
+    a = ldg_stream_f4(reinterpret_cast<const float4*>(A + m * lda + k));
+    if (stats) {
+      const float2 st = __ldg(stats + m);
+      const float c = -st.x * st.y;
+      a.x = fmaf(a.x, st.y, c); a.y = fmaf(a.y, st.y, c); a.z = fmaf(a.z, st.y, c); a.w = fmaf(a.w, st.y, c);
+    }
+  }
+  float4 h, l;
+  split_tf32_4(a, h, l);
+  reinterpret_cast<float4*>(hi)[idx] = h;
+  reinterpret_cast<float4*>(lo)[idx] = l;
+}
+
+// bias in accumulator-column order (nsplit * bn entries, zero for padding columns)
+__global__ void perm_bias_kernel(const float* __restrict__ bias, float* __restrict__ out, int N, int bn, int bg, int nsplit, int glu) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nsplit * bn) return;
+  const int split = idx / bn, local = idx - split * bn;
+  int n;
+  if (glu) n = glu_weight_row(local, split, bg, N / 2);
+  else { n = split * bn + local; if (n >= N) n = -1; }
+  out[idx] = (bias && n >= 0) ? bias[n] : 0.f;
+}
+
+constexpr int SK_MAX_STAGES = 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_constant__ CUtensorMap tmapAlo,
+                      const __grid_constant__ CUtensorMap tmapWhi, const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int bn = p.bn, kch = p.kchunks, nst = p.nstages;
+  const uint32_t w_chunk_bytes = (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = 2u * TC_CHUNK_BYTES + 2u * w_chunk_bytes;          // [A_hi 16K][A_lo 16K][W_hi][W_lo]
+  const uint32_t stage0 = base;
+  const uint32_t bars = stage0 + nst * stage_bytes;
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 8u * (SK_MAX_STAGES + s); };
+  auto bar_dfull = [&](int j) { return bars + 8u * (2 * SK_MAX_STAGES + j); };
+  auto bar_dempty = [&](int j) { return bars + 8u * (2 * SK_MAX_STAGES + 2 + j); };
+  const uint32_t tmem_slot = bars + 8u * (2 * SK_MAX_STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (2 * bn <= 32) ? 32 : (2 * bn <= 64) ? 64 : (2 * bn <= 128) ? 128 : (2 * bn <= 256) ? 256 : 512;
+  const int64_t npairs = p.ntiles * p.nsplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), TC_EPI_WARPS * 32); }
+    fence_barrier_init();
+  }
+  if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TC_TMA_WARP && lane == 0) { tma_prefetch_desc(&tmapAhi); tma_prefetch_desc(&tmapAlo); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == TC_TMA_WARP) {
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t it = blockIdx.x; it < npairs; it += gridDim.x) {
+        const int64_t tile = it / p.nsplit;
+        const int split = (int)(it - tile * p.nsplit);
+        for (int c = 0; c < kch; ++c) {
+          mbar_wait_one(bar_empty(s), ph ^ 1);
+          const uint32_t st0 = stage0 + s * stage_bytes;
+          mbar_arrive_expect_tx(bar_full(s), stage_bytes);
+          tma_load_2d(&tmapAhi, bar_full(s), st0, c * TC_KC, (int)(tile * TC_BM));
+          tma_load_2d(&tmapAlo, bar_full(s), st0 + TC_CHUNK_BYTES, c * TC_KC, (int)(tile * TC_BM));
+          tma_load_2d(&tmapWhi, bar_full(s), st0 + 2 * TC_CHUNK_BYTES, c * TC_KC, split * bn);
+          tma_load_2d(&tmapWlo, bar_full(s), st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * TC_KC, split * bn);
+          if (++s == nst) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == TC_MMA_WARP) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+      const bool three = p.nterms == 3;
+      int s = 0; uint32_t ph = 0;
+      int j = 0; uint32_t dph = 0;
+      for (int64_t it = blockIdx.x; it < npairs; it += gridDim.x) {
+        mbar_wait_one(bar_dempty(j), dph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(j * bn);
+        for (int c = 0; c < kch; ++c) {
+          mbar_wait_one(bar_full(s), ph);
+          tc_fence_after();
+          const uint32_t st0 = stage0 + s * stage_bytes;
+          const uint64_t dah0 = umma_desc_k_sw128(st0), dal0 = umma_desc_k_sw128(st0 + TC_CHUNK_BYTES);
+          const uint64_t dbh0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES), dbl0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes);
+#pragma unroll
+          for (int k = 0; k < TC_KC / 8; ++k) {
+            umma_tf32(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            if (three) {
+              umma_tf32(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
+              umma_tf32(d_tmem, dal0 + 2u * k, dbh0 + 2u * k, idesc, 1u);
+            }
+          }
+          umma_commit(bar_empty(s));
+          if (c == kch - 1) umma_commit(bar_dfull(j));
+          if (++s == nst) { s = 0; ph ^= 1; }
+        }
+        if (++j == 2) { j = 0; dph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp < TC_EPI_WARPS) {
+    tc_epilogue_stream<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), p.bias, 0, 0, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -870,6 +1149,48 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   return pl;
 }
 
+size_t tc_workspace_bytes(int N, int K);
+// plan of the streamed-operand kernel (any K % 4 == 0): 128 accumulator columns per N tile (GLU: 64 value + 64 gate columns)
+struct StreamPlan { int bn, bg, nsplit, kchunks, kpad, nstages; size_t smem; bool ok; };
+static StreamPlan make_stream_plan(int N, int K, int epilogue) {
+  StreamPlan pl{};
+  pl.ok = false;
+  if (K % 4 != 0 || K <= 0 || K > 16384) return pl;
+  pl.kpad = (K + TC_KC - 1) / TC_KC * TC_KC;
+  pl.kchunks = pl.kpad / TC_KC;
+  const bool glu = epilogue == EIGB200_EPI_GLU_RESIDUAL;
+  const int nout = glu ? N / 2 : N;
+  if (glu) { pl.bg = 64; pl.bn = 128; }
+  else { pl.bn = nout >= 128 ? 128 : (nout + 31) / 32 * 32; pl.bg = pl.bn; }
+  pl.nsplit = (nout + pl.bg - 1) / pl.bg;
+  const size_t stage_bytes = 2 * (size_t)TC_CHUNK_BYTES + 2 * (size_t)pl.bn * 128;
+  int nst = (int)((TC_SMEM_LIMIT - 2048) / stage_bytes);
+  if (nst > SK_MAX_STAGES) nst = SK_MAX_STAGES;
+  if (nst < 2) return pl;
+  pl.nstages = nst;
+  pl.smem = (size_t)nst * stage_bytes + 1024 /*alignment*/ + 1024 /*barriers*/;
+  pl.ok = true;
+  return pl;
+}
+
+static size_t stream_workspace_bytes(int64_t M, int N, int K, int epilogue) {
+  const StreamPlan pl = make_stream_plan(N, K, epilogue);
+  if (!pl.ok) return 0;
+  const size_t wrows = (size_t)pl.nsplit * pl.bn;
+  return (2 * wrows * pl.kpad + (size_t)((N + 3) / 4 * 4) + wrows + 2 * (size_t)M * pl.kpad) * sizeof(float);
+}
+
+size_t tc_workspace_bytes_m(int64_t M, int N, int K) {
+  size_t best = tc_workspace_bytes(N, K);
+  for (int epi : {EIGB200_EPI_NONE, EIGB200_EPI_GLU_RESIDUAL}) {
+    if (epi == EIGB200_EPI_GLU_RESIDUAL && N % 2) continue;
+    if (make_plan(N, K, epi).ok) continue;                          // the resident-weight kernel takes this shape
+    const size_t b = stream_workspace_bytes(M, N, K, epi);
+    if (b > best) best = b;
+  }
+  return best;
+}
+
 size_t tc_workspace_bytes(int N, int K) {
   // sized for the worst case of either epilogue family
   size_t best = 0;
@@ -887,12 +1208,73 @@ bool tc_supported(const LinearParams& p) {
   if (p.lda % 4 != 0 || p.ldc % 4 != 0 || (p.R && p.ldr % 4 != 0)) return false;
   if (((uintptr_t)p.A & 15) || ((uintptr_t)p.C & 15) || (p.R && ((uintptr_t)p.R & 15))) return false;
   if (p.M >= (1LL << 31)) return false;
-  return make_plan(p.N, p.K, p.epilogue).ok;
+  return make_plan(p.N, p.K, p.epilogue).ok || make_stream_plan(p.N, p.K, p.epilogue).ok;
+}
+
+static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
+  const StreamPlan pl = make_stream_plan(lp.N, lp.K, lp.epilogue);
+  if (!pl.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
+  const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
+  const size_t wrows = (size_t)pl.nsplit * pl.bn;
+  float* w_hi = reinterpret_cast<float*>(workspace);
+  float* w_lo = w_hi + wrows * pl.kpad;
+  float* bias2 = w_lo + wrows * pl.kpad;
+  float* bias_perm = bias2 + (lp.N + 3) / 4 * 4;
+  float* a_hi = bias_perm + wrows;
+  float* a_lo = a_hi + (size_t)lp.M * pl.kpad;
+  {
+    const int total = (int)(wrows * pl.kpad);
+    split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kpad, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0,
+                                                              lp.ln_stats ? lp.ln_gamma : nullptr);
+    EIGB_LAUNCH_CHECK("split_weights_kernel");
+  }
+  const float* bias_eff = lp.bias;
+  if (lp.ln_stats) {
+    ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
+    EIGB_LAUNCH_CHECK("ln_bias_kernel");
+    bias_eff = bias2;
+  }
+  perm_bias_kernel<<<(unsigned)((wrows + 255) / 256), 256, 0, st>>>(bias_eff, bias_perm, lp.N, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0);
+  EIGB_LAUNCH_CHECK("perm_bias_kernel");
+  {
+    const int64_t nq = lp.M * (pl.kpad / 4);
+    split_a_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(lp.A, lp.lda, reinterpret_cast<const float2*>(lp.ln_stats), a_hi, a_lo, lp.M, lp.K, pl.kpad);
+    EIGB_LAUNCH_CHECK("split_a_kernel");
+  }
+  CUtensorMap tAh, tAl, tWh, tWl;
+  int rc;
+  if ((rc = make_tmap(&tAh, a_hi, (uint64_t)lp.M, (uint64_t)pl.kpad, (uint64_t)pl.kpad, TC_BM))) return rc;
+  if ((rc = make_tmap(&tAl, a_lo, (uint64_t)lp.M, (uint64_t)pl.kpad, (uint64_t)pl.kpad, TC_BM))) return rc;
+  if ((rc = make_tmap(&tWh, w_hi, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  TcParams p{};
+  p.bias = bias_perm; p.C = lp.C; p.ldc = lp.ldc; p.R = lp.R; p.ldr = lp.ldr; p.M = lp.M; p.N = lp.N; p.K = lp.K; p.epilogue = lp.epilogue;
+  p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
+  p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
+  p.workers = 1; p.zero = 0;
+  p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
+  const int64_t npairs = p.ntiles * p.nsplit;
+  const unsigned grid = (unsigned)(npairs < (int64_t)num_sms() ? npairs : (int64_t)num_sms());
+#define SK_LAUNCH(EPI_)                                                                                                         \
+  do {                                                                                                                          \
+    EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));    \
+    gemm_tc_stream_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                                      \
+  } while (0)
+  switch (lp.epilogue) {
+    case EIGB200_EPI_NONE: SK_LAUNCH(EIGB200_EPI_NONE); break;
+    case EIGB200_EPI_GELU: SK_LAUNCH(EIGB200_EPI_GELU); break;
+    case EIGB200_EPI_GLU_RESIDUAL: SK_LAUNCH(EIGB200_EPI_GLU_RESIDUAL); break;
+    case EIGB200_EPI_RESIDUAL: SK_LAUNCH(EIGB200_EPI_RESIDUAL); break;
+    default: set_error("linear: unknown epilogue %d", lp.epilogue); return EIGB200_EINVAL;
+  }
+#undef SK_LAUNCH
+  EIGB_LAUNCH_CHECK("gemm_tc_stream_kernel");
+  return EIGB200_OK;
 }
 
 int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
   const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue);
-  if (!pl.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
+  if (!pl.ok) return launch_linear_stream(st, lp, nterms, workspace);   // K > 256 or a weight slice too large to stay resident
   const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
   float* w_hi = reinterpret_cast<float*>(workspace);
   const size_t wrows = (size_t)pl.nsplit * pl.bn;

@@ -4,6 +4,7 @@
 using namespace eigb200;
 
 extern "C" size_t eigb200_linear_workspace_bytes(int N, int K) { return tc_workspace_bytes(N, K); }
+extern "C" size_t eigb200_linear_workspace_bytes_m(int64_t M, int N, int K) { return tc_workspace_bytes_m(M, N, K); }
 
 extern "C" int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
                               float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
@@ -17,7 +18,7 @@ extern "C" int eigb200_linear(void* stream, const float* d_A, int64_t lda, const
   LinearParams p{d_A, lda, d_W, d_bias, d_C, ldc, d_R, ldr, M, N, K, epilogue};
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == EIGB200_GEMM_SIMT_F32) return launch_linear_simt(st, p);
-  const bool tc_ok = tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes(N, K);
+  const bool tc_ok = tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes_m(M, N, K);
   if (mode == EIGB200_GEMM_TC_3XTF32 || mode == EIGB200_GEMM_TC_TF32) {
     if (!tc_ok) { set_error("linear: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda); return EIGB200_EUNSUPPORTED; }
     return launch_linear_tc(st, p, mode == EIGB200_GEMM_TC_TF32 ? 1 : 3, d_workspace);
@@ -37,7 +38,7 @@ extern "C" int eigb200_linear_ln(void* stream, const float* d_A, int64_t lda, co
   EIGB_CHECK_ARG(((uintptr_t)d_ln_stats & 7) == 0, "linear_ln: row statistics must be 8-byte aligned");
   LinearParams p{d_A, lda, d_W, d_bias, d_C, ldc, d_R, ldr, M, N, K, epilogue};
   p.ln_stats = d_ln_stats; p.ln_gamma = d_ln_gamma; p.ln_beta = d_ln_beta;
-  if (!(tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes(N, K))) {
+  if (!(tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes_m(M, N, K))) {
     set_error("linear_ln: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda);
     return EIGB200_EUNSUPPORTED;
   }

@@ -291,12 +291,12 @@ GEMM_MODES = {"auto": L.GEMM_AUTO, "simt": L.GEMM_SIMT_F32, "tc3": L.GEMM_TC_3XT
 _ws_cache = {}
 
 
-def linear_workspace(N, K, device):
+def linear_workspace(N, K, device, M=0):
+    """Workspace of the tensor-core GEMM for (M, N, K): split weights (+ the split copy of A when K > 256)."""
     lib = L.load()
-    nbytes = int(lib.eigb200_linear_workspace_bytes(N, K))
+    nbytes = int(lib.eigb200_linear_workspace_bytes_m(int(M), N, K))
     if nbytes == 0:
         return None, 0
-    key = (N, K, str(device))
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
@@ -322,7 +322,7 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     if residual is not None:
         assert residual.is_cuda and residual.dtype == torch.float32 and residual.stride(-1) == 1
         ldr = residual.stride(-2) if residual.dim() >= 2 else nout
-    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
+    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
     _call(lib, "eigb200_linear", _stream(a), _p(a2), lda, _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
                                EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb, tag="N%d K%d %s" % (N, K, epilogue))
     return out
@@ -354,7 +354,7 @@ def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residua
     else:
         ldc = out.stride(-2)
     ldr = residual.stride(-2) if residual is not None else 0
-    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device)
+    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
     _call(lib, "eigb200_linear_ln", _stream(a), _p(a), K, _p(_prep(stats, torch.float32)), _p(_prep(gamma, torch.float32)),
           _p(_prep(beta, torch.float32)), _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K, EPILOGUES[epilogue], _p(ws), wsb,
           tag="N%d K%d %s" % (N, K, epilogue))
@@ -362,7 +362,7 @@ def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residua
 
 
 def linear_ln_supported(N, K):
-    return int(L.load().eigb200_linear_workspace_bytes(N, K)) > 0
+    return int(L.load().eigb200_linear_workspace_bytes_m(1024, N, K)) > 0
 
 
 def embedding(ids, word, pos=None, rowstats_out=None, ln_eps=1e-5):

@@ -210,6 +210,37 @@ def test_linear_tcgen05_3xtf32(ops, M, N, K, epi):
     assert np.abs(out[:, :nout] - simt[:, :nout]).max() <= 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 552, 512), (3000, 512, 512), (2500, 1024, 512), (1000, 96, 384), (4100, 40, 260), (2048, 1544, 512),
+                                    (70000, 256, 320)])
+@pytest.mark.parametrize("epi", ["none", "gelu", "residual", "glu_residual"])
+def test_linear_tcgen05_streamed_operands(ops, M, N, K, epi):
+    """Shapes whose weight slice cannot stay resident in shared memory (K > 256): the streamed-operand kernel (A pre-split into tf32 hi / lo)."""
+    rng = np.random.default_rng(M + N + K)
+    a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    nout = N // 2 if epi == "glu_residual" else N
+    ldc = (nout + 7) // 8 * 8
+    r = rng.normal(size=(M, ldc)).astype(np.float32)
+    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode="tc3", ldc=ldc).cpu().numpy()
+    ref = _lin_ref(a, w, bias, epi, r[:, :nout].astype(np.float64))
+    # The tensor core adds every MMA into the fp32 accumulator with truncation, 3 * K / 8 times per output: the error grows linearly with K
+    # (measured 3e-6 of the output scale at K = 512, against 1e-6 at K = 128) where the FFMA path's round-to-nearest sum grows like sqrt(K).
+    np.testing.assert_allclose(out[:, :nout], ref, rtol=1e-5, atol=1e-5 * max(1.0, K / 256))
+    assert np.abs(out[:, :nout] - ref).max() <= 6e-6 * np.abs(ref).max() * max(1.0, K / 256)
+
+
+def test_linear_ln_streamed_operands(ops):
+    rng = np.random.default_rng(3)
+    M, N, K = 3000, 552, 512
+    a = (rng.normal(size=(M, K)) * 2 + rng.normal(0, 1, (M, 1))).astype(np.float32)
+    w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    gamma = rng.normal(1, 0.3, K).astype(np.float32); beta = rng.normal(0, 0.3, K).astype(np.float32)
+    st = ops.rowstats(dev(a))
+    out = ops.linear_ln(dev(a), st, dev(gamma), dev(beta), dev(w), None, ldc=N).cpu().numpy()
+    ref = O.layer_norm(a.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64)) @ w.astype(np.float64).T
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-5)
+
+
 def test_linear_tcgen05_plain_tf32_is_coarser(ops):
     rng = np.random.default_rng(9)
     M, N, K = 2048, 128, 128
