@@ -138,7 +138,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": eps, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d sequences x T=%d x %d layers per step (throughput is batch-linear)" % (sample_b, SEQ_LEN, cfg["num_layers"])},
             "e2e": {"value": eps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -338,10 +338,27 @@ def run_eigb200(args, rank, local, world):
                                 "sample": "%d sequences x T=%d x %d layers, mean of 2 passes after 1 warm-up" % (args.cpu_sample, SEQ_LEN, nl)}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract goes to the process' original stdout; everything libraries print (NCCL's version banner goes to
+    stdout at any NCCL_DEBUG level >= VERSION) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                                  # fd 1 -> stderr for the rest of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
