@@ -214,6 +214,10 @@ int eigb200_mul_silu(void* stream, const float* d_y, const float* d_z, float* d_
 int eigb200_gelu(void* stream, const float* d_x, float* d_out, int64_t n);
 /* out[m,j] = a[m,j] * s[j]: the D * u feed-through of LRU / S5 (models/lru.py:97; s5.py:247-248). */
 int eigb200_scale_cols(void* stream, const float* d_a, const float* d_s, float* d_out, int64_t rows, int cols);
+/* SSD_LTI.forward (models/mamba.py:262-281), in place on the conv'd projection buffer (rows, ld): the single dt column (ngroups = 1) becomes
+ * dt[m, j] = softplus(buf[m, col_dt] + dt_bias[j / khead]) for the d_state columns j (khead = d_state / nheads, :200-201, :277-278) and B <- dt * B.
+ * The scan then runs with dt := beta (ones) and A := -softplus(A) (:274-275, :283-295) through eigb200_ssd_scan. */
+int eigb200_lti_scale_b(void* stream, float* d_buf, int64_t ld, int col_b, int col_dt, const float* d_dt_bias, int64_t rows, int N, int khead);
 
 #ifdef __cplusplus
 }

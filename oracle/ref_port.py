@@ -12,7 +12,7 @@ import numpy as np
 
 __all__ = [
     "softplus", "elu", "sigmoid", "norm_fn_apply",
-    "mamba2_dt_rows", "mamba2_eig", "mamba2_lti_eig", "normattn_rows", "normattn_eta",
+    "mamba2_dt_rows", "mamba2_eig", "mamba2_lti_eig", "ssd_lti_mixer_forward", "normattn_rows", "normattn_eta",
     "linattn_qk", "linattn_eta_quadratic", "linattn_eta_prefix", "softmax_eta_quadratic", "softmax_eta_closed", "smattn_forward",
     "THRESHOLDS_RADIUS", "THRESHOLDS_PHASE", "threshold_counts", "threshold_analysis", "threshold_analysis_ssm",
     "radius_phase", "batch_mean_std", "batch_mean_std_from_counts",
@@ -566,6 +566,27 @@ def ssd_mixer_forward(u, p, cfg, dtype=np.float64):
     return y.reshape(Bsz, T, di) @ np.asarray(p["out_proj.weight"], dtype).T
 
 
+def ssd_lti_mixer_forward(u, p, cfg, dtype=np.float64):
+    """SSD_LTI.forward (models/mamba.py:248-299), ngroups = 1: ONE dt column, dt = softplus(dt_raw + dt_bias) (B,L,H) tiled khead_dim = d_state / H
+    times over the state axis, B <- dt * B, then the scan with dt := beta, A := -softplus(A).  (The class cannot be constructed with current torch --
+    nn.Parameter(A, device=...) raises -- so this restatement follows the source text; no golden vector can exist.)"""
+    u = np.asarray(u, dtype)
+    di, G, N, H, hd = cfg["d_inner"], cfg["ngroups"], cfg["d_state"], cfg["nheads"], cfg["headdim"]
+    assert G == 1 and N % H == 0
+    xbcdt = u @ np.asarray(p["in_proj.weight"], dtype).T
+    xBC, dtr = xbcdt[..., : di + 2 * N], xbcdt[..., di + 2 * N:]
+    dt = softplus(dtr + np.asarray(p["dt_bias"], dtype))                        # (B,L,1) + (H,) -> (B,L,H)
+    if "conv1d.weight" in p:
+        xBC = causal_depthwise_conv_silu(xBC, p["conv1d.weight"], p["conv1d.bias"])
+    x, Bm, Cm = xBC[..., :di], xBC[..., di:di + N], xBC[..., di + N:]
+    Bm = np.repeat(dt, N // H, axis=-1) * Bm                                    # dt.unsqueeze(-1).repeat(.., khead) -> "b l (h d)"
+    Bsz, T, _ = u.shape
+    beta = np.broadcast_to(np.asarray(p.get("beta", np.ones(H)), dtype), (Bsz, T, H))
+    A = -softplus(np.asarray(p["A"], dtype))
+    y = ssd_scan_sequential(x.reshape(Bsz, T, H, hd), beta, A, Bm.reshape(Bsz, T, 1, N), Cm.reshape(Bsz, T, 1, N), np.asarray(p["D"], dtype), dtype)
+    return y.reshape(Bsz, T, di) @ np.asarray(p["out_proj.weight"], dtype).T
+
+
 def mamba_block_forward(x, p, cfg, dtype=np.float64):
     """MambaBlock.forward in eval mode / dropout 0 (models/mamba.py:328-340).  p keys are the block's
     state_dict names ('mamba.*', 'glu.linear.*', 'norm.*')."""
@@ -574,7 +595,7 @@ def mamba_block_forward(x, p, cfg, dtype=np.float64):
     if cfg.get("prenorm", True):
         x = layer_norm(x, p["norm.weight"], p["norm.bias"])
     mp = {k[len("mamba."):]: v for k, v in p.items() if k.startswith("mamba.")}
-    x = ssd_mixer_forward(x, mp, cfg, dtype)
+    x = ssd_lti_mixer_forward(x, mp, cfg, dtype) if cfg.get("pseudoLTI", False) else ssd_mixer_forward(x, mp, cfg, dtype)
     x = gelu_erf(x)
     if "glu.linear.weight" in p:
         x = glu(x, p["glu.linear.weight"], p["glu.linear.bias"])
@@ -727,8 +748,11 @@ def mamba_eval_pass(ids_or_x, state_dict, cfg, dtype=np.float64):
     for i in range(cfg["num_layers"]):
         p = _block_params(state_dict, "blocks.%d." % i)
         x = mamba_block_forward(x, p, cfg, dtype)
-        eigs.append(mamba2_eig(x, p["mamba.in_proj.weight"], p["mamba.dt_bias"], p["mamba.A_log"],
-                               cfg["d_inner"], cfg["ngroups"], cfg["d_state"], cfg["nheads"], dtype))
+        if cfg.get("pseudoLTI", False):
+            eigs.append(mamba2_lti_eig(x.shape[0], x.shape[1], p["mamba.A"], p.get("mamba.beta", np.ones(cfg["nheads"])), dtype))
+        else:
+            eigs.append(mamba2_eig(x, p["mamba.in_proj.weight"], p["mamba.dt_bias"], p["mamba.A_log"],
+                                   cfg["d_inner"], cfg["ngroups"], cfg["d_state"], cfg["nheads"], dtype))
     return np.concatenate(eigs, axis=-1), x
 
 

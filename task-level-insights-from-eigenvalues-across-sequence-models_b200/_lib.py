@@ -55,6 +55,7 @@ SIGNATURES = {
     "eigb200_mul_silu": [_vp, _vp, _vp, _vp, _i64],
     "eigb200_gelu": [_vp, _vp, _vp, _i64],
     "eigb200_scale_cols": [_vp, _vp, _vp, _vp, _i64, _i],
+    "eigb200_lti_scale_b": [_vp, _vp, _i64, _i, _i, _vp, _i64, _i, _i],
     "eigb200_ssm_lambda": [_vp, _i, _vp, _vp, _vp, _i, _vp],
 }
 _RESTYPES = {"eigb200_last_error": C.c_char_p, "eigb200_linear_workspace_bytes": C.c_size_t, "eigb200_linear_workspace_bytes_m": C.c_size_t}

@@ -194,6 +194,19 @@ static int ew_grid(int64_t n) {
   return (int)g;
 }
 
+
+// SSD_LTI.forward (models/mamba.py:262-281): dt = softplus(dt_raw + dt_bias[h]) tiled over the d_state columns (column j belongs to head j / khead), B <- dt * B,
+// in place on the conv'd projection buffer.  One thread per (row, state column).
+__global__ void lti_scale_b_kernel(float* __restrict__ buf, int64_t ld, int col_b, int col_dt, const float* __restrict__ dt_bias,
+                                   int64_t rows, int N, int khead) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * N) return;
+  const int64_t m = idx / N;
+  const int j = (int)(idx - m * N);
+  const float dt = softplus_f(buf[m * ld + col_dt] + dt_bias[j / khead]);
+  buf[m * ld + col_b + j] *= dt;
+}
+
 }  // namespace eigb200
 
 using namespace eigb200;
@@ -272,5 +285,15 @@ extern "C" int eigb200_scale_cols(void* stream, const float* d_a, const float* d
   EIGB_CHECK_ARG(d_a && d_s && d_out && rows > 0 && cols > 0, "scale_cols: bad arguments");
   scale_cols_kernel<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(d_a, d_s, d_out, rows * cols, cols);
   EIGB_LAUNCH_CHECK("scale_cols_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_lti_scale_b(void* stream, float* d_buf, int64_t ld, int col_b, int col_dt, const float* d_dt_bias,
+                                   int64_t rows, int N, int khead) {
+  EIGB_CHECK_ARG(d_buf && d_dt_bias, "lti_scale_b: null pointer");
+  EIGB_CHECK_ARG(rows > 0 && N > 0 && khead > 0 && N % khead == 0 && col_b >= 0 && col_dt >= 0 && ld > col_dt && ld >= col_b + N, "lti_scale_b: bad arguments");
+  const int64_t n = rows * N;
+  lti_scale_b_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_buf, ld, col_b, col_dt, d_dt_bias, rows, N, khead);
+  EIGB_LAUNCH_CHECK("lti_scale_b_kernel");
   return EIGB200_OK;
 }

@@ -72,6 +72,15 @@ class MambaBlockDev:
         m.in_proj = _Lin(_dev(sd, prefix + "mamba.in_proj.weight", device))
         m.out_proj = _Lin(_dev(sd, prefix + "mamba.out_proj.weight", device))
         m.dt_bias = _dev(sd, prefix + "mamba.dt_bias", device)
+        self.pseudoLTI = bool(cfg.get("pseudoLTI", False))
+        if self.pseudoLTI:                                            # SSD_LTI (models/mamba.py:156-299): A, beta instead of A_log
+            m.A = _dev(sd, prefix + "mamba.A", device)
+            m.beta = _dev(sd, prefix + "mamba.beta", device)
+            if m.beta is None:
+                m.beta = torch.ones_like(m.A)                         # register_buffer("beta", ones) (:228)
+            if (N * m.ngroups) % m.nheads != 0:
+                raise RuntimeError("SSD_LTI: d_state * ngroups must be divisible by nheads (models/mamba.py:200)")
+            m.khead_dim = (N * m.ngroups) // m.nheads
         m.A_log = _dev(sd, prefix + "mamba.A_log", device)
         m.D = _dev(sd, prefix + "mamba.D", device)
         cw = _dev(sd, prefix + "mamba.conv1d.weight", device)
@@ -80,7 +89,7 @@ class MambaBlockDev:
         m.use_conv = cw is not None
         # the dt rows of in_proj: split order [x | B | C | dt] (models/mamba.py:62-63)
         lo = d_inner + 2 * m.ngroups * N
-        m.W_dt = m.in_proj.weight[lo:lo + m.nheads].contiguous()
+        m.W_dt = m.in_proj.weight[lo:lo + (m.ngroups if self.pseudoLTI else m.nheads)].contiguous()
         self.mamba = m
         gw = _dev(sd, prefix + "glu.linear.weight", device)
         self.glu = SimpleNamespace(linear=_Lin(gw, _dev(sd, prefix + "glu.linear.bias", device))) if gw is not None else None
@@ -90,8 +99,24 @@ class MambaBlockDev:
     def fuses_layernorm(self):
         """True when the prenorm LayerNorm can ride inside the in_proj GEMM (row statistics supplied by the producer of x)."""
         m = self.mamba
-        return (self.prenorm and self.gemm_mode in ("auto", "tc3") and m.d_model % 4 == 0 and
+        return (self.prenorm and not self.pseudoLTI and self.gemm_mode in ("auto", "tc3") and m.d_model % 4 == 0 and
                 ops.linear_ln_supported(m.in_proj.weight.shape[0], m.d_model))
+
+    def _ssd_lti(self, z, ldz, B, T):
+        """SSD_LTI.forward after in_proj (models/mamba.py:262-295): conv + SiLU of [x | B | C], B <- softplus(dt + dt_bias) * B with the single dt
+        column tiled over the state columns, then the scan with dt := beta and A := -softplus(A)."""
+        m = self.mamba
+        di, N, H = m.d_inner, m.d_state, m.nheads
+        Cn = di + 2 * m.ngroups * N
+        if m.conv_w is not None:
+            zc = z.clone()
+            ops.conv_silu(z, ldz, m.conv_w, m.conv_b, B, T, Cn, out=zc, ldo=ldz)
+        else:
+            zc = z.clone()
+        ops.lti_scale_b(zc, ldz, di, Cn, m.dt_bias, N, m.khead_dim)
+        beta = m.beta.reshape(1, 1, H).expand(B, T, H).contiguous()
+        A = -torch.nn.functional.softplus(m.A)                        # parameter-sized host-side prep (:275)
+        return ops.ssd_scan_buffer(zc, ldz, 0, di, di + m.ngroups * N, beta, A, m.D, B, T, H, m.headdim, m.ngroups, N)
 
     def __call__(self, x, stats=None):
         """MambaBlock.forward (models/mamba.py:328-340) with SSD.forward (:111-154) inlined.
@@ -107,7 +132,10 @@ class MambaBlockDev:
         else:
             xn = ops.layernorm(x, self.norm.weight, self.norm.bias) if self.prenorm else x
             z = ops.linear(xn, m.in_proj.weight, None, ldc=ldz, mode=self.gemm_mode)              # (B*T, ldz) = [x | B | C | dt | pad]
-        y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
+        if self.pseudoLTI:
+            y = self._ssd_lti(z, ldz, B, T)
+        else:
+            y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
         o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode)    # GELU(out_proj(y))  (:333)
         if self.glu is not None:
             out = ops.linear(o, self.glu.linear.weight, self.glu.linear.bias, epilogue="glu_residual",
@@ -310,12 +338,18 @@ def init_mamba_state_dict(cfg, seed: Optional[int] = None) -> Dict[str, torch.Te
         sd["encoder.weight"], sd["encoder.bias"] = enc.weight.detach(), enc.bias.detach()
     for i in range(cfg["num_layers"]):
         p = "blocks.%d." % i
-        sd[p + "mamba.in_proj.weight"] = nn.Linear(D, d_inner + 2 * G * N + H, bias=False).weight.detach()
+        lti = bool(cfg.get("pseudoLTI", False))
+        sd[p + "mamba.in_proj.weight"] = nn.Linear(D, d_inner + 2 * G * N + (G if lti else H), bias=False).weight.detach()   # SSD_LTI: ngroups dt columns (:204)
         dt = torch.exp(torch.rand(H) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))        # models/mamba.py:71-77
         dt = torch.clamp(dt, min=1e-4)
         sd[p + "mamba.dt_bias"] = dt + torch.log(-torch.expm1(-dt))
-        sd[p + "mamba.A_log"] = torch.log(torch.empty(H, dtype=torch.float32).uniform_(1, 16))     # :85-86
-        sd[p + "mamba.D"] = torch.ones(H)
+        if lti:                                                                                     # :221-228 (constructor order: dt, D, A, beta)
+            sd[p + "mamba.D"] = torch.ones(H)
+            sd[p + "mamba.A"] = torch.empty(H, dtype=torch.float32).uniform_(-8, -2)
+            sd[p + "mamba.beta"] = torch.ones(H)
+        else:
+            sd[p + "mamba.A_log"] = torch.log(torch.empty(H, dtype=torch.float32).uniform_(1, 16)) # :85-86
+            sd[p + "mamba.D"] = torch.ones(H)
         if k > 0:
             conv = nn.Conv1d(d_inner + 2 * G * N, d_inner + 2 * G * N, kernel_size=k, groups=d_inner + 2 * G * N, padding=k - 1)
             sd[p + "mamba.conv1d.weight"], sd[p + "mamba.conv1d.bias"] = conv.weight.detach(), conv.bias.detach()

@@ -270,6 +270,19 @@ def ssd_scan(x, dt, A, Bm, Cm, D=None, return_final_state=False):
     return (y, fs) if return_final_state else y
 
 
+def ssd_scan_buffer(buf, ld, col_x, col_b, col_c, dt, A, D, B, T, H, P, G, N):
+    """eigb200_ssd_scan over operands that live in one projection buffer (B*T, ld): x at column col_x (H*P wide), B / C at col_b / col_c (G*N wide).
+    dt (B,T,H) dense, A (H), D (H) | None -> y (B,T,H*P)."""
+    buf = _prep(buf, torch.float32); dt = _prep(dt, torch.float32); A = _prep(A, torch.float32)
+    D = _prep(D, torch.float32) if D is not None else None
+    lib = _enter(buf)
+    y = torch.empty(B, T, H * P, dtype=torch.float32, device=buf.device)
+    base = buf.data_ptr()
+    _call(lib, "eigb200_ssd_scan", _stream(buf), C.c_void_p(base + 4 * col_x), ld, _p(dt), _p(A), C.c_void_p(base + 4 * col_b), C.c_void_p(base + 4 * col_c), ld,
+          _p(D), _p(y), H * P, None, B, T, H, P, G, N)
+    return y
+
+
 def mamba_conv_ssd(xbcdt, ldz, conv_w, conv_b, dt_bias, A_log, D, B, T, H, P, G, N, out=None):
     """Fused conv+SiLU / softplus(dt) / SSD scan over the raw in_proj output (B*T, ldz) -> y (B,T,H*P)."""
     xbcdt = _prep(xbcdt, torch.float32)
@@ -433,6 +446,14 @@ def scale_cols(a, s):
     cols = a.shape[-1]
     _call(lib, "eigb200_scale_cols", _stream(a), _p(a), _p(s), _p(out), a.numel() // cols, cols)
     return out
+
+
+def lti_scale_b(buf, ld, col_b, col_dt, dt_bias, N, khead):
+    """SSD_LTI: B <- softplus(dt_raw + dt_bias[head of column]) * B, in place on the projection buffer (rows, ld)."""
+    assert buf.is_cuda and buf.dtype == torch.float32 and buf.is_contiguous()
+    lib = _enter(buf)
+    _call(lib, "eigb200_lti_scale_b", _stream(buf), _p(buf), ld, col_b, col_dt, _p(_prep(dt_bias, torch.float32)), buf.numel() // ld, N, khead)
+    return buf
 
 
 SSM_KINDS = {"lru": 0, "s5_zoh": 1, "s5_bilinear": 2}

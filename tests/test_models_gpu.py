@@ -137,3 +137,27 @@ def test_s5_layer_call(eig, disc, bidir):
     scale = np.abs(hr).max(axis=1, keepdims=True)                # fp32 discretisation ((lam_bar - 1)/Lambda cancels), see test_lru_layer_call
     assert (np.abs(h.cpu().numpy() - hr) <= 1e-4 * scale).all()
     assert np.abs(y.cpu().numpy() - yr).max() <= 1e-4 * np.abs(yr).max()
+
+
+@pytest.mark.parametrize("H,N,prenorm", [(1, 16, True), (2, 8, False), (4, 16, True)])
+def test_mamba_pseudo_lti_pass_vs_oracle(eig, H, N, prenorm):
+    """SSD_LTI blocks (models/mamba.py:156-299, `pseudoLTI: True`) + get_eig_mamba2_LTI.  The reference class does not construct with current
+    torch, so parity is against the oracle's restatement of the source (unpinned by a reference execution)."""
+    A, Ly, E, S = eig
+    cfg = dict(layer="mamba", version="mamba2", num_layers=2, num_heads=H, input_dim=1, output_dim=16, hidden_dim=32, state_dim=N, conv_dim=4,
+               expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=prenorm, pooling="none", token_embedding=True, vocab_size=50,
+               pseudoLTI=True)
+    sd = Ly.init_mamba_state_dict(cfg, 11)
+    for k in list(sd):                                           # move the parameters off their trivial init
+        if k.endswith("mamba.beta"):
+            sd[k] = sd[k] * torch.linspace(0.5, 1.5, H)
+    model = Ly.MambaDev(cfg, sd, "cuda")
+    X = torch.randint(0, 50, (3, 45), generator=torch.Generator().manual_seed(2))
+    res = A.mamba_pass(model, X.cuda(), pseudoLTI=True)
+    ocfg = dict(num_layers=2, d_inner=32, ngroups=1, d_state=N, nheads=H, headdim=32 // H, prenorm=prenorm, pseudoLTI=True)
+    ref, xr = O.mamba_eval_pass(X.numpy(), {k: v.numpy() for k, v in sd.items()}, ocfg, np.float64)
+    assert np.abs(res.x_last.cpu().numpy() - xr).max() <= 3e-5 * np.abs(xr).max()
+    e = res.eig_host()
+    assert e.shape == ref.shape == (3, 45, H, 2)
+    np.testing.assert_allclose(e, ref, rtol=1e-5)
+    assert (res.counts.cpu().numpy()[..., 7] == 45).all()
