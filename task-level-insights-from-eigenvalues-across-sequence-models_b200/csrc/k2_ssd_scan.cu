@@ -403,7 +403,11 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <int N, int NT, int MINB, bool CONV>
+// RESCALED = true runs the recurrence of a chunk on r_t = S_t / E_t, E_t = product of the chunk's decays up to t: r_t = r_{t-1} + (dt_t x_t / E_t) B_t,
+// y_t = E_t (C_t . r_t) + D x_t -- 2 instead of 3 FMA-pipe operations per state element; S = r E at the chunk end.  E_t and 1 / E_t are formed once per
+// (sequence, head, token) in the prep phase.  A chunk whose E falls below 2^-60 (1 / E near the fp32 range) runs the direct form instead -- a CTA-uniform,
+// per-chunk decision, so both serial loops stay branch-free.  Same recurrence, different rounding (E accumulates at most 32 roundings).
+template <int N, int NT, int MINB, bool CONV, bool RESCALED>
 __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p) {
   constexpr int TC = SSD2_TC, GT = 4;                              // tokens per chunk / per unrolled group
   constexpr int RAW_ROWS = TC + SSD_HIST;
@@ -414,7 +418,8 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
   static_assert((TC * 2 * N) % NT == 0 && NT % (2 * N) == 0 && TC % GT == 0, "prep / group mapping");
   __shared__ __align__(16) float raw_s[RAW_ROWS][2 * N];
   __shared__ __align__(16) float bc_s[2][TC][2 * N];
-  __shared__ __align__(8) float2 dd_s[2][TC];
+  __shared__ __align__(16) float4 dd_s[2][TC];                     // (dt, decay, E_t, 1 / E_t)
+  __shared__ int chunk_direct_s[2];                                // RESCALED: this chunk takes the direct form (E underflow)
 
   const int P = p.P;
   const int b = blockIdx.z, h = blockIdx.y, pblk = blockIdx.x;
@@ -493,15 +498,24 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
       } else v = raw_s[r + 3][bc_col];
       bc_s[buf][r][bc_col] = v;
     }
-    if (tid < tc) {
-      const float d = p.fused ? softplus_f(dtreg + dtb) : dtreg;
-      dd_s[buf][tid] = make_float2(d, expf(d * Ah));
+    if (tid < 32) {                                                // warp 0: lane t holds (dt_t, decay_t) and the running product E_t
+      const float d = (tid < tc) ? (p.fused ? softplus_f(dtreg + dtb) : dtreg) : 0.f;
+      const float dec = (tid < tc) ? expf(d * Ah) : 1.f;
+      float E = dec;
+      if (RESCALED) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, E, o); if (tid >= o) E *= v; }   // inclusive product scan
+        const float Emin = __shfl_sync(0xffffffffu, E, 31);        // decays <= 1: the last product is the smallest
+        if (tid == 0) chunk_direct_s[buf] = (Emin < 0x1p-60f || !(Emin == Emin)) ? 1 : 0;
+      }
+      if (tid < tc) dd_s[buf][tid] = make_float4(d, dec, E, 1.f / E);
     }
   };
 
   // one token: conv + SiLU of the two x channels, state update, output
-  auto token = [&](int buf, int tt, float2 x0, float2 xm1, float2 xm2, float2 xm3, float* yp) {
-    const float2 dd = dd_s[buf][tt];
+  auto token = [&](auto resc_tag, int buf, int tt, float2 x0, float2 xm1, float2 xm2, float2 xm3, float* yp) {
+    constexpr bool RESC = decltype(resc_tag)::value;
+    const float4 dd = dd_s[buf][tt];
     const float xin[2] = {x0.x, x0.y}, a1[2] = {xm1.x, xm1.y}, a2[2] = {xm2.x, xm2.y}, a3[2] = {xm3.x, xm3.y};
     float xcv[2], uu[2], acc[2][4];
 #pragma unroll
@@ -516,20 +530,39 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
     }
     const float4* B4 = reinterpret_cast<const float4*>(&bc_s[buf][tt][0]);
     const float4* C4 = reinterpret_cast<const float4*>(&bc_s[buf][tt][N]);
+    if (!RESC) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-      const float4 bv = B4[q], cv = C4[q];
+      for (int q = 0; q < N / 4; ++q) {
+        const float4 bv = B4[q], cv = C4[q];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        s[c][4 * q + 0] = fmaf(dd.y, s[c][4 * q + 0], uu[c] * bv.x); acc[c][0] = fmaf(cv.x, s[c][4 * q + 0], acc[c][0]);
-        s[c][4 * q + 1] = fmaf(dd.y, s[c][4 * q + 1], uu[c] * bv.y); acc[c][1] = fmaf(cv.y, s[c][4 * q + 1], acc[c][1]);
-        s[c][4 * q + 2] = fmaf(dd.y, s[c][4 * q + 2], uu[c] * bv.z); acc[c][2] = fmaf(cv.z, s[c][4 * q + 2], acc[c][2]);
-        s[c][4 * q + 3] = fmaf(dd.y, s[c][4 * q + 3], uu[c] * bv.w); acc[c][3] = fmaf(cv.w, s[c][4 * q + 3], acc[c][3]);
+        for (int c = 0; c < 2; ++c) {
+          s[c][4 * q + 0] = fmaf(dd.y, s[c][4 * q + 0], uu[c] * bv.x); acc[c][0] = fmaf(cv.x, s[c][4 * q + 0], acc[c][0]);
+          s[c][4 * q + 1] = fmaf(dd.y, s[c][4 * q + 1], uu[c] * bv.y); acc[c][1] = fmaf(cv.y, s[c][4 * q + 1], acc[c][1]);
+          s[c][4 * q + 2] = fmaf(dd.y, s[c][4 * q + 2], uu[c] * bv.z); acc[c][2] = fmaf(cv.z, s[c][4 * q + 2], acc[c][2]);
+          s[c][4 * q + 3] = fmaf(dd.y, s[c][4 * q + 3], uu[c] * bv.w); acc[c][3] = fmaf(cv.w, s[c][4 * q + 3], acc[c][3]);
+        }
       }
+      const float y0 = fmaf(Dh, xcv[0], (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]));
+      const float y1 = fmaf(Dh, xcv[1], (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]));
+      *reinterpret_cast<float2*>(yp) = make_float2(y0, y1);
+    } else {
+      const float w0 = uu[0] * dd.w, w1 = uu[1] * dd.w;            // dt x / E_t
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        const float4 bv = B4[q], cv = C4[q];
+        s[0][4 * q + 0] = fmaf(w0, bv.x, s[0][4 * q + 0]); acc[0][0] = fmaf(cv.x, s[0][4 * q + 0], acc[0][0]);
+        s[0][4 * q + 1] = fmaf(w0, bv.y, s[0][4 * q + 1]); acc[0][1] = fmaf(cv.y, s[0][4 * q + 1], acc[0][1]);
+        s[0][4 * q + 2] = fmaf(w0, bv.z, s[0][4 * q + 2]); acc[0][2] = fmaf(cv.z, s[0][4 * q + 2], acc[0][2]);
+        s[0][4 * q + 3] = fmaf(w0, bv.w, s[0][4 * q + 3]); acc[0][3] = fmaf(cv.w, s[0][4 * q + 3], acc[0][3]);
+        s[1][4 * q + 0] = fmaf(w1, bv.x, s[1][4 * q + 0]); acc[1][0] = fmaf(cv.x, s[1][4 * q + 0], acc[1][0]);
+        s[1][4 * q + 1] = fmaf(w1, bv.y, s[1][4 * q + 1]); acc[1][1] = fmaf(cv.y, s[1][4 * q + 1], acc[1][1]);
+        s[1][4 * q + 2] = fmaf(w1, bv.z, s[1][4 * q + 2]); acc[1][2] = fmaf(cv.z, s[1][4 * q + 2], acc[1][2]);
+        s[1][4 * q + 3] = fmaf(w1, bv.w, s[1][4 * q + 3]); acc[1][3] = fmaf(cv.w, s[1][4 * q + 3], acc[1][3]);
+      }
+      const float y0 = fmaf(Dh, xcv[0], dd.z * ((acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3])));
+      const float y1 = fmaf(Dh, xcv[1], dd.z * ((acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3])));
+      *reinterpret_cast<float2*>(yp) = make_float2(y0, y1);
     }
-    const float y0 = fmaf(Dh, xcv[0], (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]));
-    const float y1 = fmaf(Dh, xcv[1], (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]));
-    *reinterpret_cast<float2*>(yp) = make_float2(y0, y1);
   };
 
   // x pipeline: the GT tokens of the current group in registers, the next group in flight
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
     const int tc = (int)min((int64_t)TC, T - t0);
     const bool more = t0 + TC < T;
     if (more) { raw_async(t0 + TC); dt_fetch(t0 + TC); }           // next chunk's shared operands: in flight during the serial phase
-    if (t0 + TC + 2 * GT <= T) {
+    if (RESCALED && t0 + TC + 2 * GT <= T && !chunk_direct_s[buf]) {
       // ---- guard-free serial phase: every token of the chunk and every prefetch is inside the sequence --------------------------
 #pragma unroll 1
       for (int gi = 0; gi < TC / GT; ++gi) {
@@ -560,10 +593,34 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
 #pragma unroll
         for (int j = 0; j < GT; ++j) xn[j] = ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx));   // two groups (8 tokens) ahead
         xpre += GT * ldx;
-        token(buf, gi * GT + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
-        token(buf, gi * GT + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
-        token(buf, gi * GT + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
-        token(buf, gi * GT + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
+        token(std::integral_constant<bool, true>{}, buf, gi * GT + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
+        token(std::integral_constant<bool, true>{}, buf, gi * GT + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
+        token(std::integral_constant<bool, true>{}, buf, gi * GT + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
+        token(std::integral_constant<bool, true>{}, buf, gi * GT + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
+        yptr += GT * ldy;
+        hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) { xcur[j] = xnx[j]; xnx[j] = xn[j]; }
+      }
+      {
+        const float Eend = dd_s[buf][TC - 1].z;                    // back to the true state: S = r E
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < N; ++i) s[c][i] *= Eend;
+      }
+    } else if (t0 + TC + 2 * GT <= T) {
+      // ---- guard-free serial phase: every token of the chunk and every prefetch is inside the sequence --------------------------
+#pragma unroll 1
+      for (int gi = 0; gi < TC / GT; ++gi) {
+        float2 xn[GT];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) xn[j] = ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx));   // two groups (8 tokens) ahead
+        xpre += GT * ldx;
+        token(std::integral_constant<bool, false>{}, buf, gi * GT + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
+        token(std::integral_constant<bool, false>{}, buf, gi * GT + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
+        token(std::integral_constant<bool, false>{}, buf, gi * GT + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
+        token(std::integral_constant<bool, false>{}, buf, gi * GT + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
         yptr += GT * ldy;
         hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
 #pragma unroll
@@ -580,10 +637,10 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
           xn[j] = (tn + j < T) ? ldg_stream_f2(reinterpret_cast<const float2*>(xpre + (size_t)j * ldx)) : make_float2(0.f, 0.f);
         xpre += GT * ldx;
         const int tt = gi * GT;
-        if (tt + 0 < tc) token(buf, tt + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
-        if (tt + 1 < tc) token(buf, tt + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
-        if (tt + 2 < tc) token(buf, tt + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
-        if (tt + 3 < tc) token(buf, tt + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
+        if (tt + 0 < tc) token(std::integral_constant<bool, false>{}, buf, tt + 0, xcur[0], hist[2], hist[1], hist[0], yptr);
+        if (tt + 1 < tc) token(std::integral_constant<bool, false>{}, buf, tt + 1, xcur[1], xcur[0], hist[2], hist[1], yptr + ldy);
+        if (tt + 2 < tc) token(std::integral_constant<bool, false>{}, buf, tt + 2, xcur[2], xcur[1], xcur[0], hist[2], yptr + 2 * ldy);
+        if (tt + 3 < tc) token(std::integral_constant<bool, false>{}, buf, tt + 3, xcur[3], xcur[2], xcur[1], xcur[0], yptr + 3 * ldy);
         yptr += GT * ldy;
         hist[0] = xcur[1]; hist[1] = xcur[2]; hist[2] = xcur[3];
 #pragma unroll
@@ -598,20 +655,21 @@ __global__ void __launch_bounds__(NT, MINB) ssd_scan_v3_kernel(const SsdParams p
     }
   }
   if (p.final_state) {
+    const float Eend = 1.f;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float* fs = p.final_state + (((size_t)b * p.H + h) * P + pch + c) * N;
 #pragma unroll
-      for (int i = 0; i < N; ++i) fs[i] = s[c][i];
+      for (int i = 0; i < N; ++i) fs[i] = s[c][i] * Eend;
     }
   }
 }
 
-template <int N, int NT, int MINB>
+template <int N, int NT, int MINB, bool RESCALED = false>
 static int launch_ssd_v3(cudaStream_t st, const SsdParams& p, int64_t B) {
   dim3 grid(p.P / (NT * 2), p.H, (unsigned)B);
-  if (p.fused && p.kconv > 0) ssd_scan_v3_kernel<N, NT, MINB, true><<<grid, NT, 0, st>>>(p);
-  else ssd_scan_v3_kernel<N, NT, MINB, false><<<grid, NT, 0, st>>>(p);
+  if (p.fused && p.kconv > 0) ssd_scan_v3_kernel<N, NT, MINB, true, RESCALED><<<grid, NT, 0, st>>>(p);
+  else ssd_scan_v3_kernel<N, NT, MINB, false, RESCALED><<<grid, NT, 0, st>>>(p);
   EIGB_LAUNCH_CHECK("ssd_scan_v3_kernel");
   return EIGB200_OK;
 }
@@ -654,6 +712,8 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
             case 5: return launch_ssd_v2<16, 1, 128, 8, 1>(st, p, B);
             case 6: return launch_ssd_v2<16, 1, 128, 4, 4>(st, p, B);
             case 7: return launch_ssd_v2<16, 2, 64, 2, 8>(st, p, B);
+            case 40: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 8, true>(st, p, B); break;
+            case 41: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 7, true>(st, p, B); break;
             case 20: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 8>(st, p, B); break;
             case 21: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 6>(st, p, B); break;
             case 22: if (p.P % 64 == 0) return launch_ssd_v3<16, 32, 12>(st, p, B); break;
@@ -668,8 +728,8 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
       }
 #define SSD2_CASE(N_)                                                                                                       \
       case N_:   /* v3 (strength-reduced loop) when the channels tile exactly; else v2 with U = 2, >= 8 CTAs/SM */                \
-        if (cpt == 2 && p.P % 128 == 0) return launch_ssd_v3<N_, 64, 8>(st, p, B);                                              \
-        if (cpt == 2 && p.P % 64 == 0) return launch_ssd_v3<N_, 32, 8>(st, p, B);                                               \
+        if (cpt == 2 && p.P % 128 == 0) return launch_ssd_v3<N_, 64, 8, true>(st, p, B);   /* rescaled-state form: -8 % at C2 */    \
+        if (cpt == 2 && p.P % 64 == 0) return launch_ssd_v3<N_, 32, 8, true>(st, p, B);                                         \
         if (cpt == 2) return wide ? launch_ssd_v2<N_, 2, 64, 2, 8>(st, p, B) : launch_ssd_v2<N_, 2, 32, 2, 8>(st, p, B);        \
         return wide ? launch_ssd_v2<N_, 1, 64, 4, 8>(st, p, B) : launch_ssd_v2<N_, 1, 32, 4, 8>(st, p, B);
       switch (p.N) { SSD2_CASE(16) SSD2_CASE(8) SSD2_CASE(4) default: break; }
