@@ -714,6 +714,9 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
             case 7: return launch_ssd_v2<16, 2, 64, 2, 8>(st, p, B);
             case 40: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 8, true>(st, p, B); break;
             case 41: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 7, true>(st, p, B); break;
+            case 42: if (p.P % 64 == 0) return launch_ssd_v3<16, 32, 12, true>(st, p, B); break;
+            case 43: if (p.P % 64 == 0) return launch_ssd_v3<16, 32, 16, true>(st, p, B); break;
+            case 44: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 6, true>(st, p, B); break;
             case 20: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 8>(st, p, B); break;
             case 21: if (p.P % 128 == 0) return launch_ssd_v3<16, 64, 6>(st, p, B); break;
             case 22: if (p.P % 64 == 0) return launch_ssd_v3<16, 32, 12>(st, p, B); break;
