@@ -77,6 +77,13 @@ int eigb200_mamba2_eig(void* stream, const void* d_x, int x_dtype, int64_t B, in
                        float* d_lam, int64_t lam_stride, int32_t* d_counts, const double* thresholds, int nthr, int compare_mode,
                        float* d_rowstats, float ln_eps);
 
+/* The same extractor without re-reading x: eigb200_linear_glu_extract (the GLU + residual GEMM that PRODUCES x, models/mamba.py:335-337) leaves, per row
+ * and per group of 16 output columns, (x . W_dt, mean, M2) in d_partials[(g * 3 + c) * B*T + row]; this call combines the D / 16 = ngroups16 groups in a
+ * fixed order and finishes lambda, the bin counts and the next block's LayerNorm statistics.  One head (H = 1); d_dt_bias / d_A_log are device pointers. */
+int eigb200_mamba2_eig_partials(void* stream, const float* d_partials, int ngroups16, int64_t B, int64_t T,
+                                const float* d_dt_bias, const float* d_A_log, float* d_lam, int64_t lam_stride, int32_t* d_counts,
+                                const double* thresholds, int nthr, int compare_mode, float* d_rowstats, float ln_eps);
+
 /* get_eig_mamba2_LTI (analysis/eval_eig.py:192-205): lambda[h] = exp(beta[h] * -softplus(A[h])), broadcast over (B,T).
  * d_lam (B,T,H) may be NULL; d_counts (B,H,8) accumulated. */
 int eigb200_mamba2_lti_eig(void* stream, const float* d_A, const float* d_beta, int64_t B, int64_t T, int H,
@@ -188,6 +195,11 @@ int eigb200_rowstats(void* stream, const float* d_x, int64_t rows, int D, float 
 int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
                    float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
                    int64_t M, int N, int K, int epilogue, int mode, void* d_workspace, size_t workspace_bytes);
+/* GLU + residual GEMM (epilogue GLU_RESIDUAL) whose epilogue also emits the extractor partials of its OUTPUT rows for eigb200_mamba2_eig_partials:
+ * d_W_gate (N/2) = the dt row of the block's in_proj, d_partials ((N/32) * 3 * M floats).  Tensor-core path only (K <= 256, N/2 % 16 == 0, R 32-byte aligned). */
+int eigb200_linear_glu_extract(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
+                               float* d_C, int64_t ldc, const float* d_R, int64_t ldr, int64_t M, int N, int K,
+                               const float* d_W_gate, float* d_partials, void* d_workspace, size_t workspace_bytes);
 
 /* TokenEmbeddings.forward (models/common.py:160-176): out[b,t,:] = word[ids[b,t],:] (+ pos[t,:] if d_pos != NULL). ids int64. */
 int eigb200_embedding(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,

@@ -28,6 +28,8 @@ SIGNATURES = {
     "eigb200_set_device": [_i],
     "eigb200_zero_i32": [_vp, _vp, _sz],
     "eigb200_mamba2_eig": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _dp, _i, _i, _vp, _f],
+    "eigb200_mamba2_eig_partials": [_vp, _vp, _i, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _dp, _i, _i, _vp, _f],
+    "eigb200_linear_glu_extract": [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp, _sz],
     "eigb200_mamba2_lti_eig": [_vp, _vp, _vp, _i64, _i64, _i, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_normattn_gate": [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _i, _vp],
     "eigb200_linattn_nu": [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _vp],

@@ -65,7 +65,16 @@ def mamba_pass(model: "Ly.MambaDev", X, pseudoLTI=False, want_eig=True, compare=
     nl = len(model.blocks)
     eig = torch.empty(B, T, H, nl, dtype=torch.float32, device=x.device) if want_eig else None
     counts = torch.zeros(nl, B, H, ops.NSLOT, dtype=torch.int32, device=x.device)
+    # extractor fusion: the GLU + residual GEMM that produces a block's output also leaves the per-row partials of x_out . W_dt and of the LayerNorm
+    # moments; a small kernel finishes lambda, counts and statistics from them instead of K1 re-reading x_out (one head, M >= 1024 rows)
+    fuse_x = (fuse and B * T >= 1024 and all(b.fuses_extractor() for b in model.blocks) and os.environ.get("EIGB200_EXTRACT_FUSION", "1") != "0")
+    part = torch.empty(model.blocks[0].mamba.d_model // 16, 3, B * T, dtype=torch.float32, device=x.device) if fuse_x else None
     for i, blk in enumerate(model.blocks):
+        if fuse_x:
+            x = blk(x, stats[i & 1], extract_partials=part)
+            ops.mamba2_eig_partials(part, B, T, blk.mamba.dt_bias, blk.mamba.A_log, want_lam=want_eig, counts=counts[i], compare=compare,
+                                    lam_out=eig[..., i] if want_eig else None, rowstats_out=stats[(i + 1) & 1] if i + 1 < nl else None)
+            continue
         x = blk(x, stats[i & 1]) if fuse else blk(x)
         out_i = eig[..., i] if want_eig else None
         if pseudoLTI:

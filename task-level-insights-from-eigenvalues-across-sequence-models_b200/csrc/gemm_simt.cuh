@@ -8,6 +8,8 @@ struct LinearParams {
   int64_t M; int N, K, epilogue;
   // optional LayerNorm fused into the A operand (tensor-core path only): (mean, rstd) per row, gamma / beta per column
   const float* ln_stats = nullptr; const float* ln_gamma = nullptr; const float* ln_beta = nullptr;
+  // optional extractor fusion in the GLU epilogue (tensor-core path only): gate weights (N/2) and the partials buffer ((N/32) * 3 * M floats)
+  const float* eig_w = nullptr; float* eig_part = nullptr;
 };
 int launch_linear_simt(cudaStream_t st, const LinearParams& p);
 }  // namespace eigb200

@@ -309,6 +309,67 @@ static void launch_row8(cudaStream_t st, const K1Params& q, dim3 grid, dim3 bloc
   else k1_row8_kernel<HT, NF4, false><<<grid, block, 0, st>>>(q);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Mamba-2 extractor from the partials the GLU epilogue left behind (eigb200_linear_glu_extract): per row, NG = D / 16 groups of
+// (gate dot product, mean, M2) over 16 columns each, stored part[(g * 3 + c) * rows + row].  They are combined in a FIXED order (so the result
+// does not depend on scheduling): dot = ((p0 + p1) + (p2 + p3)) + ..., moments by Chan's pairwise merge.  One thread per row; a warp's 32 rows
+// belong to one sequence when T % 32 == 0 (bin counters then flush once per warp), otherwise every thread flushes its own.
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int NG>
+__global__ void __launch_bounds__(256) k1_partials_kernel(const float* __restrict__ part, int64_t rows, int T, const float* __restrict__ dt_bias_p,
+                                                           const float* __restrict__ A_log_p, float* __restrict__ lam,
+                                                           int64_t lam_stride, int* __restrict__ counts, EdgesF e, float2* __restrict__ rowstats, float ln_eps) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = row < rows;
+  const int64_t r = ok ? row : rows - 1;
+  const float dt_bias = __ldg(dt_bias_p), A = -expf(__ldg(A_log_p));   // one head
+  float dot[NG], mean[NG], m2[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    dot[g] = ldg_stream_f1(part + (size_t)(g * 3 + 0) * rows + r);
+    mean[g] = ldg_stream_f1(part + (size_t)(g * 3 + 1) * rows + r);
+    m2[g] = ldg_stream_f1(part + (size_t)(g * 3 + 2) * rows + r);
+  }
+  float n = 16.f;
+#pragma unroll
+  for (int w = 1; w < NG; w <<= 1) {                               // pairwise tree: (0,1) (2,3) ... then (01,23) ...
+#pragma unroll
+    for (int g = 0; g + w < NG; g += 2 * w) {
+      dot[g] += dot[g + w];
+      const float delta = mean[g + w] - mean[g];
+      mean[g] = 0.5f * (mean[g] + mean[g + w]);                    // equal counts
+      m2[g] = (m2[g] + m2[g + w]) + delta * delta * (0.5f * n);
+    }
+    n *= 2.f;
+  }
+  const float dt = softplus_f(dot[0] + dt_bias);
+  const float val = expf(dt * A);
+  int cnt[EIGB_NCNT];
+#pragma unroll
+  for (int j = 0; j < EIGB_NCNT; ++j) cnt[j] = 0;
+  if (ok) {
+    if (lam) lam[(size_t)row * lam_stride] = val;
+    if (rowstats) rowstats[row] = make_float2(mean[0], rsqrtf(fmaxf(m2[0] / n, 0.f) + ln_eps));
+    bin_f32(sqrtf(__fmul_rn(val, val)), e, cnt);
+    cnt[8] = (val == val) ? 1 : 0;
+  }
+  if (counts) {
+    const int64_t b = r / T;
+    if (T % 32 == 0) {                                             // the whole warp shares the sequence: one atomic per slot per warp
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j) {
+        const int v = __reduce_add_sync(0xffffffffu, cnt[j]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[(size_t)b * EIGB200_NSLOT + slot_of(j, e.nb)], v);
+      }
+    } else if (ok) {
+#pragma unroll
+      for (int j = 0; j < EIGB_NCNT; ++j)
+        if (cnt[j]) atomicAdd(&counts[(size_t)b * EIGB200_NSLOT + slot_of(j, e.nb)], cnt[j]);
+    }
+  }
+}
+
 template <bool BF16, int EPI>
 static int launch_k1(cudaStream_t st, const K1Params& p, int64_t B) {
   int ht = 1;
@@ -591,5 +652,29 @@ extern "C" int eigb200_count_moments(void* stream, const int32_t* d_counts, int6
   const int64_t n = inner * EIGB200_NSLOT;
   count_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_counts, B, n, (long long*)d_sum, (long long*)d_sumsq);
   EIGB_LAUNCH_CHECK("count_moments_kernel");
+  return EIGB200_OK;
+}
+
+extern "C" int eigb200_mamba2_eig_partials(void* stream, const float* d_partials, int ngroups16, int64_t B, int64_t T,
+                                           const float* d_dt_bias, const float* d_A_log, float* d_lam, int64_t lam_stride, int32_t* d_counts,
+                                           const double* thresholds, int nthr, int compare_mode, float* d_rowstats, float ln_eps) {
+  EIGB_CHECK_ARG(d_partials && d_dt_bias && d_A_log, "mamba2_eig_partials: null pointer");
+  EIGB_CHECK_ARG(B > 0 && T > 0 && T < (1LL << 31), "mamba2_eig_partials: bad shape");
+  EIGB_CHECK_ARG(ngroups16 == 2 || ngroups16 == 4 || ngroups16 == 8 || ngroups16 == 16, "mamba2_eig_partials: d_model / 16 = %d must be 2, 4, 8 or 16", ngroups16);
+  EIGB_CHECK_ARG(!d_lam || lam_stride >= 1, "mamba2_eig_partials: lam_stride must be >= 1");
+  EdgesF e; double one = 1.0;
+  if (d_counts) { int rc = make_edges_f(thresholds, nthr, compare_mode, &e); if (rc) return rc; } else make_edges_f(&one, 1, 0, &e);
+  const int64_t rows = B * T;
+  const float* dtb = d_dt_bias; const float* A = d_A_log;
+  const unsigned grid = (unsigned)((rows + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  float2* rs = reinterpret_cast<float2*>(d_rowstats);
+  switch (ngroups16) {
+    case 2: k1_partials_kernel<2><<<grid, 256, 0, st>>>(d_partials, rows, (int)T, dtb, A, d_lam, lam_stride, d_counts, e, rs, ln_eps); break;
+    case 4: k1_partials_kernel<4><<<grid, 256, 0, st>>>(d_partials, rows, (int)T, dtb, A, d_lam, lam_stride, d_counts, e, rs, ln_eps); break;
+    case 8: k1_partials_kernel<8><<<grid, 256, 0, st>>>(d_partials, rows, (int)T, dtb, A, d_lam, lam_stride, d_counts, e, rs, ln_eps); break;
+    default: k1_partials_kernel<16><<<grid, 256, 0, st>>>(d_partials, rows, (int)T, dtb, A, d_lam, lam_stride, d_counts, e, rs, ln_eps); break;
+  }
+  EIGB_LAUNCH_CHECK("k1_partials_kernel");
   return EIGB200_OK;
 }

@@ -44,6 +44,7 @@ struct TcParams {
   int bn;            // columns per CTA (UMMA N), multiple of 32, <= 128
   int bg;            // GLU: value columns per CTA (bn = 2*bg); otherwise bn
   int nsplit, kchunks, nstages, nterms, workers;
+  const float* eig_w; float* eig_part;   // GLU epilogue only (nullable): per-row partial gate dot products and moments of the OUTPUT rows, see tc_epilogue
   int r_v8;          // residual rows are 32-byte aligned: add them in the accumulator layout with 256-bit loads
   int zero;          // always 0; a run-time value the compilers cannot fold (mbar_arrive_after)
   int64_t ntiles;
@@ -318,6 +319,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
   const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
   const bool use_r = p.R && (GLU || EPI == EIGB200_EPI_RESIDUAL);
   const bool r_own = use_r && p.r_v8;                                // residual added in the accumulator layout with 256-bit loads
+  const float* eigw_s = bias_s + 192;                                // [cols_out] gate weights of this CTA's output columns (768 bytes after the bias)
   int j = 0; uint32_t dph = 0;
   for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
     const int64_t own_row = tile * TC_BM + quarter * 32 + lane;      // accumulator layout: lane = row
@@ -349,6 +351,23 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         if (r_own) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += rr[i];
+        }
+        if (p.eig_part && r_own) {
+          // Extractor fusion: the finished output row segment (16 columns of x_out = GLU + skip) contributes its part of the eigenvalue gate
+          // x_out . W_dt and of the LayerNorm moments of the NEXT block, so that no kernel has to re-read x_out: per (row, 16-column group)
+          // (dot, mean, M2) go to part[(g16 * 3 + c) * M + row] (coalesced over rows), combined in a fixed order by eigb200_mamba2_eig_partials.
+          const float* we = eigw_s + (cg >> 1);
+          float dot = 0.f, sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { dot = fmaf(v[i], we[i], dot); sum += v[i]; }
+          const float mean = sum * 0.0625f;
+          float m2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
+          if (own_row < p.M) {
+            float* pp = p.eig_part + (size_t)(oc >> 4) * 3 * p.M + own_row;
+            pp[0] = dot; pp[p.M] = mean; pp[2 * p.M] = m2;
+          }
         }
         transpose4x4_f4(v, lane);
         const int n = oc + 4 * (lane & 3);
@@ -810,6 +829,10 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
     }
   }
+  if (EPI == EIGB200_EPI_GLU_RESIDUAL && p.eig_part && threadIdx.x >= 128 && threadIdx.x < 256) {   // gate weights of this CTA's bg output columns
+    float* ew = bias_s + 192;
+    for (int c = threadIdx.x - 128; c < p.bg; c += 128) { const int n = split * p.bg + c; ew[c] = n < p.N / 2 ? p.eig_w[n] : 0.f; }
+  }
   if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
   if (warp == TC_TMA_WARP && lane == 0) { tma_prefetch_desc(&tmapA); tma_prefetch_desc(&tmapWhi); tma_prefetch_desc(&tmapWlo); }
   tc_fence_before();
@@ -1212,6 +1235,7 @@ bool tc_supported(const LinearParams& p) {
 }
 
 static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
+  if (lp.eig_part) { set_error("linear_glu_extract: not available on the streamed-operand kernel (K > 256)"); return EIGB200_EUNSUPPORTED; }
   const StreamPlan pl = make_stream_plan(lp.N, lp.K, lp.epilogue);
   if (!pl.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
   const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
@@ -1309,6 +1333,14 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   // instead of the template parameter costs both shapes 3 % (the converter loop is latency-critical), hence two instantiations.
   const bool defer = pl.bn < 128;
   p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
+  p.eig_w = nullptr; p.eig_part = nullptr;
+  if (lp.eig_part) {                                                 // extractor partials ride in the GLU epilogue of the TMEM-operand kernel only
+    if (!(glu && pl.ts && p.r_v8 && (lp.N / 2) % 16 == 0 && lp.eig_w)) {
+      set_error("linear_glu_extract: needs the GLU epilogue with a 32-byte aligned residual and N/2 a multiple of 16 (N=%d)", lp.N);
+      return EIGB200_EUNSUPPORTED;
+    }
+    p.eig_w = lp.eig_w; p.eig_part = lp.eig_part;
+  }
   int workers = num_sms() / pl.nsplit;
   if (workers < 1) workers = 1;
   if ((int64_t)workers > p.ntiles) workers = (int)p.ntiles;

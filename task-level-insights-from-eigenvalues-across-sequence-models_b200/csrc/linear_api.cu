@@ -44,3 +44,18 @@ extern "C" int eigb200_linear_ln(void* stream, const float* d_A, int64_t lda, co
   }
   return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace);
 }
+
+extern "C" int eigb200_linear_glu_extract(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
+                                          float* d_C, int64_t ldc, const float* d_R, int64_t ldr, int64_t M, int N, int K,
+                                          const float* d_W_gate, float* d_partials, void* d_workspace, size_t workspace_bytes) {
+  EIGB_CHECK_ARG(d_A && d_W && d_C && d_R && d_W_gate && d_partials, "linear_glu_extract: null pointer");
+  EIGB_CHECK_ARG(M > 0 && N > 0 && N % 2 == 0 && K > 0, "linear_glu_extract: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  EIGB_CHECK_ARG(lda >= K && ldc >= N / 2 && ldr >= N / 2, "linear_glu_extract: row stride smaller than the row");
+  LinearParams p{d_A, lda, d_W, d_bias, d_C, ldc, d_R, ldr, M, N, K, EIGB200_EPI_GLU_RESIDUAL};
+  p.eig_w = d_W_gate; p.eig_part = d_partials;
+  if (!(tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes_m(M, N, K))) {
+    set_error("linear_glu_extract: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d)", (long long)M, N, K);
+    return EIGB200_EUNSUPPORTED;
+  }
+  return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace);
+}

@@ -118,10 +118,18 @@ class MambaBlockDev:
         A = -torch.nn.functional.softplus(m.A)                        # parameter-sized host-side prep (:275)
         return ops.ssd_scan_buffer(zc, ldz, 0, di, di + m.ngroups * N, beta, A, m.D, B, T, H, m.headdim, m.ngroups, N)
 
-    def __call__(self, x, stats=None):
+    def fuses_extractor(self):
+        """True when the eigenvalue extractor of this block's OUTPUT can ride in the GLU + residual GEMM's epilogue (one head, prenorm, GLU present,
+        d_model / 16 a power of two <= 16, tensor-core GEMM): x_out is then never re-read."""
+        m = self.mamba
+        return (self.fuses_layernorm() and self.glu is not None and m.nheads == 1 and not self.pseudoLTI and m.d_model % 16 == 0 and
+                (m.d_model // 16) in (2, 4, 8, 16))
+
+    def __call__(self, x, stats=None, extract_partials=None):
         """MambaBlock.forward (models/mamba.py:328-340) with SSD.forward (:111-154) inlined.
         stats: optional (B,T,2) LayerNorm (mean, rstd) of x from the kernel that produced x (embedding / previous extractor);
-        with it the normalised activations are formed inside the in_proj GEMM and never written to HBM."""
+        with it the normalised activations are formed inside the in_proj GEMM and never written to HBM.
+        extract_partials: optional (d_model/16, 3, B*T) buffer; the GLU epilogue then also leaves the extractor partials of the output rows in it."""
         m = self.mamba
         B, T, D = x.shape
         skip = x
@@ -137,7 +145,9 @@ class MambaBlockDev:
         else:
             y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
         o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode)    # GELU(out_proj(y))  (:333)
-        if self.glu is not None:
+        if self.glu is not None and extract_partials is not None and self.fuses_extractor() and B * T >= 1024:
+            out, _ = ops.linear_glu_extract(o, self.glu.linear.weight, self.glu.linear.bias, skip.reshape(B * T, D), m.W_dt[0], partials=extract_partials)
+        elif self.glu is not None:
             out = ops.linear(o, self.glu.linear.weight, self.glu.linear.bias, epilogue="glu_residual",
                              residual=skip.reshape(B * T, D), mode=self.gemm_mode)                 # GLU + skip (:335-337)
         else:

@@ -341,6 +341,44 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     return out
 
 
+def linear_glu_extract(a, weight, bias, residual, w_gate, partials=None, out=None, workspace=None):
+    """GLU + residual GEMM that also leaves the extractor partials of its output rows: -> (out (M, N/2), partials (N/32, 3, M))."""
+    assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()
+    K = a.shape[-1]
+    M = a.numel() // K
+    weight = _prep(weight, torch.float32); bias = _prep(bias, torch.float32) if bias is not None else None
+    N = weight.shape[0]
+    nout = N // 2
+    lib = _enter(a)
+    if out is None:
+        out = torch.empty(M, nout, dtype=torch.float32, device=a.device)
+    if partials is None:
+        partials = torch.empty(nout // 16, 3, M, dtype=torch.float32, device=a.device)
+    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
+    _call(lib, "eigb200_linear_glu_extract", _stream(a), _p(a), K, _p(weight), _p(bias), _p(out), out.stride(-2), _p(residual), residual.stride(-2),
+          M, N, K, _p(_prep(w_gate, torch.float32)), _p(partials), _p(ws), wsb, tag="N%d K%d glu_residual+extract" % (N, K))
+    return out, partials
+
+
+def mamba2_eig_partials(partials, B, T, dt_bias, A_log, thresholds: Sequence[float] = THRESHOLDS_RADIUS, want_lam=True, counts=None,
+                        compare="float64", lam_out=None, rowstats_out=None, ln_eps: float = 1e-5):
+    """Finish the Mamba-2 extractor (H = 1) from the GLU epilogue's partials.  -> (lam (B,T,1) | None, counts (B,1,8))."""
+    partials = _prep(partials, torch.float32)
+    ng = partials.shape[0]
+    lib = _enter(partials)
+    lam, stride = None, 1
+    if lam_out is not None:
+        lam = lam_out; stride = _uniform_stride(lam_out, (B, T, 1))
+    elif want_lam:
+        lam = torch.empty(B, T, 1, dtype=torch.float32, device=partials.device)
+    if counts is None:
+        counts = new_counts(B, 1, partials.device)
+    thr, n = L.thresholds_arg(thresholds)
+    _call(lib, "eigb200_mamba2_eig_partials", _stream(partials), _p(partials), ng, B, T, _p(_prep(dt_bias, torch.float32)), _p(_prep(A_log, torch.float32)),
+          _p(lam), stride, _p(counts), thr, n, _cmp(compare), _p(rowstats_out), float(ln_eps))
+    return lam, counts
+
+
 def rowstats(x, eps=1e-5):
     """(mean, rstd) of every row of x (..., D) -> (..., 2) float32."""
     x = _prep(x, torch.float32)

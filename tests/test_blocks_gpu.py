@@ -297,3 +297,31 @@ def test_linear_ln_fused(ops, M, N, K):
     np.testing.assert_allclose(out[:, :N], ref, rtol=2e-5, atol=2e-5)
     unfused = ops.linear(ops.layernorm(dev(a), dev(gamma), dev(beta)), dev(w), None, mode="tc3", ldc=ldc).cpu().numpy()
     assert np.abs(out[:, :N] - unfused[:, :N]).max() <= 2e-5
+
+
+@pytest.mark.parametrize("M,D", [(4096, 128), (3000, 64), (2049, 256), (1500, 32)])
+def test_glu_extract_partials_match_k1(ops, M, D):
+    """The GLU + residual GEMM's extractor partials, combined by eigb200_mamba2_eig_partials, against K1 on the GEMM's own output: lambda within fp32
+    reassociation, LayerNorm statistics, and bin counts exact for the lambdas each path wrote."""
+    rng = np.random.default_rng(M + D)
+    B, T = 1, M
+    a = rng.normal(size=(M, D)).astype(np.float32); w = (rng.normal(size=(2 * D, D)) / np.sqrt(D)).astype(np.float32)
+    bias = rng.normal(size=2 * D).astype(np.float32); r = (rng.normal(size=(M, D)) * 1.5 + rng.normal(0, 1, (M, 1))).astype(np.float32)
+    wg = (rng.normal(size=D) / np.sqrt(D) * 3).astype(np.float32)
+    dtb = np.array([-1.5], np.float32); Al = np.log(np.array([3.0], np.float32))
+    out, part = ops.linear_glu_extract(dev(a), dev(w), dev(bias), dev(r), dev(wg))
+    plain = ops.linear(dev(a), dev(w), dev(bias), epilogue="glu_residual", residual=dev(r), mode="tc3")
+    assert torch.equal(out, plain)                                                     # the extra epilogue work does not touch the GEMM result
+    st = torch.empty(B, T, 2, device="cuda")
+    lam, counts = ops.mamba2_eig_partials(part, B, T, dev(dtb), dev(Al), rowstats_out=st)
+    st_ref = torch.empty(B, T, 2, device="cuda")
+    lam_ref, counts_ref = ops.mamba2_eig(out.reshape(B, T, D), dev(wg[None]), dev(dtb), dev(Al), rowstats_out=st_ref)
+    l1, l0 = lam.cpu().numpy(), lam_ref.cpu().numpy()
+    err = np.abs(l1 - l0) / (l0 * (1 + np.abs(np.log(l0))) + 1e-37)
+    assert err.max() < 2e-6, err.max()
+    np.testing.assert_allclose(st.cpu().numpy()[..., 0], st_ref.cpu().numpy()[..., 0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st.cpu().numpy()[..., 1], st_ref.cpu().numpy()[..., 1], rtol=2e-5)
+    with np.errstate(invalid="ignore"):
+        exp = np.moveaxis(O.threshold_counts(np.sqrt(np.power(l1, 2)), O.THRESHOLDS_RADIUS, axis=1), 0, -1)
+    np.testing.assert_array_equal(counts.cpu().numpy()[..., :7], exp)
+    assert (counts.cpu().numpy()[..., 7] == T).all()
