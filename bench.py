@@ -298,9 +298,13 @@ def run_eigb200(args, rank, local, world):
            "eigb200_linear_ln[N%d K%d none]" % (d_in, D_): tokens * (D_ + d_in) * 4 + tokens * 8,
            "eigb200_linear[N%d K%d none]" % (d_in, D_): tokens * (D_ + d_in) * 4,
            "eigb200_linear[N%d K%d gelu]" % (D_, D_): tokens * 2 * D_ * 4,
-           "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): tokens * 3 * D_ * 4}
+           "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): tokens * 3 * D_ * 4,
+           # GLU + residual with the extractor partials of the output rows (D/16 groups x 3 floats per row), and the kernel that finishes them
+           "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): tokens * (3 * D_ * 4 + (D_ // 16) * 12),
+           "eigb200_mamba2_eig_partials": tokens * ((D_ // 16) * 12 + 4 * H + 8)}
     flops = {"eigb200_linear_ln[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in, "eigb200_linear[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in,
-             "eigb200_linear[N%d K%d gelu]" % (D_, D_): 2.0 * tokens * D_ * D_, "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_}
+             "eigb200_linear[N%d K%d gelu]" % (D_, D_): 2.0 * tokens * D_ * D_, "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_,
+             "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_}
     totals = {k: sum(v) for k, v in per.items()}
     step_total = sum(totals.values())
     dom = max(totals, key=totals.get)
