@@ -135,6 +135,113 @@ __global__ void __launch_bounds__(LA_THREADS) linattn_forward_kernel(const LinAt
 }
 
 
+
+// ---- layer forward, column-owner form: thread j of a (b,h) CTA keeps column j of the d x dv state in registers -------------------------------
+// out_t[j] = sum_a q_t[a] S_t[a][j] needs no cross-thread reduction, q_t / k_t are broadcast reads of shared memory (one LDS.128 feeds 4 rows of
+// every thread), v_t[j] is a per-thread scalar: 2 d FMA per thread-token against d / 2 LDS.128.  The raw q / k / v rows of the NEXT chunk arrive by
+// cp.async while the current chunk is computed; phi = elu + 1 is applied in place when the chunk becomes current, and warp 0 then forms the
+// normaliser den_t = q_t . sum_{s<=t} k_s of the chunk.  (The thread-per-(row block, column) kernel above spends as many shared-memory reads as FMAs.)
+constexpr int LC_TC = 16;
+
+__device__ __forceinline__ void lc_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+template <int D_>
+__global__ void __launch_bounds__(256) linattn_forward_col_kernel(const LinAttnParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int dv = p.dv;                                             // == blockDim.x
+  const int chunk_floats = LC_TC * (2 * D_ + dv);                  // [q TC x D_ | k TC x D_ | v TC x dv]
+  float* buf0 = sm;
+  float* buf1 = sm + chunk_floats;
+  float* dens = buf1 + chunk_floats;                               // [TC]
+  float* ksum_s = dens + LC_TC;                                    // [D_] running sum of phi(k) (normalise)
+  const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const size_t rowbase = (size_t)b * p.T;
+  const float* qb = p.q + (size_t)h * D_;
+  const float* kb = p.k + (size_t)h * D_;
+  const float* vb = p.v + (size_t)h * dv;
+  float S[D_];
+#pragma unroll
+  for (int a = 0; a < D_; ++a) S[a] = 0.f;
+  for (int a = tid; a < D_; a += nthr) ksum_s[a] = 0.f;
+
+  auto stage = [&](float* dst, int64_t t0) {                       // rows [t0, t0 + TC) -> dst, zero-filled beyond T; 16-byte pieces
+    constexpr int QF4 = D_ / 4;
+    const int vf4 = dv / 4;
+    for (int i = tid; i < LC_TC * QF4; i += nthr) {
+      const int r = i / QF4, c = i - r * QF4;
+      const bool ok = t0 + r < p.T;
+      const size_t row = (rowbase + (ok ? t0 + r : 0)) * p.ld;
+      lc_cp_async16(dst + r * D_ + 4 * c, qb + row + 4 * c, ok);
+      lc_cp_async16(dst + LC_TC * D_ + r * D_ + 4 * c, kb + row + 4 * c, ok);
+    }
+    for (int i = tid; i < LC_TC * vf4; i += nthr) {
+      const int r = i / vf4, c = i - r * vf4;
+      const bool ok = t0 + r < p.T;
+      lc_cp_async16(dst + 2 * LC_TC * D_ + r * dv + 4 * c, vb + (rowbase + (ok ? t0 + r : 0)) * p.ld + 4 * c, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(buf0, 0);
+  int cur = 0;
+  for (int64_t t0 = 0; t0 < p.T; t0 += LC_TC, cur ^= 1) {
+    const int tc = (int)min((int64_t)LC_TC, p.T - t0);
+    float* cb = cur ? buf1 : buf0;
+    float* qs = cb; float* ks = cb + LC_TC * D_; float* vs = cb + 2 * LC_TC * D_;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                               // chunk `cur` landed; every thread is done with the other buffer
+    if (t0 + LC_TC < p.T) stage(cur ? buf0 : buf1, t0 + LC_TC);    // next chunk in flight during this one
+    if (p.phi_elu) {
+      for (int i = tid; i < tc * 2 * D_; i += nthr) cb[i] = elu_f(cb[i]) + 1.f;          // q and k rows are adjacent: [0, 2 TC D_)
+      __syncthreads();
+    }
+    if (p.normalise && tid < 32) {                                 // warp 0: den_t = q_t . ksum_t, ksum_t = ksum_{t-1} + k_t (sequential over the chunk)
+      constexpr int PER = (D_ + 31) / 32;
+      float kr[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) kr[i] = (lane + 32 * i < D_) ? ksum_s[lane + 32 * i] : 0.f;
+      for (int tt = 0; tt < tc; ++tt) {
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int c = lane + 32 * i;
+          if (c < D_) { kr[i] += ks[tt * D_ + c]; part = fmaf(qs[tt * D_ + c], kr[i], part); }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) dens[tt] = part;
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) if (lane + 32 * i < D_) ksum_s[lane + 32 * i] = kr[i];
+    }
+    if (p.normalise) __syncthreads();
+    for (int tt = 0; tt < tc; ++tt) {
+      const float vj = vs[tt * dv + tid] * p.kscale;               // (k kscale) v == k (kscale v)
+      const float4* k4 = reinterpret_cast<const float4*>(ks + tt * D_);
+      const float4* q4 = reinterpret_cast<const float4*>(qs + tt * D_);
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+#pragma unroll
+      for (int a = 0; a < D_ / 4; ++a) {
+        const float4 kk = k4[a], qq = q4[a];
+        S[4 * a + 0] = fmaf(kk.x, vj, S[4 * a + 0]); n0 = fmaf(qq.x, S[4 * a + 0], n0);
+        S[4 * a + 1] = fmaf(kk.y, vj, S[4 * a + 1]); n1 = fmaf(qq.y, S[4 * a + 1], n1);
+        S[4 * a + 2] = fmaf(kk.z, vj, S[4 * a + 2]); n2 = fmaf(qq.z, S[4 * a + 2], n2);
+        S[4 * a + 3] = fmaf(kk.w, vj, S[4 * a + 3]); n3 = fmaf(qq.w, S[4 * a + 3], n3);
+      }
+      const float num = (n0 + n1) + (n2 + n3);
+      float scale = 1.f;
+      if (p.normalise) scale = 1.f / dens[tt];                     // n.pow(-1) (models/attention.py:79)
+      else if (p.gate) scale = __ldg(p.gate + (rowbase + t0 + tt) * p.H + h);
+      p.out[(rowbase + t0 + tt) * p.ldo + (size_t)h * dv + tid] = scale * num;
+    }
+  }
+}
+
 // ---- softmax attention: normaliser of get_eig_att_softmax and the layer forward, both streaming over key tiles -------------------------------
 // Reference: analysis/eval_eig.py:43-95 (the (B,T,T,H) score tensor, its multiplicative mask and the row maximum that therefore includes the
 // masked zeros) and SelfAttention.forward, models/attention.py:14-35 (k scaled by 1/sqrt(d) BEFORE the product, additive -10000 mask, softmax).
@@ -310,6 +417,20 @@ extern "C" int eigb200_linattn_forward(void* stream, const float* d_q, const flo
   const int ri = d / groups;
   EIGB_CHECK_ARG(ri >= 1 && ri <= 64 && (ri & (ri - 1)) == 0, "linattn_forward: d*dv/256 = %d must be a power of two <= 64", ri);
   LinAttnParams p{d_q, d_k, d_v, ld, d_gate, phi_elu, normalise, kscale, d_out, ldo, T, H, d, dv};
+  const bool al16 = ld % 4 == 0 && (((uintptr_t)d_q | (uintptr_t)d_k | (uintptr_t)d_v) & 15) == 0 && d % 4 == 0;   // cp.async 16-byte pieces
+  if ((d == 16 || d == 32 || d == 64 || d == 128) && dv % 32 == 0 && dv <= 256 && al16) {     // column-owner kernel: dv threads per (b,h)
+    const size_t smem2 = sizeof(float) * (2 * (size_t)LC_TC * (2 * d + dv) + LC_TC + d);
+    dim3 grid2(H, (unsigned)B);
+    cudaStream_t st2 = (cudaStream_t)stream;
+    switch (d) {
+      case 16: linattn_forward_col_kernel<16><<<grid2, dv, smem2, st2>>>(p); break;
+      case 32: linattn_forward_col_kernel<32><<<grid2, dv, smem2, st2>>>(p); break;
+      case 64: linattn_forward_col_kernel<64><<<grid2, dv, smem2, st2>>>(p); break;
+      default: linattn_forward_col_kernel<128><<<grid2, dv, smem2, st2>>>(p); break;
+    }
+    EIGB_LAUNCH_CHECK("linattn_forward_col_kernel");
+    return EIGB200_OK;
+  }
   const size_t smem = sizeof(float) * ((size_t)LA_TC * (2 * d + dv) + (size_t)LA_TC * groups * dv + (size_t)LA_TC * groups);
   dim3 grid(H, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
