@@ -231,6 +231,16 @@ int eigb200_scale_cols(void* stream, const float* d_a, const float* d_s, float* 
  * The scan then runs with dt := beta (ones) and A := -softplus(A) (:274-275, :283-295) through eigb200_ssd_scan. */
 int eigb200_lti_scale_b(void* stream, float* d_buf, int64_t ld, int col_b, int col_dt, const float* d_dt_bias, int64_t rows, int N, int khead);
 
+/* ---- S4 layer call, CNN mode (models/s4.py:50-79, :169-173) ------------------------------------------------------------
+ * eigb200_s4_kernel: kernel_DPLR for H features at once.  Parameters (H,N) complex64 interleaved (Lambda already clipped to Re <= -1e-4, :116), step (H) =
+ * exp(log_step); d_Kt (L,H) float32 out: the convolution kernel, lag-major so that the convolution reads it coalesced over features.
+ * Workspace eigb200_s4_kernel_workspace_bytes(H, L) bytes (the generating function at the L roots of unity, complex128).
+ * eigb200_s4_causal_conv: y[b,t,h] = sum_{s<=t} Kt[t-s,h] u[b,s,h] + D[h] u[b,t,h]  (causal_convolution(u, K) + D * u); u, y (B,T,H) float32, d_D nullable. */
+size_t eigb200_s4_kernel_workspace_bytes(int H, int L);
+int eigb200_s4_kernel(void* stream, const float* d_Lambda, const float* d_P, const float* d_Q, const float* d_B, const float* d_C,
+                      const float* d_step, int H, int N, int L, float* d_Kt, void* d_workspace, size_t workspace_bytes);
+int eigb200_s4_causal_conv(void* stream, const float* d_u, const float* d_Kt, const float* d_D, float* d_y, int64_t B, int64_t T, int H);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ __all__ = [
     "radius_phase", "batch_mean_std", "batch_mean_std_from_counts",
     "lru_lambda", "s5_lambda", "diag_scan", "lru_forward", "s5_discretize", "s5_forward",
     "make_hippo", "make_nplr_hippo", "make_dplr_hippo", "discrete_dplr_abar", "s4_eigvals", "dplr_exact_spectrum",
+    "s4_kernel_dplr", "s4_discrete_dplr", "s4_kernel_recurrent", "s4_forward",
     "ssd_scan_sequential", "ssd_scan_chunked", "layer_norm", "causal_depthwise_conv_silu", "gelu_erf", "glu",
     "ssd_mixer_forward", "mamba_block_forward", "token_embedding", "linattn_forward", "normattn_forward",
     "transformer_block_forward", "mamba_eval_pass", "transformer_eval_pass", "mamba_eval_pass_torch_cpu",
@@ -423,6 +424,68 @@ def s4_eigvals(layer, idx=1, dtype=np.complex128):
     P = np.asarray(layer["P"])[:, idx].astype(dtype)
     Ab = discrete_dplr_abar(Lam.astype(dtype), P, P, step, dtype)
     return Ab, np.linalg.eigvals(Ab)
+
+
+def s4_kernel_dplr(Lambda, P, Q, B, C, step, L):
+    """kernel_DPLR (models/s4.py:50-69): the length-L convolution kernel of the DPLR SSM from its truncated generating function at the roots of
+    unity (4 Cauchy sums, Woodbury correction, inverse FFT, real part).  complex128."""
+    Lambda = np.asarray(Lambda, np.complex128); P = np.asarray(P, np.complex128); Q = np.asarray(Q, np.complex128)
+    B = np.asarray(B, np.complex128); C = np.asarray(C, np.complex128)
+    Omega = np.exp((-2j * np.pi) * (np.arange(L) / L))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = (2.0 / step) * ((1.0 - Omega) / (1.0 + Omega))
+        c = 2.0 / (1.0 + Omega)
+        cauchy = lambda v: (v[None, :] / (g[:, None] - Lambda[None, :])).sum(axis=1)
+        k00 = cauchy(C.conj() * B); k01 = cauchy(C.conj() * P); k10 = cauchy(Q.conj() * B); k11 = cauchy(Q.conj() * P)
+        at_roots = c * (k00 - k01 * (1.0 / (1.0 + k11)) * k10)
+    return np.fft.ifft(at_roots, L).real
+
+
+def s4_discrete_dplr(Lambda, P, Q, B, C, step, L):
+    """discrete_DPLR with all three outputs (models/s4.py:16-40): Abar, Bbar and Cbar = conj(C~ (I - Abar^L)^-1 .conj())."""
+    Lambda = np.asarray(Lambda, np.complex128); P = np.asarray(P, np.complex128); Q = np.asarray(Q, np.complex128)
+    Bc = np.asarray(B, np.complex128)[:, None]; Ct = np.asarray(C, np.complex128)[None, :]
+    N = Lambda.shape[0]
+    I = np.eye(N)
+    A = np.diag(Lambda) - P[:, None] @ Q[:, None].conj().T
+    A0 = (2.0 / step) * I + A
+    D = np.diag(1.0 / ((2.0 / step) - Lambda))
+    Qc = Q.conj().reshape(1, -1); P2 = P.reshape(-1, 1)
+    A1 = D - (D @ P2 * (1.0 / (1 + (Qc @ D @ P2))) * Qc @ D)
+    Ab = A1 @ A0
+    Bb = 2 * A1 @ Bc
+    Cb = Ct @ np.linalg.inv(I - np.linalg.matrix_power(Ab, L)).conj()
+    return Ab, Bb, Cb.conj()
+
+
+def s4_kernel_recurrent(Lambda, P, Q, B, C, step, L):
+    """K_t = Re(Cbar Abar^t Bbar), t < L: the impulse response of the discretised SSM.  Equals s4_kernel_dplr (the S4 kernel identity) -- the
+    independent check that pins the restatement of kernel_DPLR."""
+    Ab, Bb, Cb = s4_discrete_dplr(Lambda, P, Q, B, C, step, L)
+    x = Bb
+    out = np.empty(L)
+    for t in range(L):
+        out[t] = (Cb @ x).real.item()
+        x = Ab @ x
+    return out
+
+
+def s4_forward(layer, u, dtype=np.float64):
+    """S4 (vmapped S4Layer) CNN mode (models/s4.py:107-110, :140-146, :169-173): per feature h, y[:, h] = causal_convolution(u[:, h], K_h) + D_h u[:, h],
+    K_h = kernel_DPLR(clip(Lambda_re) + i Lambda_im, P, P, B, C~, exp(log_step), L).  layer: vmapped parameter dict (axis 1 = feature); u (B,T,H)."""
+    u = np.asarray(u, dtype)
+    Bsz, T, H = u.shape
+    y = np.empty_like(u)
+    for h in range(H):
+        Lam = np.minimum(np.asarray(layer["Lambda_re"], np.float64)[:, h], -1e-4) + 1j * np.asarray(layer["Lambda_im"], np.float64)[:, h]
+        Pv = np.asarray(layer["P"])[:, h]; Bv = np.asarray(layer["B"])[:, h]
+        Cc = np.asarray(layer["C"], np.float64)[:, h, 0] + 1j * np.asarray(layer["C"], np.float64)[:, h, 1]
+        step = np.exp(np.asarray(layer["log_step"], np.float64)[0, h])
+        K = s4_kernel_dplr(Lam, Pv, Pv, Bv, Cc, step, T)
+        n = 2 * T
+        conv = np.fft.irfft(np.fft.rfft(u[:, :, h], n, axis=1) * np.fft.rfft(K, n)[None, :], n, axis=1)[:, :T]
+        y[:, :, h] = conv + np.asarray(layer["D"], np.float64)[0, h] * u[:, :, h]
+    return y
 
 
 def dplr_exact_spectrum(N, step):

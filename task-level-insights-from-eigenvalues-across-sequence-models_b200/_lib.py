@@ -58,9 +58,13 @@ SIGNATURES = {
     "eigb200_gelu": [_vp, _vp, _vp, _i64],
     "eigb200_scale_cols": [_vp, _vp, _vp, _vp, _i64, _i],
     "eigb200_lti_scale_b": [_vp, _vp, _i64, _i, _i, _vp, _i64, _i, _i],
+    "eigb200_s4_kernel_workspace_bytes": [_i, _i],
+    "eigb200_s4_kernel": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz],
+    "eigb200_s4_causal_conv": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i],
     "eigb200_ssm_lambda": [_vp, _i, _vp, _vp, _vp, _i, _vp],
 }
-_RESTYPES = {"eigb200_last_error": C.c_char_p, "eigb200_linear_workspace_bytes": C.c_size_t, "eigb200_linear_workspace_bytes_m": C.c_size_t}
+_RESTYPES = {"eigb200_last_error": C.c_char_p, "eigb200_linear_workspace_bytes": C.c_size_t, "eigb200_linear_workspace_bytes_m": C.c_size_t,
+             "eigb200_s4_kernel_workspace_bytes": C.c_size_t}
 
 
 class Eigb200Error(RuntimeError):

@@ -494,6 +494,32 @@ def lti_scale_b(buf, ld, col_b, col_dt, dt_bias, N, khead):
     return buf
 
 
+def s4_kernel(Lambda, P, Q, Bv, Cv, step, L_):
+    """kernel_DPLR for H features: (H,N) complex64 x5, step (H) f32 -> Kt (L,H) float32 (lag-major)."""
+    Lambda = _prep(Lambda, torch.complex64); P = _prep(P, torch.complex64); Q = _prep(Q, torch.complex64)
+    Bv = _prep(Bv, torch.complex64); Cv = _prep(Cv, torch.complex64); step = _prep(step, torch.float32).reshape(-1)
+    H, N = Lambda.shape
+    lib = _enter(Lambda)
+    Kt = torch.empty(L_, H, dtype=torch.float32, device=Lambda.device)
+    nb = int(lib.eigb200_s4_kernel_workspace_bytes(H, L_))
+    ws = torch.empty(nb, dtype=torch.uint8, device=Lambda.device)
+    r = torch.view_as_real
+    _call(lib, "eigb200_s4_kernel", _stream(Lambda), _p(r(Lambda)), _p(r(P)), _p(r(Q)), _p(r(Bv)), _p(r(Cv)), _p(step), H, N, L_, _p(Kt), _p(ws), nb)
+    return Kt
+
+
+def s4_causal_conv(u, Kt, D=None):
+    """y[b,t,h] = sum_{s<=t} Kt[t-s,h] u[b,s,h] + D[h] u[b,t,h]."""
+    u = _prep(u, torch.float32); Kt = _prep(Kt, torch.float32)
+    B, T, H = u.shape
+    if Kt.shape != (T, H):
+        raise L.Eigb200Error("s4_causal_conv: kernel shape %s does not match (T, H) = (%d, %d)" % (tuple(Kt.shape), T, H))
+    lib = _enter(u)
+    y = torch.empty_like(u)
+    _call(lib, "eigb200_s4_causal_conv", _stream(u), _p(u), _p(Kt), _p(_prep(D, torch.float32)) if D is not None else None, _p(y), B, T, H)
+    return y
+
+
 SSM_KINDS = {"lru": 0, "s5_zoh": 1, "s5_bilinear": 2}
 
 

@@ -239,3 +239,24 @@ def s5_forward(params, u, discretization="zoh", conj_sym=True, clip_eigs=False, 
     Du = ops.scale_cols(u.reshape(B * T, Hd), _t(params["D"]))
     y = ops.linear(torch.view_as_real(h.contiguous()).reshape(B * T, 2 * PP), Wc, None, epilogue="residual", residual=Du).reshape(B, T, Hd)
     return (y, h) if return_states else y
+
+
+def s4_forward(layer, u, return_kernel=False):
+    """S4.__call__ in CNN mode (models/s4.py:169-173; vmapped over features, :182-188) for a batch u (B,T,H) float32 on the device:
+    y[:, :, h] = causal_convolution(u[:, :, h], K_h) + D_h u[:, :, h], K_h = kernel_DPLR(clip(Lambda_re) + i Lambda_im, P, P, B, C~, exp(log_step), T)
+    (:107-139).  layer: the vmapped parameter dict (feature axis 1), as returned by get_init_layers_ssm / get_trained_layers_ssm."""
+    u = _t(u)
+    Bsz, T, H = u.shape
+    lam = (np.minimum(np.asarray(layer["Lambda_re"], np.float32), np.float32(-1e-4)) + 1j * np.asarray(layer["Lambda_im"], np.float32)).T
+    Pv = np.asarray(layer["P"]).T.astype(np.complex64)
+    Bv = np.asarray(layer["B"]).T.astype(np.complex64)
+    Cf = np.asarray(layer["C"], np.float32)
+    Cv = (Cf[..., 0] + 1j * Cf[..., 1]).T.astype(np.complex64)
+    step = np.exp(np.asarray(layer["log_step"], np.float32)).reshape(-1)
+    if not (lam.shape[0] == H and step.shape[0] == H):
+        raise L.Eigb200Error("s4_forward: parameters describe %d features, input has %d" % (lam.shape[0], H))
+    Kt = ops.s4_kernel(_t(np.ascontiguousarray(lam.astype(np.complex64)), torch.complex64), _t(np.ascontiguousarray(Pv), torch.complex64),
+                       _t(np.ascontiguousarray(Pv), torch.complex64), _t(np.ascontiguousarray(Bv), torch.complex64),
+                       _t(np.ascontiguousarray(Cv), torch.complex64), _t(step), T)
+    y = ops.s4_causal_conv(u, Kt, _t(np.asarray(layer["D"], np.float32).reshape(-1)))
+    return (y, Kt) if return_kernel else y

@@ -117,3 +117,32 @@ def test_batched_all_features(ops):
     Abn = Ab.cpu().numpy(); evn = ev.cpu().numpy().reshape(L * Hf, N)
     for m in (0, 17, L * Hf - 1):
         assert _match(evn[m], np.linalg.eigvals(Abn[m])) <= 1e-5
+
+
+def _s4_layer(rng, N, H):
+    """Vmapped S4 parameters (feature axis 1) at the HiPPO init with per-feature perturbations (models/s4.py:192-215, :98-135)."""
+    Lam, P, B, _, _ = O.make_dplr_hippo(N)
+    lam_re = np.repeat(Lam.real[:, None], H, 1) + rng.normal(0, 0.05, (N, H)); lam_im = np.repeat(Lam.imag[:, None], H, 1) + rng.normal(0, 0.05, (N, H))
+    return dict(Lambda_re=lam_re.astype(np.float32), Lambda_im=lam_im.astype(np.float32),
+                P=(np.repeat(P[:, None], H, 1) * (1 + rng.normal(0, 0.05, (N, H)))).astype(np.complex64),
+                B=(np.repeat(B[:, None], H, 1) * (1 + rng.normal(0, 0.05, (N, H)))).astype(np.complex64),
+                C=(rng.normal(size=(N, H, 2)) * 0.5 ** 0.5).astype(np.float32), D=rng.normal(1, 0.2, (1, H)).astype(np.float32),
+                log_step=rng.uniform(np.log(1e-3), np.log(1e-1), (1, H)).astype(np.float32))
+
+
+@pytest.mark.parametrize("N,H,B,T", [(16, 5, 2, 64), (64, 40, 3, 200), (8, 33, 1, 129), (64, 4, 2, 1024)])
+def test_s4_forward_cnn_mode(ops, N, H, B, T):
+    """S4 layer call (kernel_DPLR + causal convolution + D u) against the fp64 oracle; even / odd / non-power-of-two lengths, ragged feature tiles."""
+    import eigb200.ssm as S
+    rng = np.random.default_rng(N + H + T)
+    layer = _s4_layer(rng, N, H)
+    u = rng.normal(size=(B, T, H)).astype(np.float32)
+    y, Kt = S.s4_forward(layer, u, return_kernel=True)
+    yr = O.s4_forward(layer, u)
+    # the kernel itself, feature by feature
+    for h in (0, H - 1):
+        Lam = np.minimum(layer["Lambda_re"][:, h].astype(np.float64), -1e-4) + 1j * layer["Lambda_im"][:, h].astype(np.float64)
+        Cc = layer["C"][:, h, 0].astype(np.float64) + 1j * layer["C"][:, h, 1].astype(np.float64)
+        K = O.s4_kernel_dplr(Lam, layer["P"][:, h], layer["P"][:, h], layer["B"][:, h], Cc, np.exp(np.float64(layer["log_step"][0, h])), T)
+        assert np.abs(Kt.cpu().numpy()[:, h] - K).max() <= 1e-5 * np.abs(K).max()
+    assert np.abs(y.cpu().numpy() - yr).max() <= 2e-5 * np.abs(yr).max()

@@ -153,3 +153,15 @@ def test_transformer_model_pass(name):
     with np.errstate(invalid="ignore"):
         ph = O.threshold_analysis(0 * eig, O.THRESHOLDS_PHASE)
     np.testing.assert_array_equal(ph, g["percentage_phase"])
+
+
+@pytest.mark.parametrize("N,L,step", [(8, 32, 0.02), (16, 64, 0.01), (16, 50, 0.08)])
+def test_s4_kernel_identity_pins_kernel_dplr(N, L, step):
+    """The S4 kernel identity: kernel_DPLR (generating function at the roots of unity, models/s4.py:50-69) equals the impulse response
+    Re(Cbar Abar^t Bbar) of discrete_DPLR (:16-40) -- an independent route through the reference's own algebra, since JAX is not installed."""
+    Lam, P, B, _, _ = O.make_dplr_hippo(N)
+    rng = np.random.default_rng(N + L)
+    C = (rng.normal(size=N) + 1j * rng.normal(size=N)) * 0.5 ** 0.5
+    k1 = O.s4_kernel_dplr(Lam, P, P, B, C, step, L)
+    k2 = O.s4_kernel_recurrent(Lam, P, P, B, C, step, L)
+    np.testing.assert_allclose(k1, k2, rtol=0, atol=1e-12 * max(1.0, np.abs(k2).max()))

@@ -93,6 +93,23 @@ def case_k3(nmat, N):
     return fn, nmat * (4 * N * 8 + N * 8), nmat
 
 
+def case_s4_conv(B, T, H):
+    """S4 CNN-mode layer call: causal convolution with the DPLR kernel (direct form, B H T^2 / 2 FMA)."""
+    u = torch.randn(B, T, H, device="cuda"); Kt = torch.randn(T, H, device="cuda") * 0.05; D = torch.ones(H, device="cuda")
+    def fn():
+        ops.s4_causal_conv(u, Kt, D)
+    return fn, 2 * B * T * H * 4, B * H * T * (T + 1) // 2
+
+
+def case_s4_kernel(H, N, L):
+    Lam = torch.complex(-0.5 * torch.ones(H, N), 3.14159 * torch.arange(N).float().repeat(H, 1)).cuda()
+    P = torch.view_as_complex(torch.randn(H, N, 2, device="cuda") * 0.5); Bv = torch.view_as_complex(torch.randn(H, N, 2, device="cuda"))
+    Cv = torch.view_as_complex(torch.randn(H, N, 2, device="cuda") * 0.7); step = torch.exp(torch.empty(H, device="cuda").uniform_(-6.9, -2.3))
+    def fn():
+        ops.s4_kernel(Lam, P, P, Bv, Cv, step, L)
+    return fn, H * L * 4, H
+
+
 def case_normgate(B, T, D, H):
     x = torch.randn(B, T, D, device="cuda")
     W = torch.randn(H, D, device="cuda") * 0.3
@@ -156,6 +173,8 @@ CASES = {
     "lin_n64_none_tc3": lambda: case_linear(M_C2, 64, 128, "none", "tc3"),
     "diag_c3": lambda: case_diag(128, 2048, 256),
     "k3_c4": lambda: case_k3(3072, 64),
+    "s4_conv_c4": lambda: case_s4_conv(64, 2048, 128),
+    "s4_kernel_c4": lambda: case_s4_kernel(128, 64, 2048),
     "k1_c2": lambda: case_k1(4096, 512, 128, 1),
     "k1_c2_stats": lambda: case_k1_stats(4096, 512, 128, 1),
     "emb_c2": lambda: case_embed(4096, 512, 128, 8192),
