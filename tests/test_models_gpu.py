@@ -161,3 +161,37 @@ def test_mamba_pseudo_lti_pass_vs_oracle(eig, H, N, prenorm):
     assert e.shape == ref.shape == (3, 45, H, 2)
     np.testing.assert_allclose(e, ref, rtol=1e-5)
     assert (res.counts.cpu().numpy()[..., 7] == 45).all()
+
+
+@pytest.mark.parametrize("D,H,N,B,T", [(64, 1, 16, 20, 77), (128, 1, 16, 9, 130), (32, 1, 8, 40, 33), (128, 2, 16, 10, 110), (256, 1, 16, 5, 250)])
+def test_mamba_pass_tensor_core_paths_vs_oracle(eig, D, H, N, B, T):
+    """Model-level parity on shapes that take the fused device paths (>= 1024 rows: tcgen05 GEMMs with the LayerNorm in the converter, GLU epilogue with
+    the extractor partials when H = 1, SSD v3 with ragged chunks, partial 128-row tiles, T not a multiple of 32) against the fp64 oracle of the
+    reference's per-layer loop."""
+    A, Ly, E, S = eig
+    cfg = dict(layer="mamba", version="mamba2", num_layers=2, num_heads=H, input_dim=1, output_dim=32, hidden_dim=D, state_dim=N, conv_dim=4,
+               expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none", token_embedding=True, vocab_size=97)
+    sd = Ly.init_mamba_state_dict(cfg, 5)
+    for k in list(sd):                                           # spread lambda over several bins
+        if k.endswith("mamba.in_proj.weight"):
+            sd[k] = sd[k].clone(); sd[k][-H:] *= 4.0
+    model = Ly.MambaDev(cfg, sd, "cuda")
+    X = torch.randint(0, 97, (B, T), generator=torch.Generator().manual_seed(3))
+    res = A.mamba_pass(model, X.cuda())
+    ocfg = dict(num_layers=2, d_inner=D, ngroups=1, d_state=N, nheads=H, headdim=D // H, prenorm=True)
+    ref, xr = O.mamba_eval_pass(X.numpy(), {k: v.numpy() for k, v in sd.items()}, ocfg, np.float64)
+    assert np.abs(res.x_last.cpu().numpy() - xr).max() <= 3e-5 * np.abs(xr).max()
+    e = res.eig_host()
+    assert_eig_close(e, ref, rtol=3e-5)
+    rad = np.sqrt(np.power(e, 2))
+    pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(pct, O.threshold_analysis(rad, O.THRESHOLDS_RADIUS))
+    # the un-fused path (separate LayerNorm-statistics producer K1) gives the same eigenvalues to fp32 reassociation
+    import os
+    os.environ["EIGB200_EXTRACT_FUSION"] = "0"
+    try:
+        res0 = A.mamba_pass(model, X.cuda())
+    finally:
+        os.environ.pop("EIGB200_EXTRACT_FUSION")
+    assert_eig_close(res0.eig_host(), e, rtol=5e-6)
