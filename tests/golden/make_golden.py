@@ -365,6 +365,33 @@ def _gold_transformer_models(ns, only=None):
         save(name, "models/transformer.py:22-161, attention.py / norm_attention.py + analysis/eval_eig.py:528-564", **arrays)
 
 
+def gold_c1():
+    """BASELINE config C1 at its exact shapes: linear attention on MQAR-shaped tokens, seq 64, d_model = d_qk = 64, 1 head, 2 layers, vocab 8192,
+    analysis batch 8.  The 4 MB of embedding / decoder weights are NOT stored: the model is the reference's own construction under
+    torch.manual_seed(1919) (eval_eig.py:484-497), which eigb200.layers.init_transformer_state_dict reproduces bit for bit -- the fixture keeps a
+    SHA-256 of every parameter so that the test proves it, plus the token ids, the activations after every block and the eigenvalue array."""
+    import hashlib
+    ns = load_reference_models()
+    cfg = dict(input_dim=1, output_dim=8192, num_layers=2, hidden_dim=64, embedding=True, vocab_size=8192, max_pos_embed=64, pooling="none", dual=False,
+               classifier=False, mixer_dim=128, norm="layer", dropout=0.0, state_dim=64, num_heads=1, att_dropout=0.0, use_flash=False,
+               attention_fn="lin-attention", mixer="none")
+    torch.manual_seed(1919)
+    model = ns["Transformer"](dict(cfg)).eval()
+    model.encoder.device = "cpu"
+    rng = np.random.default_rng(42)
+    X = torch.from_numpy(rng.integers(0, 8192, (8, 64)))
+    ext = lambda x, layer: EV["get_eig_att_linear"](x, layer, 64, 1, 64)
+    with torch.no_grad(), np.errstate(all="ignore"):
+        eig, acts = reference_layer_loop(model, list(model.layers), X, ext)
+    hashes = {k: hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() for k, v in sd_numpy(model).items()}
+    arrays = dict(X=X.numpy(), eig=eig, **{"act_%d" % i: a for i, a in enumerate(acts)})
+    arrays["cfg_json"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+    arrays["sd_sha256_json"] = np.frombuffer(json.dumps(hashes).encode(), dtype=np.uint8)
+    with np.errstate(invalid="ignore"):
+        arrays["percentage"] = EV["threshold_analysis"](eig, np.array([0.1, 0.5, 0.9, 1.0, 10, 100]), 2, 1, 8)
+    save("c1_linattn_mqar", "BASELINE configs[0]: models/transformer.py + attention.py + analysis/eval_eig.py:528-552 at seq 64, d_model 64, 2 layers", **arrays)
+
+
 def crosscheck_ssd_against_hf():
     """Independent check of the oracle's SSD restatement against HF transformers' pure-torch Mamba2 step
     (modeling_mamba2.py torch_forward): same parameters, same input, outputs compared.  Result recorded in MANIFEST."""
@@ -418,6 +445,12 @@ def gold_report_files():
 
 
 if __name__ == "__main__":
+    if "--only-c1" in sys.argv:
+        MANIFEST.update(json.load(open(os.path.join(OUT, "MANIFEST.json"))))
+        gold_c1()
+        with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
+            json.dump(MANIFEST, f, indent=1, sort_keys=True)
+        sys.exit(0)
     if "--only-models" in sys.argv:                 # (re)generate the named transformer models without touching the other vectors
         MANIFEST.update(json.load(open(os.path.join(OUT, "MANIFEST.json"))))
         gold_models(only=sys.argv[sys.argv.index("--only-models") + 1].split(","))
@@ -438,6 +471,7 @@ if __name__ == "__main__":
     gold_hippo_s4()
     crosscheck_ssd_against_hf()
     gold_models()
+    gold_c1()
     gold_report_files()
     MANIFEST["_env"] = {"numpy": np.__version__, "torch": torch.__version__}
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:

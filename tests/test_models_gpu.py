@@ -195,3 +195,23 @@ def test_mamba_pass_tensor_core_paths_vs_oracle(eig, D, H, N, B, T):
     finally:
         os.environ.pop("EIGB200_EXTRACT_FUSION")
     assert_eig_close(res0.eig_host(), e, rtol=5e-6)
+
+
+def test_c1_linear_attention_mqar_pass_vs_reference(eig):
+    """BASELINE configs[0] at its exact shapes (seq 64, d_model = d_qk = 64, 1 head, 2 layers, vocab 8192, batch 8) against the eigenvalues and activations
+    the reference's own classes produced for the same seed-1919 model and token ids."""
+    import json
+    from conftest import load_golden
+    A, Ly, E, S = eig
+    g = load_golden("c1_linattn_mqar")
+    cfg = json.loads(bytes(g["cfg_json"]).decode())
+    sd = Ly.init_transformer_state_dict(cfg, 1919)
+    model = Ly.TransformerDev(cfg, sd, "cuda")
+    X = torch.from_numpy(g["X"]).cuda()
+    res = A.transformer_pass(model, X, cfg)
+    assert np.abs(res.x_last.cpu().numpy() - g["act_2"]).max() <= 3e-5 * np.abs(g["act_2"]).max()
+    e = res.eig_host()
+    assert e.shape == g["eig"].shape == (8, 63, 1, 2) and e.dtype == np.float64
+    np.testing.assert_allclose(e, g["eig"], rtol=3e-4)
+    pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
+    assert np.abs(pct - g["percentage"]).max() <= 100.0 / 63 + 1e-9

@@ -165,3 +165,32 @@ def test_s4_kernel_identity_pins_kernel_dplr(N, L, step):
     k1 = O.s4_kernel_dplr(Lam, P, P, B, C, step, L)
     k2 = O.s4_kernel_recurrent(Lam, P, P, B, C, step, L)
     np.testing.assert_allclose(k1, k2, rtol=0, atol=1e-12 * max(1.0, np.abs(k2).max()))
+
+
+def _c1_fixture():
+    import hashlib
+    import json
+    import torch
+    import eigb200.layers as Ly
+    g = load_golden("c1_linattn_mqar")
+    cfg = json.loads(bytes(g["cfg_json"]).decode())
+    hashes = json.loads(bytes(g["sd_sha256_json"]).decode())
+    sd = Ly.init_transformer_state_dict(cfg, 1919)
+    got = {k: hashlib.sha256(np.ascontiguousarray(v.numpy()).tobytes()).hexdigest() for k, v in sd.items()}
+    return g, cfg, sd, hashes, got
+
+
+def test_c1_model_init_is_the_reference_construction():
+    """BASELINE configs[0] (linear attention, MQAR seq 64, d_model 64, 2 layers): every parameter drawn by eigb200.layers.init_transformer_state_dict
+    under seed 1919 is bit-identical (SHA-256) to the reference's Transformer(cfg) -- so the 4 MB of weights need not be stored with the fixture."""
+    g, cfg, sd, hashes, got = _c1_fixture()
+    assert set(got) == set(hashes)
+    assert all(got[k] == hashes[k] for k in hashes), [k for k in hashes if got[k] != hashes[k]]
+
+
+def test_c1_oracle_pass_matches_reference():
+    g, cfg, sd, hashes, got = _c1_fixture()
+    eig, x = O.transformer_eval_pass(g["X"], {k: v.numpy() for k, v in sd.items()}, _tf_cfg(cfg), np.float64)
+    np.testing.assert_allclose(x, g["act_2"], rtol=0, atol=3e-5 * np.abs(g["act_2"]).max())
+    fin = np.isfinite(g["eig"])
+    np.testing.assert_allclose(eig[fin], g["eig"][fin], rtol=2e-4)
