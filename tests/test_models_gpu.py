@@ -215,3 +215,52 @@ def test_c1_linear_attention_mqar_pass_vs_reference(eig):
     np.testing.assert_allclose(e, g["eig"], rtol=3e-4)
     pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
     assert np.abs(pct - g["percentage"]).max() <= 100.0 / 63 + 1e-9
+
+
+def test_c5_shaped_mamba_pass_vs_oracle(eig):
+    """BASELINE configs[4], Mamba arm, at its layer sizes (d_model 512, 8 heads of 64 channels, d_state 16, GLU) with a short sequence: the K = 512
+    projections run on the streamed-operand tcgen05 kernel, the scan with 8 heads, the generic (H = 8, D = 512) extractor."""
+    A, Ly, E, S = eig
+    cfg = dict(layer="mamba", version="mamba2", num_layers=2, num_heads=8, input_dim=1, output_dim=64, hidden_dim=512, state_dim=16, conv_dim=4,
+               expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none", token_embedding=True, vocab_size=211)
+    sd = Ly.init_mamba_state_dict(cfg, 7)
+    model = Ly.MambaDev(cfg, sd, "cuda")
+    X = torch.randint(0, 211, (6, 192), generator=torch.Generator().manual_seed(4))        # 1152 rows
+    res = A.mamba_pass(model, X.cuda())
+    ocfg = dict(num_layers=2, d_inner=512, ngroups=1, d_state=16, nheads=8, headdim=64, prenorm=True)
+    ref, xr = O.mamba_eval_pass(X.numpy(), {k: v.numpy() for k, v in sd.items()}, ocfg, np.float64)
+    assert np.abs(res.x_last.cpu().numpy() - xr).max() <= 3e-5 * np.abs(xr).max()
+    assert_eig_close(res.eig_host(), ref, rtol=3e-5)
+
+
+def test_c5_shaped_norm_attention_pass_vs_oracle(eig):
+    """BASELINE configs[4], normalised-attention arm, at its layer sizes (d_model = d_qk = 512, 8 heads, conv 4, softplus gate, elu feature map)."""
+    A, Ly, E, S = eig
+    cfg = dict(layer="transformer", input_dim=1, output_dim=64, num_layers=2, hidden_dim=512, embedding=True, vocab_size=211, max_pos_embed=192,
+               pooling="none", dual=False, classifier=False, mixer_dim=1024, norm="layer", dropout=0.0, state_dim=512, num_heads=8, att_dropout=0.0,
+               use_flash=False, attention_fn="norm-attention", mixer="glu", mode="attention", norm_fn="softplus", approx_fn="elu", scale_B=False,
+               offset=True, offset_init="exp", learn_A=False, dim_conv=4)
+    sd = Ly.init_transformer_state_dict(cfg, 7)
+    model = Ly.TransformerDev(cfg, sd, "cuda")
+    X = torch.randint(0, 211, (6, 192), generator=torch.Generator().manual_seed(4))
+    res = A.transformer_pass(model, X.cuda(), cfg)
+    ocfg = dict(cfg, d_model=512, d_qk=512)
+    ref, xr = O.transformer_eval_pass(X.numpy(), {k: v.numpy() for k, v in sd.items()}, ocfg, np.float64)
+    assert np.abs(res.x_last.cpu().numpy() - xr).max() <= 5e-5 * np.abs(xr).max()
+    e = res.eig_host()
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(e[fin], ref[fin], rtol=3e-4)
+
+
+def test_c3_shaped_lru_layer_vs_oracle(eig):
+    """BASELINE configs[2] at its layer shape (T 2048, d_model 128, 256 complex states): B u on the resident-weight tcgen05 GEMM, the diagonal scan over the
+    full length, Re(C h) + D u with K = 512 on the streamed-operand GEMM."""
+    A, Ly, E, S = eig
+    rng = np.random.default_rng(3)
+    prm = _lru_params(rng, 256, 128)
+    u = rng.normal(size=(2, 2048, 128)).astype(np.float32)
+    y, h = S.lru_forward(prm, u, return_states=True)
+    yr, hr, _ = O.lru_forward(prm, u)
+    scale = np.abs(hr).max(axis=1, keepdims=True)
+    assert (np.abs(h.cpu().numpy() - hr) <= 2e-4 * scale).all()            # fp32 lambda: |lambda| ~ 0.999 over 2048 steps (see test_lru_layer_call)
+    assert np.abs(y.cpu().numpy() - yr).max() <= 2e-4 * np.abs(yr).max()
