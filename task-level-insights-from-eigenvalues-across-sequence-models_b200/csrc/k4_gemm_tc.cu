@@ -783,7 +783,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 constexpr int TS_MAX_STAGES = 8;
 constexpr int TS_ASTAGES = 4;
 
-template <int EPI, bool DEFER>
+template <int EPI, bool DEFER, int AST = TS_ASTAGES>   // AST operand stages in TMEM (2 for the wide single-CTA plan: 2 * bn + 64 * AST <= 512 columns)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapWhi,
                   const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
@@ -809,13 +809,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
   const uint32_t a_col0 = (uint32_t)(2 * bn);                        // first TMEM column of the operand stages
-  const uint32_t need_cols = a_col0 + TS_ASTAGES * 64;
+  const uint32_t need_cols = a_col0 + AST * 64;
   const uint32_t tmem_cols = need_cols <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_free(s), 128); }
-    for (int t = 0; t < TS_ASTAGES; ++t) { mbar_init(bar_afull(t), 128); mbar_init(bar_aempty(t), 1); }
+    for (int t = 0; t < AST; ++t) { mbar_init(bar_afull(t), 128); mbar_init(bar_aempty(t), 1); }
     for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), TC_EPI_WARPS * 32); }
     fence_barrier_init();
   }
@@ -914,7 +914,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (DEFER) t_pending = t;                                    // publish behind the next chunk's loads (converter-bound shapes)
         else { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar_afull(t)); }
         if (++s == nst) { s = 0; ph ^= 1; }
-        if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
+        if (++t == AST) { t = 0; aph ^= 1; }
       }
     }
     if (DEFER && t_pending >= 0) { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar_afull(t_pending)); }
@@ -945,7 +945,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           }
           umma_commit(bar_aempty(t));
           if (c == kch - 1) umma_commit(bar_dfull(j));
-          if (++t == TS_ASTAGES) { t = 0; aph ^= 1; }
+          if (++t == AST) { t = 0; aph ^= 1; }
         }
         if (++j == 2) { j = 0; dph ^= 1; }
       }
@@ -1130,12 +1130,18 @@ static int make_tmap(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t
   return EIGB200_OK;
 }
 
-struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages; size_t smem; bool ok; bool ts; };
+struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages, ast; size_t smem; bool ok; bool ts; };
 
 static bool use_ts_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("EIGB200_GEMM_VARIANT"); v = (e && e[0] == 's' && e[1] == 's') ? 0 : 1; }   // default: TMEM-operand kernel; "ss" selects the smem-operand kernel
   return v == 1;
+}
+
+static int gemm_wide_mode() {       // EIGB200_GEMM_WIDE: 0 = N-split plan only, 1 = wide plan (default), 2 = wide plan with the deferred publish
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EIGB200_GEMM_WIDE"); v = e ? atoi(e) : 1; }
+  return v;
 }
 
 static TcPlan make_plan(int N, int K, int epilogue) {
@@ -1148,6 +1154,23 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   if (pl.kchunks > 8) return pl;
   const bool glu = epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const int nout = glu ? N / 2 : N;
+  pl.ast = TS_ASTAGES;
+  // Wide single-CTA plan (129..192 output columns, e.g. the Mamba in_proj with N = 161): the whole weight matrix stays resident in ONE CTA
+  // (bn = N rounded up to 16), so every A tile is read and converted once instead of once per N split; what it costs is ring depth
+  // (the weights leave room for 2-3 raw stages) and TMEM operand stages (2 * bn accumulator columns leave room for 2).
+  if (pl.ts && !glu && nout > 128 && nout <= 192 && gemm_wide_mode() != 0) {
+    const int bn = (nout + 15) / 16 * 16;
+    const size_t wbytes = (size_t)2 * pl.kchunks * bn * 128;
+    const long room = (long)TC_SMEM_LIMIT - 2048 - (long)wbytes;
+    int nst = room > 0 ? (int)(room / TC_CHUNK_BYTES) : 0;
+    if (nst > TS_MAX_STAGES) nst = TS_MAX_STAGES;
+    if (nst >= 2 && 2 * bn + 2 * 64 <= 512) {
+      pl.bn = pl.bg = bn; pl.nsplit = 1; pl.nstages = nst; pl.ast = 2;
+      pl.smem = wbytes + (size_t)nst * TC_CHUNK_BYTES + 1024 + 1024;
+      pl.ok = true;
+      return pl;
+    }
+  }
   const int per_col_bytes = pl.kpad * 4 * 2 * (glu ? 2 : 1);         // hi+lo bytes per OUTPUT column
   const int stage_bytes = pl.ts ? TC_CHUNK_BYTES : 2 * TC_CHUNK_BYTES;
   const int max_w_bytes = TC_SMEM_LIMIT - 2048 - (pl.ts ? 4 : 2) * stage_bytes;   // keep room for the minimum ring
@@ -1348,7 +1371,15 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   dim3 grid(workers * pl.nsplit);
 #define TC_LAUNCH(EPI_)                                                                                                         \
   do {                                                                                                                          \
-    if (pl.ts && defer) {                                                                                                       \
+    if (pl.ts && pl.ast == 2 && EPI_ != EIGB200_EPI_GLU_RESIDUAL) {                                                             \
+      if (gemm_wide_mode() == 2) {                                                                                              \
+        EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+        gemm_tc_ts_kernel<EPI_, true, 2><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                   \
+      } else {                                                                                                                  \
+        EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+        gemm_tc_ts_kernel<EPI_, false, 2><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                  \
+      }                                                                                                                         \
+    } else if (pl.ts && defer) {                                                                                                \
       EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
       gemm_tc_ts_kernel<EPI_, true><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                        \
     } else if (pl.ts) {                                                                                                         \

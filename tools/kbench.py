@@ -147,6 +147,17 @@ def case_linear(M, N, K, epi, mode):
     return fn, nbytes, 2.0 * M * N * K
 
 
+def case_linear_ln(M, N, K, ldc):
+    a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
+    stats = torch.stack([a.mean(-1), torch.rsqrt(a.var(-1, unbiased=False) + 1e-5)], -1).contiguous()
+    g = torch.ones(K, device="cuda"); be = torch.zeros(K, device="cuda")
+    out = torch.empty(M, ldc, device="cuda")
+    ws, _ = ops.linear_workspace(N, K, "cuda", M)
+    def fn():
+        ops.linear_ln(a, stats, g, be, w, b, out=out, workspace=ws)
+    return fn, M * (K + N) * 4 + M * 8, 2.0 * M * N * K
+
+
 def case_ln(M, D):
     x = torch.randn(M, D, device="cuda"); w = torch.ones(D, device="cuda"); b = torch.zeros(D, device="cuda")
     def fn():
@@ -160,6 +171,7 @@ CASES = {
     "ssd_small": lambda: case_ssd(512),
     "ln_c2": lambda: case_ln(M_C2, 128),
     "lin_in_tc3": lambda: case_linear(M_C2, 161, 128, "none", "tc3"),
+    "lin_in_ln_tc3": lambda: case_linear_ln(M_C2, 161, 128, 168),
     "lin_out_tc3": lambda: case_linear(M_C2, 128, 128, "gelu", "tc3"),
     "lin_glu_tc3": lambda: case_linear(M_C2, 256, 128, "glu_residual", "tc3"),
     "lin_out_tc1": lambda: case_linear(M_C2, 128, 128, "gelu", "tc1"),
