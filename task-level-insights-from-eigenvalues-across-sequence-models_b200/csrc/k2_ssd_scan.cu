@@ -674,6 +674,10 @@ static int launch_ssd_v3(cudaStream_t st, const SsdParams& p, int64_t B) {
   return EIGB200_OK;
 }
 
+}  // namespace eigb200
+#include "k2_ssd_mma.cuh"
+namespace eigb200 {
+
 template <int N, int CPT, int NT, int U = 8, int MINB = 1>
 static int launch_ssd_v2(cudaStream_t st, const SsdParams& p, int64_t B) {
   dim3 grid((p.P + NT * CPT - 1) / (NT * CPT), p.H, (unsigned)B);
@@ -697,6 +701,11 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
   EIGB_CHECK_ARG(p.N % 4 == 0, "ssd_scan: d_state %d must be a multiple of 4", p.N);
   EIGB_CHECK_ARG(p.kconv >= 0 && p.kconv <= 4, "ssd_scan: conv kernel size %d not in 0..4", p.kconv);
   EIGB_CHECK_ARG(B <= 65535 && p.H <= 65535, "ssd_scan: batch/heads exceed grid limits");
+  {
+    // EIGB200_SSD_FORM: "scan" = the recurrent kernels below, "mma" = the chunked tensor-core form (k2_ssd_mma.cuh) where its shape conditions hold
+    const char* e = getenv("EIGB200_SSD_FORM");                     // read per call (cheap next to a launch) so that the tests can switch forms
+    if (e && e[0] == 'm' && ssd_mma_ok(p)) return launch_ssd_mma(st, p, B);
+  }
   {
     int cpt = 1;
     if (ssd_v2_ok(p, &cpt)) {

@@ -46,6 +46,7 @@ struct TcParams {
   int nsplit, kchunks, nstages, nterms, workers;
   const float* eig_w; float* eig_part;   // GLU epilogue only (nullable): per-row partial gate dot products and moments of the OUTPUT rows, see tc_epilogue
   int r_v8;          // residual rows are 32-byte aligned: add them in the accumulator layout with 256-bit loads
+  int c_v8;          // output rows are 32-byte aligned (and any residual is r_v8): every thread stores its own row segment with 256-bit stores
   int zero;          // always 0; a run-time value the compilers cannot fold (mbar_arrive_after)
   int64_t ntiles;
 };
@@ -224,6 +225,12 @@ __device__ __forceinline__ void ldg_stream_v8(const float* ptr, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
 }
 
+// 256-bit store (sm_100): one full 32-byte sector per thread
+__device__ __forceinline__ void stg_v8(float* ptr, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start address >> 4 in bits [0,14); LBO (unused for swizzled K-major) = 1 in [16,30); SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46);
 // descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
@@ -330,7 +337,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
       if (GLU) {
         const int oc = n_cta0 + (cg >> 1);                           // first of the 16 output columns of this group
         float rr[16];
+#ifdef EIGB_ABL_EPI                                                  // ablation build (tools/ablate_gemm.sh): wait / tcgen05.ld / release only
+        if (false) {
+#else
         if (r_own) {                                                 // residual prefetch: its DRAM latency hides behind the accumulator wait
+#endif
           const float* rptr = p.R + own_row * p.ldr + oc;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -345,6 +356,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         float a[32];
         tmem_ld_32x32(d_tmem + cg, a);
         if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
+#ifdef EIGB_ABL_EPI
+        if (a[0] == 12345.678f && a[31] == -9.f) p.C[0] = a[5];
+        continue;
+#endif
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
@@ -368,6 +383,20 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
             float* pp = p.eig_part + (size_t)(oc >> 4) * 3 * p.M + own_row;
             pp[0] = dot; pp[p.M] = mean; pp[2 * p.M] = m2;
           }
+        }
+        if (p.c_v8) {                                                // own row, 2 full sectors: no transpose
+          if (own_row < p.M) {
+            float* cptr = p.C + own_row * p.ldc + oc;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (oc + 8 * q + 8 <= nout) stg_v8(cptr + 8 * q, v + 8 * q);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (oc + 8 * q + e < nout) cptr[8 * q + e] = v[8 * q + e];
+              }
+            }
+          }
+          continue;
         }
         transpose4x4_f4(v, lane);
         const int n = oc + 4 * (lane & 3);
@@ -401,7 +430,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         const bool full = n + 3 < nout;
         const float* rptr = p.R + own_row * p.ldr + n_cta0 + cg;
         float rr[32];
+#ifdef EIGB_ABL_EPI
+        if (false) {
+#else
         if (r_own) {                                                 // prefetch behind the accumulator wait
+#endif
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (own_row < p.M && n_cta0 + cg + 8 * q + 8 <= nout) ldg_stream_v8(rptr + 8 * q, rr + 8 * q);
@@ -415,6 +448,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         float v[32];
         tmem_ld_32x32(d_tmem + cg, v);
         if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
+#ifdef EIGB_ABL_EPI
+        if (v[0] == 12345.678f && v[31] == -9.f) p.C[0] = v[5];
+        continue;
+#endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float vv = v[i] + bias_s[cg + i];
@@ -424,6 +461,20 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         if (r_own) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += rr[i];
+        }
+        if (p.c_v8) {                                                // own row, 4 full sectors: no transpose
+          if (own_row < p.M) {
+            float* cptr = p.C + own_row * p.ldc + n_cta0 + cg;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n_cta0 + cg + 8 * q + 8 <= nout) stg_v8(cptr + 8 * q, v + 8 * q);
+              else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (n_cta0 + cg + 8 * q + e < nout) cptr[8 * q + e] = v[8 * q + e];
+              }
+            }
+          }
+          continue;
         }
         transpose8x8_f4(v, lane);
         if (col_ok) {
@@ -877,6 +928,15 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); st.x = -st.x * st.y; }
       for (int c = 0; c < kch; ++c) {
         mbar_wait(bar_full(s), ph);
+#ifdef EIGB_ABL_CONV                                                 // ablation build: barrier protocol only, no loads / split / tcgen05.st
+        if (DEFER && t_pending >= 0) { tc_fence_before(); mbar_arrive(bar_afull(t_pending)); }
+        mbar_arrive(bar_free(s));
+        mbar_wait(bar_aempty(t), aph ^ 1);
+        if (DEFER) t_pending = t; else { tc_fence_before(); mbar_arrive(bar_afull(t)); }
+        if (++s == nst) { s = 0; ph ^= 1; }
+        if (++t == AST) { t = 0; aph ^= 1; }
+        continue;
+#endif
         const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage0 + s * TC_CHUNK_BYTES + row_off - smem_u32(smem_raw)));
         float a[32];
 #pragma unroll
@@ -1356,6 +1416,16 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   // instead of the template parameter costs both shapes 3 % (the converter loop is latency-critical), hence two instantiations.
   const bool defer = pl.bn < 128;
   p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
+  {
+    // EIGB200_GEMM_DIRECT_STORE: 0 = shuffle-transposed 128-bit stores (a warp instruction writes 4 full 128-byte lines), 1 = every thread stores its own
+    // row segment with 256-bit stores, 2 (default) = direct stores in the GLU epilogue only.  Measured on B200: direct stores cost the plain / GELU
+    // epilogues 10-50 % (32 scattered sectors per store instruction: DRAM write efficiency), the GLU + extractor epilogue gains 2 %.
+    static int direct = -1;
+    if (direct < 0) { const char* e = getenv("EIGB200_GEMM_DIRECT_STORE"); direct = e ? atoi(e) : 2; }
+    const bool res_ok = !lp.R || p.r_v8 || !(glu || lp.epilogue == EIGB200_EPI_RESIDUAL);
+    const bool want = direct == 1 || (direct == 2 && glu);
+    p.c_v8 = (want && (((uintptr_t)lp.C & 31) == 0) && lp.ldc % 8 == 0 && res_ok) ? 1 : 0;
+  }
   p.eig_w = nullptr; p.eig_part = nullptr;
   if (lp.eig_part) {                                                 // extractor partials ride in the GLU epilogue of the TMEM-operand kernel only
     if (!(glu && pl.ts && p.r_v8 && (lp.N / 2) % 16 == 0 && lp.eig_w)) {

@@ -71,6 +71,13 @@ def test_lru_s5_lambda(ops):
     np.testing.assert_allclose(lam, h["bil_L"], rtol=2e-5, atol=1e-7)
 
 
+@pytest.fixture(params=["scan", "mma"])
+def ssd_form(request, monkeypatch):
+    """Both forms of K2b: the recurrent scan kernels and the chunked tensor-core form (csrc/k2_ssd_mma.cuh; taken where its shape conditions hold)."""
+    monkeypatch.setenv("EIGB200_SSD_FORM", request.param)
+    return request.param
+
+
 def test_ssd_scan_golden(ops):
     g = load_golden("ssd_small")
     y = ops.ssd_scan(*(torch.from_numpy(g[k]).cuda() for k in ("x", "dt", "A", "Bm", "Cm", "D"))).cpu().numpy()
@@ -80,8 +87,9 @@ def test_ssd_scan_golden(ops):
 
 
 @pytest.mark.parametrize("B,T,H,P,G,N", [(3, 70, 1, 128, 1, 16), (2, 33, 4, 16, 2, 8), (2, 40, 2, 64, 1, 128), (1, 96, 8, 8, 1, 64), (2, 20, 3, 20, 1, 4),
-                                          (2, 512, 2, 128, 1, 16), (1, 37, 1, 64, 1, 8), (2, 3, 1, 256, 1, 16), (1, 64, 2, 64, 2, 4), (1, 100, 1, 128, 1, 16)])
-def test_ssd_scan_shapes(ops, B, T, H, P, G, N):
+                                          (2, 512, 2, 128, 1, 16), (1, 37, 1, 64, 1, 8), (2, 3, 1, 256, 1, 16), (1, 64, 2, 64, 2, 4), (1, 100, 1, 128, 1, 16),
+                                          (2, 50, 4, 64, 2, 16), (1, 16, 1, 128, 1, 16), (1, 17, 2, 192, 1, 16)])
+def test_ssd_scan_shapes(ops, ssd_form, B, T, H, P, G, N):
     rng = np.random.default_rng(T + N)
     x = rng.normal(size=(B, T, H, P)).astype(np.float32)
     dt = O.softplus(rng.normal(-1, 1, (B, T, H))).astype(np.float32)
@@ -97,7 +105,7 @@ def test_ssd_scan_shapes(ops, B, T, H, P, G, N):
 
 @pytest.mark.parametrize("P,T", [(32, 75), (128, 75), (128, 256), (64, 33)])
 @pytest.mark.parametrize("kconv", [4, 2, 0])
-def test_mamba_conv_ssd_fused(ops, kconv, P, T):
+def test_mamba_conv_ssd_fused(ops, ssd_form, kconv, P, T):
     rng = np.random.default_rng(kconv)
     B, H, G, N = 3, 2, 1, 16
     C_ = H * P + 2 * G * N

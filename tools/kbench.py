@@ -175,6 +175,8 @@ CASES = {
     "lin_out_tc3": lambda: case_linear(M_C2, 128, 128, "gelu", "tc3"),
     "lin_glu_tc3": lambda: case_linear(M_C2, 256, 128, "glu_residual", "tc3"),
     "lin_out_tc1": lambda: case_linear(M_C2, 128, 128, "gelu", "tc1"),
+    "lin_glu_tc1": lambda: case_linear(M_C2, 256, 128, "glu_residual", "tc1"),
+    "lin_in_tc1": lambda: case_linear(M_C2, 161, 128, "none", "tc1"),
     "lin_out_simt": lambda: case_linear(M_C2, 128, 128, "gelu", "simt"),
     "lin_small_tc3": lambda: case_linear(65536, 128, 128, "gelu", "tc3"),
     "lin_glu_mid_tc3": lambda: case_linear(524288, 256, 128, "glu_residual", "tc3"),
