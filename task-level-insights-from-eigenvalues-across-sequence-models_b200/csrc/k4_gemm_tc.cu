@@ -72,14 +72,17 @@ __device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, ui
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
 }
+// suspend-time hint of mbarrier.try_wait: the hardware parks the thread until the phase completes or the hint expires, instead of returning to
+// the polling loop after the (short) default window -- polling (SYNCS / BRA / YIELD) was a third of all issued instructions without it
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
   // the polling loop lives inside the asm block, so the compiler inserts no reconvergence point after it: lanes may leave it on
   // different iterations.  Every caller goes on to .sync.aligned instructions (tcgen05.ld / st / wait) or lane-0 election, which need
   // the warp converged -- without this barrier single TMEM lanes (rows) were silently dropped by tcgen05.st.
@@ -90,10 +93,10 @@ __device__ __forceinline__ void mbar_wait_one(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
 }
 // elect.sync: true in exactly one lane of the (converged) warp.  Code guarded by it is a single-thread region for the compiler, so the
 // operands of UTCHMMA / UTMALDG are trivially warp-uniform -- with `lane == 0` instead it wrapped every tcgen05.mma in an ELECT/BRA.U.ANY
