@@ -184,6 +184,14 @@ size_t eigb200_linear_workspace_bytes(int N, int K);
 /* workspace for ANY shape the tensor-core path takes: equals the above when the weight slice stays resident in shared memory (K <= 256); for larger
  * K the streamed-operand kernel additionally keeps a tf32 hi/lo copy of A (2 * M * round_up(K,32) floats) there. */
 size_t eigb200_linear_workspace_bytes_m(int64_t M, int N, int K);
+/* Weights are constants of an analysis run (nn.Module parameters in eval mode, analysis/eval_eig.py:505-520): eigb200_linear_prepare splits W into the
+ * tensor-core operand layout ONCE (tf32 hi / lo, rows in the order the CTAs consume them; with d_ln_gamma / d_ln_beta the LayerNorm scale is folded into
+ * the weights and bias + W beta is stored behind them) into a workspace of eigb200_linear_workspace_bytes(N, K) bytes that the caller keeps per layer.
+ * eigb200_linear / eigb200_linear_ln / eigb200_linear_glu_extract then take d_W = NULL with that workspace ("prepared": tensor-core path only, same N, K,
+ * epilogue and LayerNorm as prepared; d_bias is still passed except for the LayerNorm form, whose folded bias lives in the workspace) and launch no
+ * preparation kernels.  Shapes without a resident-weight plan (K > 256) return EIGB200_EUNSUPPORTED here and keep preparing per call. */
+int eigb200_linear_prepare(void* stream, const float* d_W, const float* d_bias, const float* d_ln_gamma, const float* d_ln_beta,
+                           int N, int K, int epilogue, void* d_workspace, size_t workspace_bytes);
 /* eigb200_linear with nn.LayerNorm fused into the A operand: C = epilogue(LN(A) W^T + bias), LN(A)[m,k] = (A[m,k] - mean_m) * rstd_m *
  * gamma[k] + beta[k] with d_ln_stats (M,2) = (mean, rstd) per row (from eigb200_mamba2_eig / eigb200_embedding / eigb200_rowstats).
  * Tensor-core path only (same shape limits as eigb200_linear mode TC_3XTF32); EIGB200_EUNSUPPORTED otherwise. */

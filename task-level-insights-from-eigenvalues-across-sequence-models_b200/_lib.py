@@ -49,6 +49,7 @@ SIGNATURES = {
     "eigb200_embedding": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64],
     "eigb200_embedding_stats": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64, _vp, _f],
     "eigb200_rowstats": [_vp, _vp, _i64, _i, _f, _vp],
+    "eigb200_linear_prepare": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz],
     "eigb200_linear_ln": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _sz],
     "eigb200_layernorm": [_vp, _vp, _vp, _vp, _f, _vp, _i64, _i],
     "eigb200_conv_silu": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _i64, _i64, _i64, _i],

@@ -1320,6 +1320,33 @@ bool tc_supported(const LinearParams& p) {
   return make_plan(p.N, p.K, p.epilogue).ok || make_stream_plan(p.N, p.K, p.epilogue).ok;
 }
 
+// Weight preparation of either plan: tf32 hi / lo split in the row order the CTAs consume (LayerNorm gamma folded in, GLU value / gate rows interleaved)
+// and, with LayerNorm, the folded bias b + W beta behind it.  Run per call by launch_linear_tc, or once by eigb200_linear_prepare.
+int tc_prepare(cudaStream_t st, const LinearParams& lp, void* workspace) {
+  const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
+  const bool ln = lp.ln_stats != nullptr || lp.ln_gamma != nullptr;
+  int bn, bg, nsplit, kpad;
+  const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue);
+  if (pl.ok) { bn = pl.bn; bg = pl.bg; nsplit = pl.nsplit; kpad = pl.kpad; }
+  else {
+    const StreamPlan sp = make_stream_plan(lp.N, lp.K, lp.epilogue);
+    if (!sp.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
+    bn = sp.bn; bg = sp.bg; nsplit = sp.nsplit; kpad = sp.kpad;
+  }
+  const size_t wrows = (size_t)nsplit * bn;
+  float* w_hi = reinterpret_cast<float*>(workspace);
+  float* w_lo = w_hi + wrows * kpad;
+  float* bias2 = w_lo + wrows * kpad;
+  const int total = (int)(wrows * kpad);
+  split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, kpad, bn, bg, nsplit, glu ? 1 : 0, ln ? lp.ln_gamma : nullptr);
+  EIGB_LAUNCH_CHECK("split_weights_kernel");
+  if (ln) {
+    ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
+    EIGB_LAUNCH_CHECK("ln_bias_kernel");
+  }
+  return EIGB200_OK;
+}
+
 static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
   if (lp.eig_part) { set_error("linear_glu_extract: not available on the streamed-operand kernel (K > 256)"); return EIGB200_EUNSUPPORTED; }
   const StreamPlan pl = make_stream_plan(lp.N, lp.K, lp.epilogue);
@@ -1332,18 +1359,11 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   float* bias_perm = bias2 + (lp.N + 3) / 4 * 4;
   float* a_hi = bias_perm + wrows;
   float* a_lo = a_hi + (size_t)lp.M * pl.kpad;
-  {
-    const int total = (int)(wrows * pl.kpad);
-    split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kpad, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0,
-                                                              lp.ln_stats ? lp.ln_gamma : nullptr);
-    EIGB_LAUNCH_CHECK("split_weights_kernel");
+  if (lp.W != nullptr) {                                             // not prepared by eigb200_linear_prepare
+    int rc0 = tc_prepare(st, lp, workspace);
+    if (rc0 != EIGB200_OK) return rc0;
   }
-  const float* bias_eff = lp.bias;
-  if (lp.ln_stats) {
-    ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
-    EIGB_LAUNCH_CHECK("ln_bias_kernel");
-    bias_eff = bias2;
-  }
+  const float* bias_eff = lp.ln_stats ? bias2 : lp.bias;
   perm_bias_kernel<<<(unsigned)((wrows + 255) / 256), 256, 0, st>>>(bias_eff, bias_perm, lp.N, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0);
   EIGB_LAUNCH_CHECK("perm_bias_kernel");
   {
@@ -1389,19 +1409,13 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   float* w_hi = reinterpret_cast<float*>(workspace);
   const size_t wrows = (size_t)pl.nsplit * pl.bn;
   float* w_lo = w_hi + wrows * pl.kpad;
-  {
-    const int total = (int)(wrows * pl.kpad);
-    split_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kpad, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0,
-                                                              lp.ln_stats ? lp.ln_gamma : nullptr);
-    EIGB_LAUNCH_CHECK("split_weights_kernel");
+  float* bias2 = w_lo + wrows * pl.kpad;                             // bias + W beta, behind the split weights in the workspace
+  const bool prepared = lp.W == nullptr;                             // eigb200_linear_prepare filled the workspace for this (N, K, epilogue, LayerNorm)
+  if (!prepared) {
+    int rc0 = tc_prepare(st, lp, workspace);
+    if (rc0 != EIGB200_OK) return rc0;
   }
-  const float* bias_eff = lp.bias;
-  if (lp.ln_stats) {                                                 // bias + W beta, behind the split weights in the workspace
-    float* bias2 = w_lo + wrows * pl.kpad;
-    ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
-    EIGB_LAUNCH_CHECK("ln_bias_kernel");
-    bias_eff = bias2;
-  }
+  const float* bias_eff = lp.ln_stats ? bias2 : lp.bias;
   CUtensorMap tA, tWh, tWl;
   int rc;
   if ((rc = make_tmap(&tA, lp.A, (uint64_t)lp.M, (uint64_t)lp.K, (uint64_t)lp.lda, TC_BM))) return rc;

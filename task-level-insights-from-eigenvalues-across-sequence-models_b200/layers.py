@@ -11,6 +11,8 @@ Eval-mode semantics (dropout is the identity); see DESIGN.md for the init-pass d
 """
 from __future__ import annotations
 
+import os
+
 import math
 from types import SimpleNamespace
 from typing import Dict, List, Optional
@@ -95,6 +97,18 @@ class MambaBlockDev:
         self.glu = SimpleNamespace(linear=_Lin(gw, _dev(sd, prefix + "glu.linear.bias", device))) if gw is not None else None
         self.norm = SimpleNamespace(weight=_dev(sd, prefix + "norm.weight", device), bias=_dev(sd, prefix + "norm.bias", device))
         self.gemm_mode = cfg.get("_gemm_mode", "auto")
+        # the parameters are constants of an analysis run: their tensor-core operand form is built once per layer (ops.linear_prepare), not per call
+        self.prepare_weights = os.environ.get("EIGB200_PREPARE_WEIGHTS", "1") != "0"
+        self._prep_ws = {}
+
+    def _prepared(self, key, weight, bias, epilogue, gamma=None, beta=None):
+        """Per-layer prepared workspace of one GEMM (None when its shape has no resident-weight plan).  invalidate_prepared() after changing parameters."""
+        if key not in self._prep_ws:
+            self._prep_ws[key] = ops.linear_prepare(weight, bias, epilogue, gamma, beta)
+        return self._prep_ws[key]
+
+    def invalidate_prepared(self):
+        self._prep_ws = {}
 
     def fuses_layernorm(self):
         """True when the prenorm LayerNorm can ride inside the in_proj GEMM (row statistics supplied by the producer of x)."""
@@ -135,8 +149,10 @@ class MambaBlockDev:
         skip = x
         d_in_proj = m.in_proj.weight.shape[0]
         ldz = _pad8(d_in_proj)
+        tc = self.gemm_mode in ("auto", "tc3") and B * T >= 1024 and self.prepare_weights
         if stats is not None and self.fuses_layernorm():
-            z = ops.linear_ln(x, stats, self.norm.weight, self.norm.bias, m.in_proj.weight, None, ldc=ldz)
+            z = ops.linear_ln(x, stats, self.norm.weight, self.norm.bias, m.in_proj.weight, None, ldc=ldz,
+                              prepared=self._prepared("in_ln", m.in_proj.weight, None, "none", self.norm.weight, self.norm.bias) if tc else None)
         else:
             xn = ops.layernorm(x, self.norm.weight, self.norm.bias) if self.prenorm else x
             z = ops.linear(xn, m.in_proj.weight, None, ldc=ldz, mode=self.gemm_mode)              # (B*T, ldz) = [x | B | C | dt | pad]
@@ -144,12 +160,15 @@ class MambaBlockDev:
             y = self._ssd_lti(z, ldz, B, T)
         else:
             y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
-        o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode)    # GELU(out_proj(y))  (:333)
+        o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode,
+                       prepared=self._prepared("out", m.out_proj.weight, m.out_proj.bias, "gelu") if tc else None)    # GELU(out_proj(y))  (:333)
         if self.glu is not None and extract_partials is not None and self.fuses_extractor() and B * T >= 1024:
-            out, _ = ops.linear_glu_extract(o, self.glu.linear.weight, self.glu.linear.bias, skip.reshape(B * T, D), m.W_dt[0], partials=extract_partials)
+            out, _ = ops.linear_glu_extract(o, self.glu.linear.weight, self.glu.linear.bias, skip.reshape(B * T, D), m.W_dt[0], partials=extract_partials,
+                                            prepared=self._prepared("glu", self.glu.linear.weight, self.glu.linear.bias, "glu_residual") if tc else None)
         elif self.glu is not None:
             out = ops.linear(o, self.glu.linear.weight, self.glu.linear.bias, epilogue="glu_residual",
-                             residual=skip.reshape(B * T, D), mode=self.gemm_mode)                 # GLU + skip (:335-337)
+                             residual=skip.reshape(B * T, D), mode=self.gemm_mode,
+                             prepared=self._prepared("glu", self.glu.linear.weight, self.glu.linear.bias, "glu_residual") if tc else None)   # GLU + skip (:335-337)
         else:
             out = ops.add(o, skip.reshape(B * T, D))
         out = out.reshape(B, T, D)

@@ -313,8 +313,27 @@ def linear_workspace(N, K, device, M=0):
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
-def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", out=None, ldc=None, workspace=None):
-    """a (..., K) with a.stride(-2) as the row stride -> epilogue(a W^T + bias).  weight (N,K) torch layout."""
+def linear_prepare(weight, bias=None, epilogue="none", ln_gamma=None, ln_beta=None):
+    """Split `weight` once into the tensor-core operand layout (weights are constants of an analysis run): -> workspace tensor to pass as
+    `prepared=` to linear / linear_ln / linear_glu_extract with the same weight, epilogue and LayerNorm, or None when the shape has no
+    resident-weight plan (those keep preparing per call)."""
+    weight = _prep(weight, torch.float32)
+    assert weight.is_cuda
+    N, K = weight.shape
+    lib = _enter(weight)
+    nbytes = int(lib.eigb200_linear_workspace_bytes(N, K))
+    if nbytes == 0:
+        return None
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    _call(lib, "eigb200_linear_prepare", _stream(weight), _p(weight), _p(_prep(bias, torch.float32) if bias is not None else None),
+          _p(_prep(ln_gamma, torch.float32) if ln_gamma is not None else None), _p(_prep(ln_beta, torch.float32) if ln_beta is not None else None),
+          N, K, EPILOGUES[epilogue], _p(ws), nbytes, tag="N%d K%d %s" % (N, K, epilogue))
+    return ws
+
+
+def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", out=None, ldc=None, workspace=None, prepared=None):
+    """a (..., K) with a.stride(-2) as the row stride -> epilogue(a W^T + bias).  weight (N,K) torch layout.
+    prepared: workspace from linear_prepare(weight, bias, epilogue) -- no per-call weight preparation kernels (tensor-core path only)."""
     assert a.is_cuda and a.dtype == torch.float32 and a.stride(-1) == 1
     K = a.shape[-1]
     M = a.numel() // K
@@ -335,13 +354,16 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     if residual is not None:
         assert residual.is_cuda and residual.dtype == torch.float32 and residual.stride(-1) == 1
         ldr = residual.stride(-2) if residual.dim() >= 2 else nout
-    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
-    _call(lib, "eigb200_linear", _stream(a), _p(a2), lda, _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
+    if prepared is not None:
+        ws, wsb = prepared, prepared.numel()
+    else:
+        ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
+    _call(lib, "eigb200_linear", _stream(a), _p(a2), lda, _p(weight if prepared is None else None), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K,
                                EPILOGUES[epilogue], GEMM_MODES[mode], _p(ws), wsb, tag="N%d K%d %s" % (N, K, epilogue))
     return out
 
 
-def linear_glu_extract(a, weight, bias, residual, w_gate, partials=None, out=None, workspace=None):
+def linear_glu_extract(a, weight, bias, residual, w_gate, partials=None, out=None, workspace=None, prepared=None):
     """GLU + residual GEMM that also leaves the extractor partials of its output rows: -> (out (M, N/2), partials (N/32, 3, M))."""
     assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()
     K = a.shape[-1]
@@ -354,8 +376,11 @@ def linear_glu_extract(a, weight, bias, residual, w_gate, partials=None, out=Non
         out = torch.empty(M, nout, dtype=torch.float32, device=a.device)
     if partials is None:
         partials = torch.empty(nout // 16, 3, M, dtype=torch.float32, device=a.device)
-    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
-    _call(lib, "eigb200_linear_glu_extract", _stream(a), _p(a), K, _p(weight), _p(bias), _p(out), out.stride(-2), _p(residual), residual.stride(-2),
+    if prepared is not None:
+        ws, wsb = prepared, prepared.numel()
+    else:
+        ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
+    _call(lib, "eigb200_linear_glu_extract", _stream(a), _p(a), K, _p(weight if prepared is None else None), _p(bias), _p(out), out.stride(-2), _p(residual), residual.stride(-2),
           M, N, K, _p(_prep(w_gate, torch.float32)), _p(partials), _p(ws), wsb, tag="N%d K%d glu_residual+extract" % (N, K))
     return out, partials
 
@@ -389,7 +414,7 @@ def rowstats(x, eps=1e-5):
     return out
 
 
-def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residual=None, out=None, ldc=None, workspace=None):
+def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residual=None, out=None, ldc=None, workspace=None, prepared=None):
     """epilogue(LayerNorm(a) W^T + bias) with the normalisation applied inside the GEMM's A-operand stage (tensor-core path)."""
     assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()
     K = a.shape[-1]
@@ -405,9 +430,12 @@ def linear_ln(a, stats, gamma, beta, weight, bias=None, epilogue="none", residua
     else:
         ldc = out.stride(-2)
     ldr = residual.stride(-2) if residual is not None else 0
-    ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
+    if prepared is not None:
+        ws, wsb = prepared, prepared.numel()
+    else:
+        ws, wsb = (workspace, workspace.numel()) if workspace is not None else linear_workspace(N, K, a.device, M)
     _call(lib, "eigb200_linear_ln", _stream(a), _p(a), K, _p(_prep(stats, torch.float32)), _p(_prep(gamma, torch.float32)),
-          _p(_prep(beta, torch.float32)), _p(weight), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K, EPILOGUES[epilogue], _p(ws), wsb,
+          _p(_prep(beta, torch.float32)), _p(weight if prepared is None else None), _p(bias), _p(out), ldc, _p(residual), ldr, M, N, K, EPILOGUES[epilogue], _p(ws), wsb,
           tag="N%d K%d %s" % (N, K, epilogue))
     return out
 

@@ -325,3 +325,45 @@ def test_glu_extract_partials_match_k1(ops, M, D):
         exp = np.moveaxis(O.threshold_counts(np.sqrt(np.power(l1, 2)), O.THRESHOLDS_RADIUS, axis=1), 0, -1)
     np.testing.assert_array_equal(counts.cpu().numpy()[..., :7], exp)
     assert (counts.cpu().numpy()[..., 7] == T).all()
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(4096, 161, 128, "none"), (3000, 128, 128, "gelu"), (2048, 256, 128, "glu_residual"), (1500, 96, 64, "residual")])
+def test_prepared_weights_bit_identical(ops, M, N, K, epi):
+    """eigb200_linear_prepare once + d_W = NULL calls == per-call preparation, bit for bit (same kernels, same operands)."""
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).cuda(); w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda(); b = torch.randn(N, generator=g).cuda()
+    nout = N // 2 if epi == "glu_residual" else N
+    r = torch.randn(M, nout, generator=g).cuda() if "residual" in epi else None
+    ldc = (nout + 3) // 4 * 4                                      # the tensor-core path wants 16-byte aligned output rows
+    ref = ops.linear(a, w, b, epilogue=epi, residual=r, mode="tc3", ldc=ldc)
+    ws = ops.linear_prepare(w, b, epi)
+    assert ws is not None
+    for _ in range(2):                                             # the workspace is read-only for the GEMM: a second call sees the same operands
+        out = ops.linear(a, w, b, epilogue=epi, residual=r, mode="tc3", ldc=ldc, prepared=ws)
+        assert torch.equal(out[:, :nout], ref[:, :nout])
+    with pytest.raises(Exception):
+        ops.linear(a, w, b, epilogue=epi, residual=r, mode="simt", ldc=ldc, prepared=ws)
+
+
+def test_prepared_weights_layernorm_and_extract(ops):
+    g = torch.Generator().manual_seed(5)
+    M, K = 4096, 128
+    a = (torch.randn(M, K, generator=g) * 2 + 0.5).cuda()
+    gamma = (1 + 0.1 * torch.randn(K, generator=g)).cuda(); beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    stats = torch.stack([a.mean(-1), torch.rsqrt(a.var(-1, unbiased=False) + 1e-5)], -1).contiguous()
+    w = (torch.randn(161, K, generator=g) / K ** 0.5).cuda()
+    ref = ops.linear_ln(a, stats, gamma, beta, w, None, ldc=168)
+    ws = ops.linear_prepare(w, None, "none", gamma, beta)
+    out = ops.linear_ln(a, stats, gamma, beta, w, None, ldc=168, prepared=ws)
+    assert torch.equal(out[:, :161], ref[:, :161])
+    wg = (torch.randn(256, K, generator=g) / K ** 0.5).cuda(); bg = torch.randn(256, generator=g).cuda()
+    res = torch.randn(M, 128, generator=g).cuda(); wdt = torch.randn(128, generator=g).cuda()
+    o1, p1 = ops.linear_glu_extract(a, wg, bg, res, wdt)
+    ws2 = ops.linear_prepare(wg, bg, "glu_residual")
+    o2, p2 = ops.linear_glu_extract(a, wg, bg, res, wdt, prepared=ws2)
+    assert torch.equal(o1, o2) and torch.equal(p1, p2)
+
+
+def test_linear_prepare_no_resident_plan(ops):
+    w = torch.randn(512, 512).cuda()
+    assert ops.linear_prepare(w, None, "none") is None             # K > 256: streamed-operand kernel, prepared per call
