@@ -30,10 +30,19 @@ constexpr int TC_KC = 32;                  // fp32 columns per K-chunk = one 128
 constexpr int TC_CHUNK_BYTES = TC_BM * TC_KC * 4;          // 16 KB
 constexpr int TC_EPI_WARPS = 16;           // epilogue warps: TMEM lane quarter = warp % 4, 32-column group = warp / 4 (+ TC_EPI_GROUPS per trip)
 constexpr int TC_EPI_GROUPS = TC_EPI_WARPS / 4;
+#ifdef EIGB_ROLE_ORDER                                       // experiment: producers in the lowest warp ids (converters 0-3, MMA 4, TMA 5, 6-7 idle, epilogue 8-23)
+constexpr int TC_CONV_WARP0 = 0;
+constexpr int TC_MMA_WARP = 4;
+constexpr int TC_TMA_WARP = 5;
+constexpr int TC_EPI_WARP0 = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 8) * 32;
+#else
+constexpr int TC_EPI_WARP0 = 0;
 constexpr int TC_CONV_WARP0 = TC_EPI_WARPS;                  // 4 converter warps
 constexpr int TC_TMA_WARP = TC_EPI_WARPS + 4;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + 5;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 6) * 32;
+#endif
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
@@ -814,9 +823,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp < TC_EPI_WARPS) {
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
     // ===================================== epilogue ======================================
-    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
+    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp - TC_EPI_WARP0, lane);
   }
 
   tc_fence_before();
@@ -1014,8 +1023,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp < TC_EPI_WARPS) {
-    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp, lane);
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
+    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp - TC_EPI_WARP0, lane);
   }
 
   tc_fence_before();
@@ -1150,8 +1159,8 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
       }
     }
     __syncwarp();
-  } else if (warp < TC_EPI_WARPS) {
-    tc_epilogue_stream<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), p.bias, 0, 0, warp, lane);
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
+    tc_epilogue_stream<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), p.bias, 0, 0, warp - TC_EPI_WARP0, lane);
   }
 
   tc_fence_before();
