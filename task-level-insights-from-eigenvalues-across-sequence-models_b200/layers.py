@@ -211,6 +211,11 @@ class MambaDev:
         self.encoder = _make_encoder(state_dict, device)
         self.blocks = [MambaBlockDev(state_dict, "blocks.%d." % i, cfg, device) for i in range(cfg["num_layers"])]
 
+    def invalidate_prepared(self):
+        """Drop the per-layer prepared GEMM operands (call after changing any parameter tensor in place; a captured MambaPassGraph must be rebuilt)."""
+        for blk in self.blocks:
+            blk.invalidate_prepared()
+
 
 # ======================================================================================================================
 # Transformer (linear attention / normalised attention)

@@ -197,6 +197,32 @@ def test_mamba_pass_tensor_core_paths_vs_oracle(eig, D, H, N, B, T):
     assert_eig_close(res0.eig_host(), e, rtol=5e-6)
 
 
+def test_prepared_weights_follow_parameter_changes(eig):
+    """The per-layer prepared GEMM operands are a cache of the parameters: same result as per-call preparation, stale after an in-place parameter
+    change until invalidate_prepared() is called (the documented contract)."""
+    A, Ly, E, S = eig
+    cfg = dict(layer="mamba", version="mamba2", num_layers=2, num_heads=1, input_dim=1, output_dim=32, hidden_dim=128, state_dim=16, conv_dim=4,
+               expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none", token_embedding=True, vocab_size=97)
+    sd = Ly.init_mamba_state_dict(cfg, 11)
+    model = Ly.MambaDev(cfg, sd, "cuda")
+    X = torch.randint(0, 97, (16, 96), generator=torch.Generator().manual_seed(4)).cuda()
+    e1 = A.mamba_pass(model, X).eig_host()
+    assert all(len(b._prep_ws) == 3 for b in model.blocks)                 # in_proj (+ LayerNorm), out_proj, GLU
+    for b in model.blocks:
+        b.prepare_weights = False
+    np.testing.assert_array_equal(A.mamba_pass(model, X).eig_host(), e1)    # bit-identical to per-call preparation
+    for b in model.blocks:
+        b.prepare_weights = True
+    model.blocks[0].mamba.out_proj.weight.mul_(0.5)                        # in-place parameter change
+    np.testing.assert_array_equal(A.mamba_pass(model, X).eig_host(), e1)    # stale cache: unchanged on purpose
+    model.invalidate_prepared()
+    e2 = A.mamba_pass(model, X).eig_host()
+    assert np.abs(e2[..., 0] - e1[..., 0]).max() > 1e-6                     # the extractor reads each block's OUTPUT (eval_eig.py:512-520)
+    model.blocks[0].mamba.out_proj.weight.mul_(2.0)                        # undo (exact in floating point) -> the first result again
+    model.invalidate_prepared()
+    np.testing.assert_array_equal(A.mamba_pass(model, X).eig_host(), e1)
+
+
 def test_c1_linear_attention_mqar_pass_vs_reference(eig):
     """BASELINE configs[0] at its exact shapes (seq 64, d_model = d_qk = 64, 1 head, 2 layers, vocab 8192, batch 8) against the eigenvalues and activations
     the reference's own classes produced for the same seed-1919 model and token ids."""
