@@ -374,7 +374,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 #endif
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
+        for (int i = 0; i < 16; ++i) {                               // gate bias pre-scaled by -log2(e): sigmoid(g + b) = 1 / (1 + 2^(g * -log2e + b'))
+          float e2;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(a[16 + i], -1.4426950408889634f, bias_s[cg + 16 + i])));
+          v[i] = (a[i] + bias_s[cg + i]) * fast_rcp_f(1.f + e2);
+        }
         if (r_own) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += rr[i];
@@ -705,7 +709,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       int n;
       if (GLU_) n = glu_weight_row(c, split, p.bg, nout_);
       else { n = split * bn + c; if (n >= p.N) n = -1; }
-      bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+      float bv = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+      if (GLU_ && (c & 16)) bv *= -1.4426950408889634f;            // gate columns of each 32-column accumulator group: tc_epilogue folds the scale into an FMA
+      bias_s[c] = bv;
     }
   }
   if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
@@ -889,7 +895,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       int n;
       if (GLU_) n = glu_weight_row(c, split, p.bg, nout_);
       else { n = split * bn + c; if (n >= p.N) n = -1; }
-      bias_s[c] = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+      float bv = (p.bias && n >= 0) ? p.bias[n] : 0.f;
+      if (GLU_ && (c & 16)) bv *= -1.4426950408889634f;            // gate columns of each 32-column accumulator group: tc_epilogue folds the scale into an FMA
+      bias_s[c] = bv;
     }
   }
   if (EPI == EIGB200_EPI_GLU_RESIDUAL && p.eig_part && threadIdx.x >= 128 && threadIdx.x < 256) {   // gate weights of this CTA's bg output columns
