@@ -210,6 +210,24 @@ def test_linear_tcgen05_3xtf32(ops, M, N, K, epi):
     assert np.abs(out[:, :nout] - simt[:, :nout]).max() <= 2e-5
 
 
+@pytest.mark.parametrize("N", [129, 130, 144, 145, 160, 161, 176, 177, 191, 192])
+@pytest.mark.parametrize("K,epi", [(128, "none"), (96, "gelu"), (64, "residual"), (32, "none"), (128, "residual")])
+def test_linear_tcgen05_wide_plan(ops, N, K, epi):
+    """129..192 output columns: the single-CTA wide plan (all columns resident, 2 TMEM operand stages, partial last 32-column group, ragged last row tile)."""
+    M = 1500
+    rng = np.random.default_rng(N * 7 + K)
+    a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    ldc = (N + 7) // 8 * 8
+    r = rng.normal(size=(M, ldc)).astype(np.float32)
+    out = torch.full((M, ldc), 7.0, device="cuda")
+    ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :N] if epi == "residual" else None, mode="tc3", out=out)
+    out = out.cpu().numpy()
+    ref = _lin_ref(a, w, bias, epi, r[:, :N].astype(np.float64))
+    np.testing.assert_allclose(out[:, :N], ref, rtol=1e-5, atol=1e-5)
+    assert (out[:, N:] == 7.0).all()                               # the pad columns between N and ldc are never written
+
+
 @pytest.mark.parametrize("M,N,K", [(4096, 552, 512), (3000, 512, 512), (2500, 1024, 512), (1000, 96, 384), (4100, 40, 260), (2048, 1544, 512),
                                     (70000, 256, 320)])
 @pytest.mark.parametrize("epi", ["none", "gelu", "residual", "glu_residual"])
