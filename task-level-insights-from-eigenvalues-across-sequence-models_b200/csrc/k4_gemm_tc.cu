@@ -55,6 +55,8 @@ struct TcParams {
   int nsplit, kchunks, nstages, nterms, workers;
   const float* eig_w; float* eig_part;   // GLU epilogue only (nullable): per-row partial gate dot products and moments of the OUTPUT rows, see tc_epilogue
   int r_v8;          // residual rows are 32-byte aligned: add them in the accumulator layout with 256-bit loads
+  int epi_stage;     // bytes of per-warp staging tiles behind the raw ring (16 warps x 2 KB): the plain / GELU / residual epilogues transpose through
+                     // shared memory (4 STS + 4 LDS per 16 columns) instead of 192 shuffle / select instructions per 32 columns
   int c_v8;          // output rows are 32-byte aligned (and any residual is r_v8): every thread stores its own row segment with 256-bit stores
   int zero;          // always 0; a run-time value the compilers cannot fold (mbar_arrive_after)
   int64_t ntiles;
@@ -327,7 +329,7 @@ __device__ __forceinline__ void transpose4x4_f4(float (&v)[16], int lane) {
 
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int bn, uint32_t bar_dfull0, uint32_t bar_dempty0,
-                                            const float* bias_s, int worker, int split, int warp, int lane) {
+                                            const float* bias_s, int worker, int split, int warp, int lane, float* stage_s = nullptr) {
   auto bar_dfull = [&](int j) { return bar_dfull0 + 8u * j; };
   auto bar_dempty = [&](int j) { return bar_dempty0 + 8u * j; };
   constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
@@ -477,6 +479,38 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
         if (r_own) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += rr[i];
+        }
+        if (stage_s != nullptr) {
+          // transpose through this warp's 2 KB staging tile, 16 columns at a time: thread = row writes 4 quads (quad position XOR-swizzled by the
+          // row pair: conflict-free), then 4 lanes cover 64 contiguous bytes of a row and a store instruction writes 8 rows x 64 B
+          float* st = stage_s + warp * 512;
+          const int srow = lane >> 2, sq = lane & 3;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(st + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2)) =
+                  make_float4(v[16 * half + 4 * q], v[16 * half + 4 * q + 1], v[16 * half + 4 * q + 2], v[16 * half + 4 * q + 3]);
+            __syncwarp();
+            const int ncol = n_cta0 + cg + 16 * half + 4 * sq;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr_ = 8 * it + srow;
+              const float4 o = *reinterpret_cast<const float4*>(st + rr_ * 16 + ((sq ^ ((rr_ >> 1) & 3)) << 2));
+              const int64_t mrow = tile * TC_BM + quarter * 32 + rr_;
+              if (mrow < p.M && ncol < nout) {
+                float* cptr = p.C + mrow * p.ldc + ncol;
+                if (ncol + 3 < nout) *reinterpret_cast<float4*>(cptr) = o;
+                else {
+                  const float oe[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) if (ncol + e < nout) cptr[e] = oe[e];
+                }
+              }
+            }
+            __syncwarp();
+          }
+          continue;
         }
         if (p.c_v8) {                                                // own row, 4 full sectors: no transpose
           if (own_row < p.M) {
@@ -863,7 +897,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const uint32_t whi = base;
   const uint32_t wlo = whi + kch * w_chunk_bytes;
   const uint32_t stage0 = wlo + kch * w_chunk_bytes;                 // stage s: raw 16 KB chunk
-  const uint32_t bars = stage0 + nst * TC_CHUNK_BYTES;
+  const uint32_t epi_stage0 = stage0 + nst * TC_CHUNK_BYTES;         // optional staging tiles of the epilogue warps (p.epi_stage bytes)
+  const uint32_t bars = epi_stage0 + (uint32_t)p.epi_stage;
   const uint32_t bar_w = bars;
   auto bar_full = [&](int s) { return bars + 8u * (1 + s); };                              // TMA landed the raw chunk
   auto bar_free = [&](int s) { return bars + 8u * (1 + TS_MAX_STAGES + s); };              // converters have read it
@@ -1032,7 +1067,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
-    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp - TC_EPI_WARP0, lane);
+    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp - TC_EPI_WARP0, lane,
+                     p.epi_stage ? reinterpret_cast<float*>(smem_raw + (epi_stage0 - smem_u32(smem_raw))) : nullptr);
   }
 
   tc_fence_before();
@@ -1459,6 +1495,17 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
     const bool res_ok = !lp.R || p.r_v8 || !(glu || lp.epilogue == EIGB200_EPI_RESIDUAL);
     const bool want = direct == 1 || (direct == 2 && glu);
     p.c_v8 = (want && (((uintptr_t)lp.C & 31) == 0) && lp.ldc % 8 == 0 && res_ok) ? 1 : 0;
+  }
+  {
+    // EIGB200_GEMM_EPI_STAGE: the non-GLU epilogues of the TMEM-operand kernel can transpose through 32 KB of shared memory taken from the raw ring
+    // (two 16 KB stages) when at least 4 stages remain.  0 = shuffle transposes, 1 (default) = staged for the GELU epilogue only, 2 = staged for
+    // all of them.  Measured: GELU (issue-bound epilogue) -2...-4 %, bias-only (87 % of the HBM peak, wants the ring depth) +1...+5 %.
+    static int stage = -1;
+    if (stage < 0) { const char* e = getenv("EIGB200_GEMM_EPI_STAGE"); stage = e ? atoi(e) : 1; }
+    const bool res_ok = !lp.R || p.r_v8 || lp.epilogue != EIGB200_EPI_RESIDUAL;
+    p.epi_stage = 0;
+    const bool want = stage == 2 || (stage == 1 && lp.epilogue == EIGB200_EPI_GELU);
+    if (want && pl.ts && !glu && pl.ast == TS_ASTAGES && pl.nstages - 2 >= 4 && res_ok && !p.c_v8) { p.epi_stage = 2 * TC_CHUNK_BYTES; p.nstages = pl.nstages - 2; }
   }
   p.eig_w = nullptr; p.eig_part = nullptr;
   if (lp.eig_part) {                                                 // extractor partials ride in the GLU epilogue of the TMEM-operand kernel only
