@@ -1504,7 +1504,8 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
     if (stage < 0) { const char* e = getenv("EIGB200_GEMM_EPI_STAGE"); stage = e ? atoi(e) : 1; }
     const bool res_ok = !lp.R || p.r_v8 || lp.epilogue != EIGB200_EPI_RESIDUAL;
     p.epi_stage = 0;
-    const bool want = stage == 2 || (stage == 1 && lp.epilogue == EIGB200_EPI_GELU);
+    // default: GELU whenever 4 stages remain; the HBM-paced bias-only / residual epilogues only when 6 remain (narrow N: -2...-3.5 % at N = 64)
+    const bool want = stage == 2 || (stage == 1 && (lp.epilogue == EIGB200_EPI_GELU || pl.nstages - 2 >= 6));
     if (want && pl.ts && !glu && pl.ast == TS_ASTAGES && pl.nstages - 2 >= 4 && res_ok && !p.c_v8) { p.epi_stage = 2 * TC_CHUNK_BYTES; p.nstages = pl.nstages - 2; }
   }
   p.eig_w = nullptr; p.eig_part = nullptr;
