@@ -133,6 +133,9 @@ int eigb200_ratio_hist(void* stream, const void* d_a, int dtype, int mode, int64
  * behind np.mean / np.std over the batch axis (analysis/eval_eig.py:620-623, :677-680).  d_counts (B,inner,8);
  * d_sum, d_sumsq (inner,8) int64, overwritten. */
 int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq);
+/* The same for the (L,B,inner,8) count buffer of a whole pass in ONE launch: d_sum, d_sumsq (L,inner,8) int64, overwritten.  This 2 x L x inner x 8
+ * int64 buffer is everything a rank contributes to the single all-reduce of the path (eigb200_stats_allreduce below). */
+int eigb200_count_moments_layers(void* stream, const int32_t* d_counts, int64_t L, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq);
 
 /* ---- K2a: diagonal complex recurrence  h_t = lam * h_{t-1} + Bu_t  ---------------------------------------------------
  * What jax.lax.associative_scan(binary_operator_diag, (Lambda_elements, Bu_elements)) evaluates (models/lru.py:14-19, :95;

@@ -38,6 +38,7 @@ SIGNATURES = {
     "eigb200_softmax_attn_forward": [_vp, _vp, _vp, _vp, _i64, _f, _vp, _i64, _i64, _i64, _i, _i, _i],
     "eigb200_ratio_hist": [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_count_moments": [_vp, _vp, _i64, _i64, _vp, _vp],
+    "eigb200_count_moments_layers": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
     "eigb200_diag_scan": [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i],
     "eigb200_ssd_scan": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i],
     "eigb200_mamba_conv_ssd": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i],

@@ -99,22 +99,30 @@ class MambaPassGraph:
     work between the ~40 kernels of a 4-layer pass.  run(X) copies the token ids into the static input and replays; the returned PassResult
     (eig, counts) is overwritten by the next run()."""
 
-    def __init__(self, model: "Ly.MambaDev", X_example, pseudoLTI=False, want_eig=True, compare="float64", warmup=2):
+    def __init__(self, model: "Ly.MambaDev", X_example, pseudoLTI=False, want_eig=True, compare="float64", warmup=2, moments=False):
+        """moments=True: the pass also leaves the batch moments (2,L,H,8) int64 of its bin counts in self.moments (inside the graph) -- the
+        buffer a multi-GPU run all-reduces (eval_eig.py:620-623), so that no host work sits between the pass and the exchange."""
         if not X_example.is_cuda:
             raise L.Eigb200Error("MambaPassGraph: the example batch must live on the CUDA device")
         self.X = X_example.clone()
+        self.moments = None
+
+        def one_pass():
+            res = mamba_pass(model, self.X, pseudoLTI, want_eig=want_eig, compare=compare)
+            mom = ops.count_moments_layers(res.counts) if moments else None
+            return res, mom
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):                       # first calls may set function attributes / fill caches: outside the capture
-                mamba_pass(model, self.X, pseudoLTI, want_eig=want_eig, compare=compare)
+                one_pass()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         n0 = ops.LAUNCHES["n"]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.result = mamba_pass(model, self.X, pseudoLTI, want_eig=want_eig, compare=compare)
+            self.result, self.moments = one_pass()
         self.launches_per_run = ops.LAUNCHES["n"] - n0
 
     def run(self, X=None) -> PassResult:
@@ -271,11 +279,27 @@ def _save_results(args, conf_args, wandb_config, data_config, model_config, trai
 # ----------------------------------------------------------------------------------------------------------------------
 
 def _first_batch(loader, device, lo=None, hi=None):
-    X, y, _ = next(iter(loader))                                           # eval_eig.py:502 -- first batch only
-    if lo is not None:
-        X = X[lo:hi]
+    """eval_eig.py:502 -- first batch only.  With several ranks the batch is drawn ONCE, on rank 0, and broadcast: a shuffling loader (or
+    per-rank RNG state) would otherwise hand every rank a different batch and the all-reduced statistics would silently mix them."""
     if not torch.cuda.is_available():
         raise L.Eigb200Error("eval_eig needs a CUDA device (the reference refuses to run without one too, launch.py:63-64)")
+    rank, world = D.rank_world()
+    if world > 1:
+        import torch.distributed as tdist
+        meta = [None]
+        X = None
+        if rank == 0:
+            X, _y, _ = next(iter(loader))
+            X = torch.as_tensor(X)
+            meta = [(tuple(X.shape), X.dtype)]
+        tdist.broadcast_object_list(meta, src=0)
+        shape, dtype = meta[0]
+        Xd = X.to(device) if rank == 0 else torch.empty(shape, dtype=dtype, device=device)
+        tdist.broadcast(Xd, src=0)
+        return Xd[lo:hi].contiguous() if lo is not None else Xd
+    X, y, _ = next(iter(loader))
+    if lo is not None:
+        X = X[lo:hi]
     return X.to(device, non_blocking=True)
 
 
@@ -319,7 +343,14 @@ def eval_eig(args, conf_args, wandb_config, data_config, loader, path_file, perf
             res.eig, res.counts = eig, counts
             return res
 
-        # init pass: the reference constructs the model under torch.manual_seed(seed) (:484-497)
+        # init pass: the reference constructs the model under torch.manual_seed(seed) (:484-497) and never calls model.eval() on it, so
+        # with dropout > 0 its eig_init / percentage_init carry one random dropout mask; this path is deterministic (dropout = identity
+        # in both passes).  All reference analysis configs use dropout 0; say so loudly otherwise.
+        if float(model_config.get("dropout", 0.0) or 0.0) > 0.0 or float(model_config.get("att_dropout", 0.0) or 0.0) > 0.0:
+            import warnings
+            warnings.warn("eigb200.eval_eig: dropout > 0 -- the reference's init pass runs in train mode (random dropout mask in eig_init); "
+                          "eigb200 evaluates both passes without dropout, so eig_init / percentage_init differ from the reference's sample",
+                          RuntimeWarning)
         if layer_type == "mamba":
             init_sd = Ly.init_mamba_state_dict(model_config, seed)
         else:

@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(256) linattn_forward_col_kernel(const LinAttnP
     __syncthreads();                                               // chunk `cur` landed; every thread is done with the other buffer
     if (t0 + LC_TC < p.T) stage(cur ? buf0 : buf1, t0 + LC_TC);    // next chunk in flight during this one
     if (p.phi_elu) {
-      for (int i = tid; i < tc * 2 * D_; i += nthr) cb[i] = elu_f(cb[i]) + 1.f;          // q and k rows are adjacent: [0, 2 TC D_)
+      // q rows live at [0, TC D_), k rows at [TC D_, 2 TC D_) whatever tc is: transform both regions in full (on a partial last chunk the rows
+      // beyond tc are zero-filled by stage() and never read, so phi of them is harmless; `tc * 2 * D_` here left k rows raw when T % 16 != 0)
+      for (int i = tid; i < LC_TC * 2 * D_; i += nthr) cb[i] = elu_f(cb[i]) + 1.f;
       __syncthreads();
     }
     if (p.normalise && tid < 32) {                                 // warp 0: den_t = q_t . ksum_t, ksum_t = ksum_{t-1} + k_t (sequential over the chunk)

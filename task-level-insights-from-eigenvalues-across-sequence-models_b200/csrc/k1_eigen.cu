@@ -521,12 +521,30 @@ __global__ void __launch_bounds__(256) ratio_hist_kernel(const RatioParams p) {
   }
 }
 
-__global__ void count_moments_kernel(const int* counts, int64_t B, int64_t inner8, long long* sum, long long* sumsq) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= inner8) return;
-  long long s = 0, s2 = 0;
-  for (int64_t b = 0; b < B; ++b) { const long long c = counts[b * inner8 + i]; s += c; s2 += c * c; }
-  sum[i] = s; sumsq[i] = s2;
+// sum_b c and sum_b c^2 of the per-sample bin counts (eval_eig.py:620-623 forms mean / std over the batch axis from them): counts (L, B, inner8)
+// -> sum, sumsq (L, inner8) int64.  A CTA takes CM_ROWS samples of one layer x up to 256 columns: thread = (row lane, column), partial sums meet in
+// shared memory (integer atomics: order-independent, bit-reproducible) and leave with ONE global 64-bit atomic per column and CTA.
+constexpr int CM_ROWS = 512;
+__global__ void __launch_bounds__(256) count_moments_kernel(const int* __restrict__ counts, int64_t B, int64_t inner8,
+                                                            unsigned long long* __restrict__ sum, unsigned long long* __restrict__ sumsq) {
+  __shared__ unsigned long long s_sum[256], s_sq[256];
+  const int ncol = (int)min((int64_t)256, inner8 - (int64_t)blockIdx.y * 256);     // columns of this CTA
+  const int col = threadIdx.x % ncol, rlane = threadIdx.x / ncol, nrl = 256 / ncol;
+  const int64_t c0 = (int64_t)blockIdx.y * 256, layer = blockIdx.z;
+  s_sum[threadIdx.x] = 0ull; s_sq[threadIdx.x] = 0ull;
+  __syncthreads();
+  const int64_t b0 = (int64_t)blockIdx.x * CM_ROWS, b1 = min(B, b0 + CM_ROWS);
+  const int* base = counts + (layer * B) * inner8 + c0 + col;
+  unsigned long long s = 0ull, s2 = 0ull;
+  if (rlane < nrl) {
+    for (int64_t b = b0 + rlane; b < b1; b += nrl) { const long long c = __ldg(base + b * inner8); s += (unsigned long long)c; s2 += (unsigned long long)(c * c); }
+    atomicAdd(&s_sum[col], s); atomicAdd(&s_sq[col], s2);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < ncol) {
+    atomicAdd(sum + layer * inner8 + c0 + threadIdx.x, s_sum[threadIdx.x]);
+    atomicAdd(sumsq + layer * inner8 + c0 + threadIdx.x, s_sq[threadIdx.x]);
+  }
 }
 
 __global__ void zero_i32_kernel(int* p, size_t n) {
@@ -647,12 +665,25 @@ extern "C" int eigb200_softmax_eta(void* stream, const double* d_nu, const float
   return EIGB200_OK;
 }
 
-extern "C" int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq) {
-  EIGB_CHECK_ARG(d_counts && d_sum && d_sumsq && B > 0 && inner > 0, "count_moments: bad arguments");
+static int launch_count_moments(cudaStream_t st, const int32_t* d_counts, int64_t L, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq) {
   const int64_t n = inner * EIGB200_NSLOT;
-  count_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_counts, B, n, (long long*)d_sum, (long long*)d_sumsq);
+  EIGB_CHECK_ARG(L > 0 && L <= 65535 && (n + 255) / 256 <= 65535, "count_moments: too many layers / columns");
+  EIGB_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)(L * n) * sizeof(int64_t), st));
+  EIGB_CUDA(cudaMemsetAsync(d_sumsq, 0, (size_t)(L * n) * sizeof(int64_t), st));
+  dim3 grid((unsigned)((B + CM_ROWS - 1) / CM_ROWS), (unsigned)((n + 255) / 256), (unsigned)L);
+  count_moments_kernel<<<grid, 256, 0, st>>>(d_counts, B, n, (unsigned long long*)d_sum, (unsigned long long*)d_sumsq);
   EIGB_LAUNCH_CHECK("count_moments_kernel");
   return EIGB200_OK;
+}
+
+extern "C" int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq) {
+  EIGB_CHECK_ARG(d_counts && d_sum && d_sumsq && B > 0 && inner > 0, "count_moments: bad arguments");
+  return launch_count_moments((cudaStream_t)stream, d_counts, 1, B, inner, d_sum, d_sumsq);
+}
+
+extern "C" int eigb200_count_moments_layers(void* stream, const int32_t* d_counts, int64_t L, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq) {
+  EIGB_CHECK_ARG(d_counts && d_sum && d_sumsq && L > 0 && B > 0 && inner > 0, "count_moments_layers: bad arguments");
+  return launch_count_moments((cudaStream_t)stream, d_counts, L, B, inner, d_sum, d_sumsq);
 }
 
 extern "C" int eigb200_mamba2_eig_partials(void* stream, const float* d_partials, int ngroups16, int64_t B, int64_t T,

@@ -7,7 +7,8 @@ activations through one block with the eigb200 kernels.
 Reference: models/mamba.py (SSD :25-154, MambaBlock :301-340, Mamba :342-389), models/transformer.py
 (TransformerBlock :22-111, Transformer :113-161), models/attention.py (MHA :85-182), models/norm_attention.py
 (MHNA :160-258), models/common.py (GLU :50-58, MLP :33-48, TokenEmbeddings :117-176).
-Eval-mode semantics (dropout is the identity); see DESIGN.md for the init-pass dropout quirk.
+Eval-mode semantics (dropout is the identity).  The reference's INIT pass runs in train mode (eval_eig.py:484-564 never calls model.eval()), so with
+dropout > 0 its eig_init is one random sample; eval_eig warns in that case.
 """
 from __future__ import annotations
 

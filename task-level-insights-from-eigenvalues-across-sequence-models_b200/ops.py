@@ -182,6 +182,20 @@ def count_moments(counts):
     return s, s2
 
 
+def count_moments_layers(counts, out=None):
+    """counts (L,B,inner...,8) int32 of a whole pass -> moments (2,L,inner,8) int64: [0] = sum_b c, [1] = sum_b c^2, one launch.
+    This buffer is all a rank contributes to the path's single all-reduce (dist.allreduce_moments)."""
+    counts = _prep(counts, torch.int32)
+    Ln, B = counts.shape[0], counts.shape[1]
+    inner = counts.numel() // (Ln * B * NSLOT)
+    lib = _enter(counts)
+    if out is None:
+        out = torch.empty(2, Ln, inner, NSLOT, dtype=torch.int64, device=counts.device)
+    assert out.is_contiguous() and out.dtype == torch.int64 and out.numel() == 2 * Ln * inner * NSLOT
+    _call(lib, "eigb200_count_moments_layers", _stream(counts), _p(counts), Ln, B, inner, _p(out[0]), _p(out[1]))
+    return out
+
+
 # ---- K1'': linear attention ---------------------------------------------------------------------------------------
 def linattn_nu(qk_buf, ld: int, B: int, T: int, H: int, d: int, k_offset: int):
     """qk_buf: projection buffer (B*T, ld) f32 with q at column 0 and k at column `k_offset`.  -> nu (B,T,H) f64."""
@@ -337,8 +351,12 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     assert a.is_cuda and a.dtype == torch.float32 and a.stride(-1) == 1
     K = a.shape[-1]
     M = a.numel() // K
-    a2 = a.reshape(M, K) if a.is_contiguous() else a
-    lda = a2.stride(0) if a2.dim() == 2 else K
+    if a.is_contiguous():
+        a2 = a.reshape(M, K); lda = K
+    elif a.dim() == 2:
+        a2 = a; lda = a.stride(0)                                   # strided 2-D view (column slice of a projection buffer): row stride passed through
+    else:
+        a2 = a.contiguous().reshape(M, K); lda = K                  # an N-D non-contiguous view has no single row stride: compact it first
     weight = _prep(weight, torch.float32)
     N = weight.shape[0]
     assert weight.shape[1] == K

@@ -159,8 +159,11 @@ def _unflatten(flat):
 
 def get_trained_layers_ssm(path):
     """analysis/eval_eig.py:241-252.  Accepts the reference's orbax PyTree checkpoint when orbax is importable, and otherwise a
-    mirror of the same tree: a `.npz` with '/'-joined keys (model/params/encoder/layers_0/seq/nu_log ...), a pickle, or a
-    torch-saved nested dict {"model": {"params": ...}} (a directory may hold `params.npz`)."""
+    mirror of the same tree: a `.npz` with '/'-joined keys (model/params/encoder/layers_0/seq/nu_log ...) or a torch-saved
+    nested dict {"model": {"params": ...}} of tensors (a directory may hold `params.npz`).
+    A checkpoint path is user input: nothing here unpickles arbitrary objects (np.load(allow_pickle=False),
+    torch.load(weights_only=True)) -- the reference restores through orbax, which does not execute code either.  Legacy pickle /
+    non-tensor torch files load only with EIGB200_ALLOW_PICKLE=1 in the environment."""
     if os.path.isdir(path) and not os.path.exists(os.path.join(path, "params.npz")):
         try:
             import orbax.checkpoint as ocp
@@ -170,14 +173,18 @@ def get_trained_layers_ssm(path):
         return _layers_from_params(raw["model"]["params"])
     if os.path.isdir(path):
         path = os.path.join(path, "params.npz")
+    allow_pickle = os.environ.get("EIGB200_ALLOW_PICKLE", "0") == "1"
     if path.endswith(".npz"):
-        z = np.load(path)
+        z = np.load(path, allow_pickle=False)
         tree = _unflatten({k: z[k] for k in z.files})
     elif path.endswith((".pkl", ".pickle")):
+        if not allow_pickle:
+            raise L.Eigb200Error("'%s': pickle checkpoints execute code on load and are refused; export the parameter tree as .npz "
+                                 "(or set EIGB200_ALLOW_PICKLE=1 for a file you trust)" % path)
         with open(path, "rb") as f:
             tree = pickle.load(f)
     else:
-        tree = torch.load(path, weights_only=False, map_location="cpu")
+        tree = torch.load(path, weights_only=not allow_pickle, map_location="cpu")
     params = tree["model"]["params"] if "model" in tree else tree.get("params", tree)
     return _layers_from_params(params)
 

@@ -112,6 +112,28 @@ def test_linattn_forward(ops, H, d, dv, normalise):
     np.testing.assert_allclose(out.reshape(B, T, H, dv), ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("T", [24, 45, 64, 7])
+@pytest.mark.parametrize("H,d,dv,normalise", [(1, 64, 64, True), (4, 32, 64, False), (2, 16, 32, True), (1, 128, 128, False)])
+def test_linattn_forward_column_owner_tail(ops, T, H, d, dv, normalise):
+    """The column-owner kernel (d in {16,32,64,128}, dv % 32 == 0, ld % 4 == 0: the C1 / C5 shapes) with T % 16 != 0: phi must reach the k rows of a
+    partial last chunk (`tc * 2 * D_` covered q rows only)."""
+    rng = np.random.default_rng(1000 * T + d + dv)
+    B = 3
+    ld = 2 * H * d + H * dv + 4                                   # multiple of 4: 16-byte cp.async pieces => column-owner kernel
+    assert ld % 4 == 0
+    buf = rng.normal(size=(B * T, ld)).astype(np.float32)
+    gate = rng.uniform(0.1, 1.0, (B, T, H)).astype(np.float32)
+    out = ops.linattn_forward(dev(buf), ld, 0, H * d, 2 * H * d, B, T, H, d, dv, gate=None if normalise else dev(gate),
+                              phi_elu=True, normalise=normalise, kscale=1.0 if normalise else 0.25).cpu().numpy()
+    b3 = buf.reshape(B, T, ld).astype(np.float64)
+    q = O.elu(b3[..., :H * d].reshape(B, T, H, d)) + 1; k = O.elu(b3[..., H * d:2 * H * d].reshape(B, T, H, d)) + 1
+    v = b3[..., 2 * H * d:2 * H * d + H * dv].reshape(B, T, H, dv)
+    kv = np.cumsum(np.einsum("bthd,bthe->bthde", k * (1.0 if normalise else 0.25), v), axis=1)
+    num = np.einsum("bthd,bthde->bthe", q, kv)
+    ref = num / np.einsum("bthd,bthd->bth", q, np.cumsum(k, axis=1))[..., None] if normalise else num * gate[..., None]
+    np.testing.assert_allclose(out.reshape(B, T, H, dv), ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
+
+
 def test_linattn_nu_and_eta(ops):
     from conftest import load_golden
     g = load_golden("lin_softmax_extractor")

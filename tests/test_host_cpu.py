@@ -102,10 +102,34 @@ def test_trained_layer_readers(tmp_path):
     layers = S.get_trained_layers_ssm(p)
     assert len(layers) == 3 and set(layers[0]) == {"nu_log", "theta_log"}
     np.testing.assert_array_equal(layers[2]["nu_log"], flat["model/params/encoder/layers_10/seq/nu_log"])   # numeric, not string, order
-    tree = {"model": {"params": {"encoder": {"layers_0": {"seq": {"nu_log": np.zeros(3)}}, "encoder": {"kernel": np.zeros(2)}}}}}
+    tree = {"model": {"params": {"encoder": {"layers_0": {"seq": {"nu_log": torch.zeros(3)}}, "encoder": {"kernel": torch.zeros(2)}}}}}
     p2 = str(tmp_path / "ckpt.pt")
     torch.save(tree, p2)
     assert len(S.get_trained_layers_ssm(p2)) == 1
+
+
+def test_trained_layer_readers_refuse_pickle(tmp_path, monkeypatch):
+    """A checkpoint path is user input: pickle files and torch files holding arbitrary objects are refused unless the caller opts in."""
+    import pickle
+    import eigb200._lib as L
+    import eigb200.ssm as S
+    monkeypatch.delenv("EIGB200_ALLOW_PICKLE", raising=False)
+    tree = {"model": {"params": {"encoder": {"layers_0": {"seq": {"nu_log": np.zeros(3)}}}}}}
+    p = str(tmp_path / "ckpt.pkl")
+    with open(p, "wb") as f:
+        pickle.dump(tree, f)
+    with pytest.raises(L.Eigb200Error, match="pickle"):
+        S.get_trained_layers_ssm(p)
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("executed on load",))
+    p2 = str(tmp_path / "evil.pt")
+    torch.save({"model": {"params": Evil()}}, p2)
+    with pytest.raises(Exception):
+        S.get_trained_layers_ssm(p2)                              # weights_only=True rejects the non-tensor payload
+    monkeypatch.setenv("EIGB200_ALLOW_PICKLE", "1")
+    assert len(S.get_trained_layers_ssm(p)) == 1                  # explicit opt-in for a trusted legacy file
 
 
 def test_init_layers_distributions():
@@ -130,3 +154,51 @@ def test_cpu_baseline_port_matches_reference_golden():
     eig, pct, ph = O.mamba_eval_pass_torch_cpu(g["X"], sd, c, chunk=8)
     np.testing.assert_allclose(eig, g["eig"], rtol=2e-5)
     assert np.abs(pct - g["percentage"]).max() <= 100.0 / eig.shape[1] + 1e-9
+
+
+def test_gpu_baseline_ssd_matches_oracle():
+    """tools/gpu_baseline.py is the eager-PyTorch comparator of bench.py: its chunked SSD must compute the same recurrence as the oracle
+    (a comparator that computed something else would make the speed-up meaningless)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gpu_baseline as GB
+    rng = np.random.default_rng(0)
+    B, T, H, P, N = 2, 150, 2, 8, 16
+    x = rng.normal(size=(B, T, H, P)).astype(np.float32); dt = rng.uniform(0.01, 0.2, (B, T, H)).astype(np.float32)
+    A = -rng.uniform(1, 8, H).astype(np.float32); Bm = rng.normal(size=(B, T, 1, N)).astype(np.float32); Cm = rng.normal(size=(B, T, 1, N)).astype(np.float32)
+    D = rng.normal(size=H).astype(np.float32)
+    y = GB._ssd_torch_chunked(*[torch.from_numpy(a).double() for a in (x, dt, A, Bm, Cm, D)], chunk=64).numpy()
+    ref = O.ssd_scan_sequential(x, dt, A, Bm, Cm, D)
+    np.testing.assert_allclose(y, ref, rtol=1e-9, atol=1e-10)
+
+
+def test_gpu_baseline_pass_matches_oracle_port():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gpu_baseline as GB
+    sd, cfg, g = golden_model("model_mamba2")
+    sdt = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+    eig, pct = GB.mamba_pass_eager(torch.from_numpy(g["X"]), sdt, cfg, ssd_impl="torch")
+    np.testing.assert_allclose(eig, g["eig"], rtol=2e-5)
+    assert np.abs(pct - g["percentage"]).max() <= 100.0 / eig.shape[1] + 1e-9
+
+
+def test_bench_arms_share_one_config():
+    """The driver compares the `config` object of the eigb200 arm with the --impl reference arm's: both come from one function, and the strong-scaling
+    plan shards BASELINE configs[1]'s 4096 sequences over the GPUs."""
+    import argparse
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    a = argparse.Namespace(config="c2", scaling="strong", batch=4096, batch_other=0)
+    assert bench.batch_plan(a, 8) == (512, 4096) and bench.batch_plan(a, 1) == (4096, 4096) and bench.batch_plan(a, 3) == (1366, 4096)
+    a.scaling = "weak"
+    assert bench.batch_plan(a, 8) == (4096, 32768)
+    a.scaling = "strong"
+    c8 = bench.workload_config(a, 8)
+    assert c8["global_batch"] == 4096 and c8["batch_per_gpu"] == 512 and c8["scaling"] == "strong"
+    assert bench.workload_config(a, 8) == c8                       # deterministic: no arm-specific keys in it
+    assert "launch" not in c8 and "gemm" not in c8
+    alg, _ = bench.c2_alg_bytes(4096 * 512, 128, 16, 1)
+    assert alg["eigb200_linear_glu_extract[N256 K128 glu_residual+extract]"] == 4096 * 512 * 3 * 128 * 4   # strict: no extractor partials

@@ -152,6 +152,20 @@ def test_count_moments(ops):
     np.testing.assert_allclose(std, pct.std(0), rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("L,B,inner", [(4, 4096, 1), (3, 37, 6), (12, 1000, 8), (2, 5, 40), (1, 513, 3)])
+def test_count_moments_layers(ops, L, B, inner):
+    """The per-pass moments buffer (2,L,inner,8) -- what a rank contributes to the path's single all-reduce -- in one launch, exact in int64."""
+    rng = np.random.default_rng(L * 1000 + B)
+    c = rng.integers(0, 2049, (L, B, inner, 8)).astype(np.int32)
+    m = ops.count_moments_layers(_dev(c)).cpu().numpy()
+    assert m.shape == (2, L, inner, 8) and m.dtype == np.int64
+    np.testing.assert_array_equal(m[0], c.astype(np.int64).sum(1))
+    np.testing.assert_array_equal(m[1], (c.astype(np.int64) ** 2).sum(1))
+    for l in range(L):                                            # agrees with the single-layer entry point
+        s, s2 = ops.count_moments(_dev(c[l]))
+        np.testing.assert_array_equal(s.cpu().numpy(), m[0, l]); np.testing.assert_array_equal(s2.cpu().numpy(), m[1, l])
+
+
 def test_full_size_properties_c2(ops):
     """BASELINE config C2 K1 shape (4096 x 512 x 128, H=1): properties that need no CPU pass over 1 GB."""
     torch.manual_seed(0)

@@ -1,0 +1,309 @@
+"""Synthetic workloads of the BASELINE.json configs other than the headline C2 (bench.py --config ...).
+
+Each workload builds random-init parameters of the named architecture and synthetic inputs of the task's shape (there is no network for
+datasets or checkpoints), and exposes
+
+    step()          one pass of the hot path with the inputs already resident in HBM -> a device tensor that belongs to the result
+    step_e2e()      the same from pinned HOST inputs to pinned HOST results (copies inside), returns nothing
+    units           work units per step (eigenvalues / state updates / matrices -- `unit` says which)
+    cpu(sample)     the oracle port of the same pass on the host cores over `sample` sequences / matrices -> (units, seconds)   [bench.py only]
+
+C1  linear attention on MQAR (seq 64, d_model 64, 2 layers, vocab 8192)              eigenvalues = B (T-1) H L
+C3  LRU / S5 on ListOps-shaped input (seq 2048, d_model 128, P = 256 states, 6 layers): parameter eigenvalues + bin counts, then the diagonal
+    recurrence they drive (B u GEMM, scan, Re(C h) + D u GEMM) through all layers       units = state updates B T P L
+C4  S4 (DPLR, N = 64) on LRA-shaped input: Abar = discrete_DPLR, eigenvalues of every (feature, layer) matrix   units = matrices H L
+C5  Mamba-2 / normalised attention LM (seq 1024, d_model 512, 8 heads, 12 layers, vocab 50257): eigenvalues = B T' H L
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 1919
+
+
+def _pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+class _Base:
+    unit = "eigenvalues/s"
+    dtype = "f32"
+
+    def cpu(self, sample, threads):
+        raise NotImplementedError
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# transformers (C1 linear attention, C5 normalised attention)
+# ----------------------------------------------------------------------------------------------------------------------
+def transformer_cfg(kind):
+    if kind == "c1":
+        return dict(layer="transformer", input_dim=1, output_dim=8192, num_layers=2, hidden_dim=64, embedding=True, vocab_size=8192, max_pos_embed=0,
+                    pooling="none", dual=False, classifier=False, mixer_dim=0, norm="layer", dropout=0.0, state_dim=64, num_heads=1, att_dropout=0.0,
+                    use_flash=False, attention_fn="lin-attention", mixer="none", mode="attention", dim_conv=0), 64
+    if kind == "c5-normattn":
+        return dict(layer="transformer", input_dim=1, output_dim=50257, num_layers=12, hidden_dim=512, embedding=True, vocab_size=50257, max_pos_embed=1024,
+                    pooling="none", dual=False, classifier=False, mixer_dim=2048, norm="layer", dropout=0.0, state_dim=512, num_heads=8, att_dropout=0.0,
+                    use_flash=False, attention_fn="norm-attention", mixer="glu", mode="attention", norm_fn="softplus", approx_fn="elu", scale_B=False,
+                    offset=True, offset_init="exp", learn_A=False, dim_conv=4), 1024
+    raise KeyError(kind)
+
+
+class TransformerWorkload(_Base):
+    def __init__(self, kind, batch, dev, layers=None, seed_offset=0):
+        import eigb200.layers as Ly
+        self.cfg, self.T = transformer_cfg(kind)
+        if layers:
+            self.cfg["num_layers"] = layers
+        self.kind, self.B = kind, batch
+        self.sd = Ly.init_transformer_state_dict(self.cfg, SEED)
+        self.model = Ly.TransformerDev(self.cfg, self.sd, dev) if dev is not None else None
+        g = torch.Generator().manual_seed(42 + seed_offset)
+        self.X_host = _pin(torch.randint(0, self.cfg["vocab_size"], (batch, self.T), generator=g))
+        self.X = self.X_host.to(dev) if dev is not None else None
+        H, L = self.cfg["num_heads"], self.cfg["num_layers"]
+        self.units = batch * (self.T - 1) * H * L
+        self.eig_host = _pin(torch.empty(batch, self.T - 1, H, L, dtype=torch.float64)) if dev is not None else None
+        self.workload = "%s: %s T=%d d_model=%d d_qk=%d heads=%d layers=%d vocab=%d" % (
+            kind, self.cfg["attention_fn"], self.T, self.cfg["hidden_dim"], self.cfg["state_dim"], H, L, self.cfg["vocab_size"])
+        self.h2d, self.d2h = self.X_host.numel() * 8, self.units * 8 + L * batch * H * 8 * 4
+
+    def step(self, X=None):
+        import eigb200.analysis as A
+        return A.transformer_pass(self.model, self.X if X is None else X, self.cfg, want_eig=True)
+
+    def step_e2e(self):
+        Xd = self.X_host.to(self.X.device, non_blocking=True)
+        res = self.step(Xd)
+        self.eig_host.copy_(res.eig, non_blocking=True)
+        c = res.counts.cpu()
+        torch.cuda.synchronize()
+        return c
+
+    def cpu(self, sample, threads):
+        import oracle as O
+        torch.set_num_threads(threads)
+        X = self.X_host[:sample].numpy()
+        sd = {k: v.numpy() for k, v in self.sd.items()}
+        ocfg = dict(self.cfg, d_model=self.cfg["hidden_dim"], d_qk=self.cfg["state_dim"])
+        t0 = time.perf_counter()
+        eig, _ = O.transformer_eval_pass(X, sd, ocfg, np.float32)
+        return eig.size, time.perf_counter() - t0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Mamba-2 at the C5 shape
+# ----------------------------------------------------------------------------------------------------------------------
+def mamba_cfg(kind):
+    if kind == "c5-mamba":
+        return dict(layer="mamba", version="mamba2", num_layers=12, num_heads=8, input_dim=1, output_dim=50257, hidden_dim=512, state_dim=16,
+                    conv_dim=4, expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none", token_embedding=True,
+                    vocab_size=50257), 1024
+    if kind == "c2":
+        return dict(layer="mamba", version="mamba2", num_layers=4, num_heads=1, input_dim=1, output_dim=8192, hidden_dim=128, state_dim=16,
+                    conv_dim=4, expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none",
+                    token_embedding=True, vocab_size=8192), 512
+    raise KeyError(kind)
+
+
+class MambaWorkload(_Base):
+    def __init__(self, kind, batch, dev, layers=None, seed_offset=0):
+        import eigb200.layers as Ly
+        self.cfg, self.T = mamba_cfg(kind)
+        if layers:
+            self.cfg["num_layers"] = layers
+        self.kind, self.B = kind, batch
+        self.sd = Ly.init_mamba_state_dict(self.cfg, SEED)
+        self.model = Ly.MambaDev(self.cfg, self.sd, dev) if dev is not None else None
+        g = torch.Generator().manual_seed(42 + seed_offset)
+        self.X_host = _pin(torch.randint(0, self.cfg["vocab_size"], (batch, self.T), generator=g))
+        self.X = self.X_host.to(dev) if dev is not None else None
+        H, L = self.cfg["num_heads"], self.cfg["num_layers"]
+        self.units = batch * self.T * H * L
+        self.eig_host = _pin(torch.empty(batch, self.T, H, L, dtype=torch.float32)) if dev is not None else None
+        self.workload = "%s: mamba2 T=%d d_model=%d heads=%d d_state=%d conv=4 glu prenorm layers=%d vocab=%d" % (
+            kind, self.T, self.cfg["hidden_dim"], H, self.cfg["state_dim"], L, self.cfg["vocab_size"])
+        self.h2d, self.d2h = self.X_host.numel() * 8, self.units * 4 + L * batch * H * 8 * 4
+
+    def step(self, X=None):
+        import eigb200.analysis as A
+        return A.mamba_pass(self.model, self.X if X is None else X, want_eig=True)
+
+    def step_e2e(self):
+        Xd = self.X_host.to(self.X.device, non_blocking=True)
+        res = self.step(Xd)
+        self.eig_host.copy_(res.eig, non_blocking=True)
+        c = res.counts.cpu()
+        torch.cuda.synchronize()
+        return c
+
+    def cpu(self, sample, threads):
+        import oracle as O
+        torch.set_num_threads(threads)
+        D = self.cfg["hidden_dim"]; hd = D // self.cfg["num_heads"]
+        ocfg = dict(num_layers=self.cfg["num_layers"], d_inner=D, ngroups=1, d_state=self.cfg["state_dim"], nheads=D // hd, headdim=hd, prenorm=True)
+        X = self.X_host[:sample]
+        t0 = time.perf_counter()
+        eig, _, _ = O.mamba_eval_pass_torch_cpu(X, self.sd, ocfg)
+        return eig.size, time.perf_counter() - t0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C3: LRU / S5 -- parameter eigenvalues + the diagonal recurrence through 6 layers
+# ----------------------------------------------------------------------------------------------------------------------
+def _lru_params(rng, P, H):
+    lam = np.sqrt(rng.uniform(0.9 ** 2, 0.999 ** 2, P))
+    return dict(nu_log=np.log(-np.log(lam)).astype(np.float32), theta_log=np.log(6.28 * rng.uniform(size=P)).astype(np.float32),
+                gamma_log=np.log(np.sqrt(1 - lam ** 2)).astype(np.float32),
+                B_re=(rng.normal(size=(P, H)) / np.sqrt(2 * H)).astype(np.float32), B_im=(rng.normal(size=(P, H)) / np.sqrt(2 * H)).astype(np.float32),
+                C_re=(rng.normal(size=(H, P)) / np.sqrt(P)).astype(np.float32), C_im=(rng.normal(size=(H, P)) / np.sqrt(P)).astype(np.float32),
+                D=rng.normal(size=H).astype(np.float32))
+
+
+def _s5_params(rng, P, H):
+    return dict(Lambda_re=(-np.abs(rng.normal(0.5, 0.2, P))).astype(np.float32), Lambda_im=rng.normal(0, 6, P).astype(np.float32),
+                B=(rng.normal(size=(P, H, 2)) / np.sqrt(H)).astype(np.float32), C=(rng.normal(size=(H, P, 2)) / np.sqrt(P)).astype(np.float32),
+                D=rng.normal(size=H).astype(np.float32), log_step=rng.uniform(np.log(1e-3), np.log(1e-1), (P, 1)).astype(np.float32))
+
+
+class DiagSsmWorkload(_Base):
+    unit = "state updates/s"
+    dtype = "c64"
+
+    def __init__(self, kind, batch, dev, layers=6, T=2048, Hd=128, P=256, seed_offset=0):
+        self.kind, self.B, self.T, self.Hd, self.P, self.L = kind, batch, T, Hd, P, layers
+        self.layer = "lru" if kind == "c3-lru" else "s5"
+        rng = np.random.default_rng(SEED)
+        mk = _lru_params if self.layer == "lru" else _s5_params
+        self.params_np = [mk(rng, P, Hd) for _ in range(layers)]
+        self.params = [{k: torch.from_numpy(v).to(dev) for k, v in p.items()} for p in self.params_np] if dev is not None else None
+        g = torch.Generator().manual_seed(42 + seed_offset)
+        self.u_host = _pin(torch.randn(batch, T, Hd, generator=g))
+        self.u = self.u_host.to(dev) if dev is not None else None
+        self.units = batch * T * P * layers
+        self.y_host = _pin(torch.empty(batch, T, Hd)) if dev is not None else None
+        self.workload = "%s: %s T=%d d_model=%d P=%d complex states layers=%d" % (kind, self.layer, T, Hd, P, layers)
+        self.h2d, self.d2h = self.u_host.numel() * 4, self.u_host.numel() * 4 + layers * P * 8
+
+    def _eigs(self):
+        """get_eigvals_ssm (eval_eig.py:303-329) for every layer + radius / phase bin counts, on the device."""
+        import eigb200.ops as ops
+        import eigb200._lib as L
+        lams = []
+        for p in self.params:
+            if self.layer == "lru":
+                lams.append(ops.ssm_lambda("lru", p["nu_log"], p["theta_log"]))
+            else:
+                lams.append(ops.ssm_lambda("s5_zoh", p["Lambda_re"], p["Lambda_im"], p["log_step"]))
+        lam = torch.stack(lams, dim=-1)                                          # (P, L) complex64
+        rad = torch.abs(lam).T.contiguous().reshape(self.L, self.P, 1)           # layer = "batch" axis of the counter
+        _, counts = ops.ratio_hist(rad, L.RATIO_NONE, want_out=False)
+        return lam, counts
+
+    def step(self, u=None):
+        import eigb200.ssm as S
+        lam, counts = self._eigs()
+        x = self.u if u is None else u
+        for p in self.params:
+            x = S.lru_forward(p, x) if self.layer == "lru" else S.s5_forward(p, x)
+        self.last = (lam, counts)
+        return x
+
+    def step_e2e(self):
+        ud = self.u_host.to(self.u.device, non_blocking=True)
+        y = self.step(ud)
+        self.y_host.copy_(y, non_blocking=True)
+        lam = self.last[0].cpu()
+        torch.cuda.synchronize()
+        return lam
+
+    def cpu(self, sample, threads):
+        import oracle as O
+        u = self.u_host[:sample].numpy()
+        t0 = time.perf_counter()
+        x = u
+        for p in self.params_np:
+            if self.layer == "lru":
+                O.lru_lambda(p["nu_log"], p["theta_log"])
+                x = O.lru_forward(p, x, dtype=np.complex64)[0].astype(np.float32)
+            else:
+                O.s5_lambda(p["Lambda_re"], p["Lambda_im"], p["log_step"])
+                x = O.s5_forward(p, x, dtype=np.complex64)[0].astype(np.float32)
+        return sample * self.T * self.P * self.L, time.perf_counter() - t0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# C4: S4 DPLR (N = 64): discretise + eigenvalues of every (feature, layer) matrix
+# ----------------------------------------------------------------------------------------------------------------------
+class S4EigWorkload(_Base):
+    unit = "matrices/s"
+    dtype = "f64"
+
+    def __init__(self, kind, batch, dev, layers=6, H=512, N=64, seed_offset=0):
+        # `batch` is the number of features per layer here (the analysis of S4 has no data batch: eigenvalues are parameter-only, eval_eig.py:254-301)
+        self.kind, self.H, self.N, self.L = kind, batch or H, N, layers
+        H = self.H
+        rng = np.random.default_rng(SEED)
+        n = H * layers
+        lam = (-0.5 + 1j * np.pi * np.arange(N))[None].repeat(n, 0) + (rng.normal(size=(n, N)) + 1j * rng.normal(size=(n, N))) * 0.05
+        self.Lam_np = lam.astype(np.complex64)
+        self.P_np = ((rng.normal(size=(n, N)) + 1j * rng.normal(size=(n, N))) * 0.5).astype(np.complex64)
+        self.step_np = np.exp(rng.uniform(np.log(1e-3), np.log(1e-1), n)).astype(np.float32)
+        self.units = n
+        if dev is not None:
+            self.Lam_h = _pin(torch.from_numpy(self.Lam_np)); self.P_h = _pin(torch.from_numpy(self.P_np)); self.st_h = _pin(torch.from_numpy(self.step_np))
+            self.Lam, self.Pv, self.st = self.Lam_h.to(dev), self.P_h.to(dev), self.st_h.to(dev)
+            self.ev_host = _pin(torch.empty(n, N, dtype=torch.complex64))
+        self.workload = "%s: s4 DPLR N=%d, %d features x %d layers = %d matrices (discrete_DPLR + nonsymmetric eigenvalues)" % (kind, N, H, layers, n)
+        self.h2d, self.d2h = n * (2 * N * 8 + 4), n * N * 8
+
+    def step(self, ops_in=None):
+        import eigb200.ops as ops
+        Lam, Pv, st = ops_in if ops_in is not None else (self.Lam, self.Pv, self.st)
+        Ab = ops.dplr_abar(Lam, Pv, Pv, st)
+        ev, info = ops.eigvals_c64(Ab)
+        self.info = info
+        return ev
+
+    def step_e2e(self):
+        dev = self.Lam.device
+        ev = self.step((self.Lam_h.to(dev, non_blocking=True), self.P_h.to(dev, non_blocking=True), self.st_h.to(dev, non_blocking=True)))
+        self.ev_host.copy_(ev, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def cpu(self, sample, threads):
+        """discrete_DPLR + np.linalg.eigvals (LAPACK zgeev through NumPy, complex128 like the reference's call) on `sample` matrices."""
+        import oracle as O
+        t0 = time.perf_counter()
+        for i in range(sample):
+            Ab = O.discrete_dplr_abar(self.Lam_np[i], self.P_np[i], self.P_np[i], float(self.step_np[i]))
+            np.linalg.eigvals(Ab)
+        return sample, time.perf_counter() - t0
+
+
+DEFAULT_BATCH = {"c1": 8, "c3-lru": 128, "c3-s5": 128, "c4": 512, "c5-mamba": 1024, "c5-normattn": 1024}
+CPU_SAMPLE = {"c1": 8, "c3-lru": 2, "c3-s5": 2, "c4": 128, "c5-mamba": 2, "c5-normattn": 1}
+BATCH_NOTE = {"c1": "reference analysis batch (small)", "c3-lru": "1024 sequences / 8 GPUs", "c3-s5": "1024 sequences / 8 GPUs",
+              "c4": "features per layer", "c5-mamba": "8192 sequences / 8 GPUs", "c5-normattn": "8192 sequences / 8 GPUs"}
+
+
+def make(kind, batch, dev, layers=None, seed_offset=0):
+    if kind in ("c1", "c5-normattn"):
+        return TransformerWorkload(kind, batch, dev, layers, seed_offset)
+    if kind == "c5-mamba":
+        return MambaWorkload(kind, batch, dev, layers, seed_offset)
+    if kind in ("c3-lru", "c3-s5"):
+        return DiagSsmWorkload(kind, batch, dev, layers or 6, seed_offset=seed_offset)
+    if kind == "c4":
+        return S4EigWorkload(kind, batch, dev, layers or 6, seed_offset=seed_offset)
+    raise KeyError(kind)
