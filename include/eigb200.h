@@ -50,7 +50,7 @@ enum { EIGB200_F32 = 0, EIGB200_F64 = 1, EIGB200_BF16 = 2 };
 /* epilogues of eigb200_linear */
 enum { EIGB200_EPI_NONE = 0, EIGB200_EPI_GELU = 1, EIGB200_EPI_GLU_RESIDUAL = 2, EIGB200_EPI_RESIDUAL = 3 };
 /* math mode of eigb200_linear */
-enum { EIGB200_GEMM_AUTO = 0, EIGB200_GEMM_SIMT_F32 = 1, EIGB200_GEMM_TC_3XTF32 = 2, EIGB200_GEMM_TC_TF32 = 3 };
+enum { EIGB200_GEMM_AUTO = 0, EIGB200_GEMM_SIMT_F32 = 1, EIGB200_GEMM_TC_3XTF32 = 2, EIGB200_GEMM_TC_TF32 = 3, EIGB200_GEMM_TC_F16X3 = 4 };
 
 int         eigb200_version(void);
 const char* eigb200_last_error(void);
@@ -206,11 +206,35 @@ int eigb200_rowstats(void* stream, const float* d_x, int64_t rows, int D, float 
 int eigb200_linear(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
                    float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
                    int64_t M, int N, int K, int epilogue, int mode, void* d_workspace, size_t workspace_bytes);
+/* Operand precision of the tensor-core GEMMs.  The reference runs every nn.Linear as a full-fp32 cuBLAS SGEMM (torch default allow_tf32 = False), so both
+ * tensor-core forms are error-compensated splits with fp32 accumulation and fp32-level accuracy:
+ *   TC_3XTF32  a = hi + lo in tf32, 3 kind::tf32 MMAs per product;
+ *   TC_F16X3   a S_a = hi + lo in fp16 with power-of-two scales (S_w from max |w| at preparation, S_a fixed), 3 kind::f16 MMAs per product at twice the
+ *              tensor rate and half the operand footprint (resident-weight shapes, K <= 256).  An activation beyond 65504 / S_a (S_a = 16, or 1024 behind a
+ *              fused LayerNorm) cannot be represented: the result holds inf / NaN there AND the sticky flag below is raised -- rerun with TC_3XTF32.
+ * eigb200_gemm_precision(): 0 / 1 = what EIGB200_GEMM_AUTO, eigb200_linear_ln, eigb200_linear_glu_extract and eigb200_linear_prepare use (environment
+ * EIGB200_GEMM_PRECISION = tf32x3 | f16x3).  eigb200_gemm_overflow: copies the flag of the current device to *h_flag (synchronises `stream`), optionally clears it. */
+int eigb200_gemm_precision(void);
+/* kind 0 (3xTF32) / 1 (fp16 split) overrides the environment for this process, any other value restores it.  Workspaces filled by eigb200_linear_prepare hold
+ * the operands of the precision that was current when they were prepared: prepare again after switching. */
+int eigb200_set_gemm_precision(int kind);
+int eigb200_gemm_overflow(void* stream, int reset, int* h_flag);
 /* GLU + residual GEMM (epilogue GLU_RESIDUAL) whose epilogue also emits the extractor partials of its OUTPUT rows for eigb200_mamba2_eig_partials:
  * d_W_gate (N/2) = the dt row of the block's in_proj, d_partials ((N/32) * 3 * M floats).  Tensor-core path only (K <= 256, N/2 % 16 == 0, R 32-byte aligned). */
 int eigb200_linear_glu_extract(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
                                float* d_C, int64_t ldc, const float* d_R, int64_t ldr, int64_t M, int N, int K,
                                const float* d_W_gate, float* d_partials, void* d_workspace, size_t workspace_bytes);
+
+/* The tail of MambaBlock.forward (models/mamba.py:333-337) as ONE kernel:  C = GLU(GELU(y W_out^T + b_out) W_glu^T + b_glu) + R, optionally with the extractor
+ * partials of the output rows (as eigb200_linear_glu_extract).  The intermediate GELU(out_proj(y)) never reaches HBM: the GELU epilogue of the first GEMM
+ * writes it, split into fp16 hi / lo, into the shared-memory operand of the second.  d_ws_out / d_ws_glu: workspaces filled by eigb200_linear_prepare for
+ * (W_out, EPI_GELU) and (W_glu, EPI_GLU_RESIDUAL) under the fp16-split precision (eigb200_gemm_precision() == 1; EIGB200_EINVAL otherwise).
+ * Shapes: d_model D = 128, d_inner K1 a multiple of 32 <= 128 (eigb200_out_glu_fused_supported); y rows 16-byte, R / C rows 32-byte aligned.
+ * d_W_gate / d_partials both NULL: no extractor partials.  Overflow of the fp16 range raises the flag of eigb200_gemm_overflow. */
+int eigb200_out_glu_fused_supported(int D, int K1);
+int eigb200_out_glu_fused(void* stream, const float* d_y, int64_t ldy, const void* d_ws_out, const float* d_bias_out,
+                          const void* d_ws_glu, const float* d_bias_glu, float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
+                          int64_t M, int D, int K1, const float* d_W_gate, float* d_partials);
 
 /* TokenEmbeddings.forward (models/common.py:160-176): out[b,t,:] = word[ids[b,t],:] (+ pos[t,:] if d_pos != NULL). ids int64. */
 int eigb200_embedding(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,

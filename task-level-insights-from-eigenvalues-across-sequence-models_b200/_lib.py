@@ -15,7 +15,7 @@ NORM_FN = {"exp": 0, "elu": 1, "softplus": 2, "sigmoid": 3}
 RATIO_NONE, RATIO_NEXT_OVER_CUR, RATIO_CUR_OVER_NEXT = 0, 1, 2
 F32, F64, BF16 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_GLU_RESIDUAL, EPI_RESIDUAL = 0, 1, 2, 3
-GEMM_AUTO, GEMM_SIMT_F32, GEMM_TC_3XTF32, GEMM_TC_TF32 = 0, 1, 2, 3
+GEMM_AUTO, GEMM_SIMT_F32, GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_TC_F16X3 = 0, 1, 2, 3, 4
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _dp = C.POINTER(C.c_double)
@@ -47,6 +47,11 @@ SIGNATURES = {
     "eigb200_linear_workspace_bytes": [_i, _i],
     "eigb200_linear_workspace_bytes_m": [_i64, _i, _i],
     "eigb200_linear": [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _sz],
+    "eigb200_out_glu_fused_supported": [_i, _i],
+    "eigb200_out_glu_fused": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp],
+    "eigb200_gemm_precision": [],
+    "eigb200_set_gemm_precision": [_i],
+    "eigb200_gemm_overflow": [_vp, _i, C.POINTER(_i)],
     "eigb200_embedding": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64],
     "eigb200_embedding_stats": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i64, _vp, _f],
     "eigb200_rowstats": [_vp, _vp, _i64, _i, _f, _vp],

@@ -424,12 +424,12 @@ extern "C" int eigb200_linattn_forward(void* stream, const float* d_q, const flo
     const size_t smem2 = sizeof(float) * (2 * (size_t)LC_TC * (2 * d + dv) + LC_TC + d);
     dim3 grid2(H, (unsigned)B);
     cudaStream_t st2 = (cudaStream_t)stream;
-    switch (d) {
-      case 16: linattn_forward_col_kernel<16><<<grid2, dv, smem2, st2>>>(p); break;
-      case 32: linattn_forward_col_kernel<32><<<grid2, dv, smem2, st2>>>(p); break;
-      case 64: linattn_forward_col_kernel<64><<<grid2, dv, smem2, st2>>>(p); break;
-      default: linattn_forward_col_kernel<128><<<grid2, dv, smem2, st2>>>(p); break;
-    }
+    // d = 128 with dv >= 128 needs more than the 48 KB a kernel gets without opting in (the launch failed with "invalid argument" before)
+#define LC_CASE(D_) case D_: \
+      if (smem2 > 48 * 1024) EIGB_CUDA(cudaFuncSetAttribute(linattn_forward_col_kernel<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+      linattn_forward_col_kernel<D_><<<grid2, dv, smem2, st2>>>(p); break;
+    switch (d) { LC_CASE(16) LC_CASE(32) LC_CASE(64) LC_CASE(128) default: break; }
+#undef LC_CASE
     EIGB_LAUNCH_CHECK("linattn_forward_col_kernel");
     return EIGB200_OK;
   }

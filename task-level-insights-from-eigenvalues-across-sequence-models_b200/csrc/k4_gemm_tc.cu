@@ -20,7 +20,7 @@
 // Warp roles (448 threads): warps 0-7 epilogue (TMEM lane quarter = warp % 4, even / odd 32-column groups = warp / 4), warps 8-11 converters,
 // warp 12 TMA producer, warp 13 MMA issuer.
 #include "gemm_tc.cuh"
-#include <cuda.h>
+#include "tc_ptx.cuh"
 #include <stdlib.h>
 
 namespace eigb200 {
@@ -60,211 +60,10 @@ struct TcParams {
   int c_v8;          // output rows are 32-byte aligned (and any residual is r_v8): every thread stores its own row segment with 256-bit stores
   int zero;          // always 0; a run-time value the compilers cannot fold (mbar_arrive_after)
   int64_t ntiles;
+  // fp16-split operands (kind::f16, see "fp16 split" below): weight chunks of 64 K-values, activation pre-scale S_a (a power of two; folded into the
+  // LayerNorm constants when there is one), 1 / (S_a S_w) for the epilogue (device scalar written by the weight preparation), sticky overflow flag
+  int kch_w; float a_scale; const float* out_scale; int* ovf_flag;
 };
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
-}
-// Arrive that is DATA-dependent on `dep`: the barrier address is bar + (dep & zero) with `zero` a kernel parameter that is 0 at run time, so
-// neither nvcc nor ptxas can fold the dependency away and the arrive cannot issue before the registers that feed `dep` -- the values loaded
-// from the buffer being released -- have landed.  (An asm operand that the template does not reference creates no dependency in the PTX:
-// with it the arrive overtook the last LDS of the chunk and TMA refilled the slot under the reader.)
-__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep, uint32_t zero) {
-  mbar_arrive(bar + (dep & zero));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
-}
-// suspend-time hint of mbarrier.try_wait: the hardware parks the thread until the phase completes or the hint expires, instead of returning to
-// the polling loop after the (short) default window -- polling (SYNCS / BRA / YIELD) was a third of all issued instructions without it
-constexpr uint32_t MBAR_SUSPEND_HINT_NS = 0x989680u;
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
-  // the polling loop lives inside the asm block, so the compiler inserts no reconvergence point after it: lanes may leave it on
-  // different iterations.  Every caller goes on to .sync.aligned instructions (tcgen05.ld / st / wait) or lane-0 election, which need
-  // the warp converged -- without this barrier single TMEM lanes (rows) were silently dropped by tcgen05.st.
-  __syncwarp();
-}
-// spin on the barrier from a single elected thread (no warp re-convergence: the caller is the only active lane of its warp)
-__device__ __forceinline__ void mbar_wait_one(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" :: "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
-}
-// elect.sync: true in exactly one lane of the (converged) warp.  Code guarded by it is a single-thread region for the compiler, so the
-// operands of UTCHMMA / UTMALDG are trivially warp-uniform -- with `lane == 0` instead it wrapped every tcgen05.mma in an ELECT/BRA.U.ANY
-// waterfall loop and the issue rate, not the tensor pipe, paced the kernel.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-// 32 lanes x 32 columns of 32-bit: thread i of the warp receives columns [col, col+32) of TMEM lane (lane_base + i)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// store 32 columns of 32-bit into TMEM: thread i of the warp writes columns [col, col+32) of lane (lane_base + i)
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      :: "r"(taddr),
-         "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-         "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-         "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-         "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-         "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-         "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-         "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-         "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (128 lanes = rows, 8 columns = the K step of tf32 values) is read from TMEM
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// Converter split a = hi + lo for the 3xTF32 product.  hi = a rounded to tf32 (nearest, ties away: integer add of half a tf32 ulp, then
-// mask -- the same result as cvt.rna.tf32.f32 for finite a, in 2 ALU operations instead of the ~5 the cvt expands to); lo = a - hi is
-// exact in fp32 and is handed to the tensor core unrounded: kind::tf32 reads the top 19 bits of the container, so lo is truncated to
-// tf32 by the hardware (|error| <= 2^-21 |a|, sign of lo, i.e. unbiased), the same order as the dropped a_lo * w_lo term.
-__device__ __forceinline__ void split_tf32(float a, float& h, float& l) {
-  h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
-  l = a - h;
-}
-__device__ __forceinline__ void split_tf32_4(const float4 a, float4& h, float4& l) {
-  split_tf32(a.x, h.x, l.x); split_tf32(a.y, h.y, l.y); split_tf32(a.z, h.z, l.z); split_tf32(a.w, h.w, l.w);
-}
-
-// 8x8 transpose of float4 items inside each group of 8 lanes.  In: lane (8g+i) holds, for its accumulator row 8g+i, the eight
-// float4 column quads q = 0..7 of a 32-column group.  Out: the same lane holds quad q = i of rows 8g+j, j = 0..7 -- so that for
-// every j the 8 lanes of a group cover one row's 128 contiguous bytes and a warp store instruction writes 4 full lines.
-__device__ __forceinline__ void transpose8x8_f4(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 4; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if ((q & s) == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float lo = v[4 * q + e], hi = v[4 * (q | s) + e];
-          const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, s);
-          v[4 * q + e] = up ? recv : lo;
-          v[4 * (q | s) + e] = up ? hi : recv;
-        }
-      }
-    }
-  }
-}
-
-// 256-bit streaming load (sm_100): one full 32-byte sector per thread
-__device__ __forceinline__ void ldg_stream_v8(const float* ptr, float* v) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
-}
-
-// 256-bit store (sm_100): one full 32-byte sector per thread
-__device__ __forceinline__ void stg_v8(float* ptr, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               :: "l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-// start address >> 4 in bits [0,14); LBO (unused for swizzled K-major) = 1 in [16,30); SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46);
-// descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9, 10-12 = 2), both K-major
-// (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// GLU column order inside a CTA slice (bn = 2*bg accumulator columns): 32-column accumulator group k holds the VALUE columns of output
-// columns [16k, 16k+16) of the slice in its first half and their GATE columns in its second half, so ONE tcgen05.ld hands a warp both
-// factors of 16 finished output columns and every accumulator group is independent work for an epilogue warp.
-__host__ __device__ __forceinline__ int glu_weight_row(int local, int split, int bg, int nout) {
-  const int c = split * bg + (local >> 5) * 16 + (local & 15);
-  if (c >= nout) return -1;
-  return (local & 16) ? nout + c : c;
-}
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // weight preparation: split W (N,K) into tf32 hi / lo in the per-split row order the CTAs consume, zero padded
@@ -289,6 +88,45 @@ __global__ void split_weights_kernel(const float* __restrict__ W, float* __restr
   const float h = to_tf32(w);
   hi[idx] = h;
   lo[idx] = to_tf32(w - h);
+}
+
+// fp16 split of the weights.  Pass 1: max |w gamma| (positive floats order like their bit patterns -> atomicMax on the bits).
+__global__ void absmax_weights_kernel(const float* __restrict__ W, const float* __restrict__ gamma, int N, int K, unsigned* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * K; idx += gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(W[idx] * (gamma ? gamma[idx % K] : 1.f)));
+#pragma unroll
+  for (int ofs = 16; ofs >= 1; ofs >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, ofs));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+// S_w = 2^floor(log2(2^14 / max|w|)): the largest weight lands in [2^13, 2^14], far from fp16's overflow and with 25 octaves above its subnormals
+__device__ __forceinline__ float weight_scale_f16(float absmax) {
+  if (!(absmax > 0.f) || !isfinite(absmax)) return 1.f;
+  int e;
+  frexpf(16384.f / absmax, &e);                                    // x = m 2^e, m in [0.5, 1)  =>  floor(log2 x) = e - 1
+  e = min(max(e - 1, -100), 100);
+  return ldexpf(1.f, e);
+}
+// Pass 2: hi = fp16(w gamma S_w), lo = fp16(w gamma S_w - hi) in the per-split row order the CTAs consume, rows of kp64 halfs (zero padded);
+// scal[0] = 1 / (S_a S_w) for the epilogue, scal[2] = S_w, scal[3] = S_a.
+__global__ void split_weights_f16_kernel(const float* __restrict__ W, __half* __restrict__ hi, __half* __restrict__ lo,
+                                         int N, int K, int kp64, int bn, int bg, int nsplit, int glu, const float* __restrict__ gamma,
+                                         float* __restrict__ scal, float a_scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = nsplit * bn * kp64;
+  const float sw = weight_scale_f16(__uint_as_float(reinterpret_cast<const unsigned*>(scal)[1]));
+  if (idx == 0) { scal[0] = 1.f / (a_scale * sw); scal[2] = sw; scal[3] = a_scale; }
+  if (idx >= total) return;
+  const int k = idx % kp64, row = idx / kp64;
+  const int split = row / bn, local = row - split * bn;
+  int n;
+  if (glu) n = glu_weight_row(local, split, bg, N / 2);
+  else n = split * bn + local;
+  float w = 0.f;
+  if (n >= 0 && n < N && k < K) w = W[(size_t)n * K + k] * (gamma ? gamma[k] : 1.f) * sw;
+  const __half h = __float2half_rn(w);
+  hi[idx] = h;
+  lo[idx] = __float2half_rn(w - __half2float(h));
 }
 
 // bias2[n] = bias[n] + sum_k W[n,k] beta[k]: one warp per output column
@@ -327,12 +165,15 @@ __device__ __forceinline__ void transpose4x4_f4(float (&v)[16], int lane) {
   }
 }
 
-template <int EPI>
+// SC: the accumulator carries the operand scales S_a S_w of the fp16 split; 1 / (S_a S_w) rides in the FMA that adds the bias
+template <int EPI, bool SC = false>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int bn, uint32_t bar_dfull0, uint32_t bar_dempty0,
                                             const float* bias_s, int worker, int split, int warp, int lane, float* stage_s = nullptr) {
   auto bar_dfull = [&](int j) { return bar_dfull0 + 8u * j; };
   auto bar_dempty = [&](int j) { return bar_dempty0 + 8u * j; };
   constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
+  const float osc = SC ? __ldg(p.out_scale) : 1.f;
+  const float osc_gate = -1.4426950408889634f * osc;
   const int nout = GLU ? p.N / 2 : p.N;
   const int cols_out = GLU ? p.bg : bn;                              // output columns produced by this CTA
   const int n_cta0 = split * cols_out;
@@ -378,8 +219,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 #pragma unroll
         for (int i = 0; i < 16; ++i) {                               // gate bias pre-scaled by -log2(e): sigmoid(g + b) = 1 / (1 + 2^(g * -log2e + b'))
           float e2;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(a[16 + i], -1.4426950408889634f, bias_s[cg + 16 + i])));
-          v[i] = (a[i] + bias_s[cg + i]) * fast_rcp_f(1.f + e2);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(a[16 + i], SC ? osc_gate : -1.4426950408889634f, bias_s[cg + 16 + i])));
+          v[i] = (SC ? fmaf(a[i], osc, bias_s[cg + i]) : (a[i] + bias_s[cg + i])) * fast_rcp_f(1.f + e2);
         }
         if (r_own) {
 #pragma unroll
@@ -472,7 +313,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 #endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float vv = v[i] + bias_s[cg + i];
+          float vv = SC ? fmaf(v[i], osc, bias_s[cg + i]) : v[i] + bias_s[cg + i];
           if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
           v[i] = vv;
         }
@@ -886,17 +727,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 constexpr int TS_MAX_STAGES = 8;
 constexpr int TS_ASTAGES = 4;
 
-template <int EPI, bool DEFER, int AST = TS_ASTAGES>   // AST operand stages in TMEM (2 for the wide single-CTA plan: 2 * bn + 64 * AST <= 512 columns)
+// fp16 split (F16 = true).  kind::f16 runs at twice the kind::tf32 rate and its operands take half the shared memory / TMEM, and an fp16 significand
+// has the same 11 bits as a tf32 one, so  a S_a = a_hi + a_lo,  w S_w = w_hi + w_lo  (hi = fp16(x), lo = fp16(x - hi), products exact in the fp32
+// accumulator) gives the 3xTF32 accuracy -- PROVIDED both halves stay in fp16's normal range, which tf32 (8 exponent bits) gave for free.  Hence the
+// power-of-two scales: S_w puts max |w| at 2^14 (chosen on the device by the weight preparation), S_a is 2^10 behind a LayerNorm (|a| <= sqrt(K))
+// and 2^4 otherwise; 1 / (S_a S_w) rides in the epilogue's bias FMA.  Elements below 2^-12 / S_a lose relative (not absolute) accuracy: absolute
+// error <= 2^-25 / S_a per element (tools/split_error_study.py: 5e-8 of sum |a||w| at unit scale like 3xTF32, 7e-7 for activations of 1e-3).
+// |a| S_a > 65504 would overflow to inf: the converter raises a sticky flag (eigb200_gemm_overflow) and the caller reruns with 3xTF32.
+template <int EPI, bool DEFER, int AST = TS_ASTAGES, bool F16 = false>   // AST operand stages in TMEM (2 for the wide single-CTA tf32 plan: 2 * bn + 64 * AST <= 512 columns)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapWhi,
                   const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int bn = p.bn, kch = p.kchunks, nst = p.nstages;
+  const int kchw = F16 ? p.kch_w : kch;                              // weight chunks: bn rows x 128 bytes = 32 tf32 or 64 fp16 K-values
+  constexpr uint32_t ACOLS = F16 ? 32u : 64u;                        // TMEM columns of one operand stage [hi | lo]
   const uint32_t w_chunk_bytes = (uint32_t)bn * 128u;
   const uint32_t whi = base;
-  const uint32_t wlo = whi + kch * w_chunk_bytes;
-  const uint32_t stage0 = wlo + kch * w_chunk_bytes;                 // stage s: raw 16 KB chunk
+  const uint32_t wlo = whi + kchw * w_chunk_bytes;
+  const uint32_t stage0 = wlo + kchw * w_chunk_bytes;                // stage s: raw 16 KB chunk
   const uint32_t epi_stage0 = stage0 + nst * TC_CHUNK_BYTES;         // optional staging tiles of the epilogue warps (p.epi_stage bytes)
   const uint32_t bars = epi_stage0 + (uint32_t)p.epi_stage;
   const uint32_t bar_w = bars;
@@ -913,7 +763,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = blockIdx.x / p.nsplit, split = blockIdx.x - worker * p.nsplit;
   const uint32_t a_col0 = (uint32_t)(2 * bn);                        // first TMEM column of the operand stages
-  const uint32_t need_cols = a_col0 + AST * 64;
+  const uint32_t need_cols = a_col0 + AST * ACOLS;
   const uint32_t tmem_cols = need_cols <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
@@ -949,10 +799,10 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (warp == TC_TMA_WARP) {
     // ===================================== TMA producer ======================================
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar_w, 2u * kch * w_chunk_bytes);
-      for (int c = 0; c < kch; ++c) {
-        tma_load_2d(&tmapWhi, bar_w, whi + c * w_chunk_bytes, c * TC_KC, split * bn);
-        tma_load_2d(&tmapWlo, bar_w, wlo + c * w_chunk_bytes, c * TC_KC, split * bn);
+      mbar_arrive_expect_tx(bar_w, 2u * kchw * w_chunk_bytes);
+      for (int c = 0; c < kchw; ++c) {
+        tma_load_2d(&tmapWhi, bar_w, whi + c * w_chunk_bytes, c * (F16 ? 64 : TC_KC), split * bn);
+        tma_load_2d(&tmapWlo, bar_w, wlo + c * w_chunk_bytes, c * (F16 ? 64 : TC_KC), split * bn);
       }
       int s = 0; uint32_t ph = 0;
       for (int64_t tile = worker; tile < p.ntiles; tile += p.workers) {
@@ -981,6 +831,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       // plain N-split shapes (A/B on the same GPU), for a 2 % gain on the LayerNorm shape.
       float2 st = make_float2(0.f, 1.f);
       if (ln) { const int64_t m = tile * TC_BM + r; st = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f); st.x = -st.x * st.y; }
+      if (F16) { st.x *= p.a_scale; st.y *= p.a_scale; }             // S_a folded into the (a - mu) rstd FMA; without LayerNorm st = (0, S_a)
+      float amax = 0.f;
       for (int c = 0; c < kch; ++c) {
         mbar_wait(bar_full(s), ph);
 #ifdef EIGB_ABL_CONV                                                 // ablation build: barrier protocol only, no loads / split / tcgen05.st
@@ -1003,6 +855,37 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_afull(t_pending));
+        }
+        if constexpr (F16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], st.y, st.x);
+          uint32_t hi2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hi2[i] = pack_f16x2(a[2 * i], a[2 * i + 1]);
+            amax = fmaxf(amax, fmaxf(fabsf(a[2 * i]), fabsf(a[2 * i + 1])));
+          }
+          {                                                          // the raw slot can be refilled: its values are in registers
+            uint32_t dep = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dep ^= hi2[2 * q];
+            mbar_arrive_after(bar_free(s), dep, (uint32_t)p.zero);
+          }
+          mbar_wait(bar_aempty(t), aph ^ 1);                         // MMAs that read this operand stage have retired
+          tc_fence_after();
+          const uint32_t acol = tmem_base + lane_sel + a_col0 + (uint32_t)t * ACOLS;
+          tmem_st_32x16(acol, hi2);
+          if (p.nterms == 3) {
+            uint32_t lo2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) lo2[i] = pack_f16x2(a[2 * i] - f16_lo_to_f32(hi2[i]), a[2 * i + 1] - f16_hi_to_f32(hi2[i]));
+            tmem_st_32x16(acol + 16u, lo2);
+          }
+          if (DEFER) t_pending = t;
+          else { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar_afull(t)); }
+          if (++s == nst) { s = 0; ph ^= 1; }
+          if (++t == AST) { t = 0; aph ^= 1; }
+          continue;
         }
         if (ln) {
 #pragma unroll
@@ -1031,12 +914,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (++s == nst) { s = 0; ph ^= 1; }
         if (++t == AST) { t = 0; aph ^= 1; }
       }
+      if (F16 && !(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);        // |a| S_a beyond fp16 (or NaN): the result of this tile is inf / NaN, say so
     }
     if (DEFER && t_pending >= 0) { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar_afull(t_pending)); }
   } else if (warp == TC_MMA_WARP) {
     // ===================================== MMA issuer ======================================
     if (elect_one()) {                                               // ONE thread runs the whole issue loop
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+      const uint32_t idesc = F16 ? umma_idesc_f16(TC_BM, bn) : umma_idesc_tf32(TC_BM, bn);
       const bool three = p.nterms == 3;
       mbar_wait_one(bar_w, 0);
       int t = 0; uint32_t aph = 0;
@@ -1048,6 +932,25 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         for (int c = 0; c < kch; ++c) {
           mbar_wait_one(bar_afull(t), aph);
           tc_fence_after();
+          if constexpr (F16) {
+            // activation chunk c = 32 K-values = half of weight chunk c / 2 (64 fp16 per 128-byte swizzle row): +64 bytes = +4 in the address field
+            const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)t * ACOLS, a_lo = a_hi + 16u;
+            const uint32_t wofs = (uint32_t)(c >> 1) * w_chunk_bytes;
+            const uint64_t kofs = (c & 1) ? 4u : 0u;
+            const uint64_t dbh0 = umma_desc_k_sw128(whi + wofs) + kofs, dbl0 = umma_desc_k_sw128(wlo + wofs) + kofs;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {                            // UMMA K = 16 fp16 = 32 bytes of the swizzled row, 8 TMEM columns of the operand
+              umma_f16_ts(d_tmem, a_hi + 8u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              if (three) {
+                umma_f16_ts(d_tmem, a_hi + 8u * k, dbl0 + 2u * k, idesc, 1u);
+                umma_f16_ts(d_tmem, a_lo + 8u * k, dbh0 + 2u * k, idesc, 1u);
+              }
+            }
+            umma_commit(bar_aempty(t));
+            if (c == kch - 1) umma_commit(bar_dfull(j));
+            if (++t == AST) { t = 0; aph ^= 1; }
+            continue;
+          }
           const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)t * 64u, a_lo = a_hi + 32u;
           const uint64_t dbh0 = umma_desc_k_sw128(whi + c * w_chunk_bytes), dbl0 = umma_desc_k_sw128(wlo + c * w_chunk_bytes);
 #pragma unroll
@@ -1067,8 +970,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
-    tc_epilogue<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp - TC_EPI_WARP0, lane,
-                     p.epi_stage ? reinterpret_cast<float*>(smem_raw + (epi_stage0 - smem_u32(smem_raw))) : nullptr);
+    tc_epilogue<EPI, F16>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), bias_s, worker, split, warp - TC_EPI_WARP0, lane,
+                          p.epi_stage ? reinterpret_cast<float*>(smem_raw + (epi_stage0 - smem_u32(smem_raw))) : nullptr);
   }
 
   tc_fence_before();
@@ -1246,7 +1149,49 @@ static int make_tmap(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t
   return EIGB200_OK;
 }
 
-struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages, ast; size_t smem; bool ok; bool ts; };
+// 2-D fp16 tensor map of the split weights: inner dimension `cols` halfs, box = 64 halfs (one 128-byte swizzle row) x box_rows
+static int make_tmap_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EIGB200_ECUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp16 weights) failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, box_rows); return EIGB200_ECUDA; }
+  return EIGB200_OK;
+}
+
+// ---- operand precision of the resident-weight kernels ---------------------------------------------------------------------------------
+// 0 = 3xTF32 (kind::tf32), 1 = fp16 split (kind::f16).  EIGB200_GEMM_PRECISION = tf32x3 | f16x3 selects what EIGB200_GEMM_AUTO, eigb200_linear_ln,
+// eigb200_linear_glu_extract and eigb200_linear_prepare use; eigb200_linear(mode = TC_3XTF32 / TC_F16X3) asks for one explicitly.
+static int g_kind_override = -1;
+void tc_set_default_kind(int kind) { g_kind_override = (kind == 0 || kind == 1) ? kind : -1; }
+int tc_default_kind() {
+  static int v = -1;
+  if (g_kind_override >= 0) return g_kind_override;
+  if (v < 0) { const char* e = getenv("EIGB200_GEMM_PRECISION"); v = (e && e[0] == 'f') ? 1 : (e && e[0] == 't') ? 0 : EIGB200_GEMM_DEFAULT_KIND; }
+  return v;
+}
+__device__ int g_gemm_overflow = 0;
+static int* overflow_flag_ptr() {
+  int* ptr = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&ptr), g_gemm_overflow) != cudaSuccess) return nullptr;   // per device (cudaSetDevice'd by the caller)
+  return ptr;
+}
+int tc_overflow_query(cudaStream_t st, int reset, int* h_flag) {
+  int* d = overflow_flag_ptr();
+  if (!d) { set_error("gemm_overflow: cannot resolve the device flag"); return EIGB200_ECUDA; }
+  EIGB_CUDA(cudaMemcpyAsync(h_flag, d, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (reset) EIGB_CUDA(cudaMemsetAsync(d, 0, sizeof(int), st));
+  EIGB_CUDA(cudaStreamSynchronize(st));
+  return EIGB200_OK;
+}
+
+struct TcPlan { int bn, bg, nsplit, kchunks, kpad, nstages, ast; size_t smem; bool ok; bool ts; int kp64, kch_w; };
 
 static bool use_ts_variant() {
   static int v = -1;
@@ -1260,34 +1205,37 @@ static int gemm_wide_mode() {       // EIGB200_GEMM_WIDE: 0 = N-split plan only,
   return v;
 }
 
-static TcPlan make_plan(int N, int K, int epilogue) {
+static TcPlan make_plan(int N, int K, int epilogue, int kind = 0) {
   TcPlan pl{};
   pl.ok = false;
-  pl.ts = use_ts_variant();
+  pl.ts = use_ts_variant() || kind == 1;                              // the fp16 split exists in the TMEM-operand kernel only
   if (K % 4 != 0 || K <= 0) return pl;
   pl.kpad = (K + TC_KC - 1) / TC_KC * TC_KC;
   pl.kchunks = pl.kpad / TC_KC;
+  pl.kp64 = (K + 63) / 64 * 64;
+  pl.kch_w = pl.kp64 / 64;
   if (pl.kchunks > 8) return pl;
   const bool glu = epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const int nout = glu ? N / 2 : N;
   pl.ast = TS_ASTAGES;
+  const int wchunks = kind == 1 ? pl.kch_w : pl.kchunks;             // 128-byte weight chunks per row and per hi / lo
   // Wide single-CTA plan (129..192 output columns, e.g. the Mamba in_proj with N = 161): the whole weight matrix stays resident in ONE CTA
   // (bn = N rounded up to 16), so every A tile is read and converted once instead of once per N split; what it costs is ring depth
   // (the weights leave room for 2-3 raw stages) and TMEM operand stages (2 * bn accumulator columns leave room for 2).
   if (pl.ts && !glu && nout > 128 && nout <= 192 && gemm_wide_mode() != 0) {
     const int bn = (nout + 15) / 16 * 16;
-    const size_t wbytes = (size_t)2 * pl.kchunks * bn * 128;
+    const size_t wbytes = (size_t)2 * wchunks * bn * 128;
     const long room = (long)TC_SMEM_LIMIT - 2048 - (long)wbytes;
     int nst = room > 0 ? (int)(room / TC_CHUNK_BYTES) : 0;
     if (nst > TS_MAX_STAGES) nst = TS_MAX_STAGES;
     if (nst >= 2 && 2 * bn + 2 * 64 <= 512) {
-      pl.bn = pl.bg = bn; pl.nsplit = 1; pl.nstages = nst; pl.ast = 2;
+      pl.bn = pl.bg = bn; pl.nsplit = 1; pl.nstages = nst; pl.ast = kind == 1 ? TS_ASTAGES : 2;   // fp16 operand stages are 32 columns: 4 of them fit
       pl.smem = wbytes + (size_t)nst * TC_CHUNK_BYTES + 1024 + 1024;
       pl.ok = true;
       return pl;
     }
   }
-  const int per_col_bytes = pl.kpad * 4 * 2 * (glu ? 2 : 1);         // hi+lo bytes per OUTPUT column
+  const int per_col_bytes = wchunks * 128 * 2 * (glu ? 2 : 1);       // hi+lo bytes per OUTPUT column
   const int stage_bytes = pl.ts ? TC_CHUNK_BYTES : 2 * TC_CHUNK_BYTES;
   const int max_w_bytes = TC_SMEM_LIMIT - 2048 - (pl.ts ? 4 : 2) * stage_bytes;   // keep room for the minimum ring
   int max_cols = max_w_bytes / per_col_bytes;
@@ -1301,7 +1249,7 @@ static TcPlan make_plan(int N, int K, int epilogue) {
   cols = (cols + gran - 1) / gran * gran;
   pl.bg = cols;
   pl.bn = glu ? 2 * cols : cols;
-  const size_t wbytes = (size_t)2 * pl.kchunks * pl.bn * 128;
+  const size_t wbytes = (size_t)2 * wchunks * pl.bn * 128;
   int nst = (int)((TC_SMEM_LIMIT - 2048 - (long)wbytes) / stage_bytes);
   if (nst > (pl.ts ? TS_MAX_STAGES : TC_MAX_STAGES)) nst = pl.ts ? TS_MAX_STAGES : TC_MAX_STAGES;
   if (nst < 2) return pl;
@@ -1358,10 +1306,14 @@ size_t tc_workspace_bytes(int N, int K) {
   size_t best = 0;
   for (int epi : {EIGB200_EPI_NONE, EIGB200_EPI_GLU_RESIDUAL}) {
     if (epi == EIGB200_EPI_GLU_RESIDUAL && N % 2) continue;
-    TcPlan pl = make_plan(N, K, epi);
-    if (!pl.ok) continue;
-    const size_t b = (size_t)2 * pl.nsplit * pl.bn * pl.kpad * sizeof(float) + (size_t)((N + 3) / 4 * 4) * sizeof(float);   // + folded LayerNorm bias
-    if (b > best) best = b;
+    for (int kind = 0; kind < 2; ++kind) {
+      TcPlan pl = make_plan(N, K, epi, kind);
+      if (!pl.ok) continue;
+      // tf32: hi + lo floats; fp16: hi + lo halfs of kp64 columns; then the folded LayerNorm bias and 4 scale words
+      const size_t wb = kind == 1 ? (size_t)2 * pl.nsplit * pl.bn * pl.kp64 * 2 : (size_t)2 * pl.nsplit * pl.bn * pl.kpad * sizeof(float);
+      const size_t b = wb + (size_t)((N + 3) / 4 * 4) * sizeof(float) + 16;
+      if (b > best) best = b;
+    }
   }
   return best;
 }
@@ -1375,18 +1327,39 @@ bool tc_supported(const LinearParams& p) {
 
 // Weight preparation of either plan: tf32 hi / lo split in the row order the CTAs consume (LayerNorm gamma folded in, GLU value / gate rows interleaved)
 // and, with LayerNorm, the folded bias b + W beta behind it.  Run per call by launch_linear_tc, or once by eigb200_linear_prepare.
-int tc_prepare(cudaStream_t st, const LinearParams& lp, void* workspace) {
+int tc_prepare(cudaStream_t st, const LinearParams& lp, void* workspace, int kind) {
   const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const bool ln = lp.ln_stats != nullptr || lp.ln_gamma != nullptr;
   int bn, bg, nsplit, kpad;
-  const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue);
+  const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue, kind);
   if (pl.ok) { bn = pl.bn; bg = pl.bg; nsplit = pl.nsplit; kpad = pl.kpad; }
   else {
+    kind = 0;                                                        // the streamed-operand kernel is 3xTF32 only
     const StreamPlan sp = make_stream_plan(lp.N, lp.K, lp.epilogue);
     if (!sp.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
     bn = sp.bn; bg = sp.bg; nsplit = sp.nsplit; kpad = sp.kpad;
   }
   const size_t wrows = (size_t)nsplit * bn;
+  if (kind == 1) {
+    // [hi halfs wrows x kp64][lo halfs][bias2 floats][scal: 1/(S_a S_w), max|w| bits, S_w, S_a]
+    __half* w_hi = reinterpret_cast<__half*>(workspace);
+    __half* w_lo = w_hi + wrows * pl.kp64;
+    float* bias2 = reinterpret_cast<float*>(w_lo + wrows * pl.kp64);
+    float* scal = bias2 + (lp.N + 3) / 4 * 4;
+    const float a_scale = ln ? 1024.f : 16.f;
+    EIGB_CUDA(cudaMemsetAsync(scal, 0, 16, st));
+    const int nk = lp.N * lp.K;
+    absmax_weights_kernel<<<(nk + 1023) / 1024 > 64 ? 64 : (nk + 1023) / 1024, 256, 0, st>>>(lp.W, ln ? lp.ln_gamma : nullptr, lp.N, lp.K, reinterpret_cast<unsigned*>(scal) + 1);
+    EIGB_LAUNCH_CHECK("absmax_weights_kernel");
+    const int total = (int)(wrows * pl.kp64);
+    split_weights_f16_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kp64, bn, bg, nsplit, glu ? 1 : 0, ln ? lp.ln_gamma : nullptr, scal, a_scale);
+    EIGB_LAUNCH_CHECK("split_weights_f16_kernel");
+    if (ln) {
+      ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
+      EIGB_LAUNCH_CHECK("ln_bias_kernel");
+    }
+    return EIGB200_OK;
+  }
   float* w_hi = reinterpret_cast<float*>(workspace);
   float* w_lo = w_hi + wrows * kpad;
   float* bias2 = w_lo + wrows * kpad;
@@ -1398,6 +1371,23 @@ int tc_prepare(cudaStream_t st, const LinearParams& lp, void* workspace) {
     EIGB_LAUNCH_CHECK("ln_bias_kernel");
   }
   return EIGB200_OK;
+}
+
+// ---- helpers for the fused out_proj -> GLU kernel (k4_gemm_fused.cu) -------------------------------------------------------------------------
+int tc_make_tmap_f32(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) { return make_tmap(map, ptr, rows, cols, ld, box_rows); }
+int tc_make_tmap_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) { return make_tmap_f16(map, ptr, rows, cols, box_rows); }
+int* tc_overflow_flag() { return overflow_flag_ptr(); }
+bool tc_prepared_layout_f16(int N, int K, int epilogue, const void* ws, TcPrepared* out) {
+  const TcPlan pl = make_plan(N, K, epilogue, 1);
+  if (!pl.ok) return false;
+  const size_t wrows = (size_t)pl.nsplit * pl.bn;
+  const __half* w_hi = reinterpret_cast<const __half*>(ws);
+  const __half* w_lo = w_hi + wrows * pl.kp64;
+  out->w_hi = w_hi; out->w_lo = w_lo;
+  out->bias2 = reinterpret_cast<const float*>(w_lo + wrows * pl.kp64);
+  out->scal = out->bias2 + (N + 3) / 4 * 4;
+  out->bn = pl.bn; out->bg = pl.bg; out->nsplit = pl.nsplit; out->kp64 = pl.kp64; out->kch_w = pl.kch_w; out->wrows = (int)wrows;
+  return true;
 }
 
 static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
@@ -1413,7 +1403,7 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   float* a_hi = bias_perm + wrows;
   float* a_lo = a_hi + (size_t)lp.M * pl.kpad;
   if (lp.W != nullptr) {                                             // not prepared by eigb200_linear_prepare
-    int rc0 = tc_prepare(st, lp, workspace);
+    int rc0 = tc_prepare(st, lp, workspace, 0);
     if (rc0 != EIGB200_OK) return rc0;
   }
   const float* bias_eff = lp.ln_stats ? bias2 : lp.bias;
@@ -1455,25 +1445,37 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   return EIGB200_OK;
 }
 
-int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
-  const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue);
+int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace, int kind) {
+  TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue, kind);
   if (!pl.ok) return launch_linear_stream(st, lp, nterms, workspace);   // K > 256 or a weight slice too large to stay resident
+  if (!pl.ts) kind = 0;
   const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
-  float* w_hi = reinterpret_cast<float*>(workspace);
   const size_t wrows = (size_t)pl.nsplit * pl.bn;
-  float* w_lo = w_hi + wrows * pl.kpad;
-  float* bias2 = w_lo + wrows * pl.kpad;                             // bias + W beta, behind the split weights in the workspace
-  const bool prepared = lp.W == nullptr;                             // eigb200_linear_prepare filled the workspace for this (N, K, epilogue, LayerNorm)
+  const bool prepared = lp.W == nullptr;                             // eigb200_linear_prepare filled the workspace for this (N, K, epilogue, LayerNorm, precision)
   if (!prepared) {
-    int rc0 = tc_prepare(st, lp, workspace);
+    int rc0 = tc_prepare(st, lp, workspace, kind);
     if (rc0 != EIGB200_OK) return rc0;
   }
-  const float* bias_eff = lp.ln_stats ? bias2 : lp.bias;
   CUtensorMap tA, tWh, tWl;
   int rc;
   if ((rc = make_tmap(&tA, lp.A, (uint64_t)lp.M, (uint64_t)lp.K, (uint64_t)lp.lda, TC_BM))) return rc;
-  if ((rc = make_tmap(&tWh, w_hi, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
-  if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  const float* bias2;
+  const float* scal = nullptr;
+  if (kind == 1) {
+    const __half* w_hi = reinterpret_cast<const __half*>(workspace);
+    const __half* w_lo = w_hi + wrows * pl.kp64;
+    bias2 = reinterpret_cast<const float*>(w_lo + wrows * pl.kp64);
+    scal = bias2 + (lp.N + 3) / 4 * 4;
+    if ((rc = make_tmap_f16(&tWh, w_hi, wrows, (uint64_t)pl.kp64, (uint32_t)pl.bn))) return rc;
+    if ((rc = make_tmap_f16(&tWl, w_lo, wrows, (uint64_t)pl.kp64, (uint32_t)pl.bn))) return rc;
+  } else {
+    float* w_hi = reinterpret_cast<float*>(workspace);
+    float* w_lo = w_hi + wrows * pl.kpad;
+    bias2 = w_lo + wrows * pl.kpad;                                  // bias + W beta, behind the split weights in the workspace
+    if ((rc = make_tmap(&tWh, w_hi, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+    if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  }
+  const float* bias_eff = lp.ln_stats ? bias2 : lp.bias;
 
   TcParams p{};
   p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats);
@@ -1481,6 +1483,11 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
   p.zero = 0;
+  p.kch_w = pl.kch_w; p.a_scale = lp.ln_stats ? 1024.f : 16.f; p.out_scale = scal; p.ovf_flag = nullptr;
+  if (kind == 1) {
+    p.ovf_flag = overflow_flag_ptr();
+    if (!p.ovf_flag) { set_error("tcgen05 GEMM: cannot resolve the overflow flag"); return EIGB200_ECUDA; }
+  }
   // TMEM-operand converter: DEFER publishes a chunk after the next chunk's shared-memory loads were issued.  Measured: +10 % on the converter-bound
   // N-split shape (bn = 96, in_proj), -6 % on the tensor-bound GLU shape (bn = 128) where the MMA wants its operand at once; a run-time flag
   // instead of the template parameter costs both shapes 3 % (the converter loop is latency-critical), hence two instantiations.
@@ -1521,25 +1528,25 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
   if ((int64_t)workers > p.ntiles) workers = (int)p.ntiles;
   p.workers = workers;
   dim3 grid(workers * pl.nsplit);
+#define TC_LAUNCH_K(KERNEL_)                                                                                                    \
+  do {                                                                                                                          \
+    EIGB_CUDA(cudaFuncSetAttribute(KERNEL_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));                        \
+    KERNEL_<<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                                                \
+  } while (0)
 #define TC_LAUNCH(EPI_)                                                                                                         \
   do {                                                                                                                          \
-    if (pl.ts && pl.ast == 2 && EPI_ != EIGB200_EPI_GLU_RESIDUAL) {                                                             \
-      if (gemm_wide_mode() == 2) {                                                                                              \
-        EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-        gemm_tc_ts_kernel<EPI_, true, 2><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                   \
-      } else {                                                                                                                  \
-        EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-        gemm_tc_ts_kernel<EPI_, false, 2><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                  \
-      }                                                                                                                         \
+    if (kind == 1) {                                                                                                            \
+      if (defer) TC_LAUNCH_K((gemm_tc_ts_kernel<EPI_, true, TS_ASTAGES, true>));                                                \
+      else TC_LAUNCH_K((gemm_tc_ts_kernel<EPI_, false, TS_ASTAGES, true>));                                                     \
+    } else if (pl.ts && pl.ast == 2 && EPI_ != EIGB200_EPI_GLU_RESIDUAL) {                                                      \
+      if (gemm_wide_mode() == 2) TC_LAUNCH_K((gemm_tc_ts_kernel<EPI_, true, 2>));                                               \
+      else TC_LAUNCH_K((gemm_tc_ts_kernel<EPI_, false, 2>));                                                                    \
     } else if (pl.ts && defer) {                                                                                                \
-      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-      gemm_tc_ts_kernel<EPI_, true><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                        \
+      TC_LAUNCH_K((gemm_tc_ts_kernel<EPI_, true>));                                                                             \
     } else if (pl.ts) {                                                                                                         \
-      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_ts_kernel<EPI_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-      gemm_tc_ts_kernel<EPI_, false><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                       \
+      TC_LAUNCH_K((gemm_tc_ts_kernel<EPI_, false>));                                                                            \
     } else {                                                                                                                    \
-      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));         \
-      gemm_tc_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tA, tWh, tWl, p);                                                 \
+      TC_LAUNCH_K((gemm_tc_kernel<EPI_>));                                                                                      \
     }                                                                                                                           \
   } while (0)
   switch (lp.epilogue) {
@@ -1550,6 +1557,7 @@ int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* 
     default: set_error("linear: unknown epilogue %d", lp.epilogue); return EIGB200_EINVAL;
   }
 #undef TC_LAUNCH
+#undef TC_LAUNCH_K
   EIGB_LAUNCH_CHECK("gemm_tc_kernel");
   return EIGB200_OK;
 }

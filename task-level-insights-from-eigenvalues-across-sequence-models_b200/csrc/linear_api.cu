@@ -24,12 +24,14 @@ extern "C" int eigb200_linear(void* stream, const float* d_A, int64_t lda, const
     return launch_linear_simt(st, p);
   }
   const bool tc_ok = tc_supported(p) && d_workspace && workspace_bytes >= tc_workspace_bytes_m(M, N, K);
-  if (mode == EIGB200_GEMM_TC_3XTF32 || mode == EIGB200_GEMM_TC_TF32) {
+  if (mode == EIGB200_GEMM_TC_3XTF32 || mode == EIGB200_GEMM_TC_TF32 || mode == EIGB200_GEMM_TC_F16X3) {
     if (!tc_ok) { set_error("linear: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda); return EIGB200_EUNSUPPORTED; }
-    return launch_linear_tc(st, p, mode == EIGB200_GEMM_TC_TF32 ? 1 : 3, d_workspace);
+    const int kind = mode == EIGB200_GEMM_TC_F16X3 ? 1 : 0;
+    EIGB_CHECK_ARG(!prepared || kind == tc_default_kind(), "linear: a prepared workspace holds the operands of the default precision (EIGB200_GEMM_PRECISION), not of mode %d", mode);
+    return launch_linear_tc(st, p, mode == EIGB200_GEMM_TC_TF32 ? 1 : 3, d_workspace, kind);
   }
   EIGB_CHECK_ARG(mode == EIGB200_GEMM_AUTO, "linear: unknown mode %d", mode);
-  if (tc_ok && (M >= 1024 || prepared)) return launch_linear_tc(st, p, 3, d_workspace);
+  if (tc_ok && (M >= 1024 || prepared)) return launch_linear_tc(st, p, 3, d_workspace, tc_default_kind());
   EIGB_CHECK_ARG(!prepared, "linear: a prepared workspace serves the tensor-core path only (M=%lld N=%d K=%d)", (long long)M, N, K);
   return launch_linear_simt(st, p);
 }
@@ -49,7 +51,7 @@ extern "C" int eigb200_linear_ln(void* stream, const float* d_A, int64_t lda, co
     set_error("linear_ln: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda);
     return EIGB200_EUNSUPPORTED;
   }
-  return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace);
+  return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace, tc_default_kind());
 }
 
 extern "C" int eigb200_linear_glu_extract(void* stream, const float* d_A, int64_t lda, const float* d_W, const float* d_bias,
@@ -64,7 +66,7 @@ extern "C" int eigb200_linear_glu_extract(void* stream, const float* d_A, int64_
     set_error("linear_glu_extract: shape/workspace not supported by the tensor-core path (M=%lld N=%d K=%d)", (long long)M, N, K);
     return EIGB200_EUNSUPPORTED;
   }
-  return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace);
+  return launch_linear_tc((cudaStream_t)stream, p, 3, d_workspace, tc_default_kind());
 }
 
 extern "C" int eigb200_linear_prepare(void* stream, const float* d_W, const float* d_bias, const float* d_ln_gamma, const float* d_ln_beta,
@@ -81,5 +83,13 @@ extern "C" int eigb200_linear_prepare(void* stream, const float* d_W, const floa
   }
   LinearParams p{nullptr, K, d_W, d_bias, nullptr, N, nullptr, 0, 0, N, K, epilogue};
   p.ln_gamma = d_ln_gamma; p.ln_beta = d_ln_beta;
-  return tc_prepare((cudaStream_t)stream, p, d_workspace);
+  return tc_prepare((cudaStream_t)stream, p, d_workspace, tc_default_kind());
+}
+
+extern "C" int eigb200_gemm_precision(void) { return tc_default_kind(); }
+extern "C" int eigb200_set_gemm_precision(int kind) { tc_set_default_kind(kind); return EIGB200_OK; }
+
+extern "C" int eigb200_gemm_overflow(void* stream, int reset, int* h_flag) {
+  EIGB_CHECK_ARG(h_flag, "gemm_overflow: null pointer");
+  return tc_overflow_query((cudaStream_t)stream, reset, h_flag);
 }

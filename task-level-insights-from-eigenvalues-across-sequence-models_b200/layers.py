@@ -100,10 +100,12 @@ class MambaBlockDev:
         self.gemm_mode = cfg.get("_gemm_mode", "auto")
         # the parameters are constants of an analysis run: their tensor-core operand form is built once per layer (ops.linear_prepare), not per call
         self.prepare_weights = os.environ.get("EIGB200_PREPARE_WEIGHTS", "1") != "0"
+        self.fuse_tail = os.environ.get("EIGB200_FUSE_TAIL", "1") != "0"      # out_proj + GELU + GLU + residual (+ extractor partials) as one kernel
         self._prep_ws = {}
 
     def _prepared(self, key, weight, bias, epilogue, gamma=None, beta=None):
         """Per-layer prepared workspace of one GEMM (None when its shape has no resident-weight plan).  invalidate_prepared() after changing parameters."""
+        key = (key, ops.gemm_precision())                           # the operand form is precision-specific (tf32 hi / lo or scaled fp16 hi / lo)
         if key not in self._prep_ws:
             self._prep_ws[key] = ops.linear_prepare(weight, bias, epilogue, gamma, beta)
         return self._prep_ws[key]
@@ -161,9 +163,16 @@ class MambaBlockDev:
             y = self._ssd_lti(z, ldz, B, T)
         else:
             y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)
+        want_x = self.glu is not None and extract_partials is not None and self.fuses_extractor() and B * T >= 1024
+        if (tc and self.glu is not None and self.prenorm and self.fuse_tail and ops.out_glu_fused_supported(D, m.d_inner) and D == m.out_proj.weight.shape[0]):
+            # GELU(out_proj(y)) -> GLU + skip (:333-337) in one kernel: the intermediate never reaches HBM (fp16-split precision, d_model 128)
+            out, _ = ops.out_glu_fused(y, self._prepared("out", m.out_proj.weight, m.out_proj.bias, "gelu"), m.out_proj.bias,
+                                       self._prepared("glu", self.glu.linear.weight, self.glu.linear.bias, "glu_residual"), self.glu.linear.bias,
+                                       skip.reshape(B * T, D), m.W_dt[0] if want_x else None, extract_partials if want_x else None)
+            return out.reshape(B, T, D)
         o = ops.linear(y, m.out_proj.weight, m.out_proj.bias, epilogue="gelu", mode=self.gemm_mode,
                        prepared=self._prepared("out", m.out_proj.weight, m.out_proj.bias, "gelu") if tc else None)    # GELU(out_proj(y))  (:333)
-        if self.glu is not None and extract_partials is not None and self.fuses_extractor() and B * T >= 1024:
+        if want_x:
             out, _ = ops.linear_glu_extract(o, self.glu.linear.weight, self.glu.linear.bias, skip.reshape(B * T, D), m.W_dt[0], partials=extract_partials,
                                             prepared=self._prepared("glu", self.glu.linear.weight, self.glu.linear.bias, "glu_residual") if tc else None)
         elif self.glu is not None:

@@ -314,7 +314,29 @@ def mamba_conv_ssd(xbcdt, ldz, conv_w, conv_b, dt_bias, A_log, D, B, T, H, P, G,
 
 # ---- K4 + glue ----------------------------------------------------------------------------------------------------
 EPILOGUES = {"none": L.EPI_NONE, "gelu": L.EPI_GELU, "glu_residual": L.EPI_GLU_RESIDUAL, "residual": L.EPI_RESIDUAL}
-GEMM_MODES = {"auto": L.GEMM_AUTO, "simt": L.GEMM_SIMT_F32, "tc3": L.GEMM_TC_3XTF32, "tc1": L.GEMM_TC_TF32}
+GEMM_MODES = {"auto": L.GEMM_AUTO, "simt": L.GEMM_SIMT_F32, "tc3": L.GEMM_TC_3XTF32, "tc1": L.GEMM_TC_TF32, "f16x3": L.GEMM_TC_F16X3}
+
+
+def gemm_precision() -> str:
+    """Operand precision the tensor-core GEMMs use by default (EIGB200_GEMM_PRECISION): "tf32x3" or "f16x3"."""
+    return "f16x3" if int(L.load().eigb200_gemm_precision()) == 1 else "tf32x3"
+
+
+def set_gemm_precision(name) -> None:
+    """ "tf32x3" | "f16x3" | None (back to EIGB200_GEMM_PRECISION).  Prepared workspaces of the other precision become stale: MambaDev.invalidate_prepared()."""
+    L.load().eigb200_set_gemm_precision({"tf32x3": 0, "f16x3": 1, None: -1}[name])
+
+
+def gemm_overflow(device=None, reset=True) -> bool:
+    """True when an fp16-split GEMM met an activation beyond its range since the last reset (its output holds inf / NaN there): rerun with 3xTF32.
+    Synchronises the current stream of `device`."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    lib = L.load()
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    L.check(lib.eigb200_set_device(idx), "eigb200_set_device")
+    flag = C.c_int(0)
+    L.check(lib.eigb200_gemm_overflow(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), int(reset), C.byref(flag)), "eigb200_gemm_overflow")
+    return flag.value != 0
 _ws_cache = {}
 
 
@@ -401,6 +423,28 @@ def linear_glu_extract(a, weight, bias, residual, w_gate, partials=None, out=Non
     _call(lib, "eigb200_linear_glu_extract", _stream(a), _p(a), K, _p(weight if prepared is None else None), _p(bias), _p(out), out.stride(-2), _p(residual), residual.stride(-2),
           M, N, K, _p(_prep(w_gate, torch.float32)), _p(partials), _p(ws), wsb, tag="N%d K%d glu_residual+extract" % (N, K))
     return out, partials
+
+
+def out_glu_fused_supported(D, K1) -> bool:
+    return gemm_precision() == "f16x3" and int(L.load().eigb200_out_glu_fused_supported(int(D), int(K1))) == 1
+
+
+def out_glu_fused(y, prepared_out, bias_out, prepared_glu, bias_glu, residual, w_gate=None, partials=None, out=None):
+    """GLU(GELU(y W_out^T + b_out) W_glu^T + b_glu) + residual in one kernel (fp16-split precision, prepared operands): -> (out (M, D), partials | None)."""
+    assert y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and residual.is_cuda and residual.dtype == torch.float32
+    K1 = y.shape[-1]
+    M = y.numel() // K1
+    D = residual.shape[-1]
+    lib = _enter(y)
+    if out is None:
+        out = torch.empty(M, D, dtype=torch.float32, device=y.device)
+    if w_gate is not None and partials is None:
+        partials = torch.empty(D // 16, 3, M, dtype=torch.float32, device=y.device)
+    _call(lib, "eigb200_out_glu_fused", _stream(y), _p(y), K1, _p(prepared_out), _p(_prep(bias_out, torch.float32) if bias_out is not None else None),
+          _p(prepared_glu), _p(_prep(bias_glu, torch.float32) if bias_glu is not None else None), _p(out), out.stride(-2), _p(residual), residual.stride(-2),
+          M, D, K1, _p(_prep(w_gate, torch.float32) if w_gate is not None else None), _p(partials if w_gate is not None else None),
+          tag="D%d K%d out_proj+gelu -> glu_residual%s" % (D, K1, "+extract" if w_gate is not None else ""))
+    return out, (partials if w_gate is not None else None)
 
 
 def mamba2_eig_partials(partials, B, T, dt_bias, A_log, thresholds: Sequence[float] = THRESHOLDS_RADIUS, want_lam=True, counts=None,

@@ -212,10 +212,23 @@ def _lin_ref(a, w, bias, epi, r):
     return z
 
 
+TCMODE = {"tf32x3": "tc3", "f16x3": "f16x3"}
+
+
+@pytest.fixture(params=["tf32x3", "f16x3"])
+def prec(request, ops):
+    """Both error-compensated operand splits of the tensor-core GEMMs (3 kind::tf32 MMAs / 3 kind::f16 MMAs per product) are held to the SAME fp32-level
+    bounds.  The fixture also makes the split the process default, which is what linear_ln / linear_glu_extract / linear_prepare use."""
+    ops.set_gemm_precision(request.param)
+    yield request.param
+    ops.set_gemm_precision(None)
+    assert not ops.gemm_overflow()                                 # no test below may leave the sticky overflow flag raised
+
+
 @pytest.mark.parametrize("M,N,K", [(4096, 161, 128), (5000, 128, 128), (3000, 256, 128), (1000, 64, 64), (129, 96, 32), (777, 200, 256),
-                                    (2048, 48, 100), (300000, 128, 128)])
+                                    (2048, 48, 100), (300000, 128, 128), (1300, 72, 96), (2000, 136, 160)])
 @pytest.mark.parametrize("epi", ["none", "gelu", "residual", "glu_residual"])
-def test_linear_tcgen05_3xtf32(ops, M, N, K, epi):
+def test_linear_tcgen05_3xtf32(ops, prec, M, N, K, epi):
     if epi == "glu_residual" and N % 2:
         N += 1
     rng = np.random.default_rng(M + N + K)
@@ -224,7 +237,7 @@ def test_linear_tcgen05_3xtf32(ops, M, N, K, epi):
     nout = N // 2 if epi == "glu_residual" else N
     ldc = (nout + 3) // 4 * 4
     r = rng.normal(size=(M, ldc)).astype(np.float32)
-    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode="tc3", ldc=ldc).cpu().numpy()
+    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode=TCMODE[prec], ldc=ldc).cpu().numpy()
     ref = _lin_ref(a, w, bias, epi, r[:, :nout].astype(np.float64))
     # fp32-level accuracy: same bound the FFMA path is held to
     np.testing.assert_allclose(out[:, :nout], ref, rtol=1e-5, atol=1e-5)
@@ -234,7 +247,7 @@ def test_linear_tcgen05_3xtf32(ops, M, N, K, epi):
 
 @pytest.mark.parametrize("N", [129, 130, 144, 145, 160, 161, 176, 177, 191, 192])
 @pytest.mark.parametrize("K,epi", [(128, "none"), (96, "gelu"), (64, "residual"), (32, "none"), (128, "residual")])
-def test_linear_tcgen05_wide_plan(ops, N, K, epi):
+def test_linear_tcgen05_wide_plan(ops, prec, N, K, epi):
     """129..192 output columns: the single-CTA wide plan (all columns resident, 2 TMEM operand stages, partial last 32-column group, ragged last row tile)."""
     M = 1500
     rng = np.random.default_rng(N * 7 + K)
@@ -243,7 +256,7 @@ def test_linear_tcgen05_wide_plan(ops, N, K, epi):
     ldc = (N + 7) // 8 * 8
     r = rng.normal(size=(M, ldc)).astype(np.float32)
     out = torch.full((M, ldc), 7.0, device="cuda")
-    ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :N] if epi == "residual" else None, mode="tc3", out=out)
+    ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :N] if epi == "residual" else None, mode=TCMODE[prec], out=out)
     out = out.cpu().numpy()
     ref = _lin_ref(a, w, bias, epi, r[:, :N].astype(np.float64))
     np.testing.assert_allclose(out[:, :N], ref, rtol=1e-5, atol=1e-5)
@@ -325,7 +338,7 @@ def test_rowstats_sources_agree(ops, D):
 
 
 @pytest.mark.parametrize("M,N,K", [(4096, 161, 128), (1000, 50, 32), (3000, 384, 128), (700, 96, 64)])
-def test_linear_ln_fused(ops, M, N, K):
+def test_linear_ln_fused(ops, prec, M, N, K):
     rng = np.random.default_rng(M + N)
     a = (rng.normal(size=(M, K)) * 2 + rng.normal(0, 1, (M, 1))).astype(np.float32)
     w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
@@ -335,12 +348,12 @@ def test_linear_ln_fused(ops, M, N, K):
     out = ops.linear_ln(dev(a), st, dev(gamma), dev(beta), dev(w), None, ldc=ldc).cpu().numpy()
     ref = O.layer_norm(a.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64)) @ w.astype(np.float64).T
     np.testing.assert_allclose(out[:, :N], ref, rtol=2e-5, atol=2e-5)
-    unfused = ops.linear(ops.layernorm(dev(a), dev(gamma), dev(beta)), dev(w), None, mode="tc3", ldc=ldc).cpu().numpy()
+    unfused = ops.linear(ops.layernorm(dev(a), dev(gamma), dev(beta)), dev(w), None, mode=TCMODE[prec], ldc=ldc).cpu().numpy()
     assert np.abs(out[:, :N] - unfused[:, :N]).max() <= 2e-5
 
 
 @pytest.mark.parametrize("M,D", [(4096, 128), (3000, 64), (2049, 256), (1500, 32)])
-def test_glu_extract_partials_match_k1(ops, M, D):
+def test_glu_extract_partials_match_k1(ops, prec, M, D):
     """The GLU + residual GEMM's extractor partials, combined by eigb200_mamba2_eig_partials, against K1 on the GEMM's own output: lambda within fp32
     reassociation, LayerNorm statistics, and bin counts exact for the lambdas each path wrote."""
     rng = np.random.default_rng(M + D)
@@ -350,7 +363,7 @@ def test_glu_extract_partials_match_k1(ops, M, D):
     wg = (rng.normal(size=D) / np.sqrt(D) * 3).astype(np.float32)
     dtb = np.array([-1.5], np.float32); Al = np.log(np.array([3.0], np.float32))
     out, part = ops.linear_glu_extract(dev(a), dev(w), dev(bias), dev(r), dev(wg))
-    plain = ops.linear(dev(a), dev(w), dev(bias), epilogue="glu_residual", residual=dev(r), mode="tc3")
+    plain = ops.linear(dev(a), dev(w), dev(bias), epilogue="glu_residual", residual=dev(r), mode=TCMODE[prec])
     assert torch.equal(out, plain)                                                     # the extra epilogue work does not touch the GEMM result
     st = torch.empty(B, T, 2, device="cuda")
     lam, counts = ops.mamba2_eig_partials(part, B, T, dev(dtb), dev(Al), rowstats_out=st)
@@ -368,24 +381,27 @@ def test_glu_extract_partials_match_k1(ops, M, D):
 
 
 @pytest.mark.parametrize("M,N,K,epi", [(4096, 161, 128, "none"), (3000, 128, 128, "gelu"), (2048, 256, 128, "glu_residual"), (1500, 96, 64, "residual")])
-def test_prepared_weights_bit_identical(ops, M, N, K, epi):
+def test_prepared_weights_bit_identical(ops, prec, M, N, K, epi):
     """eigb200_linear_prepare once + d_W = NULL calls == per-call preparation, bit for bit (same kernels, same operands)."""
     g = torch.Generator().manual_seed(M + N)
     a = torch.randn(M, K, generator=g).cuda(); w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda(); b = torch.randn(N, generator=g).cuda()
     nout = N // 2 if epi == "glu_residual" else N
     r = torch.randn(M, nout, generator=g).cuda() if "residual" in epi else None
     ldc = (nout + 3) // 4 * 4                                      # the tensor-core path wants 16-byte aligned output rows
-    ref = ops.linear(a, w, b, epilogue=epi, residual=r, mode="tc3", ldc=ldc)
+    ref = ops.linear(a, w, b, epilogue=epi, residual=r, mode=TCMODE[prec], ldc=ldc)
     ws = ops.linear_prepare(w, b, epi)
     assert ws is not None
     for _ in range(2):                                             # the workspace is read-only for the GEMM: a second call sees the same operands
-        out = ops.linear(a, w, b, epilogue=epi, residual=r, mode="tc3", ldc=ldc, prepared=ws)
+        out = ops.linear(a, w, b, epilogue=epi, residual=r, mode=TCMODE[prec], ldc=ldc, prepared=ws)
         assert torch.equal(out[:, :nout], ref[:, :nout])
+    other = "f16x3" if prec == "tf32x3" else "tc3"                 # a prepared workspace holds the operands of ONE precision: asking for the other is refused
+    with pytest.raises(Exception):
+        ops.linear(a, w, b, epilogue=epi, residual=r, mode=other, ldc=ldc, prepared=ws)
     with pytest.raises(Exception):
         ops.linear(a, w, b, epilogue=epi, residual=r, mode="simt", ldc=ldc, prepared=ws)
 
 
-def test_prepared_weights_layernorm_and_extract(ops):
+def test_prepared_weights_layernorm_and_extract(ops, prec):
     g = torch.Generator().manual_seed(5)
     M, K = 4096, 128
     a = (torch.randn(M, K, generator=g) * 2 + 0.5).cuda()
@@ -407,3 +423,81 @@ def test_prepared_weights_layernorm_and_extract(ops):
 def test_linear_prepare_no_resident_plan(ops):
     w = torch.randn(512, 512).cuda()
     assert ops.linear_prepare(w, None, "none") is None             # K > 256: streamed-operand kernel, prepared per call
+
+
+@pytest.mark.parametrize("scale,wscale", [(1e-3, 1.0), (300.0, 1.0), (1.0, 1e-4), (1.0, 50.0), (1e-2, 1e-3)])
+@pytest.mark.parametrize("epi,N", [("none", 161), ("gelu", 128), ("glu_residual", 256)])
+def test_linear_f16_split_operand_scales(ops, scale, wscale, epi, N):
+    """The fp16 split keeps fp32-level accuracy off the unit scale: S_w is chosen from max |w| at preparation (weights of 1e-4 or 50 are as good as
+    0.1), activations carry S_a = 16.  Bound: 2e-6 of sum_k |a||w| per output (the 3xTF32 path passes the same bound; a plain fp32 SGEMM sits at ~3e-7)."""
+    M, K = 3000, 128
+    rng = np.random.default_rng(int(scale * 1000) + N)
+    a = (rng.normal(size=(M, K)) * scale).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K) * wscale).astype(np.float32)
+    nout = N // 2 if epi == "glu_residual" else N
+    ldc = (nout + 7) // 8 * 8
+    bound = 2e-6 * (np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T)
+    for mode in ("f16x3", "tc3"):
+        out = ops.linear(dev(a), dev(w), None, epilogue="none", mode=mode, ldc=(N + 7) // 8 * 8).cpu().numpy()[:, :N]
+        err = np.abs(out - a.astype(np.float64) @ w.astype(np.float64).T)
+        assert (err <= bound + 1e-30).all(), (mode, float((err / (bound + 1e-300)).max()))
+    if epi != "none":                                              # and through the fused epilogues
+        bias = rng.normal(size=N).astype(np.float32); r = rng.normal(size=(M, ldc)).astype(np.float32)
+        out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode="f16x3", ldc=ldc).cpu().numpy()
+        ref = _lin_ref(a, w, bias, epi, r[:, :nout].astype(np.float64))
+        # an fp32 GEMM's error scales with sum_k |a||w| of the pre-activation, not with the (possibly cancelled) output: the absolute term follows it
+        np.testing.assert_allclose(out[:, :nout], ref, rtol=1e-5, atol=1e-5 + 2e-6 * float(bound.max()))
+    assert not ops.gemm_overflow()
+
+
+def test_linear_f16_split_overflow_is_loud(ops):
+    """An activation beyond 65504 / S_a cannot be represented by the fp16 split: the result is non-finite there AND the sticky flag is raised, so the
+    caller can rerun with 3xTF32 (which has fp32's exponent range) -- never a silently wrong finite number."""
+    M, N, K = 2048, 128, 128
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    a[1000, 5] = 1e5
+    assert not ops.gemm_overflow()
+    out = ops.linear(dev(a), dev(w), None, mode="f16x3").cpu().numpy()
+    assert ops.gemm_overflow(reset=False) and ops.gemm_overflow()                      # sticky until reset ...
+    assert not ops.gemm_overflow()                                                     # ... and cleared by it
+    assert not np.isfinite(out[1000]).all()
+    good = np.ones(M, bool); good[1000] = False
+    np.testing.assert_allclose(out[good], (a.astype(np.float64) @ w.astype(np.float64).T)[good], rtol=1e-5, atol=1e-5)   # other rows are unaffected
+    out3 = ops.linear(dev(a), dev(w), None, mode="tc3").cpu().numpy()
+    np.testing.assert_allclose(out3, a.astype(np.float64) @ w.astype(np.float64).T, rtol=1e-5, atol=2e-3)
+    assert not ops.gemm_overflow()
+
+
+@pytest.mark.parametrize("M,K1", [(4096, 128), (3001, 128), (129, 128), (2048, 64), (1500, 96), (40000, 32)])
+@pytest.mark.parametrize("extract", [True, False])
+def test_out_glu_fused_matches_two_kernels(ops, M, K1, extract):
+    """eigb200_out_glu_fused (GELU(out_proj) never leaves the SM) against the two-kernel form on the same prepared fp16-split operands, and against fp64."""
+    ops.set_gemm_precision("f16x3")
+    try:
+        D = 128
+        rng = np.random.default_rng(M + K1)
+        y = rng.normal(size=(M, K1)).astype(np.float32)
+        w1 = (rng.normal(size=(D, K1)) / np.sqrt(K1)).astype(np.float32); b1 = (rng.normal(size=D) * 0.3).astype(np.float32)
+        w2 = (rng.normal(size=(2 * D, D)) / np.sqrt(D)).astype(np.float32); b2 = rng.normal(size=2 * D).astype(np.float32)
+        r = (rng.normal(size=(M, D)) * 1.5).astype(np.float32); wg = (rng.normal(size=D) / np.sqrt(D) * 3).astype(np.float32)
+        assert ops.out_glu_fused_supported(D, K1)
+        ws1 = ops.linear_prepare(dev(w1), dev(b1), "gelu"); ws2 = ops.linear_prepare(dev(w2), dev(b2), "glu_residual")
+        out, part = ops.out_glu_fused(dev(y), ws1, dev(b1), ws2, dev(b2), dev(r), dev(wg) if extract else None)
+        o = ops.linear(dev(y), dev(w1), dev(b1), epilogue="gelu", mode="f16x3")
+        if extract:
+            ref2, part2 = ops.linear_glu_extract(o, dev(w2), dev(b2), dev(r), dev(wg))
+        else:
+            ref2 = ops.linear(o, dev(w2), dev(b2), epilogue="glu_residual", residual=dev(r), mode="f16x3"); part2 = None
+        # same operands, same split, same order of the fp32 accumulation: the fused kernel reproduces the two-kernel result exactly
+        assert torch.equal(out, ref2), float((out - ref2).abs().max())
+        if extract:
+            assert torch.equal(part, part2)
+        else:
+            assert part is None
+        o64 = _lin_ref(y, w1, b1, "gelu", None)
+        z = o64 @ w2.astype(np.float64).T + b2
+        ref = z[:, :D] / (1 + np.exp(-z[:, D:])) + r
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+        assert not ops.gemm_overflow()
+    finally:
+        ops.set_gemm_precision(None)

@@ -22,11 +22,21 @@ def eig():
     return A, Ly, E, S
 
 
+@pytest.fixture(params=["tf32x3", "f16x3"])
+def prec(request):
+    """Model-level parity under both operand splits of the tensor-core GEMMs; f16x3 also takes the fused out_proj -> GLU tail kernel at d_model 128."""
+    import eigb200.ops as ops
+    ops.set_gemm_precision(request.param)
+    yield request.param
+    ops.set_gemm_precision(None)
+    assert not ops.gemm_overflow()
+
+
 def _sd_torch(sd):
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 
-def test_mamba_model_pass_vs_reference(eig):
+def test_mamba_model_pass_vs_reference(eig, prec):
     A, Ly, E, S = eig
     sd, cfg, g = golden_model("model_mamba2")
     model = Ly.MambaDev(cfg, _sd_torch(sd), "cuda")
@@ -164,7 +174,7 @@ def test_mamba_pseudo_lti_pass_vs_oracle(eig, H, N, prenorm):
 
 
 @pytest.mark.parametrize("D,H,N,B,T", [(64, 1, 16, 20, 77), (128, 1, 16, 9, 130), (32, 1, 8, 40, 33), (128, 2, 16, 10, 110), (256, 1, 16, 5, 250)])
-def test_mamba_pass_tensor_core_paths_vs_oracle(eig, D, H, N, B, T):
+def test_mamba_pass_tensor_core_paths_vs_oracle(eig, prec, D, H, N, B, T):
     """Model-level parity on shapes that take the fused device paths (>= 1024 rows: tcgen05 GEMMs with the LayerNorm in the converter, GLU epilogue with
     the extractor partials when H = 1, SSD v3 with ragged chunks, partial 128-row tiles, T not a multiple of 32) against the fp64 oracle of the
     reference's per-layer loop."""
@@ -243,7 +253,7 @@ def test_c1_linear_attention_mqar_pass_vs_reference(eig):
     assert np.abs(pct - g["percentage"]).max() <= 100.0 / 63 + 1e-9
 
 
-def test_c5_shaped_mamba_pass_vs_oracle(eig):
+def test_c5_shaped_mamba_pass_vs_oracle(eig, prec):
     """BASELINE configs[4], Mamba arm, at its layer sizes (d_model 512, 8 heads of 64 channels, d_state 16, GLU) with a short sequence: the K = 512
     projections run on the streamed-operand tcgen05 kernel, the scan with 8 heads, the generic (H = 8, D = 512) extractor."""
     A, Ly, E, S = eig

@@ -136,7 +136,7 @@ def case_ssd(B, T=512, H=1, P=128, G=1, N=16):
 def case_linear(M, N, K, epi, mode):
     a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     nout = N // 2 if epi == "glu_residual" else N
-    ldc = (nout + 3) // 4 * 4
+    ldc = (nout + 7) // 8 * 8
     r = torch.randn(M, nout, device="cuda") if ("residual" in epi and not epi.endswith("_nores")) else None
     epi = epi.replace("_nores", "")
     out = torch.empty(M, ldc, device="cuda")
@@ -177,6 +177,11 @@ CASES = {
     "lin_out_tc1": lambda: case_linear(M_C2, 128, 128, "gelu", "tc1"),
     "lin_glu_tc1": lambda: case_linear(M_C2, 256, 128, "glu_residual", "tc1"),
     "lin_in_tc1": lambda: case_linear(M_C2, 161, 128, "none", "tc1"),
+    "lin_in_f16": lambda: case_linear(M_C2, 161, 128, "none", "f16x3"),
+    "lin_out_f16": lambda: case_linear(M_C2, 128, 128, "gelu", "f16x3"),
+    "lin_glu_f16": lambda: case_linear(M_C2, 256, 128, "glu_residual", "f16x3"),
+    "lin_out_none_f16": lambda: case_linear(M_C2, 128, 128, "none", "f16x3"),
+    "lin_glu_nores_f16": lambda: case_linear(M_C2, 256, 128, "glu_residual_nores", "f16x3"),
     "lin_out_simt": lambda: case_linear(M_C2, 128, 128, "gelu", "simt"),
     "lin_small_tc3": lambda: case_linear(65536, 128, 128, "gelu", "tc3"),
     "lin_glu_mid_tc3": lambda: case_linear(524288, 256, 128, "glu_residual", "tc3"),
