@@ -9,8 +9,10 @@ bool tc_supported(const LinearParams& p);
 // nsplit = 3: error-compensated split (fp32-level accuracy); nsplit = 1: one rounded operand (plain TF32 / fp16).
 // kind = 0: kind::tf32 operands (3xTF32), 1: kind::f16 operands (scaled fp16 split, twice the tensor rate; resident-weight kernels only).
 // p.W == nullptr: the workspace already holds the prepared weights (tc_prepare / eigb200_linear_prepare) of this (N, K, epilogue, LayerNorm, kind).
+// Default: the fp16 split.  Same accuracy class as 3xTF32 in every test (tests parametrise both) and in tools/split_error_study.py; measured on B200 at
+// BASELINE C2: GLU GEMM 0.807 -> 0.731 ms, pass 11.6 -> 11.0 ms, and it is what lets the out_proj -> GLU tail run as one kernel (10.2 ms).
 #ifndef EIGB200_GEMM_DEFAULT_KIND
-#define EIGB200_GEMM_DEFAULT_KIND 0
+#define EIGB200_GEMM_DEFAULT_KIND 1
 #endif
 void tc_set_default_kind(int kind);                    // 0 / 1 overrides the environment, anything else restores it
 int tc_default_kind();                                   // EIGB200_GEMM_PRECISION = tf32x3 | f16x3, else EIGB200_GEMM_DEFAULT_KIND
