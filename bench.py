@@ -345,10 +345,12 @@ def c2_alg_bytes(tokens, D_, N_, H):
            "eigb200_linear[N%d K%d gelu]" % (D_, D_): tokens * 2 * D_ * 4,
            "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): tokens * 3 * D_ * 4,
            "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): tokens * 3 * D_ * 4,
+           "eigb200_out_glu_fused[D%d K%d out_proj+gelu -> glu_residual+extract]" % (D_, D_): tokens * 3 * D_ * 4,   # read y, read the skip, write x_out
            "eigb200_mamba2_eig_partials": tokens * (4 * H + 8)}
     flops = {"eigb200_linear_ln[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in, "eigb200_linear[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in,
              "eigb200_linear[N%d K%d gelu]" % (D_, D_): 2.0 * tokens * D_ * D_, "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_,
-             "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_}
+             "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_,
+             "eigb200_out_glu_fused[D%d K%d out_proj+gelu -> glu_residual+extract]" % (D_, D_): 2.0 * tokens * D_ * 3 * D_}
     return alg, flops
 
 

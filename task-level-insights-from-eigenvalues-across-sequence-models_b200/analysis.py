@@ -93,6 +93,27 @@ def mamba_pass(model: "Ly.MambaDev", X, pseudoLTI=False, want_eig=True, compare=
     return PassResult(eig, counts, T, x)
 
 
+def with_range_fallback(run_pass, model=None):
+    """Run one analysis pass; if an fp16-split GEMM met an activation beyond its range (sticky device flag, see eigb200_gemm_overflow) the pass is
+    repeated with the 3xTF32 operands, which have fp32's exponent range.  The flag is read once per pass, at a point where the host waits anyway."""
+    ops.gemm_overflow(reset=True)
+    res = run_pass()
+    if ops.gemm_precision() == "f16x3" and ops.gemm_overflow(reset=True):
+        import warnings
+        warnings.warn("eigb200: an activation exceeded the range of the fp16-split GEMM operands; repeating the pass with 3xTF32", RuntimeWarning)
+        ops.set_gemm_precision("tf32x3")
+        try:
+            if model is not None and hasattr(model, "invalidate_prepared"):
+                model.invalidate_prepared()
+            res = run_pass()
+            torch.cuda.synchronize()
+        finally:
+            ops.set_gemm_precision(None)
+            if model is not None and hasattr(model, "invalidate_prepared"):
+                model.invalidate_prepared()
+    return res
+
+
 class MambaPassGraph:
     """One analysis pass captured as a CUDA graph: every kernel of mamba_pass is stream-ordered and allocation-free on the device side
     (outputs come from the graph's private pool), so a batch of fixed shape replays with ONE launch -- no per-kernel launch gaps and no host
@@ -332,10 +353,10 @@ def eval_eig(args, conf_args, wandb_config, data_config, loader, path_file, perf
             X = _first_batch(loader, device, lo if world > 1 else None, hi if world > 1 else None)
             if layer_type == "mamba":
                 model = Ly.MambaDev(model_config, state_dict, device)
-                res = mamba_pass(model, X, pseudoLTI, want_eig=materialize, compare=compare)
+                res = with_range_fallback(lambda: mamba_pass(model, X, pseudoLTI, want_eig=materialize, compare=compare), model)
             else:
                 model = Ly.TransformerDev(model_config, state_dict, device)
-                res = transformer_pass(model, X, model_config, want_eig=materialize, compare=compare)
+                res = with_range_fallback(lambda: transformer_pass(model, X, model_config, want_eig=materialize, compare=compare), None)
             counts = D.allreduce_counts(res.counts, batch_size, lo, batch_axis=1)          # the one exchange step
             eig = res.eig
             if eig is not None and world > 1:

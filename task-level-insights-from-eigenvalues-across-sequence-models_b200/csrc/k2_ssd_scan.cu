@@ -15,7 +15,7 @@
 // in shared memory with coalesced 128-bit loads, a prep phase turns them into conv'd B_t, C_t and (dt_t, exp(dt_t A)),
 // then the serial phase runs TC steps out of shared memory (broadcast LDS.128 for B_t/C_t).  Several CTAs per SM overlap
 // one CTA's staging with another's recurrence.
-#include "common.cuh"
+#include "ssd.cuh"
 #include <type_traits>
 #include <stdlib.h>
 
@@ -25,20 +25,6 @@ constexpr int SSD_TC = 32;          // tokens per staged chunk
 constexpr int SSD_HIST = 3;         // history rows kept for the conv (max 4 taps)
 constexpr int SSD_THREADS = 128;
 
-struct SsdParams {
-  // x channels, B channels, C channels, dt: each (b,t) row-major with its own row stride (elements)
-  const float* x; int64_t ldx;
-  const float* Bm; const float* Cm; int64_t ldbc;
-  const float* dt; int64_t lddt;
-  const float* A;            // fused: A_log (A = -exp(A_log));  plain: A itself
-  const float* D;
-  const float* dt_bias;      // fused only
-  const float* conv_w;       // fused only: (H*P + 2*G*N, kconv) row-major over channels [x | B | C]
-  const float* conv_b;
-  float* y; int64_t ldy;
-  float* final_state;        // (B,H,P,N) or null
-  int64_t T; int H, P, G, N, kconv, fused;
-};
 
 template <int NS>
 __global__ void __launch_bounds__(SSD_THREADS) ssd_scan_kernel(const SsdParams p) {
@@ -702,9 +688,12 @@ static int launch_ssd(cudaStream_t st, const SsdParams& p, int64_t B) {
   EIGB_CHECK_ARG(p.kconv >= 0 && p.kconv <= 4, "ssd_scan: conv kernel size %d not in 0..4", p.kconv);
   EIGB_CHECK_ARG(B <= 65535 && p.H <= 65535, "ssd_scan: batch/heads exceed grid limits");
   {
-    // EIGB200_SSD_FORM: "scan" = the recurrent kernels below, "mma" = the chunked tensor-core form (k2_ssd_mma.cuh) where its shape conditions hold
-    const char* e = getenv("EIGB200_SSD_FORM");                     // read per call (cheap next to a launch) so that the tests can switch forms
+    // EIGB200_SSD_FORM: "scan" = the recurrent kernels below, "mma" = the chunked mma.sync form (k2_ssd_mma.cuh), "tc" = the chunked tcgen05 form
+    // (k2_ssd_tc.cu), each where its shape conditions hold.  Read per call (cheap next to a launch) so that the tests can switch forms.
+    const char* e = getenv("EIGB200_SSD_FORM");
     if (e && e[0] == 'm' && ssd_mma_ok(p)) return launch_ssd_mma(st, p, B);
+    const bool want_tc = e ? (e[0] == 't') : (EIGB200_SSD_DEFAULT_TC != 0);
+    if (want_tc && ssd_tc_ok(p)) return launch_ssd_tc(st, p, B);
   }
   {
     int cpt = 1;

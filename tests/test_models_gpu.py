@@ -302,3 +302,34 @@ def test_c3_shaped_lru_layer_vs_oracle(eig):
     scale = np.abs(hr).max(axis=1, keepdims=True)
     assert (np.abs(h.cpu().numpy() - hr) <= 2e-4 * scale).all()            # fp32 lambda: |lambda| ~ 0.999 over 2048 steps (see test_lru_layer_call)
     assert np.abs(y.cpu().numpy() - yr).max() <= 2e-4 * np.abs(yr).max()
+
+
+def test_fp16_split_range_fallback(eig):
+    """Activations beyond the fp16-split range raise the sticky flag and analysis.with_range_fallback repeats the pass with 3xTF32: the result is finite and
+    matches the oracle; without the fallback the same pass holds non-finite eigenvalues (loud, never silently wrong)."""
+    import warnings
+    import eigb200.ops as ops
+    A, Ly, E, S = eig
+    cfg = dict(layer="mamba", version="mamba2", num_layers=2, num_heads=1, input_dim=1, output_dim=32, hidden_dim=128, state_dim=16, conv_dim=4,
+               expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none", token_embedding=True, vocab_size=97)
+    sd = Ly.init_mamba_state_dict(cfg, 5)
+    sd["blocks.0.mamba.D"] = sd["blocks.0.mamba.D"] * 3e4                 # y = C.h + D x: |y| ~ 1e5 > 65504 / 16
+    sd["blocks.0.mamba.out_proj.weight"] = sd["blocks.0.mamba.out_proj.weight"] * 1e-4
+    model = Ly.MambaDev(cfg, sd, "cuda")
+    X = torch.randint(0, 97, (12, 100), generator=torch.Generator().manual_seed(3)).cuda()
+    ops.set_gemm_precision("f16x3")
+    try:
+        ops.gemm_overflow(reset=True)
+        raw = A.mamba_pass(model, X)
+        assert ops.gemm_overflow(reset=True)
+        assert not np.isfinite(raw.eig.cpu().numpy()).all()
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            res = A.with_range_fallback(lambda: A.mamba_pass(model, X), model)
+        assert any("3xTF32" in str(x.message) for x in w)
+        assert ops.gemm_precision() == "f16x3" and not ops.gemm_overflow()
+    finally:
+        ops.set_gemm_precision(None)
+    ocfg = dict(num_layers=2, d_inner=128, ngroups=1, d_state=16, nheads=1, headdim=128, prenorm=True)
+    ref, _ = O.mamba_eval_pass(X.cpu().numpy(), {k: v.numpy() for k, v in sd.items()}, ocfg, np.float64)
+    assert_eig_close(res.eig_host(), ref, rtol=3e-5)

@@ -71,9 +71,10 @@ def test_lru_s5_lambda(ops):
     np.testing.assert_allclose(lam, h["bil_L"], rtol=2e-5, atol=1e-7)
 
 
-@pytest.fixture(params=["scan", "mma"])
+@pytest.fixture(params=["scan", "mma", "tc"])
 def ssd_form(request, monkeypatch):
-    """Both forms of K2b: the recurrent scan kernels and the chunked tensor-core form (csrc/k2_ssd_mma.cuh; taken where its shape conditions hold)."""
+    """All forms of K2b: the recurrent scan kernels, the chunked mma.sync form (csrc/k2_ssd_mma.cuh) and the chunked tcgen05 form (csrc/k2_ssd_tc.cu: fused
+    conv + SSD with head dim 128, d_state 16), each taken where its shape conditions hold."""
     monkeypatch.setenv("EIGB200_SSD_FORM", request.param)
     return request.param
 
@@ -124,3 +125,35 @@ def test_mamba_conv_ssd_fused(ops, ssd_form, kconv, P, T):
                                 xBC[..., H * P:H * P + G * N].reshape(B, T, G, N), xBC[..., H * P + G * N:].reshape(B, T, G, N), Dv.astype(np.float64))
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert (np.abs(y.reshape(B, T, H, P) - ref) <= 1e-5 * scale + 1e-6).all()
+
+
+@pytest.mark.parametrize("B,T,H,G,kconv", [(2, 64, 1, 1, 4), (3, 512, 1, 1, 4), (2, 130, 2, 1, 4), (5, 1, 1, 1, 4), (4, 63, 1, 1, 3), (2, 65, 4, 2, 4), (310, 96, 1, 1, 4),
+                                            (1, 1000, 1, 1, 1)])
+def test_mamba_conv_ssd_tcgen05_form(ops, monkeypatch, B, T, H, G, kconv):
+    """The chunked tcgen05 form (k2_ssd_tc.cu) on its own shapes: chunk-aligned and ragged sequence lengths (T % 64 in {0, 1, 2, 63, ...}), T < 64, several chunks
+    (state carried through TMEM), heads sharing a B / C group, more (sequence, head) items than SMs (CTAs walk several items: state reset), short conv kernels.
+    Same bound as the recurrent form: 1e-5 of the per-(sequence, channel) output scale."""
+    monkeypatch.setenv("EIGB200_SSD_FORM", "tc")
+    rng = np.random.default_rng(B * 1000 + T)
+    P, N = 128, 16
+    C_ = H * P + 2 * G * N
+    ldz = (C_ + H + 7) // 8 * 8
+    z = rng.normal(size=(B, T, ldz)).astype(np.float32)
+    cw = rng.normal(size=(C_, kconv)).astype(np.float32) * 0.5; cb = rng.normal(size=C_).astype(np.float32) * 0.1
+    dtb = rng.normal(-1, 1, H).astype(np.float32); Al = np.log(rng.uniform(1, 16, H)).astype(np.float32); Dv = rng.normal(size=H).astype(np.float32)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    y = ops.mamba_conv_ssd(dev(z), ldz, dev(cw), dev(cb), dev(dtb), dev(Al), dev(Dv), B, T, H, P, G, N)
+    monkeypatch.setenv("EIGB200_SSD_FORM", "scan")
+    y_scan = ops.mamba_conv_ssd(dev(z), ldz, dev(cw), dev(cb), dev(dtb), dev(Al), dev(Dv), B, T, H, P, G, N).cpu().numpy()
+    y = y.cpu().numpy()
+    nb = min(B, 6)                                                 # fp64 oracle on a few sequences (first and last), the recurrent kernel on all of them
+    sel = np.unique(np.r_[np.arange(nb // 2), B - 1 - np.arange(nb - nb // 2)])
+    z64 = z[sel].astype(np.float64)
+    xBC = O.causal_depthwise_conv_silu(z64[..., :C_], cw.astype(np.float64), cb.astype(np.float64))
+    dt = O.softplus(z64[..., C_:C_ + H] + dtb)
+    ref = O.ssd_scan_sequential(xBC[..., :H * P].reshape(len(sel), T, H, P), dt, -np.exp(Al.astype(np.float64)),
+                                xBC[..., H * P:H * P + G * N].reshape(len(sel), T, G, N), xBC[..., H * P + G * N:].reshape(len(sel), T, G, N), Dv.astype(np.float64))
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(y[sel].reshape(len(sel), T, H, P) - ref) <= 1e-5 * scale + 1e-6).all()
+    sc2 = np.abs(y_scan).reshape(B, T, H * P).max(axis=1, keepdims=True)
+    assert (np.abs(y - y_scan) <= 2e-5 * sc2 + 1e-6).all()
