@@ -43,8 +43,8 @@ constexpr uint32_t ST_BW_HI = 98304, ST_BW_LO = 102400;             // (B e^{cum
 constexpr uint32_t ST_YST = 106496;                                 // 3 x [64 tokens][128 channels] fp32
 constexpr uint32_t ST_RAWB = ST_YST + 3 * 32768;                    // 2 x [67][16] fp32, padded to 4352
 constexpr uint32_t ST_RAWC = ST_RAWB + 2 * 4352;
-constexpr uint32_t ST_DTS = ST_RAWC + 2 * 4352;                     // dt_s[2][64], cum_s[2][64]
-constexpr uint32_t ST_CWBC = ST_DTS + 1024;                         // conv weights of the B / C channels: [32][4] + bias [32]
+constexpr uint32_t ST_DTS = ST_RAWC + 2 * 4352;                     // dt_s[2][64], cum_s hi [2][64] (+512), cum_s lo [2][64] (+1024)
+constexpr uint32_t ST_CWBC = ST_DTS + 2048;                         // conv weights of the B / C channels: [32][4] + bias [32]
 constexpr uint32_t ST_BARS = ST_CWBC + 1024;
 constexpr uint32_t ST_SMEM = ST_BARS + 512;
 constexpr uint32_t ST_RAW_BYTES = ST_RAWROWS * ST_N * 4;            // 4288
@@ -160,33 +160,49 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
     __syncwarp();
   } else if (warp >= ST_WARP_T0 && warp < ST_WARP_T0 + 4) {
     // ===================================== T group: thread = token ======================================
+    // Software-pipelined over the CTA's chunk sequence w = 0, 1, ... (all chunks of its items, in order): iteration w first PREPARES chunk w + 1 (conv, dt, cum,
+    // operands of G) so that the tensor core computes G(w + 1) while this group forms M(w) from G(w) -- the G round trip is off the critical path.
     const int wq = warp - ST_WARP_T0;                               // TMEM lane quarter of this warp
     const int tok = 32 * (wq & 1) + lane;                           // token of the chunk this thread owns
     const int hb = wq >> 1;                                         // 0: B channels / columns 0-31 of G, 1: C channels / columns 32-63
     const int tid_t = threadIdx.x - ST_WARP_T0 * 32;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
     const int sw = tok & 7;
-    int64_t cc = 0;
-    for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-      const int b = (int)(item / p.H), h = (int)(item - (int64_t)b * p.H);
-      const int g = h / (p.H / p.G);
-      const float Ah = -expf(p.A_log[h]), dtb = p.dt_bias[h];
-      const float* dtp = p.z + ((size_t)b * T) * p.ldz + p.colDt + h;
-      named_bar_sync(2, 128);                                       // every T thread is done with the previous item's conv weights
-      if (tid_t < 32) {                                             // conv weights of this item's B / C channels (group g) -> shared
-        const int ch = (tid_t < 16 ? p.colB : p.colC) - 0 + g * ST_N + (tid_t & 15);   // column of the projection buffer == conv channel index
+    const int64_t my_items = (p.nitems - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x;
+    const int64_t nwork = my_items * nch;
+    float vc[16], vn[16];                                           // conv + SiLU of this token's B or C channels: current chunk, next chunk
+    float cum_c = 0.f, cuml_c = 0.f, cumQ_c = 0.f, cumQl_c = 0.f, cum_n = 0.f, cuml_n = 0.f, cumQ_n = 0.f, cumQl_n = 0.f;
+    float dtr0 = 0.f, dtr1 = 0.f, Ah = 0.f, dtb = 0.f;
+    const float* dtp = p.z;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sts_f1(cwbc + (tid_t * 4 + k) * 4, (k >= 4 - p.kconv) ? p.conv_w[(size_t)ch * p.kconv + k - (4 - p.kconv)] : 0.f);
-        sts_f1(cwbc + 512 + tid_t * 4, p.conv_b[ch]);
-      }
-      named_bar_sync(2, 128);
-      float dtr0 = (lane < T) ? __ldg(dtp + (size_t)lane * p.ldz) : 0.f;                 // raw dt of tokens lane, lane + 32 of the first chunk
-      float dtr1 = (32 + lane < T) ? __ldg(dtp + (size_t)(32 + lane) * p.ldz) : 0.f;
-      for (int c = 0; c < nch; ++c, ++cc) {
-        const int buf = (int)(cc & 1); const uint32_t u = (uint32_t)(cc >> 1);
+    for (int i = 0; i < 16; ++i) { vc[i] = 0.f; vn[i] = 0.f; }
+    for (int64_t w = -1; w < nwork; ++w) {
+      if (w + 1 < nwork) {
+        // ================= prepare chunk wn = w + 1 =================
+        const int64_t wn = w + 1;
+        const int64_t k = wn / nch;
+        const int c = (int)(wn - k * nch);
+        const int64_t item = (int64_t)blockIdx.x + k * (int64_t)gridDim.x;
+        const int b = (int)(item / p.H), h = (int)(item - (int64_t)b * p.H);
+        const int buf = (int)(wn & 1); const uint32_t u = (uint32_t)(wn >> 1);
         const int64_t t0 = (int64_t)c * ST_Q;
+        if (c == 0) {                                               // a new (sequence, head): scalars, conv weights of its B / C group, first dt rows
+          const int g = h / (p.H / p.G);
+          Ah = -expf(p.A_log[h]); dtb = p.dt_bias[h];
+          dtp = p.z + ((size_t)b * T) * p.ldz + p.colDt + h;
+          named_bar_sync(2, 128);                                   // every T thread is done with the previous item's conv weights
+          if (tid_t < 32) {
+            const int ch = (tid_t < 16 ? p.colB : p.colC) + g * ST_N + (tid_t & 15);   // column of the projection buffer == conv channel index
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) sts_f1(cwbc + (tid_t * 4 + kk) * 4, (kk >= 4 - p.kconv) ? p.conv_w[(size_t)ch * p.kconv + kk - (4 - p.kconv)] : 0.f);
+            sts_f1(cwbc + 512 + tid_t * 4, p.conv_b[ch]);
+          }
+          named_bar_sync(2, 128);
+          dtr0 = (lane < T) ? __ldg(dtp + (size_t)lane * p.ldz) : 0.f;
+          dtr1 = (32 + lane < T) ? __ldg(dtp + (size_t)(32 + lane) * p.ldz) : 0.f;
+        }
         const float r0 = dtr0, r1 = dtr1;
-        if (c + 1 < nch) {                                          // prefetch the next chunk's raw dt
+        if (c + 1 < nch) {                                          // prefetch the raw dt of the chunk after this one
           const int64_t tn = t0 + ST_Q;
           dtr0 = (tn + lane < T) ? __ldg(dtp + (size_t)(tn + lane) * p.ldz) : 0.f;
           dtr1 = (tn + 32 + lane < T) ? __ldg(dtp + (size_t)(tn + 32 + lane) * p.ldz) : 0.f;
@@ -194,27 +210,31 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
         // ---- dt, cum: every T warp scans all 64 tokens (lane: tokens lane and lane + 32) ----
         const float d0 = (t0 + lane < T) ? softplus_f(r0 + dtb) : 0.f;
         const float d1 = (t0 + 32 + lane < T) ? softplus_f(r1 + dtb) : 0.f;
-        float c0 = d0 * Ah, c1 = d1 * Ah;
+        // The mask needs exp(cum_i - cum_j) for NEARBY i, j deep into the chunk: |cum| reaches 30-60 there, so a single float (ulp 2e-6 .. 4e-6) would put
+        // that error on weights of order one.  The scan runs in double; cum is kept as a float pair (hi, lo) and differences are formed pairwise.
+        double c0d = (double)(d0 * Ah), c1d = (double)(d1 * Ah);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const float v0 = __shfl_up_sync(0xffffffffu, c0, o), v1 = __shfl_up_sync(0xffffffffu, c1, o);
-          if (lane >= o) { c0 += v0; c1 += v1; }
+          const double v0 = __shfl_up_sync(0xffffffffu, c0d, o), v1 = __shfl_up_sync(0xffffffffu, c1d, o);
+          if (lane >= o) { c0d += v0; c1d += v1; }
         }
-        c1 += __shfl_sync(0xffffffffu, c0, 31);
-        const float cumQ = __shfl_sync(0xffffffffu, c1, 31);
-        const float my_cum = (wq & 1) ? c1 : c0;
-        if (cc >= 2) {                                              // dt_s / cum_s[buf] of chunk cc - 2 are no longer read (X group, Y group)
+        c1d += __shfl_sync(0xffffffffu, c0d, 31);
+        const double cumQd = __shfl_sync(0xffffffffu, c1d, 31);
+        const float c0 = (float)c0d, c1 = (float)c1d, c0l = (float)(c0d - (double)c0), c1l = (float)(c1d - (double)c1);
+        cumQ_n = (float)cumQd; cumQl_n = (float)(cumQd - (double)cumQ_n);
+        cum_n = (wq & 1) ? c1 : c0; cuml_n = (wq & 1) ? c1l : c0l;
+        if (wn >= 2) {                                              // dt_s / cum_s[buf] of chunk wn - 2 are no longer read (X group, Y group)
           mbar_wait(bar_xd_full(buf), (u - 1) & 1);
           mbar_wait(bar_ydone(buf), (u - 1) & 1);
         }
         if (wq == 0) {
           sts_f1(dts + (buf * 64 + lane) * 4, d0); sts_f1(dts + (buf * 64 + 32 + lane) * 4, d1);
           sts_f1(dts + 512 + (buf * 64 + lane) * 4, c0); sts_f1(dts + 512 + (buf * 64 + 32 + lane) * 4, c1);
+          sts_f1(dts + 1024 + (buf * 64 + lane) * 4, c0l); sts_f1(dts + 1024 + (buf * 64 + 32 + lane) * 4, c1l);
         }
         // ---- conv + SiLU of this token's 16 B (hb = 0) or C (hb = 1) channels ----
         mbar_wait(bar_raw_full(buf), u & 1);
         const uint32_t raw = base + (hb ? ST_RAWC : ST_RAWB) + buf * 4352 + tok * (ST_N * 4);   // row tok = token t0 + tok - 3: the first tap
-        float v[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 x0 = lds_f4(raw + q * 16), x1 = lds_f4(raw + 64 + q * 16), x2 = lds_f4(raw + 128 + q * 16), x3 = lds_f4(raw + 192 + q * 16);
@@ -222,62 +242,66 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int ch = hb * 16 + 4 * q + e;
-            const float4 w = lds_f4(cwbc + ch * 16);
+            const float4 wv = lds_f4(cwbc + ch * 16);
             const float bias = lds_f1(cwbc + 512 + ch * 4);
-            v[4 * q + e] = st_silu(fmaf(w.w, xs3[e], fmaf(w.z, xs2[e], fmaf(w.y, xs1[e], fmaf(w.x, xs0[e], bias)))));
+            vn[4 * q + e] = st_silu(fmaf(wv.w, xs3[e], fmaf(wv.z, xs2[e], fmaf(wv.y, xs1[e], fmaf(wv.x, xs0[e], bias)))));
           }
         }
         {
           uint32_t dep = 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dep ^= __float_as_uint(v[i]);
+          for (int i = 0; i < 16; ++i) dep ^= __float_as_uint(vn[i]);
           mbar_arrive_after(bar_raw_free(buf), dep, (uint32_t)p.zero);    // the raw rows are in registers: TMA may refill the buffer
         }
         mbar_arrive(bar_tprep(buf));
         // ---- operands of G = C B^T:  [C; C] (128 rows) and B (64 rows), 16 K-values = logical 16-byte slots 0-3 of each 128-byte row ----
-        mbar_wait(bar_gop_free, (uint32_t)(cc & 1) ^ 1u);
+        if (wn >= 1) mbar_wait(bar_gop_free, (uint32_t)((wn - 1) & 1));   // G(wn - 1) has read the previous operands
         {
           float hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(v[i]); lo[i] = v[i] - hi[i]; }
+          for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(vn[i]); lo[i] = tf32_hi(vn[i] - hi[i]); }
           const uint32_t rowo = (uint32_t)tok * 128u;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const uint32_t so = (uint32_t)((s ^ sw) << 4);
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const uint32_t so = (uint32_t)((s4 ^ sw) << 4);
             if (hb) {
-              sts_f4(base + ST_GA_HI + rowo + so, hi[4 * s], hi[4 * s + 1], hi[4 * s + 2], hi[4 * s + 3]);
-              sts_f4(base + ST_GA_HI + 8192 + rowo + so, hi[4 * s], hi[4 * s + 1], hi[4 * s + 2], hi[4 * s + 3]);
-              sts_f4(base + ST_GA_LO + rowo + so, lo[4 * s], lo[4 * s + 1], lo[4 * s + 2], lo[4 * s + 3]);
-              sts_f4(base + ST_GA_LO + 8192 + rowo + so, lo[4 * s], lo[4 * s + 1], lo[4 * s + 2], lo[4 * s + 3]);
+              sts_f4(base + ST_GA_HI + rowo + so, hi[4 * s4], hi[4 * s4 + 1], hi[4 * s4 + 2], hi[4 * s4 + 3]);
+              sts_f4(base + ST_GA_HI + 8192 + rowo + so, hi[4 * s4], hi[4 * s4 + 1], hi[4 * s4 + 2], hi[4 * s4 + 3]);
+              sts_f4(base + ST_GA_LO + rowo + so, lo[4 * s4], lo[4 * s4 + 1], lo[4 * s4 + 2], lo[4 * s4 + 3]);
+              sts_f4(base + ST_GA_LO + 8192 + rowo + so, lo[4 * s4], lo[4 * s4 + 1], lo[4 * s4 + 2], lo[4 * s4 + 3]);
             } else {
-              sts_f4(base + ST_GB_HI + rowo + so, hi[4 * s], hi[4 * s + 1], hi[4 * s + 2], hi[4 * s + 3]);
-              sts_f4(base + ST_GB_LO + rowo + so, lo[4 * s], lo[4 * s + 1], lo[4 * s + 2], lo[4 * s + 3]);
+              sts_f4(base + ST_GB_HI + rowo + so, hi[4 * s4], hi[4 * s4 + 1], hi[4 * s4 + 2], hi[4 * s4 + 3]);
+              sts_f4(base + ST_GB_LO + rowo + so, lo[4 * s4], lo[4 * s4 + 1], lo[4 * s4 + 2], lo[4 * s4 + 3]);
             }
           }
         }
         fence_proxy_async();
         mbar_arrive(bar_gop_full);
+      }
+      if (w >= 0) {
+        // ================= finish chunk w: dS / state operands, then G(w) -> M(w) =================
+        const int buf = (int)(w & 1); const uint32_t u = (uint32_t)(w >> 1);
         // ---- (B e^{cum_Q - cum})^T for dS (hb = 0) and C e^{cum} for the state part of Y (hb = 1) ----
-        mbar_wait(bar_mc_free, (uint32_t)(cc & 1) ^ 1u);
+        mbar_wait(bar_mc_free, (uint32_t)(w & 1) ^ 1u);
         if (hb == 0) {
-          const float wdec = expf(cumQ - my_cum);
+          const float wdec = expf((cumQ_c - cum_c) + (cumQl_c - cuml_c));
           const uint32_t kc = (uint32_t)(tok >> 5) * 2048u, kk = (uint32_t)(tok & 31);
 #pragma unroll
           for (int n = 0; n < 16; ++n) {                            // element (row n, K index tok): slot (kk >> 2) ^ (n & 7), word kk & 3
-            const float val = v[n] * wdec, hi = tf32_hi(val);
+            const float val = vc[n] * wdec, hi = tf32_hi(val);
             const uint32_t off = kc + (uint32_t)n * 128u + ((((kk >> 2) ^ (uint32_t)(n & 7)) << 4) | ((kk & 3u) << 2));
             sts_f1(base + ST_BW_HI + off, hi);
-            sts_f1(base + ST_BW_LO + off, val - hi);
+            sts_f1(base + ST_BW_LO + off, tf32_hi(val - hi));
           }
         } else {
-          const float e = expf(my_cum);
+          const float e = expf(cum_c);
           const uint32_t rowo = 2u * 8192u + (uint32_t)tok * 128u;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
+          for (int s4 = 0; s4 < 4; ++s4) {
             float hi[4], lo[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { const float val = v[4 * s + k] * e; hi[k] = tf32_hi(val); lo[k] = val - hi[k]; }
-            const uint32_t so = (uint32_t)((s ^ sw) << 4);
+            for (int kk = 0; kk < 4; ++kk) { const float val = vc[4 * s4 + kk] * e; hi[kk] = tf32_hi(val); lo[kk] = tf32_hi(val - hi[kk]); }
+            const uint32_t so = (uint32_t)((s4 ^ sw) << 4);
             sts_f4(base + ST_MC_HI + rowo + so, hi[0], hi[1], hi[2], hi[3]);
             sts_f4(base + ST_MC_LO + rowo + so, lo[0], lo[1], lo[2], lo[3]);
           }
@@ -296,8 +320,8 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
               const int j = 32 * hb + jj;
-              const float cj = lds_f1(dts + 512 + (buf * 64 + j) * 4);
-              const float m = gv[jj] * fast_exp_f(my_cum - cj);
+              const float cj = lds_f1(dts + 512 + (buf * 64 + j) * 4), cjl = lds_f1(dts + 1024 + (buf * 64 + j) * 4);
+              const float m = gv[jj] * fast_exp_f((cum_c - cj) + (cuml_c - cjl));
               gv[jj] = (j <= tok) ? m : 0.f;
             }
           } else {
@@ -306,11 +330,11 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
           }
           const uint32_t rowo = (uint32_t)hb * 8192u + (uint32_t)tok * 128u;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
+          for (int s8 = 0; s8 < 8; ++s8) {
             float hi[4], lo[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { hi[k] = tf32_hi(gv[4 * s + k]); lo[k] = gv[4 * s + k] - hi[k]; }
-            const uint32_t so = (uint32_t)((s ^ sw) << 4);
+            for (int kk = 0; kk < 4; ++kk) { hi[kk] = tf32_hi(gv[4 * s8 + kk]); lo[kk] = tf32_hi(gv[4 * s8 + kk] - hi[kk]); }
+            const uint32_t so = (uint32_t)((s8 ^ sw) << 4);
             sts_f4(base + ST_MC_HI + rowo + so, hi[0], hi[1], hi[2], hi[3]);
             sts_f4(base + ST_MC_LO + rowo + so, lo[0], lo[1], lo[2], lo[3]);
           }
@@ -318,6 +342,9 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
         fence_proxy_async();
         mbar_arrive(bar_mc_full);
       }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vc[i] = vn[i];
+      cum_c = cum_n; cuml_c = cuml_n; cumQ_c = cumQ_n; cumQl_c = cumQl_n;
     }
   } else if (warp < ST_WARP_Y0) {
     // ===================================== X group: thread = channel, warp half = tokens [32 hx, 32 hx + 32) ======================================
@@ -338,11 +365,14 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
         const int buf = (int)(cc & 1); const uint32_t u = (uint32_t)(cc >> 1);
         const int ys = (int)(cc % 3); const uint32_t uy = (uint32_t)(cc / 3);
         const int64_t t0 = (int64_t)c * ST_Q + 32 * hx;             // first token of this warp's half
-        float xr[35];                                               // raw x of tokens t0 - 3 .. t0 + 31
+        float xr[35];                                               // raw x of tokens t0 - 3 .. t0 + 31 (zero outside the sequence)
+        {
+          const float* xrow = xp + (t0 - ST_HIST) * p.ldz;          // never dereferenced outside [i_lo, i_hi)
+          const int i_lo = t0 >= ST_HIST ? 0 : (int)(ST_HIST - t0);
+          const int64_t left = T - t0 + ST_HIST;
+          const int i_hi = left >= 35 ? 35 : (left > 0 ? (int)left : 0);
 #pragma unroll
-        for (int i = 0; i < 35; ++i) {
-          const int64_t t = t0 - ST_HIST + i;
-          xr[i] = (t >= 0 && t < T) ? __ldg(xp + (size_t)t * p.ldz) : 0.f;
+          for (int i = 0; i < 35; ++i) xr[i] = (i >= i_lo && i < i_hi) ? __ldg(xrow + (int64_t)i * p.ldz) : 0.f;
         }
         mbar_wait(bar_tprep(buf), u & 1);
         mbar_wait(bar_ysfree(ys), (uy & 1) ^ 1);
@@ -361,7 +391,7 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
             sts_f1(yst + (uint32_t)j * 512u, Dh * xv);
             const float xdv = lds_f1(dts + (buf * 64 + j) * 4) * xv;
             const float h_ = tf32_hi(xdv);
-            hi[jj] = __float_as_uint(h_); lo[jj] = __float_as_uint(xdv - h_);
+            hi[jj] = __float_as_uint(h_); lo[jj] = __float_as_uint(tf32_hi(xdv - h_));
           }
           tmem_st_32x16(xd + (uint32_t)(32 * hx + 16 * bt), hi);
           tmem_st_32x16(xd + 64u + (uint32_t)(32 * hx + 16 * bt), lo);
@@ -398,7 +428,7 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
         for (int n = 0; n < 16; ++n) {
           S[n] = fmaf(decay, S[n], ds[n]);
           const float h_ = tf32_hi(S[n]);
-          hi[n] = __float_as_uint(h_); lo[n] = __float_as_uint(S[n] - h_);
+          hi[n] = __float_as_uint(h_); lo[n] = __float_as_uint(tf32_hi(S[n] - h_));
         }
         const uint32_t sop = tmem_base + lane_sel + ST_COL_SOP + (uint32_t)(cc & 1) * 32u;
         tmem_st_32x16(sop, hi);
@@ -438,64 +468,70 @@ ssd_tc_kernel(const __grid_constant__ CUtensorMap tmapZ, const __grid_constant__
       const uint32_t idesc_g = umma_idesc_tf32(128, ST_Q), idesc_s = umma_idesc_tf32(128, ST_N);
       const uint64_t d_gah = umma_desc_k_sw128(base + ST_GA_HI), d_gal = umma_desc_k_sw128(base + ST_GA_LO);
       const uint64_t d_gbh = umma_desc_k_sw128(base + ST_GB_HI), d_gbl = umma_desc_k_sw128(base + ST_GB_LO);
-      int64_t cc = 0;
-      for (int64_t item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-        for (int c = 0; c < nch; ++c, ++cc) {
-          const int buf = (int)(cc & 1); const uint32_t u = (uint32_t)(cc >> 1);
-          const uint32_t d_yg = tmem_base + ST_COL_YG + (uint32_t)buf * 64u;
-          const uint32_t a_xh = tmem_base + ST_COL_XD + (uint32_t)buf * 128u, a_xl = a_xh + 64u;
-          // ---- G = C B^T (K = 16) ----
-          mbar_wait_one(bar_gop_full, (uint32_t)(cc & 1));
-          mbar_wait_one(bar_yg_free(buf), (u & 1) ^ 1);
+      const int64_t my_items = (p.nitems - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x;
+      const int64_t nwork = my_items * nch;
+      for (int64_t w = -1; w < nwork; ++w) {
+        if (w + 1 < nwork) {
+          // ---- G(w + 1) = C B^T (K = 16), one chunk ahead of the products that need M ----
+          const int64_t wn = w + 1;
+          const int bufn = (int)(wn & 1); const uint32_t un = (uint32_t)(wn >> 1);
+          const uint32_t d_g = tmem_base + ST_COL_YG + (uint32_t)bufn * 64u;
+          mbar_wait_one(bar_gop_full, (uint32_t)(wn & 1));
+          mbar_wait_one(bar_yg_free(bufn), (un & 1) ^ 1);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            umma_tf32(d_yg, d_gah + 2u * k, d_gbh + 2u * k, idesc_g, k > 0 ? 1u : 0u);
-            umma_tf32(d_yg, d_gah + 2u * k, d_gbl + 2u * k, idesc_g, 1u);
-            umma_tf32(d_yg, d_gal + 2u * k, d_gbh + 2u * k, idesc_g, 1u);
+            umma_tf32(d_g, d_gah + 2u * k, d_gbh + 2u * k, idesc_g, k > 0 ? 1u : 0u);
+            umma_tf32(d_g, d_gah + 2u * k, d_gbl + 2u * k, idesc_g, 1u);
+            umma_tf32(d_g, d_gal + 2u * k, d_gbh + 2u * k, idesc_g, 1u);
           }
-          umma_commit(bar_g_full(buf));
+          umma_commit(bar_g_full(bufn));
           umma_commit(bar_gop_free);
-          // ---- dS = Xd^T (B e^{cum_Q - cum})  (K = 64 tokens, N = 16) ----
-          mbar_wait_one(bar_xd_full(buf), u & 1);
-          mbar_wait_one(bar_bw_full, (uint32_t)(cc & 1));
-          if (cc > 0) mbar_wait_one(bar_sop_full, (uint32_t)((cc - 1) & 1));   // the Y group has read the previous dS (and written the state operand)
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t dbh = umma_desc_k_sw128(base + ST_BW_HI + (uint32_t)(ks >> 2) * 2048u) + 2u * (ks & 3);
-            const uint64_t dbl = umma_desc_k_sw128(base + ST_BW_LO + (uint32_t)(ks >> 2) * 2048u) + 2u * (ks & 3);
-            umma_tf32_ts(tmem_base + ST_COL_DS, a_xh + 8u * ks, dbh, idesc_s, ks > 0 ? 1u : 0u);
-            umma_tf32_ts(tmem_base + ST_COL_DS, a_xh + 8u * ks, dbl, idesc_s, 1u);
-            umma_tf32_ts(tmem_base + ST_COL_DS, a_xl + 8u * ks, dbh, idesc_s, 1u);
-          }
-          umma_commit(bar_ds_full);
-          // ---- Y^T = Xd^T M^T (K = 64 tokens) + S_prev (C e^{cum})^T (K = 16 states; not for the first chunk of a sequence: S = 0) ----
-          mbar_wait_one(bar_mc_full, (uint32_t)(cc & 1));
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t dbh = umma_desc_k_sw128(base + ST_MC_HI + (uint32_t)(ks >> 2) * 8192u) + 2u * (ks & 3);
-            const uint64_t dbl = umma_desc_k_sw128(base + ST_MC_LO + (uint32_t)(ks >> 2) * 8192u) + 2u * (ks & 3);
-            umma_tf32_ts(d_yg, a_xh + 8u * ks, dbh, idesc_g, ks > 0 ? 1u : 0u);
-            umma_tf32_ts(d_yg, a_xh + 8u * ks, dbl, idesc_g, 1u);
-            umma_tf32_ts(d_yg, a_xl + 8u * ks, dbh, idesc_g, 1u);
-          }
-          if (c > 0) {
-            const uint32_t a_sh = tmem_base + ST_COL_SOP + (uint32_t)((cc - 1) & 1) * 32u, a_sl = a_sh + 16u;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint64_t dbh = umma_desc_k_sw128(base + ST_MC_HI + 2u * 8192u) + 2u * k;
-              const uint64_t dbl = umma_desc_k_sw128(base + ST_MC_LO + 2u * 8192u) + 2u * k;
-              umma_tf32_ts(d_yg, a_sh + 8u * k, dbh, idesc_g, 1u);
-              umma_tf32_ts(d_yg, a_sh + 8u * k, dbl, idesc_g, 1u);
-              umma_tf32_ts(d_yg, a_sl + 8u * k, dbh, idesc_g, 1u);
-            }
-          }
-          umma_commit(bar_y_full(buf));
-          umma_commit(bar_xd_free(buf));
-          umma_commit(bar_mc_free);
         }
+        if (w < 0) continue;
+        const int buf = (int)(w & 1); const uint32_t u = (uint32_t)(w >> 1);
+        const int c = (int)(w % nch);                               // chunk index inside its sequence
+        const uint32_t d_yg = tmem_base + ST_COL_YG + (uint32_t)buf * 64u;
+        const uint32_t a_xh = tmem_base + ST_COL_XD + (uint32_t)buf * 128u, a_xl = a_xh + 64u;
+        // ---- dS = Xd^T (B e^{cum_Q - cum})  (K = 64 tokens, N = 16) ----
+        mbar_wait_one(bar_xd_full(buf), u & 1);
+        mbar_wait_one(bar_bw_full, (uint32_t)(w & 1));
+        if (w > 0) mbar_wait_one(bar_sop_full, (uint32_t)((w - 1) & 1));   // the Y group has read the previous dS (and written the state operand)
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dbh = umma_desc_k_sw128(base + ST_BW_HI + (uint32_t)(ks >> 2) * 2048u) + 2u * (ks & 3);
+          const uint64_t dbl = umma_desc_k_sw128(base + ST_BW_LO + (uint32_t)(ks >> 2) * 2048u) + 2u * (ks & 3);
+          umma_tf32_ts(tmem_base + ST_COL_DS, a_xh + 8u * ks, dbh, idesc_s, ks > 0 ? 1u : 0u);
+          umma_tf32_ts(tmem_base + ST_COL_DS, a_xh + 8u * ks, dbl, idesc_s, 1u);
+          umma_tf32_ts(tmem_base + ST_COL_DS, a_xl + 8u * ks, dbh, idesc_s, 1u);
+        }
+        umma_commit(bar_ds_full);
+        // ---- Y^T = Xd^T M^T (K = 64 tokens) + S_prev (C e^{cum})^T (K = 16 states; not for the first chunk of a sequence: S = 0) ----
+        mbar_wait_one(bar_mc_full, (uint32_t)(w & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dbh = umma_desc_k_sw128(base + ST_MC_HI + (uint32_t)(ks >> 2) * 8192u) + 2u * (ks & 3);
+          const uint64_t dbl = umma_desc_k_sw128(base + ST_MC_LO + (uint32_t)(ks >> 2) * 8192u) + 2u * (ks & 3);
+          umma_tf32_ts(d_yg, a_xh + 8u * ks, dbh, idesc_g, ks > 0 ? 1u : 0u);
+          umma_tf32_ts(d_yg, a_xh + 8u * ks, dbl, idesc_g, 1u);
+          umma_tf32_ts(d_yg, a_xl + 8u * ks, dbh, idesc_g, 1u);
+        }
+        if (c > 0) {
+          const uint32_t a_sh = tmem_base + ST_COL_SOP + (uint32_t)((w - 1) & 1) * 32u, a_sl = a_sh + 16u;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t dbh = umma_desc_k_sw128(base + ST_MC_HI + 2u * 8192u) + 2u * k;
+            const uint64_t dbl = umma_desc_k_sw128(base + ST_MC_LO + 2u * 8192u) + 2u * k;
+            umma_tf32_ts(d_yg, a_sh + 8u * k, dbh, idesc_g, 1u);
+            umma_tf32_ts(d_yg, a_sh + 8u * k, dbl, idesc_g, 1u);
+            umma_tf32_ts(d_yg, a_sl + 8u * k, dbh, idesc_g, 1u);
+          }
+        }
+        umma_commit(bar_y_full(buf));
+        umma_commit(bar_xd_free(buf));
+        umma_commit(bar_mc_free);
       }
     }
     __syncwarp();

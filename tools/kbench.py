@@ -169,6 +169,10 @@ M_C2 = 4096 * 512
 CASES = {
     "ssd_c2": lambda: case_ssd(4096),
     "ssd_small": lambda: case_ssd(512),
+    "ssd_c2_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(4096))[1],
+    "ssd_small_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(512))[1],
+    "ssd_c2_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(4096))[1],
+    "ssd_small_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(512))[1],
     "ln_c2": lambda: case_ln(M_C2, 128),
     "lin_in_tc3": lambda: case_linear(M_C2, 161, 128, "none", "tc3"),
     "lin_in_ln_tc3": lambda: case_linear_ln(M_C2, 161, 128, 168),
