@@ -117,7 +117,7 @@ def test_normattn_eta_golden(ops, fn, use_off):
     ref = g["eta_%s_%d" % (fn, use_off)][..., 0]
     fin = np.isfinite(ref)
     assert (np.isfinite(eta) == fin).all()
-    np.testing.assert_allclose(eta[fin], ref[fin], rtol=5e-4)
+    np.testing.assert_allclose(eta[fin], ref[fin], rtol=2e-4 if fn == "exp" else 2e-5)   # vs the reference's own fp32 eta; vs fp64: test_parity_fullshape_gpu.py
     # n itself against the fp64 formula
     x64 = g["x"].astype(np.float64)
     raw = x64 @ g["weight"][rows].astype(np.float64).T + g["bias"][rows] + (g["offset"] if use_off else 0)

@@ -90,11 +90,11 @@ def test_transformer_model_pass_vs_reference(eig, name):
         r = g["eig"][..., i:i + 1]
         assert eta.shape == r.shape and eta.dtype == np.float64
         fin = np.isfinite(r)
-        np.testing.assert_allclose(eta[fin], r[fin], rtol=3e-4)
+        np.testing.assert_allclose(eta[fin], r[fin], rtol=5e-5)      # measured worst 3.3e-6 (tests/test_parity_fullshape_gpu.py prints it per model)
     res = A.transformer_pass(model, X, cfg)
     e = res.eig_host()
     fin = np.isfinite(g["eig"])
-    np.testing.assert_allclose(e[fin], g["eig"][fin], rtol=3e-4)
+    np.testing.assert_allclose(e[fin], g["eig"][fin], rtol=5e-5)
     pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
     with np.errstate(invalid="ignore"):
         np.testing.assert_array_equal(pct, O.threshold_analysis(e, O.THRESHOLDS_RADIUS))
@@ -250,7 +250,7 @@ def test_c1_linear_attention_mqar_pass_vs_reference(eig):
     assert np.abs(res.x_last.cpu().numpy() - g["act_2"]).max() <= 3e-5 * np.abs(g["act_2"]).max()
     e = res.eig_host()
     assert e.shape == g["eig"].shape == (8, 63, 1, 2) and e.dtype == np.float64
-    np.testing.assert_allclose(e, g["eig"], rtol=3e-4)
+    np.testing.assert_allclose(e, g["eig"], rtol=5e-5)
     pct = E.percentages_from_counts(res.counts.cpu().numpy(), res.n_per_seq, 7)
     assert np.abs(pct - g["percentage"]).max() <= 100.0 / 63 + 1e-9
 
@@ -287,7 +287,7 @@ def test_c5_shaped_norm_attention_pass_vs_oracle(eig):
     assert np.abs(res.x_last.cpu().numpy() - xr).max() <= 5e-5 * np.abs(xr).max()
     e = res.eig_host()
     fin = np.isfinite(ref)
-    np.testing.assert_allclose(e[fin], ref[fin], rtol=3e-4)
+    np.testing.assert_allclose(e[fin], ref[fin], rtol=3e-4)      # softplus gate with offsets 4..9: d ln eta = dz, |z| ~ 10: conditioning, see test_parity_fullshape_gpu.py
 
 
 def test_c3_shaped_lru_layer_vs_oracle(eig):
