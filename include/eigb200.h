@@ -137,6 +137,19 @@ int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int6
  * int64 buffer is everything a rank contributes to the single all-reduce of the path (eigb200_stats_allreduce below). */
 int eigb200_count_moments_layers(void* stream, const int32_t* d_counts, int64_t L, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq);
 
+/* The ONE exchange step of the path: every GPU holds the moments (eigb200_count_moments_layers: 2 x L x inner x 8 int64) of ITS slice of the analysis
+ * batch; their sum over the GPUs is all that np.mean / np.std over the batch axis need (analysis/eval_eig.py:620-623).  Integer sums: order independent, the
+ * combined statistics are bit-reproducible.  eigb200_stats_allreduce sums d_moments in place over the ranks of `comm` (an ncclComm_t: one process per GPU as
+ * torch.distributed / the reference's launcher creates it, or from eigb200_stats_comm_init_all for ONE process that drives several GPUs; then bracket the per-GPU
+ * calls with eigb200_stats_group_start / _end).  Stream-ordered on `stream` of the current device.  NCCL is dlopen'ed at run time (the copy already in the process,
+ * else $EIGB200_NCCL_LIB, else libnccl.so.2); EIGB200_EUNSUPPORTED when there is none (eigb200_stats_available() == 0). */
+int eigb200_stats_available(void);
+int eigb200_stats_comm_init_all(int ndev, const int* devs, void** comms);
+int eigb200_stats_comm_destroy(void* comm);
+int eigb200_stats_group_start(void);
+int eigb200_stats_group_end(void);
+int eigb200_stats_allreduce(void* stream, void* comm, int64_t* d_moments, size_t count);
+
 /* ---- K2a: diagonal complex recurrence  h_t = lam * h_{t-1} + Bu_t  ---------------------------------------------------
  * What jax.lax.associative_scan(binary_operator_diag, (Lambda_elements, Bu_elements)) evaluates (models/lru.py:14-19, :95;
  * models/s5.py:51-62, :82, :85 with reverse).  complex64 as interleaved (re,im) float pairs.

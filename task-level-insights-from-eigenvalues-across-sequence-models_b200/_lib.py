@@ -39,6 +39,12 @@ SIGNATURES = {
     "eigb200_ratio_hist": [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_count_moments": [_vp, _vp, _i64, _i64, _vp, _vp],
     "eigb200_count_moments_layers": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
+    "eigb200_stats_available": [],
+    "eigb200_stats_comm_init_all": [_i, C.POINTER(_i), C.POINTER(_vp)],
+    "eigb200_stats_comm_destroy": [_vp],
+    "eigb200_stats_group_start": [],
+    "eigb200_stats_group_end": [],
+    "eigb200_stats_allreduce": [_vp, _vp, _vp, _sz],
     "eigb200_diag_scan": [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i],
     "eigb200_ssd_scan": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i],
     "eigb200_mamba_conv_ssd": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i],

@@ -94,3 +94,43 @@ def _uneven_all_gather(parts, t, sizes):
         if r == dist.get_rank():
             p.copy_(t)
         dist.broadcast(p, src=r)
+
+
+class StatsComm:
+    """Single-process, several-GPU form of the exchange step through the C ABI (include/eigb200.h: eigb200_stats_comm_init_all / eigb200_stats_allreduce):
+    one communicator per listed device, allreduce(moments) sums the per-device (2, L, inner, 8) int64 moment buffers in place on every device."""
+
+    def __init__(self, devices):
+        import ctypes as C
+        from . import _lib as L
+        self._L, self._C = L, C
+        self.devices = [int(d) for d in devices]
+        lib = L.load()
+        if not lib.eigb200_stats_available():
+            raise L.Eigb200Error("NCCL is not available to libeigb200.so (set EIGB200_NCCL_LIB)")
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        comms = (C.c_void_p * len(self.devices))()
+        L.check(lib.eigb200_stats_comm_init_all(len(self.devices), devs, comms), "eigb200_stats_comm_init_all")
+        self.comms = [C.c_void_p(c) for c in comms]
+
+    def allreduce(self, moments):
+        """moments: one contiguous int64 CUDA tensor per device of the communicator (same shape); summed in place."""
+        L, C = self._L, self._C
+        lib = L.load()
+        assert len(moments) == len(self.devices)
+        L.check(lib.eigb200_stats_group_start(), "eigb200_stats_group_start")
+        try:
+            for dev, comm, m in zip(self.devices, self.comms, moments):
+                assert m.is_cuda and m.dtype == torch.int64 and m.is_contiguous() and m.device.index == dev
+                L.check(lib.eigb200_set_device(dev), "eigb200_set_device")
+                st = torch.cuda.current_stream(m.device).cuda_stream
+                L.check(lib.eigb200_stats_allreduce(C.c_void_p(st), comm, C.c_void_p(m.data_ptr()), m.numel()), "eigb200_stats_allreduce")
+        finally:
+            L.check(lib.eigb200_stats_group_end(), "eigb200_stats_group_end")
+        return moments
+
+    def close(self):
+        lib = self._L.load()
+        for c in self.comms:
+            lib.eigb200_stats_comm_destroy(c)
+        self.comms = []

@@ -186,3 +186,28 @@ def test_full_size_properties_c2(ops):
     z = x[idx].double() @ W.double().T + dt_bias.double()
     ref = torch.exp(torch.nn.functional.softplus(z) * -torch.exp(A_log.double()))
     assert_eig_close(lam[idx].cpu().numpy(), ref.cpu().numpy(), rtol=1e-5)
+
+
+def test_stats_allreduce_c_abi(ops):
+    """The exchange step through the C ABI (eigb200_stats_comm_init_all / eigb200_stats_allreduce, NCCL dlopen'ed at run time): every visible GPU (1 on the
+    driver's test box, 2+ under `gpurun --gpus N`) contributes the moments of its slice; the in-place int64 sum equals the moments of the whole batch."""
+    import eigb200.dist as D
+    ndev = min(torch.cuda.device_count(), 4)
+    rng = np.random.default_rng(0)
+    L_, B, H = 3, 16 * ndev, 2
+    c = rng.integers(0, 513, (L_, B, H, 8)).astype(np.int32)
+    comm = D.StatsComm(list(range(ndev)))
+    try:
+        parts = []
+        for d in range(ndev):
+            with torch.cuda.device(d):
+                sl = torch.from_numpy(np.ascontiguousarray(c[:, d * 16:(d + 1) * 16])).cuda(d)
+                parts.append(ops.count_moments_layers(sl))
+        comm.allreduce(parts)
+        for d in range(ndev):
+            torch.cuda.synchronize(d)
+        ref = np.stack([c.astype(np.int64).sum(1), (c.astype(np.int64) ** 2).sum(1)])
+        for d in range(ndev):
+            np.testing.assert_array_equal(parts[d].cpu().numpy(), ref)
+    finally:
+        comm.close()
