@@ -137,6 +137,14 @@ int eigb200_count_moments(void* stream, const int32_t* d_counts, int64_t B, int6
  * int64 buffer is everything a rank contributes to the single all-reduce of the path (eigb200_stats_allreduce below). */
 int eigb200_count_moments_layers(void* stream, const int32_t* d_counts, int64_t L, int64_t B, int64_t inner, int64_t* d_sum, int64_t* d_sumsq);
 
+/* Log-spaced histogram / quantiles of a (B,N,inner) array per `inner` column (the finer, on-device view of the eigenvalue radii per layer / head / state that
+ * the north star asks for; the reference itself only has the fixed threshold bins above).  d_hist (inner, nbins + 3) int64, ACCUMULATED (zero it first; sum it
+ * over batches / GPUs with eigb200_stats_allreduce): slot 0 = v < lo (incl. v <= 0), slots 1..nbins = log-spaced bins of [lo, hi), slot nbins + 1 = v >= hi,
+ * slot nbins + 2 = NaN.  eigb200_hist_quantiles: d_q (nq) doubles in [0,1] (device) -> d_out (inner, nq) float64, log-linear interpolation inside a bin (NaN
+ * entries excluded; values outside [lo, hi) report the range edge). */
+int eigb200_log_hist(void* stream, const void* d_values, int dtype, int64_t B, int64_t N, int64_t inner, double lo, double hi, int nbins, int64_t* d_hist);
+int eigb200_hist_quantiles(void* stream, const int64_t* d_hist, int64_t inner, double lo, double hi, int nbins, const double* d_q, int nq, double* d_out);
+
 /* The ONE exchange step of the path: every GPU holds the moments (eigb200_count_moments_layers: 2 x L x inner x 8 int64) of ITS slice of the analysis
  * batch; their sum over the GPUs is all that np.mean / np.std over the batch axis need (analysis/eval_eig.py:620-623).  Integer sums: order independent, the
  * combined statistics are bit-reproducible.  eigb200_stats_allreduce sums d_moments in place over the ranks of `comm` (an ncclComm_t: one process per GPU as

@@ -39,6 +39,8 @@ SIGNATURES = {
     "eigb200_ratio_hist": [_vp, _vp, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _dp, _i, _i],
     "eigb200_count_moments": [_vp, _vp, _i64, _i64, _vp, _vp],
     "eigb200_count_moments_layers": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
+    "eigb200_log_hist": [_vp, _vp, _i, _i64, _i64, _i64, C.c_double, C.c_double, _i, _vp],
+    "eigb200_hist_quantiles": [_vp, _vp, _i64, C.c_double, C.c_double, _i, _vp, _i, _vp],
     "eigb200_stats_available": [],
     "eigb200_stats_comm_init_all": [_i, C.POINTER(_i), C.POINTER(_vp)],
     "eigb200_stats_comm_destroy": [_vp],

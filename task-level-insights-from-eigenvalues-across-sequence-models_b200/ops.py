@@ -171,6 +171,32 @@ def ratio_hist(a, mode: int, thresholds=THRESHOLDS_RADIUS, want_out=True, counts
     return out, counts
 
 
+def log_hist(a, lo=1e-8, hi=1e2, nbins=512, hist=None):
+    """Log-spaced histogram of a (B,N,inner...) f32|f64 array per inner column -> (inner, nbins + 3) int64, accumulated into `hist` when given."""
+    a = _prep(a, name="a")
+    if a.dtype not in (torch.float32, torch.float64):
+        raise L.Eigb200Error("log_hist: float32 or float64 input required")
+    B, N = a.shape[0], a.shape[1]
+    inner = int(np.prod(a.shape[2:])) if a.dim() > 2 else 1
+    lib = _enter(a)
+    if hist is None:
+        hist = torch.zeros(inner, nbins + 3, dtype=torch.int64, device=a.device)
+    assert hist.is_contiguous() and hist.dtype == torch.int64 and tuple(hist.shape) == (inner, nbins + 3)
+    _call(lib, "eigb200_log_hist", _stream(a), _p(a), L.F32 if a.dtype == torch.float32 else L.F64, B, N, inner, float(lo), float(hi), int(nbins), _p(hist))
+    return hist
+
+
+def hist_quantiles(hist, qs, lo=1e-8, hi=1e2):
+    """Quantiles (inner, len(qs)) float64 from a log_hist histogram, on the device."""
+    hist = _prep(hist, torch.int64)
+    inner, nslot = hist.shape
+    q = torch.as_tensor(np.asarray(qs, np.float64), device=hist.device)
+    lib = _enter(hist)
+    out = torch.empty(inner, q.numel(), dtype=torch.float64, device=hist.device)
+    _call(lib, "eigb200_hist_quantiles", _stream(hist), _p(hist), inner, float(lo), float(hi), nslot - 3, _p(q), q.numel(), _p(out))
+    return out
+
+
 def count_moments(counts):
     counts = _prep(counts, torch.int32)
     B = counts.shape[0]

@@ -171,3 +171,37 @@ def test_full_size_pass_properties_c2(A):
     idx = [0, 511, 1023]
     ref, _ = O.mamba_eval_pass(X[idx].cpu().numpy(), {k: v.numpy() for k, v in sd.items()}, _mamba_ocfg(cfg), np.float64)
     assert_eig_close(eig[idx].cpu().numpy(), ref, rtol=3e-5)
+
+
+def test_eval_eig_optional_quantiles(A, tmp_path, monkeypatch):
+    """`quantiles:` in the analysis YAML (beyond the reference's keys): on-device log-spaced histogram of the radii per (head, layer) and its quantiles, saved next to
+    the reference's 10 files; without the key nothing extra is written and the 6-tuple is unchanged."""
+    sd, cfg, g = golden_model("model_mamba2")
+    ckpt = str(tmp_path / "model.pth")
+    torch.save({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, ckpt)
+    X = torch.from_numpy(g["X"])
+    loader = [(X, torch.zeros(X.shape[0]), None)]
+    monkeypatch.chdir(tmp_path)
+    qs = [0.1, 0.5, 0.9]
+    outs = {}
+    for tag, conf in (("plain", {"batch_size": X.shape[0], "save_path": str(tmp_path) + "/plain_"}),
+                      ("q", {"batch_size": X.shape[0], "save_path": str(tmp_path) + "/q_", "quantiles": qs})):
+        args = {"seed": 1919, "model": dict(cfg, layer="mamba", seq_len=X.shape[1]), "train": {"lr": 0.01}, "dataset": {"name": "MQAR"}}
+        outs[tag] = A.eval_eig(args, conf, None, args["dataset"], loader, ckpt, 0.9)
+    for a, b in zip(outs["plain"], outs["q"]):
+        np.testing.assert_array_equal(a, b)
+    dq = [d for d in os.listdir(tmp_path) if d.startswith("q_")][0]
+    dp = [d for d in os.listdir(tmp_path) if d.startswith("plain_")][0]
+    assert not os.path.exists(tmp_path / dp / "radius_quantiles.npy")
+    quant = np.load(tmp_path / dq / "radius_quantiles.npy"); hist = np.load(tmp_path / dq / "radius_loghist.npy")
+    eig = outs["q"][0]
+    H, L = eig.shape[2], eig.shape[3]
+    assert quant.shape == (3, H, L) and hist.shape == (H * L, 515) and hist.sum() == eig.size
+    width = (1e2 / 1e-8) ** (1 / 512)
+    n = eig.shape[0] * eig.shape[1]
+    for h in range(H):
+        for l in range(L):
+            srt = np.sort(np.abs(eig[:, :, h, l].astype(np.float64)).ravel())
+            for qi, qq in enumerate(qs):                           # between neighbouring order statistics, +- one bin
+                k = int(np.ceil(qq * n))
+                assert srt[max(k - 2, 0)] / width / 1.001 <= quant[qi, h, l] <= srt[min(k, n - 1)] * width * 1.001, (h, l, qq, quant[qi, h, l])

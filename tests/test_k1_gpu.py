@@ -211,3 +211,36 @@ def test_stats_allreduce_c_abi(ops):
             np.testing.assert_array_equal(parts[d].cpu().numpy(), ref)
     finally:
         comm.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("B,N,inner", [(7, 300, 5), (64, 512, 4), (3, 50, 70)])
+def test_log_hist_and_quantiles(ops, dtype, B, N, inner):
+    """On-device log-spaced histogram + quantiles per (layer, head) column: exact bin counts against NumPy on the same fp32 bin coordinate, quantiles within one
+    bin width of np.quantile; special values (0, negative, NaN, beyond the range) land in their slots; a second call accumulates."""
+    rng = np.random.default_rng(B + inner)
+    v = np.exp(rng.normal(-3, 3, (B, N, inner))).astype(dtype)
+    v[0, 0, 0] = 0.0; v[0, 1, 0] = -1.0; v[0, 2, 0] = np.nan; v[0, 3, 0] = 1e9; v[0, 4, 0] = 1e-12
+    lo, hi, nb = 1e-8, 1e2, 512
+    h = ops.log_hist(_dev(v), lo, hi, nb)
+    hh = h.cpu().numpy()
+    assert hh.shape == (inner, nb + 3) and hh.sum() == v.size
+    x = v.astype(np.float32).reshape(-1, inner)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        t = (np.log2(x) - np.float32(np.log2(lo))) * np.float32(nb / (np.log2(hi) - np.log2(lo)))
+    slot = np.where(np.isnan(x), nb + 2, np.where(~(x > 0), 0, np.where(t < 0, 0, np.where(t >= nb, nb + 1, 1 + np.floor(np.nan_to_num(t, nan=0.0)).astype(np.int64)))))
+    ref = np.stack([np.bincount(slot[:, c], minlength=nb + 3) for c in range(inner)])
+    assert np.abs(hh - ref).sum() <= max(4, v.size // 20000)          # __log2f vs np.log2 may move a value sitting on a bin edge
+    assert hh[0, 0] >= 3 and hh[0, nb + 1] >= 1 and hh[0, nb + 2] == 1
+    qs = [0.05, 0.25, 0.5, 0.75, 0.95]
+    q = ops.hist_quantiles(h, qs, lo, hi).cpu().numpy()
+    width = (hi / lo) ** (1.0 / nb)
+    n = B * N
+    for c in range(1, inner):                                        # column 0 holds the planted specials
+        srt = np.sort(v[:, :, c].astype(np.float64).ravel())
+        for qi, qq in enumerate(qs):                                 # the value where the cumulative count reaches q n: between neighbouring order statistics, +- a bin
+            k = int(np.ceil(qq * n))
+            lo_v, hi_v = srt[max(k - 2, 0)] / width / 1.001, srt[min(k, n - 1)] * width * 1.001
+            assert lo_v <= q[c, qi] <= hi_v, (c, qq, q[c, qi], lo_v, hi_v)
+    h2 = ops.log_hist(_dev(v), lo, hi, nb, hist=h)
+    np.testing.assert_array_equal(h2.cpu().numpy(), 2 * hh)
