@@ -61,18 +61,6 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// S * GELU(z), exact-erf form through Abramowitz-Stegun 7.1.26 (gelu_fast_f of common.cuh with the operand scale folded into the leading 0.5)
-__device__ __forceinline__ float gelu_fast_scaled_f(float z, float half_scale) {
-  const float x = fabsf(z) * 0.70710678118654752440f;
-  const float t = fast_rcp_f(fmaf(0.3275911f, x, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float q = p * t * fast_exp_f(-x * x);
-  return half_scale * z * (z >= 0.f ? 2.f - q : q);
-}
-
 __global__ void __launch_bounds__(FG_THREADS, 1)
 gemm_out_glu_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW1h, const __grid_constant__ CUtensorMap tmapW1l,
                     const __grid_constant__ CUtensorMap tmapW2h, const __grid_constant__ CUtensorMap tmapW2l, const FgParams p) {
@@ -321,8 +309,9 @@ gemm_out_glu_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       uint32_t hi2[16], lo2[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float o0 = gelu_fast_scaled_f(fmaf(v[2 * i], osc1, b1s[32 * g + 2 * i]), 0.5f * FG_SA);
-        const float o1 = gelu_fast_scaled_f(fmaf(v[2 * i + 1], osc1, b1s[32 * g + 2 * i + 1]), 0.5f * FG_SA);
+        const float z0 = fmaf(v[2 * i], osc1, b1s[32 * g + 2 * i]), z1 = fmaf(v[2 * i + 1], osc1, b1s[32 * g + 2 * i + 1]);
+        const float o0 = gelu_fast_scaled_f(z0, z0 * FG_SA, FG_SA);      // S_a GELU(z): the operand scale of GEMM 2 rides in the constants
+        const float o1 = gelu_fast_scaled_f(z1, z1 * FG_SA, FG_SA);
         amax = fmaxf(amax, fmaxf(fabsf(o0), fabsf(o1)));
         hi2[i] = pack_f16x2(o0, o1);
         lo2[i] = pack_f16x2(o0 - f16_lo_to_f32(hi2[i]), o1 - f16_hi_to_f32(hi2[i]));

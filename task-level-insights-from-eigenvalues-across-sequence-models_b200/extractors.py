@@ -138,6 +138,30 @@ def get_eig_att_softmax(x, layer, d_qk, num_heads, d_model):
     return np.expand_dims(eta.cpu().numpy(), axis=-1)
 
 
+def get_eig_from_qkv_att_softmax_device(q, k, v=None, want_eig=True, counts=None):
+    """notebooks/lm_eigvals.ipynb, cell 13 (`get_eig_from_qkv_att_softmax`): the softmax-attention eigenvalues from hooked q_proj / k_proj outputs of a
+    pretrained LM (cells 11-16: OLMo-3).  q (B,T,Hq,d), k (B,T,Hkv,d) in any float dtype (the notebook hooks fp16 activations); v is accepted and unused,
+    as in the notebook.  Grouped-query attention: with Hkv < Hq every query head h reads key head h // (Hq / Hkv), the `repeat_kv` convention of the
+    HF models the notebook loads (the notebook's own einsum needs Hkv == Hq; OLMo-3-7B has 32 / 32).  Same formula and masking quirk as
+    get_eig_att_softmax (eval_eig.py:43-95), O(T) memory.  -> (eta (B,T-1,Hq) float64 device tensor, counts (B,Hq,8))."""
+    q = _cuda(q).float(); k = _cuda(k).float()
+    B, T, Hq, d = q.shape
+    Hkv = k.shape[2]
+    if k.shape[0] != B or k.shape[1] != T or k.shape[3] != d or Hq % Hkv != 0:
+        raise L.Eigb200Error("get_eig_from_qkv_att_softmax: q %s and k %s do not describe (grouped-query) attention heads" % (tuple(q.shape), tuple(k.shape)))
+    if Hkv != Hq:
+        k = k.repeat_interleave(Hq // Hkv, dim=2)
+    qk = torch.cat([q.reshape(B * T, Hq * d), k.reshape(B * T, Hq * d)], dim=1).contiguous()          # [q (h d) | k (h d)], the layout softmax_nu reads
+    nu, m = ops.softmax_nu(qk, 2 * Hq * d, B, T, Hq, d, Hq * d)
+    return ops.softmax_eta(nu, m, want_out=want_eig, counts=counts)
+
+
+def get_eig_from_qkv_att_softmax(q, k, v=None):
+    """Drop-in for the notebook function: -> eta (B,T-1,Hq,1) float64 numpy."""
+    eta, _ = get_eig_from_qkv_att_softmax_device(q, k, v)
+    return np.expand_dims(eta.cpu().numpy(), axis=-1)
+
+
 # ---- threshold statistics ---------------------------------------------------------------------------------------------------
 def threshold_counts_device(eig_val, thresholds, compare="float64"):
     """eig_val (B,N,...) device tensor -> counts (B, inner, 8) int32 (slots: see include/eigb200.h)."""

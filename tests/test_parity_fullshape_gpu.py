@@ -141,6 +141,24 @@ def test_transformer_extractor_on_device_activations_vs_fp64(eig, name):
     assert worst_ref <= 5e-5
 
 
+@pytest.mark.parametrize("Hq,Hkv,dtype", [(4, 4, np.float32), (8, 2, np.float32), (6, 1, np.float16)])
+def test_notebook_qkv_softmax_extractor_gqa(eig, Hq, Hkv, dtype):
+    """notebooks/lm_eigvals.ipynb cell 13 on hooked q / k projections, incl. grouped-query heads (query head h -> key head h // (Hq / Hkv)) and fp16 inputs:
+    against the oracle's closed form of the same formula on the widened keys."""
+    A, Ly, E, S, ops = eig
+    rng = np.random.default_rng(Hq * 10 + Hkv)
+    B, T, d = 2, 150, 32
+    q = (rng.normal(size=(B, T, Hq, d)) * 0.5).astype(dtype); k = (rng.normal(size=(B, T, Hkv, d)) * 0.5).astype(dtype)
+    eta = E.get_eig_from_qkv_att_softmax(torch.from_numpy(q), torch.from_numpy(k), None)
+    assert eta.shape == (B, T - 1, Hq, 1) and eta.dtype == np.float64
+    kw = np.repeat(k.astype(np.float32), Hq // Hkv, axis=2)
+    ref = O.softmax_eta_closed(q.astype(np.float32).astype(np.float64), kw.astype(np.float64), np.float64)
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(eta[fin], ref[fin], rtol=1e-5)
+    with pytest.raises(Exception):
+        E.get_eig_from_qkv_att_softmax(torch.from_numpy(q[:, :, :3]), torch.from_numpy(k[:, :, :2] if Hkv >= 2 else np.concatenate([k, k], 2)), None)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # BASELINE C5 at full sequence length and depth (sampled sequences vs the fp64 oracle)
 # ----------------------------------------------------------------------------------------------------------------------
