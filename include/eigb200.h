@@ -257,6 +257,19 @@ int eigb200_out_glu_fused(void* stream, const float* d_y, int64_t ldy, const voi
                           const void* d_ws_glu, const float* d_bias_glu, float* d_C, int64_t ldc, const float* d_R, int64_t ldr,
                           int64_t M, int D, int K1, const float* d_W_gate, float* d_partials);
 
+/* The FRONT of MambaBlock.forward as ONE kernel: prenorm LayerNorm (models/mamba.py:329-331) -> in_proj (:118) -> split [x | B | C | dt] -> conv1d + SiLU
+ * (:123-127) -> softplus(dt + dt_bias), A = -exp(A_log) (:129-133) -> mamba_chunk_scan_combined(..., D=D) (:138-150).  The projection is computed transposed
+ * on the tensor cores (weights = A operand, a 32-token chunk = B operand), so the accumulator in TMEM already has the thread = channel layout of the
+ * recurrence and the in_proj output never reaches HBM.
+ *   d_x (B*T, D) row stride ldx, 16-byte aligned rows; d_ln_stats (B*T, 2) = (mean, rstd) per row (as eigb200_linear_ln);
+ *   d_ws_in: workspace filled by eigb200_linear_prepare(W_in, NULL, gamma, beta, N = d_inner + 2 N + 1, K = D, EPI_NONE) under the fp16-split precision;
+ *   d_conv_w (d_inner + 2 N, kconv), d_conv_b (d_inner + 2 N), d_dt_bias (1), d_A_log (1), d_D (1) or NULL; d_y (B*T, d_inner) row stride ldy.
+ * Shapes (eigb200_mamba_front_fused_supported): D = d_inner = 128, one head, one group, d_state 16, 1 <= kconv <= 4.  Any T >= 1. */
+int eigb200_mamba_front_fused_supported(int D, int d_inner, int H, int G, int N, int kconv);
+int eigb200_mamba_front_fused(void* stream, const float* d_x, int64_t ldx, const float* d_ln_stats, const void* d_ws_in,
+                              const float* d_conv_w, const float* d_conv_b, int kconv, const float* d_dt_bias, const float* d_A_log,
+                              const float* d_D, float* d_y, int64_t ldy, int64_t B, int64_t T, int D, int d_inner, int N);
+
 /* TokenEmbeddings.forward (models/common.py:160-176): out[b,t,:] = word[ids[b,t],:] (+ pos[t,:] if d_pos != NULL). ids int64. */
 int eigb200_embedding(void* stream, const int64_t* d_ids, const float* d_word, const float* d_pos, float* d_out,
                       int64_t B, int64_t T, int D, int64_t vocab);

@@ -57,6 +57,8 @@ SIGNATURES = {
     "eigb200_linear": [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _sz],
     "eigb200_out_glu_fused_supported": [_i, _i],
     "eigb200_out_glu_fused": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp],
+    "eigb200_mamba_front_fused_supported": [_i, _i, _i, _i, _i, _i],
+    "eigb200_mamba_front_fused": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i],
     "eigb200_gemm_precision": [],
     "eigb200_set_gemm_precision": [_i],
     "eigb200_gemm_overflow": [_vp, _i, C.POINTER(_i)],

@@ -100,6 +100,7 @@ class MambaBlockDev:
         self.gemm_mode = cfg.get("_gemm_mode", "auto")
         # the parameters are constants of an analysis run: their tensor-core operand form is built once per layer (ops.linear_prepare), not per call
         self.prepare_weights = os.environ.get("EIGB200_PREPARE_WEIGHTS", "1") != "0"
+        self.fuse_front = os.environ.get("EIGB200_FUSE_FRONT", "1") != "0"    # LayerNorm + in_proj + conv + SSD scan as one kernel
         self.fuse_tail = os.environ.get("EIGB200_FUSE_TAIL", "1") != "0"      # out_proj + GELU + GLU + residual (+ extractor partials) as one kernel
         self._prep_ws = {}
 
@@ -153,13 +154,21 @@ class MambaBlockDev:
         d_in_proj = m.in_proj.weight.shape[0]
         ldz = _pad8(d_in_proj)
         tc = self.gemm_mode in ("auto", "tc3") and B * T >= 1024 and self.prepare_weights
-        if stats is not None and self.fuses_layernorm():
+        y = None
+        if (stats is not None and self.fuses_layernorm() and tc and self.fuse_front and m.conv_w is not None and
+                ops.mamba_front_fused_supported(D, m.d_inner, m.nheads, m.ngroups, m.d_state, m.conv_w.shape[1])):
+            # LayerNorm -> in_proj -> conv + SiLU -> SSD scan (:329-331, :118-150) in one kernel: the projection never reaches HBM
+            y = ops.mamba_front_fused(x, stats, self._prepared("in_ln", m.in_proj.weight, None, "none", self.norm.weight, self.norm.bias),
+                                      m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, m.d_inner, m.d_state)
+        elif stats is not None and self.fuses_layernorm():
             z = ops.linear_ln(x, stats, self.norm.weight, self.norm.bias, m.in_proj.weight, None, ldc=ldz,
                               prepared=self._prepared("in_ln", m.in_proj.weight, None, "none", self.norm.weight, self.norm.bias) if tc else None)
         else:
             xn = ops.layernorm(x, self.norm.weight, self.norm.bias) if self.prenorm else x
             z = ops.linear(xn, m.in_proj.weight, None, ldc=ldz, mode=self.gemm_mode)              # (B*T, ldz) = [x | B | C | dt | pad]
-        if self.pseudoLTI:
+        if y is not None:
+            pass
+        elif self.pseudoLTI:
             y = self._ssd_lti(z, ldz, B, T)
         else:
             y = ops.mamba_conv_ssd(z, ldz, m.conv_w, m.conv_b, m.dt_bias, m.A_log, m.D, B, T, m.nheads, m.headdim, m.ngroups, m.d_state)

@@ -473,6 +473,25 @@ def out_glu_fused(y, prepared_out, bias_out, prepared_glu, bias_glu, residual, w
     return out, (partials if w_gate is not None else None)
 
 
+def mamba_front_fused_supported(D, d_inner, H, G, N, kconv) -> bool:
+    return gemm_precision() == "f16x3" and int(L.load().eigb200_mamba_front_fused_supported(int(D), int(d_inner), int(H), int(G), int(N), int(kconv))) == 1
+
+
+def mamba_front_fused(x, stats, prepared_in, conv_w, conv_b, dt_bias, A_log, D, d_inner, N, out=None):
+    """LayerNorm -> in_proj -> conv + SiLU -> softplus(dt) -> SSD scan in one kernel (models/mamba.py:329-331, :118-150): x (B,T,D) -> y (B,T,d_inner).
+    stats (B,T,2) = (mean, rstd) of the rows of x; prepared_in = linear_prepare(W_in, None, "none", gamma, beta) under the fp16-split precision."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and stats.is_cuda and stats.dtype == torch.float32 and stats.is_contiguous()
+    B, T, Dm = x.shape
+    lib = _enter(x)
+    conv_w = _prep(conv_w, torch.float32).reshape(conv_w.shape[0], -1)
+    conv_b = _prep(conv_b, torch.float32)
+    y = out if out is not None else torch.empty(B, T, d_inner, dtype=torch.float32, device=x.device)
+    _call(lib, "eigb200_mamba_front_fused", _stream(x), _p(x), Dm, _p(stats), _p(prepared_in), _p(conv_w), _p(conv_b), conv_w.shape[1],
+          _p(_prep(dt_bias, torch.float32)), _p(_prep(A_log, torch.float32)), _p(_prep(D, torch.float32) if D is not None else None),
+          _p(y), d_inner, B, T, Dm, d_inner, N, tag="D%d P%d N%d ln+in_proj+conv+ssd" % (Dm, d_inner, N))
+    return y
+
+
 def mamba2_eig_partials(partials, B, T, dt_bias, A_log, thresholds: Sequence[float] = THRESHOLDS_RADIUS, want_lam=True, counts=None,
                         compare="float64", lam_out=None, rowstats_out=None, ln_eps: float = 1e-5):
     """Finish the Mamba-2 extractor (H = 1) from the GLU epilogue's partials.  -> (lam (B,T,1) | None, counts (B,1,8))."""

@@ -133,6 +133,22 @@ def case_ssd(B, T=512, H=1, P=128, G=1, N=16):
     return fn, B * T * (Cn + H + H * P) * 4, B * T * H
 
 
+def case_front(B, T=512, D=128, P=128, N=16):
+    """LayerNorm + in_proj + conv + SiLU + SSD scan as one kernel (k7_front_fused.cu): reads x once, writes y once."""
+    ops.set_gemm_precision("f16x3")
+    x = torch.randn(B, T, D, device="cuda")
+    stats = ops.rowstats(x)
+    w = torch.randn(P + 2 * N + 1, D, device="cuda") / D ** 0.5
+    ws = ops.linear_prepare(w, None, "none", torch.ones(D, device="cuda"), torch.zeros(D, device="cuda"))
+    Cn = P + 2 * N
+    cw = torch.randn(Cn, 4, device="cuda") * 0.3; cb = torch.zeros(Cn, device="cuda")
+    dtb = torch.full((1,), -1.0, device="cuda"); Al = torch.zeros(1, device="cuda"); Dv = torch.ones(1, device="cuda")
+    y = torch.empty(B, T, P, device="cuda")
+    def fn():
+        ops.mamba_front_fused(x, stats, ws, cw, cb, dtb, Al, Dv, P, N, out=y)
+    return fn, B * T * (D + P + 2) * 4, B * T
+
+
 def case_linear(M, N, K, epi, mode):
     a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     nout = N // 2 if epi == "glu_residual" else N
@@ -173,6 +189,8 @@ CASES = {
     "ssd_small_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(512))[1],
     "ssd_c2_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(4096))[1],
     "ssd_small_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(512))[1],
+    "front_c2": lambda: case_front(4096),
+    "front_small": lambda: case_front(592),
     "ln_c2": lambda: case_ln(M_C2, 128),
     "lin_in_tc3": lambda: case_linear(M_C2, 161, 128, "none", "tc3"),
     "lin_in_ln_tc3": lambda: case_linear_ln(M_C2, 161, 128, 168),
