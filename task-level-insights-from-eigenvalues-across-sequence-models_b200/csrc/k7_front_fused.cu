@@ -9,23 +9,34 @@
 // TMEM lane), a 32-token chunk of one sequence is the B operand (N = token = TMEM column).  The accumulator then already has the layout the recurrence
 // wants -- thread = channel, its tokens along the columns -- so the scan threads read their channel's chunk straight out of TMEM with tcgen05.ld, run conv +
 // SiLU along the registers and the selective-scan recurrence with the state row in registers, and only y is stored.  While the scan warps of one sequence
-// work through a chunk, TMA, the converter warps and the tensor core prepare the next chunks of the other resident sequences.
+// work through a chunk, TMA, the converter warps and the tensor core prepare the next chunks of the resident sequences.
 //
 // Shape (the C2 / MQAR family): d_model K = 128, d_inner P = 128, one head, one group, d_state N = 16, conv taps <= 4; fp16-split operands (kind::f16, prepared
 // by eigb200_linear_prepare with the LayerNorm folded in, see k4_gemm_tc.cu).
 //
-// Per CTA (one per SM, 704 threads), FF_SLOTS = 4 sequences resident at a time, each walking its 32-token chunks in order:
-//   TMA warp    : x chunk (32 tokens x 128 fp32 = 16 KB, four SWIZZLE_128B boxes) into a 6-stage ring, round-robin over the slots
-//   converters  : 4 warps, thread = (token, 32-column box): (a - mu) rstd S_a -> fp16 hi / lo -> written IN PLACE over the raw chunk as the K-major
-//                 SWIZZLE_128B B operand [K chunk of 64][32 tokens][128 B] (hi 8 KB | lo 8 KB), fence.proxy.async, mbarrier
+// Per CTA (one per SM, 768 threads), FF_SLOTS = 4 sequences resident at a time, each walking its 32-token chunks in order:
+//   start       : the prepared weights (hi / lo fp16, 161 rows padded to 192) go global -> shared (TMA, staged in the ring) -> TMEM (tcgen05.st, lane = weight
+//                 row): the A operand of every MMA then comes from TMEM -- with A in shared memory each M 128 x N 32 x K 16 MMA fetched 5 KB of operands and the
+//                 48 MMAs of a chunk took 240 KB of shared-memory bandwidth, more than the recurrence's own broadcast loads (measured: 45 cycles per MMA)
+//   TMA warp    : x chunk (32 tokens x 128 fp32 = 16 KB, four SWIZZLE_128B boxes) + its 32 (mean, rstd) pairs (bulk copy) into an 8-stage ring
+//   converters  : 4 warps, thread = (token, 32-column box): (a - mu) rstd S_a -> fp16 hi / lo, written IN PLACE over the 128 bytes the thread read as
+//                 [hi 64 B | lo 64 B]: the box stays a SWIZZLE_128B K-major [32 tokens][128 B] tile, the hi / lo operands of a K step are 32-byte slices of it
 //   MMA warp    : per chunk two M = 128, N = 32 accumulators: tile 1 = the 128 x channels, tile 2 = rows [B 16 | C 16 | dt 1 | zero padding] of W_in;
-//                 3 kind::f16 MMAs per K step (hi hi, lo hi, hi lo), A (weights, resident, 96 KB) and B from shared memory
-//   scan warps  : 4 per slot (warp % 4 = TMEM lane quarter), thread = channel.  Warp 0 of the slot first turns tile 2 lanes 0-31 into conv + SiLU'ed
-//                 B_t / C_t rows in shared memory, warp 1 turns lane 32 (dt) into (dt, e^{dt A}, E_t, 1 / E_t); then all four pull their channel's tokens
-//                 8 at a time from TMEM and run the recurrence exactly as ssd_scan_v3 does (rescaled-state form, direct form on decay underflow).
-// TMEM: 4 slots x (32 + 32) columns.  Shared memory: 96 KB weights + 96 KB ring + 16 KB B/C rows + 3 KB = 212 KB.
+//                 3 kind::f16 MMAs per K step (hi hi, lo hi, hi lo), A from TMEM, B from the ring
+//   prep warps  : warp 20 (TMEM lanes 0-31 of tile 2): conv + SiLU of the B_t / C_t rows -> shared memory; warp 21 (lane 32 = the dt row): softplus,
+//                 decay, running decay product E_t of the chunk -> planes dt, e^{dt A}, E_t, dt / E_t; both double-buffered per slot
+//   scan warps  : 4 per slot (warp % 4 = TMEM lane quarter), thread = channel: pull the channel's tokens 16 at a time from TMEM (tcgen05.ld; the accumulator
+//                 is handed back to the tensor core after the second pull, half way through the chunk), conv + SiLU along the registers, then the recurrence
+//                 as ssd_scan_v3 runs it (rescaled-state form r_t = S_t / E_t, 2 FMA-pipe operations per state element; direct form for a chunk whose decay
+//                 product underflows), y stored straight from registers (a warp = 128 contiguous bytes per token)
+// Registers: setmaxnreg moves the budget to the scan warps (88 each, 64 for the others: the pool is the CTA's own launch allocation of 768 x 80).
+// TMEM (512 columns): 4 slots x (32 + 32) accumulator columns | weights: tile 1 hi 64, lo 64, tile 2 hi 64, lo 64 (two fp16 per column).
+// Shared memory: 128 KB ring + 32 KB B / C rows + 4 KB dt planes + 2 KB statistics = 166 KB.
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
+#include <type_traits>
+#include <cstdio>
+#include <cstdlib>
 
 namespace eigb200 {
 
@@ -35,20 +46,31 @@ constexpr int FF_P = 128;                        // d_inner = x channels = lanes
 constexpr int FF_N = 16;                         // d_state
 constexpr int FF_SLOTS = 4;
 constexpr int FF_SCAN_WARPS = 4 * FF_SLOTS;
-constexpr int FF_CONV_WARP0 = FF_SCAN_WARPS;
-constexpr int FF_TMA_WARP = FF_SCAN_WARPS + 4, FF_MMA_WARP = FF_SCAN_WARPS + 5;
-constexpr int FF_THREADS = (FF_SCAN_WARPS + 6) * 32;
-constexpr int FF_NST = 6;
+constexpr int FF_CONV_WARP0 = FF_SCAN_WARPS;     // 16..19
+constexpr int FF_BC_WARP = 20, FF_DT_WARP = 21;  // warp % 4 = 0 / 1: the TMEM lane quarters that hold the B / C rows and the dt row of tile 2
+constexpr int FF_TMA_WARP = 22, FF_MMA_WARP = 23;
+constexpr int FF_THREADS = 24 * 32;
+#ifndef FF_NST_OVERRIDE
+constexpr int FF_NST = 8;
+#else
+constexpr int FF_NST = FF_NST_OVERRIDE;
+#endif
+static_assert(FF_NST >= 6, "the ring doubles as the 96 KB staging area of the weights");
 constexpr int FF_STAGE_BYTES = FF_Q * FF_K * 4;  // 16 KB: raw fp32 chunk = fp16 hi (8 KB) + lo (8 KB) operand
-constexpr int FF_G = 8;                          // tokens per unrolled group of the recurrence
-constexpr uint32_t FF_W_HI = 0, FF_W_LO = 49152, FF_RING = 98304;
-constexpr uint32_t FF_BC = FF_RING + FF_NST * FF_STAGE_BYTES;          // [slot][token][B 16 | C 16] fp32
-constexpr uint32_t FF_DD = FF_BC + FF_SLOTS * FF_Q * 2 * FF_N * 4;     // [slot][token] (dt, decay, E, 1 / E)
-constexpr uint32_t FF_DTRAW = FF_DD + FF_SLOTS * FF_Q * 16;            // [slot][token] raw dt accumulator
-constexpr uint32_t FF_FLAGS = FF_DTRAW + FF_SLOTS * FF_Q * 4;          // [slot] chunk takes the direct form
-constexpr uint32_t FF_BARS = FF_FLAGS + 64;
+constexpr int FF_H = 16;                         // tokens per unrolled half chunk of the recurrence
+constexpr uint32_t FF_RING = 0;
+constexpr uint32_t FF_BC = FF_RING + FF_NST * FF_STAGE_BYTES;          // [slot][buffer][token][B 16 | C 16] fp32
+constexpr uint32_t FF_BC_BYTES = FF_Q * 2 * FF_N * 4;                  // 4 KB per (slot, buffer)
+constexpr uint32_t FF_DD = FF_BC + FF_SLOTS * 2 * FF_BC_BYTES;         // [slot][buffer][plane: dt, decay, E, dt / E][token]
+constexpr uint32_t FF_DD_BYTES = 4 * FF_Q * 4;
+constexpr uint32_t FF_DTRAW = FF_DD + FF_SLOTS * 2 * FF_DD_BYTES;      // [token] raw dt accumulator (scratch of the dt warp)
+constexpr uint32_t FF_FLAGS = FF_DTRAW + FF_Q * 4;                     // [slot][buffer] chunk takes the direct form
+constexpr uint32_t FF_STATS = FF_FLAGS + 64;                           // [stage][token] (mean, rstd): bulk-copied next to the x chunk
+constexpr uint32_t FF_BARS = FF_STATS + FF_NST * FF_Q * 8;
 constexpr uint32_t FF_SMEM = FF_BARS + 512;
 constexpr float FF_SA = 1024.f;                  // activation pre-scale behind a LayerNorm (tc_prepare)
+constexpr uint32_t FF_COL_W = 256;               // TMEM: weights behind the accumulators: + 64 job, job = 0 tile 1 hi, 1 tile 1 lo, 2 tile 2 hi, 3 tile 2 lo
+constexpr int FF_REGS_SCAN = 88, FF_REGS_OTHER = 64;
 
 struct FfParams {
   const float2* ln_stats;                        // (M) (mean, rstd)
@@ -57,41 +79,56 @@ struct FfParams {
   const float* dt_bias; const float* A_log; const float* D;
   float* y; int64_t ldy;
   int64_t B, T, M; int nchunks; int zero; int* ovf_flag;
+  long long* trace;                              // FF_TRACE builds: per-role time stamps of CTA 0 (tools/front_trace.py)
+  int stats_bulk;                                // the statistics of a chunk can be bulk-copied (16-byte aligned source: T even, aligned base)
 };
 
-__device__ __forceinline__ void ff_umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void ff_tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void ff_tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void ff_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void ff_tmem_st_32x32u(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+         "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void ff_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ float4 ff_lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint4 ff_lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void ff_sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void ff_sts_f4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void ff_sts_f1(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(a) : "memory"); }
-__device__ __forceinline__ float ff_lds_f1(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ int ff_lds_i1(uint32_t addr) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ void ff_sts_i1(uint32_t addr, int a) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(a) : "memory"); }
 __device__ __forceinline__ float ff_silu(float z) { return z * sigmoid_fast_f(z); }
+template <int R> __device__ __forceinline__ void ff_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(R)); }
+template <int R> __device__ __forceinline__ void ff_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(R)); }
 
+#ifdef FF_TRACE
+#define FF_TR(role, item, k) do { if (blockIdx.x == 0 && (item) < 256 && p.trace) p.trace[((role) * 256 + (item)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define FF_TR(role, item, k) do { } while (0)
+#endif
 // sequences of slot s of this CTA: b = blockIdx.x + gridDim.x * (FF_SLOTS * k + s), k = 0, 1, ...
 __device__ __forceinline__ int ff_nseq(int64_t B, int s) {
   const int64_t first = (int64_t)blockIdx.x + (int64_t)gridDim.x * s;
@@ -100,19 +137,25 @@ __device__ __forceinline__ int ff_nseq(int64_t B, int s) {
   return (int)((B - first + stride - 1) / stride);
 }
 
+// DENSE: y rows are FF_P floats apart (the pass's own y buffer): every store address is the chunk pointer plus an immediate
+template <bool DENSE>
 __global__ void __launch_bounds__(FF_THREADS, 1)
 mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapWh, const __grid_constant__ CUtensorMap tmapWl,
                    const FfParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const sm = smem_raw + (base - smem_u32(smem_raw));                       // generic pointer to the aligned base
   const uint32_t bars = base + FF_BARS;
   const uint32_t bar_w = bars;
   auto bar_raw = [&](int s) { return bars + 8u * (1 + s); };                        // TMA landed the raw chunk
   auto bar_op = [&](int s) { return bars + 8u * (1 + FF_NST + s); };                // converters wrote the operand
   auto bar_free = [&](int s) { return bars + 8u * (1 + 2 * FF_NST + s); };          // MMAs that read the stage retired
-  auto bar_dfull = [&](int sl) { return bars + 8u * (1 + 3 * FF_NST + sl); };       // both accumulator tiles of the slot's chunk are complete
-  auto bar_dempty = [&](int sl) { return bars + 8u * (1 + 3 * FF_NST + FF_SLOTS + sl); };   // the scan warps have pulled them into registers
-  const uint32_t tmem_slot = bars + 8u * (1 + 3 * FF_NST + 2 * FF_SLOTS);
+  constexpr int B0 = 1 + 3 * FF_NST;
+  auto bar_dfull = [&](int sl) { return bars + 8u * (B0 + sl); };                   // both accumulator tiles of the slot's chunk are complete
+  auto bar_dempty = [&](int sl) { return bars + 8u * (B0 + 4 + sl); };              // scan + prep warps have pulled them into registers
+  auto bar_bcfull = [&](int sb) { return bars + 8u * (B0 + 8 + sb); };              // sb = 2 slot + buffer: B / C rows and the dt planes of the chunk are in shared memory
+  auto bar_bcfree = [&](int sb) { return bars + 8u * (B0 + 16 + sb); };             // the scan warps are done with them
+  const uint32_t tmem_slot = bars + 8u * (B0 + 24);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,33 +164,217 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < FF_NST; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_op(s), 128); mbar_init(bar_free(s), 1); }
-    for (int sl = 0; sl < FF_SLOTS; ++sl) { mbar_init(bar_dfull(sl), 1); mbar_init(bar_dempty(sl), 128); }
+    for (int sl = 0; sl < FF_SLOTS; ++sl) { mbar_init(bar_dfull(sl), 1); mbar_init(bar_dempty(sl), 128 + 64); }
+    for (int sb = 0; sb < 2 * FF_SLOTS; ++sb) { mbar_init(bar_bcfull(sb), 64); mbar_init(bar_bcfree(sb), 128); }
     fence_barrier_init();
   }
-  if (warp == FF_MMA_WARP) tmem_alloc(tmem_slot, 256);
+  if (warp == FF_MMA_WARP) tmem_alloc(tmem_slot, 512);
   if (warp == FF_TMA_WARP && lane == 0) { tma_prefetch_desc(&tmapX); tma_prefetch_desc(&tmapWh); tma_prefetch_desc(&tmapWl); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // ---- weights: global -> ring (staging) -> TMEM, once per CTA -------------------------------------------------------------------------------------------
+  // staging: tile 1 hi at 0, tile 1 lo at 32 KB: [K chunk of 64][128 rows][128 B]; tile 2 (W rows 128-191; 176+ are out of bounds and arrive as zeros)
+  // at 64 KB: per K chunk (16 KB apart) [hi 64 rows][lo 64 rows]; lanes 64-127 of tile 2 are never read
+  if (warp == FF_TMA_WARP) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_w, 2u * 49152u);
+      for (int kch = 0; kch < 2; ++kch) {
+        tma_load_2d(&tmapWh, bar_w, base + FF_RING + kch * 16384, kch * 64, 0);
+        tma_load_2d(&tmapWh, bar_w, base + FF_RING + kch * 16384 + 8192, kch * 64, 64);
+        tma_load_2d(&tmapWl, bar_w, base + FF_RING + 32768 + kch * 16384, kch * 64, 0);
+        tma_load_2d(&tmapWl, bar_w, base + FF_RING + 32768 + kch * 16384 + 8192, kch * 64, 64);
+        tma_load_2d(&tmapWh, bar_w, base + FF_RING + 65536 + kch * 16384, kch * 64, 128);
+        tma_load_2d(&tmapWl, bar_w, base + FF_RING + 65536 + kch * 16384 + 8192, kch * 64, 128);
+      }
+    }
+    __syncwarp();
+  }
+  if (warp < FF_SCAN_WARPS) {
+    const int job = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;                                              // weight row of the tile = TMEM lane
+    mbar_wait(bar_w, 0);
+    const bool tile2 = job >= 2;
+    if (!tile2 || quarter < 2) {
+      const uint32_t src0 = base + FF_RING + (tile2 ? 65536u + (job == 3 ? 8192u : 0u) : (uint32_t)job * 32768u) + (uint32_t)r * 128u;
+#pragma unroll
+      for (int kch = 0; kch < 2; ++kch) {
+        uint32_t w[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {                                               // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+          const uint4 v = ff_lds_u4(src0 + (uint32_t)kch * 16384u + (uint32_t)((q ^ (r & 7)) * 16));
+          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        ff_tmem_st_32x32u(tmem_base + ((uint32_t)(quarter * 32) << 16) + FF_COL_W + (uint32_t)(job * 64 + kch * 32), w);
+      }
+      tmem_st_wait();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();                                                                  // weights are in TMEM: the ring is free for the x chunks
+  tc_fence_after();
+
   int nseq[FF_SLOTS];
 #pragma unroll
   for (int s = 0; s < FF_SLOTS; ++s) nseq[s] = ff_nseq(p.B, s);
   const int nsteps = nseq[0] * nchunks;                              // slot 0 never has fewer sequences than the others
 
-  if (warp == FF_TMA_WARP) {
-    // ===================================== TMA producer ======================================
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_w, 2u * 49152u);
-      for (int kch = 0; kch < 2; ++kch) {                            // tile 1: rows 0-127 (two 64-row boxes); tile 2: rows 128-191 (176+ are out of bounds: zero)
-        tma_load_2d(&tmapWh, bar_w, base + FF_W_HI + kch * 16384, kch * 64, 0);
-        tma_load_2d(&tmapWh, bar_w, base + FF_W_HI + kch * 16384 + 8192, kch * 64, 64);
-        tma_load_2d(&tmapWh, bar_w, base + FF_W_HI + 32768 + kch * 8192, kch * 64, 128);
-        tma_load_2d(&tmapWl, bar_w, base + FF_W_LO + kch * 16384, kch * 64, 0);
-        tma_load_2d(&tmapWl, bar_w, base + FF_W_LO + kch * 16384 + 8192, kch * 64, 64);
-        tma_load_2d(&tmapWl, bar_w, base + FF_W_LO + 32768 + kch * 8192, kch * 64, 128);
+  if (warp < FF_SCAN_WARPS) {
+    // ===================================== scan warps: slot = warp / 4, thread = channel ======================================
+    ff_reg_inc<FF_REGS_SCAN>();
+    const int slot = warp >> 2, quarter = warp & 3;
+    const int ch = quarter * 32 + lane;
+    const uint32_t d_x = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 64);
+    const float osc = __ldg(p.osc);
+    const float Dh = p.D ? __ldg(p.D) : 0.f;
+    const int kconv = p.kconv;
+    float cw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)ch * kconv + j - (4 - kconv)) : 0.f;
+    const float cb = __ldg(p.conv_b + ch);
+    const float bias_x = __ldg(p.bias2 + ch);
+    const int64_t ldy = DENSE ? (int64_t)FF_P : p.ldy;
+    float s[FF_N];
+    float h1 = 0.f, h2 = 0.f, h3 = 0.f;                              // x of the tokens t-1, t-2, t-3 (before the conv)
+
+    // one half chunk of FF_H tokens.  RESC: recurrence on r_t = S_t / E_t (w = x dt / E_t; y = E_t (C . r) + D x); else the direct form.
+    // Per group of 8 tokens: phase A (independent of the state) conv + SiLU and the per-token scalars, phase B the state recurrence.
+    auto half = [&](auto resc_tag, auto guard_tag, const float (&xr)[FF_H], const float4* __restrict__ bc4, const float4* __restrict__ pl, float* yp, int nvalid) {
+      constexpr bool RESC = decltype(resc_tag)::value, GUARD = decltype(guard_tag)::value;
+#pragma unroll
+      for (int g = 0; g < FF_H / 8; ++g) {
+        float xv[8], w0[8], ez[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 wq = pl[(RESC ? 3 : 0) * (FF_Q / 4) + 2 * g + q];   // RESC: dt / E_t; direct: dt
+          const float4 eq = pl[(RESC ? 2 : 1) * (FF_Q / 4) + 2 * g + q];   // RESC: E_t;      direct: decay
+          w0[4 * q] = wq.x; w0[4 * q + 1] = wq.y; w0[4 * q + 2] = wq.z; w0[4 * q + 3] = wq.w;
+          ez[4 * q] = eq.x; ez[4 * q + 1] = eq.y; ez[4 * q + 2] = eq.z; ez[4 * q + 3] = eq.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * g + jj;
+          const float xm1 = j >= 1 ? xr[j >= 1 ? j - 1 : 0] : h1, xm2 = j >= 2 ? xr[j >= 2 ? j - 2 : 0] : (j == 1 ? h1 : h2),
+                      xm3 = j >= 3 ? xr[j >= 3 ? j - 3 : 0] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+          const float c = fmaf(cw[3], xr[j], fmaf(cw[2], xm1, fmaf(cw[1], xm2, fmaf(cw[0], xm3, cb))));
+          xv[jj] = ff_silu(c);
+          w0[jj] *= xv[jj];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * g + jj;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int q = 0; q < FF_N / 4; ++q) {
+            const float4 bv = bc4[j * 8 + q], cv = bc4[j * 8 + 4 + q];
+            if (RESC) {
+              s[4 * q + 0] = fmaf(w0[jj], bv.x, s[4 * q + 0]); s[4 * q + 1] = fmaf(w0[jj], bv.y, s[4 * q + 1]);
+              s[4 * q + 2] = fmaf(w0[jj], bv.z, s[4 * q + 2]); s[4 * q + 3] = fmaf(w0[jj], bv.w, s[4 * q + 3]);
+            } else {
+              s[4 * q + 0] = fmaf(ez[jj], s[4 * q + 0], w0[jj] * bv.x); s[4 * q + 1] = fmaf(ez[jj], s[4 * q + 1], w0[jj] * bv.y);
+              s[4 * q + 2] = fmaf(ez[jj], s[4 * q + 2], w0[jj] * bv.z); s[4 * q + 3] = fmaf(ez[jj], s[4 * q + 3], w0[jj] * bv.w);
+            }
+            a0 = fmaf(cv.x, s[4 * q + 0], a0); a1 = fmaf(cv.y, s[4 * q + 1], a1);
+            a2 = fmaf(cv.z, s[4 * q + 2], a2); a3 = fmaf(cv.w, s[4 * q + 3], a3);
+          }
+          const float dot = (a0 + a1) + (a2 + a3);
+          const float yv = fmaf(Dh, xv[jj], RESC ? ez[jj] * dot : dot);
+          if (!GUARD || j < nvalid) yp[(int64_t)j * ldy] = yv;
+        }
       }
+      h3 = xr[FF_H - 3]; h2 = xr[FF_H - 2]; h1 = xr[FF_H - 1];
+    };
+
+    const int my_steps = nseq[slot] * nchunks;
+    for (int i = 0; i < my_steps; ++i) {
+      const int k = i / nchunks, c = i - k * nchunks;
+      const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + slot);
+      const int64_t t0 = (int64_t)c * FF_Q;
+      const int tc = (int)min((int64_t)FF_Q, p.T - t0);
+      const int sb = 2 * slot + (i & 1);
+      if (c == 0) {
+#pragma unroll
+        for (int n = 0; n < FF_N; ++n) s[n] = 0.f;
+        h1 = h2 = h3 = 0.f;
+      }
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 0);
+      mbar_wait(bar_bcfull(sb), (uint32_t)(i >> 1) & 1u);            // the prep warps publish after their own wait on bar_dfull
+      mbar_wait(bar_dfull(slot), (uint32_t)i & 1u);
+      tc_fence_after();
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 1);
+      const bool direct = reinterpret_cast<const int*>(sm + FF_FLAGS)[sb] != 0;
+      const float4* bc4 = reinterpret_cast<const float4*>(sm + FF_BC + (uint32_t)sb * FF_BC_BYTES);
+      const float4* pl4 = reinterpret_cast<const float4*>(sm + FF_DD + (uint32_t)sb * FF_DD_BYTES);
+      float* yp = p.y + (b * p.T + t0) * ldy + ch;
+#pragma unroll 1
+      for (int hf = 0; hf < FF_Q / FF_H; ++hf) {
+        float xr[FF_H];
+        ff_tmem_ld_32x16(d_x + (uint32_t)(hf * FF_H), xr);
+        if (hf == FF_Q / FF_H - 1) { tc_fence_before(); mbar_arrive(bar_dempty(slot)); }    // the tensor core may overwrite the slot's accumulators
+#pragma unroll
+        for (int j = 0; j < FF_H; ++j) xr[j] = fmaf(xr[j], osc, bias_x);
+        const float4* bch = bc4 + hf * FF_H * 8;
+        const float4* plh = pl4 + hf * (FF_H / 4);
+        float* yph = yp + (int64_t)(hf * FF_H) * ldy;
+#ifdef FF_ABL_SCAN
+        if (xr[0] == 123.456f) yph[0] = xr[1];
+        continue;
+#endif
+        if (tc == FF_Q) {
+          if (!direct) half(std::true_type{}, std::false_type{}, xr, bch, plh, yph, FF_H);
+          else half(std::false_type{}, std::false_type{}, xr, bch, plh, yph, FF_H);
+        } else {
+          if (!direct) half(std::true_type{}, std::true_type{}, xr, bch, plh, yph, tc - hf * FF_H);
+          else half(std::false_type{}, std::true_type{}, xr, bch, plh, yph, tc - hf * FF_H);
+        }
+      }
+      if (!direct) {                                                 // back to the true state: S = r E
+        const float Eend = reinterpret_cast<const float*>(pl4)[2 * FF_Q + FF_Q - 1];
+#pragma unroll
+        for (int n = 0; n < FF_N; ++n) s[n] *= Eend;
+      }
+      mbar_arrive(bar_bcfree(sb));                                   // this thread is done with the chunk's shared rows
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 2);
+    }
+  } else {
+    ff_reg_dec<FF_REGS_OTHER>();
+    if (warp == FF_TMA_WARP) {
+      // ===================================== TMA producer ======================================
+      if (elect_one()) {
+        int st = 0; uint32_t ph = 0;
+        for (int i = 0; i < nsteps; ++i) {
+          const int k = i / nchunks, c = i - k * nchunks;
+#pragma unroll
+          for (int s = 0; s < FF_SLOTS; ++s) {
+            if (k >= nseq[s]) continue;
+            const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + s);
+            const int row0 = (int)(b * p.T + (int64_t)c * FF_Q);
+            FF_TR(0, i * 4 + s, 0);
+            mbar_wait_one(bar_free(st), ph ^ 1);
+            FF_TR(0, i * 4 + s, 1);
+            int nst_rows = 0;
+            if (p.stats_bulk) { const int64_t left = p.M - row0; nst_rows = left < FF_Q ? (int)left : FF_Q; }    // even: T and FF_Q are
+            mbar_arrive_expect_tx(bar_raw(st), FF_STAGE_BYTES + (uint32_t)nst_rows * 8u);
+            if (nst_rows > 0) ff_bulk_load(base + FF_STATS + st * (FF_Q * 8), p.ln_stats + row0, (uint32_t)nst_rows * 8u, bar_raw(st));
+            const uint32_t dst = base + FF_RING + st * FF_STAGE_BYTES;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) tma_load_2d(&tmapX, bar_raw(st), dst + kc * 4096, kc * 32, row0);
+            if (++st == FF_NST) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp >= FF_CONV_WARP0 && warp < FF_CONV_WARP0 + 4) {
+      // ===================================== converters: thread = (token r, 32-column box kc) ======================================
+      // Each thread rewrites the 128 bytes it read -- 32 fp32 of row r of box kc -- as [fp16 hi of those 32 values (64 B) | fp16 lo (64 B)] in the same row:
+      // the box stays a [32 tokens][128 B] SWIZZLE_128B K-major tile whose first two 32-byte K steps are the hi operand and whose last two are the lo
+      // operand of K columns [32 kc, 32 kc + 32).  No thread touches another thread's bytes, so no barrier is needed between the read and the write.
+      const int r = lane, kc = warp - FF_CONV_WARP0;
+      const int sw = r & 7;
+      const uint32_t row_off = (uint32_t)kc * 4096u + (uint32_t)r * 128u;
+      float amax = 0.f;
       int st = 0; uint32_t ph = 0;
       for (int i = 0; i < nsteps; ++i) {
         const int k = i / nchunks, c = i - k * nchunks;
@@ -155,253 +382,176 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
         for (int s = 0; s < FF_SLOTS; ++s) {
           if (k >= nseq[s]) continue;
           const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + s);
-          const int row0 = (int)(b * p.T + (int64_t)c * FF_Q);
-          mbar_wait_one(bar_free(st), ph ^ 1);
-          mbar_arrive_expect_tx(bar_raw(st), FF_STAGE_BYTES);
-          const uint32_t dst = base + FF_RING + st * FF_STAGE_BYTES;
+          const int64_t m = b * p.T + (int64_t)c * FF_Q + r;
+          float2 stt = make_float2(0.f, 0.f);
+          if (!p.stats_bulk && m < p.M) stt = __ldg(p.ln_stats + m);
+          const uint32_t row = base + FF_RING + st * FF_STAGE_BYTES + row_off;
+          if (kc == 0 && lane == 0) FF_TR(1, i * 4 + s, 0);
+          mbar_wait(bar_raw(st), ph);
+          if (kc == 0 && lane == 0) FF_TR(1, i * 4 + s, 1);
+          if (p.stats_bulk && m < p.M) stt = reinterpret_cast<const float2*>(sm + FF_STATS + st * (FF_Q * 8))[r];
+          stt.x = -stt.x * stt.y;                                    // (a - mu) rstd = fma(a, rstd, -mu rstd), as the converter of gemm_tc_ts_kernel
+          stt.x *= FF_SA; stt.y *= FF_SA;
+#ifndef FF_ABL_CONV
+          float a[32];
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) tma_load_2d(&tmapX, bar_raw(st), dst + kc * 4096, kc * 32, row0);
+          for (int q = 0; q < 8; ++q) {                              // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+            const float4 v = ff_lds_f4(row + (uint32_t)((q ^ sw) * 16));
+            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) a[e] = fmaf(a[e], stt.y, stt.x);
+          uint32_t hi2[16], lo2[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
+            amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ff_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
+            ff_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
+          }
+#endif
+          fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core (async proxy)
+          mbar_arrive(bar_op(st));
+          if (kc == 0 && lane == 0) FF_TR(1, i * 4 + s, 2);
           if (++st == FF_NST) { st = 0; ph ^= 1; }
         }
       }
-    }
-    __syncwarp();
-  } else if (warp >= FF_CONV_WARP0 && warp < FF_CONV_WARP0 + 4) {
-    // ===================================== converters: thread = (token r, 32-column box kc) ======================================
-    const int r = lane, kc = warp - FF_CONV_WARP0;
-    const int sw = r & 7;
-    const uint32_t src_off = (uint32_t)kc * 4096u + (uint32_t)r * 128u;
-    const uint32_t dst_off = (uint32_t)(kc >> 1) * 4096u + (uint32_t)r * 128u;
-    const int slot0 = (kc & 1) * 4;                                  // first 16-byte slot of this thread's 32 halfs inside the 128-byte operand row
-    float amax = 0.f;
-    int st = 0; uint32_t ph = 0;
-    for (int i = 0; i < nsteps; ++i) {
-      const int k = i / nchunks, c = i - k * nchunks;
+      if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
+    } else if (warp == FF_MMA_WARP) {
+      // ===================================== MMA issuer ======================================
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_f16(128, FF_Q);
+        int st = 0; uint32_t ph = 0;
+        for (int i = 0; i < nsteps; ++i) {
+          const int k = i / nchunks;
 #pragma unroll
-      for (int s = 0; s < FF_SLOTS; ++s) {
-        if (k >= nseq[s]) continue;
-        const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + s);
-        const int64_t m = b * p.T + (int64_t)c * FF_Q + r;
-        float2 stt = m < p.M ? __ldg(p.ln_stats + m) : make_float2(0.f, 0.f);
-        stt.x = -stt.x * stt.y;                                      // (a - mu) rstd = fma(a, rstd, -mu rstd), as the converter of gemm_tc_ts_kernel
-        stt.x *= FF_SA; stt.y *= FF_SA;
-        const uint32_t stage = base + FF_RING + st * FF_STAGE_BYTES;
-        mbar_wait(bar_raw(st), ph);
-        float a[32];
+          for (int s = 0; s < FF_SLOTS; ++s) {
+            if (k >= nseq[s]) continue;
+            FF_TR(2, i * 4 + s, 0);
+            mbar_wait_one(bar_op(st), ph);
+            FF_TR(2, i * 4 + s, 1);
+            mbar_wait_one(bar_dempty(s), ((uint32_t)i & 1u) ^ 1u);   // chunk i - 1 of this slot is in the scan / prep warps' registers
+            FF_TR(2, i * 4 + s, 2);
+            tc_fence_after();
+            const uint32_t stage = base + FF_RING + st * FF_STAGE_BYTES;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {                                // logical 16-byte slot q sits at physical slot q ^ (row & 7)
-          const float4 v = ff_lds_f4(stage + src_off + (uint32_t)((q ^ sw) * 16));
-          a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+            for (int tile = 0; tile < 2; ++tile) {
+              const uint32_t d = tmem_base + (uint32_t)(s * 64 + tile * 32);
+              const uint32_t a_hi = tmem_base + FF_COL_W + (uint32_t)(tile * 128), a_lo = a_hi + 64u;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {                       // K step of 16: weights 8 TMEM columns; activations [box of 32 columns][hi 64 B | lo 64 B]
+                const uint64_t bh = umma_desc_k_sw128(stage + (uint32_t)(ks >> 1) * 4096u) + 2u * (ks & 1), bl = bh + 4u;
+#ifndef FF_ABL_MMA                                                    // ablation builds (tools/ablate_front.sh): timing only, wrong results
+                umma_f16_ts(d, a_hi + 8u * ks, bh, idesc, ks > 0 ? 1u : 0u);
+                umma_f16_ts(d, a_lo + 8u * ks, bh, idesc, 1u);
+                umma_f16_ts(d, a_hi + 8u * ks, bl, idesc, 1u);
+#endif
+              }
+            }
+            umma_commit(bar_free(st));
+            umma_commit(bar_dfull(s));
+            FF_TR(2, i * 4 + s, 3);
+            if (++st == FF_NST) { st = 0; ph ^= 1; }
+          }
         }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) a[e] = fmaf(a[e], stt.y, stt.x);
-        uint32_t hi2[16], lo2[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
-          amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
-        ff_bar_sync(5, 128);                                         // every converter thread has its raw values in registers: the chunk may be overwritten
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t o = stage + dst_off + (uint32_t)(((slot0 + j) ^ sw) * 16);
-          ff_sts_u4(o, hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
-          ff_sts_u4(o + 8192u, lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
-        }
-        fence_proxy_async();                                         // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(bar_op(st));
-        if (++st == FF_NST) { st = 0; ph ^= 1; }
       }
-    }
-    if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
-  } else if (warp == FF_MMA_WARP) {
-    // ===================================== MMA issuer ======================================
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(128, FF_Q);
-      mbar_wait_one(bar_w, 0);
-      int st = 0; uint32_t ph = 0;
+      __syncwarp();
+    } else if (warp == FF_BC_WARP) {
+      // ===================================== B / C rows: thread = conv channel 128 + lane (B_0..15, C_0..15) ======================================
+      const float osc = __ldg(p.osc);
+      const int kconv = p.kconv;
+      const int bch = FF_P + lane;
+      float bw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)bch * kconv + j - (4 - kconv)) : 0.f;
+      const float bbias = __ldg(p.conv_b + bch), bias_bc = __ldg(p.bias2 + bch);
+      float g1[FF_SLOTS], g2[FF_SLOTS], g3[FF_SLOTS];                // raw values of the tokens t-1, t-2, t-3 per slot
       for (int i = 0; i < nsteps; ++i) {
-        const int k = i / nchunks;
+        const int k = i / nchunks, c = i - k * nchunks;
 #pragma unroll
         for (int s = 0; s < FF_SLOTS; ++s) {
           if (k >= nseq[s]) continue;
-          mbar_wait_one(bar_op(st), ph);
-          mbar_wait_one(bar_dempty(s), (uint32_t)(i & 1) ^ 1u);       // chunk i - 1 of this slot is in the scan warps' registers
+          if (c == 0) g1[s] = g2[s] = g3[s] = 0.f;
+          const int sb = 2 * s + (i & 1);
+          if (lane == 0) FF_TR(3, i * 4 + s, 0);
+          mbar_wait(bar_dfull(s), (uint32_t)i & 1u);
+          if (lane == 0) FF_TR(3, i * 4 + s, 1);
           tc_fence_after();
-          const uint32_t stage = base + FF_RING + st * FF_STAGE_BYTES;
+          float v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t)(s * 64 + 32), v);
+          tc_fence_before();
+          mbar_arrive(bar_dempty(s));
+          mbar_wait(bar_bcfree(sb), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+          if (lane == 0) FF_TR(3, i * 4 + s, 2);
+          float* dst = reinterpret_cast<float*>(sm + FF_BC + (uint32_t)sb * FF_BC_BYTES) + lane;
+          float a1 = g1[s], a2 = g2[s], a3 = g3[s];
+#ifdef FF_ABL_PREP
+          if (v[0] == 123.456f) dst[0] = v[1];
+#else
 #pragma unroll
-          for (int tile = 0; tile < 2; ++tile) {
-            const uint32_t d = tmem_base + (uint32_t)(s * 64 + tile * 32);
-#pragma unroll
-            for (int kch = 0; kch < 2; ++kch) {
-              const uint32_t wofs = tile == 0 ? (uint32_t)kch * 16384u : 32768u + (uint32_t)kch * 8192u;
-              const uint64_t ah = umma_desc_k_sw128(base + FF_W_HI + wofs), al = umma_desc_k_sw128(base + FF_W_LO + wofs);
-              const uint64_t bh = umma_desc_k_sw128(stage + kch * 4096), bl = umma_desc_k_sw128(stage + 8192 + kch * 4096);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                ff_umma_f16_ss(d, ah + 2u * ks, bh + 2u * ks, idesc, (kch > 0 || ks > 0) ? 1u : 0u);
-                ff_umma_f16_ss(d, al + 2u * ks, bh + 2u * ks, idesc, 1u);
-                ff_umma_f16_ss(d, ah + 2u * ks, bl + 2u * ks, idesc, 1u);
-              }
-            }
+          for (int j = 0; j < 32; ++j) {
+            const float raw = fmaf(v[j], osc, bias_bc);
+            const float o = fmaf(bw[3], raw, fmaf(bw[2], a1, fmaf(bw[1], a2, fmaf(bw[0], a3, bbias))));
+            a3 = a2; a2 = a1; a1 = raw;
+            dst[j * 2 * FF_N] = ff_silu(o);
           }
-          umma_commit(bar_free(st));
-          umma_commit(bar_dfull(s));
-          if (++st == FF_NST) { st = 0; ph ^= 1; }
+#endif
+          g1[s] = a1; g2[s] = a2; g3[s] = a3;
+          mbar_arrive(bar_bcfull(sb));
+          if (lane == 0) FF_TR(3, i * 4 + s, 3);
         }
       }
-    }
-    __syncwarp();
-  } else {
-    // ===================================== scan warps: slot = warp / 4, thread = channel ======================================
-    const int slot = warp >> 2, quarter = warp & 3;
-    const int ch = quarter * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const uint32_t d_x = tmem_base + lane_sel + (uint32_t)(slot * 64), d_bc = d_x + 32u;
-    const uint32_t bc_s = base + FF_BC + (uint32_t)slot * (FF_Q * 2 * FF_N * 4);
-    const uint32_t dd_s = base + FF_DD + (uint32_t)slot * (FF_Q * 16);
-    const uint32_t dtraw_s = base + FF_DTRAW + (uint32_t)slot * (FF_Q * 4);
-    const uint32_t flag_s = base + FF_FLAGS + (uint32_t)slot * 4;
-    const float osc = __ldg(p.osc);
-    const float Ah = -expf(__ldg(p.A_log));
-    const float Dh = p.D ? __ldg(p.D) : 0.f;
-    const float dtb = __ldg(p.dt_bias);
-    const int kconv = p.kconv;
-    float cw[4], cb;
-    {
+    } else if (warp == FF_DT_WARP) {
+      // ===================================== dt row: lane 0 of this warp = TMEM lane 32 of tile 2 ======================================
+      const float osc = __ldg(p.osc);
+      const float Ah = -expf(__ldg(p.A_log));
+      const float dtb = __ldg(p.dt_bias);
+      const float bias_dt = __ldg(p.bias2 + FF_P + 2 * FF_N);
+      float* const dtraw = reinterpret_cast<float*>(sm + FF_DTRAW);
+      for (int i = 0; i < nsteps; ++i) {
+        const int k = i / nchunks, c = i - k * nchunks;
+        const int tc = (int)min((int64_t)FF_Q, p.T - (int64_t)c * FF_Q);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)ch * kconv + j - (4 - kconv)) : 0.f;
-      cb = __ldg(p.conv_b + ch);
-    }
-    const float bias_x = __ldg(p.bias2 + ch);
-    // warp 0 of the slot: conv channel 128 + lane (B_0..15, C_0..15); warp 1: the dt row
-    float bw[4] = {0.f, 0.f, 0.f, 0.f}, bbias = 0.f, bias_bc = 0.f, bias_dt = 0.f;
-    if (quarter == 0) {
-      const int bch = FF_P + lane;
+        for (int s = 0; s < FF_SLOTS; ++s) {
+          if (k >= nseq[s]) continue;
+          const int sb = 2 * s + (i & 1);
+          mbar_wait(bar_dfull(s), (uint32_t)i & 1u);
+          tc_fence_after();
+          float v[32];
+          tmem_ld_32x32(tmem_base + (32u << 16) + (uint32_t)(s * 64 + 32), v);
+          tc_fence_before();
+          mbar_arrive(bar_dempty(s));
+          if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)bch * kconv + j - (4 - kconv)) : 0.f;
-      bbias = __ldg(p.conv_b + bch);
-      bias_bc = __ldg(p.bias2 + bch);
-    } else if (quarter == 1) {
-      bias_dt = __ldg(p.bias2 + FF_P + 2 * FF_N);
-    }
-    float s[FF_N];
-    float h1 = 0.f, h2 = 0.f, h3 = 0.f;                              // raw x of the tokens t-1, t-2, t-3
-    float g1 = 0.f, g2 = 0.f, g3 = 0.f;                              // the same for this thread's B / C channel (warp 0 of the slot)
-    const int my_steps = nseq[slot] * nchunks;
-    for (int i = 0; i < my_steps; ++i) {
-      const int k = i / nchunks, c = i - k * nchunks;
-      const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + slot);
-      const int64_t t0 = (int64_t)c * FF_Q;
-      const int tc = (int)min((int64_t)FF_Q, p.T - t0);
-      if (c == 0) {
-#pragma unroll
-        for (int n = 0; n < FF_N; ++n) s[n] = 0.f;
-        h1 = h2 = h3 = 0.f; g1 = g2 = g3 = 0.f;
-      }
-      mbar_wait(bar_dfull(slot), (uint32_t)(i & 1));
-      tc_fence_after();
-      if (quarter == 0) {
-        float v[32];
-        tmem_ld_32x32(d_bc, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float raw = fmaf(v[j], osc, bias_bc);
-          float o = fmaf(bw[3], raw, fmaf(bw[2], g1, fmaf(bw[1], g2, fmaf(bw[0], g3, bbias))));
-          o = ff_silu(o);
-          g3 = g2; g2 = g1; g1 = raw;
-          ff_sts_f1(bc_s + (uint32_t)(j * 2 * FF_N + lane) * 4u, o);
-        }
-      } else if (quarter == 1) {
-        float v[32];
-        tmem_ld_32x32(d_bc, v);                                      // lane 0 of this warp = TMEM lane 32 = the dt row
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ff_sts_f4(dtraw_s + 16u * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        __syncwarp();
-        const float z = fmaf(ff_lds_f1(dtraw_s + 4u * lane), osc, bias_dt);
-        const float d = (lane < tc) ? softplus_f(z + dtb) : 0.f;
-        const float dec = (lane < tc) ? expf(d * Ah) : 1.f;
-        float E = dec;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, E, o); if (lane >= o) E *= u; }   // inclusive product scan
-        const float Emin = __shfl_sync(0xffffffffu, E, 31);          // decays <= 1: the last product is the smallest
-        if (lane == 0) ff_sts_i1(flag_s, (Emin < 0x1p-60f || !(Emin == Emin)) ? 1 : 0);
-        ff_sts_f4(dd_s + 16u * lane, d, dec, E, 1.f / E);
-        __syncwarp();
-      }
-      ff_bar_sync(1 + slot, 128);                                    // B / C rows and (dt, decay, E, 1 / E) of the chunk are in shared memory
-      const bool direct = ff_lds_i1(flag_s) != 0;
-      float* yp = p.y + (size_t)(b * p.T + t0) * p.ldy + ch;
-#pragma unroll 1
-      for (int g = 0; g < FF_Q / FF_G; ++g) {
-        float xr[FF_G];
-        ff_tmem_ld_32x8(d_x + (uint32_t)(g * FF_G), xr);
-        if (g == FF_Q / FF_G - 1) { tc_fence_before(); mbar_arrive(bar_dempty(slot)); }     // the tensor core may overwrite both tiles of this slot
-#pragma unroll
-        for (int j = 0; j < FF_G; ++j) xr[j] = fmaf(xr[j], osc, bias_x);
-        if (!direct) {
-#pragma unroll
-          for (int j = 0; j < FF_G; ++j) {
-            const int tt = g * FF_G + j;
-            const float4 dd = ff_lds_f4(dd_s + 16u * tt);
-            const float xm1 = j >= 1 ? xr[j - 1] : h1, xm2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2), xm3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
-            float xv = fmaf(cw[3], xr[j], fmaf(cw[2], xm1, fmaf(cw[1], xm2, fmaf(cw[0], xm3, cb))));
-            xv = ff_silu(xv);
-            const float w0 = (xv * dd.x) * dd.w;                     // dt x / E_t
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int q = 0; q < FF_N / 4; ++q) {
-              const float4 bv = ff_lds_f4(bc_s + (uint32_t)(tt * 2 * FF_N + 4 * q) * 4u);
-              const float4 cv = ff_lds_f4(bc_s + (uint32_t)(tt * 2 * FF_N + FF_N + 4 * q) * 4u);
-              s[4 * q + 0] = fmaf(w0, bv.x, s[4 * q + 0]); a0 = fmaf(cv.x, s[4 * q + 0], a0);
-              s[4 * q + 1] = fmaf(w0, bv.y, s[4 * q + 1]); a1 = fmaf(cv.y, s[4 * q + 1], a1);
-              s[4 * q + 2] = fmaf(w0, bv.z, s[4 * q + 2]); a2 = fmaf(cv.z, s[4 * q + 2], a2);
-              s[4 * q + 3] = fmaf(w0, bv.w, s[4 * q + 3]); a3 = fmaf(cv.w, s[4 * q + 3], a3);
-            }
-            const float yv = fmaf(Dh, xv, dd.z * ((a0 + a1) + (a2 + a3)));
-            if (tt < tc) yp[(size_t)tt * p.ldy] = yv;
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dtraw)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-        } else {
+          __syncwarp();
+          const float z = fmaf(dtraw[lane], osc, bias_dt);
+          __syncwarp();
+          const float d = (lane < tc) ? softplus_f(z + dtb) : 0.f;
+          const float dec = (lane < tc) ? expf(d * Ah) : 1.f;
+          float E = dec;
 #pragma unroll
-          for (int j = 0; j < FF_G; ++j) {
-            const int tt = g * FF_G + j;
-            const float4 dd = ff_lds_f4(dd_s + 16u * tt);
-            const float xm1 = j >= 1 ? xr[j - 1] : h1, xm2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2), xm3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
-            float xv = fmaf(cw[3], xr[j], fmaf(cw[2], xm1, fmaf(cw[1], xm2, fmaf(cw[0], xm3, cb))));
-            xv = ff_silu(xv);
-            const float uu = xv * dd.x;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int q = 0; q < FF_N / 4; ++q) {
-              const float4 bv = ff_lds_f4(bc_s + (uint32_t)(tt * 2 * FF_N + 4 * q) * 4u);
-              const float4 cv = ff_lds_f4(bc_s + (uint32_t)(tt * 2 * FF_N + FF_N + 4 * q) * 4u);
-              s[4 * q + 0] = fmaf(dd.y, s[4 * q + 0], uu * bv.x); a0 = fmaf(cv.x, s[4 * q + 0], a0);
-              s[4 * q + 1] = fmaf(dd.y, s[4 * q + 1], uu * bv.y); a1 = fmaf(cv.y, s[4 * q + 1], a1);
-              s[4 * q + 2] = fmaf(dd.y, s[4 * q + 2], uu * bv.z); a2 = fmaf(cv.z, s[4 * q + 2], a2);
-              s[4 * q + 3] = fmaf(dd.y, s[4 * q + 3], uu * bv.w); a3 = fmaf(cv.w, s[4 * q + 3], a3);
-            }
-            const float yv = fmaf(Dh, xv, (a0 + a1) + (a2 + a3));
-            if (tt < tc) yp[(size_t)tt * p.ldy] = yv;
-          }
+          for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, E, o); if (lane >= o) E *= u; }   // inclusive product scan
+          const float Emin = __shfl_sync(0xffffffffu, E, 31);        // decays <= 1: the last product is the smallest
+          mbar_wait(bar_bcfree(sb), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+          if (lane == 0) reinterpret_cast<int*>(sm + FF_FLAGS)[sb] = (Emin < 0x1p-60f || !(Emin == Emin)) ? 1 : 0;
+          float* pl = reinterpret_cast<float*>(sm + FF_DD + (uint32_t)sb * FF_DD_BYTES) + lane;
+          pl[0] = d; pl[FF_Q] = dec; pl[2 * FF_Q] = E; pl[3 * FF_Q] = d * (1.f / E);
+          mbar_arrive(bar_bcfull(sb));
         }
-        h3 = xr[FF_G - 3]; h2 = xr[FF_G - 2]; h1 = xr[FF_G - 1];
       }
-      if (!direct) {                                                 // back to the true state: S = r E
-        const float Eend = ff_lds_f4(dd_s + 16u * (FF_Q - 1)).z;
-#pragma unroll
-        for (int n = 0; n < FF_N; ++n) s[n] *= Eend;
-      }
-      ff_bar_sync(1 + slot, 128);                                    // all four warps are done with the chunk's shared rows
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == FF_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == FF_MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 bool mamba_front_fused_supported(int D, int d_inner, int H, int G, int N, int kconv) {
@@ -432,12 +582,22 @@ int launch_mamba_front_fused(cudaStream_t st, const float* x, int64_t ldx, const
   p.dt_bias = dt_bias; p.A_log = A_log; p.D = D;
   p.y = y; p.ldy = ldy; p.B = B; p.T = T; p.M = M;
   p.nchunks = (int)((T + FF_Q - 1) / FF_Q); p.zero = 0;
+#ifdef FF_TRACE
+  { static long long* tr = nullptr; if (!tr) { cudaMalloc(&tr, 8 * 256 * 4 * 8); } cudaMemsetAsync(tr, 0, 8 * 256 * 4 * 8, st); p.trace = tr;
+    if (const char* e = getenv("FF_TRACE_PTR_FILE")) { FILE* f = fopen(e, "w"); if (f) { fprintf(f, "%llu\n", (unsigned long long)(uintptr_t)tr); fclose(f); } } }
+#endif
+  p.stats_bulk = (T % 2 == 0 && ((uintptr_t)ln_stats & 15) == 0) ? 1 : 0;
   p.ovf_flag = tc_overflow_flag();
   if (!p.ovf_flag) { set_error("mamba_front_fused: cannot resolve the overflow flag"); return EIGB200_ECUDA; }
   const int64_t grid = B < (int64_t)num_sms() ? B : (int64_t)num_sms();
   const size_t smem = (size_t)FF_SMEM + 1024 /*alignment*/;
-  EIGB_CUDA(cudaFuncSetAttribute(mamba_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mamba_front_kernel<<<(unsigned)grid, FF_THREADS, smem, st>>>(tX, tWh, tWl, p);
+  if (ldy == FF_P) {
+    EIGB_CUDA(cudaFuncSetAttribute(mamba_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mamba_front_kernel<true><<<(unsigned)grid, FF_THREADS, smem, st>>>(tX, tWh, tWl, p);
+  } else {
+    EIGB_CUDA(cudaFuncSetAttribute(mamba_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mamba_front_kernel<false><<<(unsigned)grid, FF_THREADS, smem, st>>>(tX, tWh, tWl, p);
+  }
   EIGB_LAUNCH_CHECK("mamba_front_kernel");
   return EIGB200_OK;
 }
