@@ -14,22 +14,26 @@
 // Shape (the C2 / MQAR family): d_model K = 128, d_inner P = 128, one head, one group, d_state N = 16, conv taps <= 4; fp16-split operands (kind::f16, prepared
 // by eigb200_linear_prepare with the LayerNorm folded in, see k4_gemm_tc.cu).
 //
-// Per CTA (one per SM, 768 threads), FF_SLOTS = 4 sequences resident at a time, each walking its 32-token chunks in order:
+// Per CTA (one per SM, 576 threads): FF_SLOTS = 4 sequences resident at a time, each owned by 4 warps (warp % 4 = TMEM lane quarter, thread = channel) that
+// walk the sequence's 32-token chunks in order and do ALL the SIMT work of their sequence; two more warps issue TMA and MMA for the four slots.
 //   start       : the prepared weights (hi / lo fp16, 161 rows padded to 192) go global -> shared (TMA, staged in the ring) -> TMEM (tcgen05.st, lane = weight
 //                 row): the A operand of every MMA then comes from TMEM -- with A in shared memory each M 128 x N 32 x K 16 MMA fetched 5 KB of operands and the
-//                 48 MMAs of a chunk took 240 KB of shared-memory bandwidth, more than the recurrence's own broadcast loads (measured: 45 cycles per MMA)
+//                 48 MMAs of a chunk took 240 KB of shared-memory bandwidth, more than the recurrence's own broadcast loads (measured: 45 cycles per MMA).
+//                 Tile 1 = the 128 x channels.  Tile 2: lanes 0-31, 32-63 and 64-95 each hold the rows [B 16 | C 16] (three copies: the lanes would otherwise
+//                 idle, and every lane quarter can then prepare a third of the chunk's tokens), lane 96 holds the dt row.
 //   TMA warp    : x chunk (32 tokens x 128 fp32 = 16 KB, four SWIZZLE_128B boxes) + its 32 (mean, rstd) pairs (bulk copy) into an 8-stage ring
-//   converters  : 4 warps, thread = (token, 32-column box): (a - mu) rstd S_a -> fp16 hi / lo, written IN PLACE over the 128 bytes the thread read as
-//                 [hi 64 B | lo 64 B]: the box stays a SWIZZLE_128B K-major [32 tokens][128 B] tile, the hi / lo operands of a K step are 32-byte slices of it
-//   MMA warp    : per chunk two M = 128, N = 32 accumulators: tile 1 = the 128 x channels, tile 2 = rows [B 16 | C 16 | dt 1 | zero padding] of W_in;
-//                 3 kind::f16 MMAs per K step (hi hi, lo hi, hi lo), A from TMEM, B from the ring
-//   prep warps  : warp 20 (TMEM lanes 0-31 of tile 2): conv + SiLU of the B_t / C_t rows -> shared memory; warp 21 (lane 32 = the dt row): softplus,
-//                 decay, running decay product E_t of the chunk -> planes dt, e^{dt A}, E_t, dt / E_t; both double-buffered per slot
-//   scan warps  : 4 per slot (warp % 4 = TMEM lane quarter), thread = channel: pull the channel's tokens 16 at a time from TMEM (tcgen05.ld; the accumulator
-//                 is handed back to the tensor core after the second pull, half way through the chunk), conv + SiLU along the registers, then the recurrence
-//                 as ssd_scan_v3 runs it (rescaled-state form r_t = S_t / E_t, 2 FMA-pipe operations per state element; direct form for a chunk whose decay
-//                 product underflows), y stored straight from registers (a warp = 128 contiguous bytes per token)
-// Registers: setmaxnreg moves the budget to the scan warps (88 each, 64 for the others: the pool is the CTA's own launch allocation of 768 x 80).
+//   MMA warp    : per chunk two M = 128, N = 32 accumulators (tile 1, tile 2), 3 kind::f16 MMAs per K step (hi hi, lo hi, hi lo), A from TMEM, B from the ring
+//   slot warps, per chunk i of their sequence:
+//     convert   : chunk i + 1 (already landed): thread = (token, 32-column box): (a - mu) rstd S_a -> fp16 hi / lo, written IN PLACE over the 128 bytes the
+//                 thread read as [hi 64 B | lo 64 B]: the box stays a SWIZZLE_128B K-major [32 tokens][128 B] tile, the hi / lo operands of a K step are
+//                 32-byte slices of it; fence.proxy.async, mbarrier -> the tensor core projects chunk i + 1 under the recurrence of chunk i
+//     prepare   : tile 2 of chunk i from TMEM: quarters 0-2 conv + SiLU of the B_t / C_t rows of their third of the tokens -> shared memory; quarter 3 the dt
+//                 row: softplus, decay, running decay product E_t -> planes dt, e^{dt A}, E_t, dt / E_t; one named barrier of the slot's 128 threads
+//     scan      : pull the channel's tokens 16 at a time from TMEM (tcgen05.ld; the accumulators go back to the tensor core after the second pull), conv +
+//                 SiLU along the registers, then the recurrence as ssd_scan_v3 runs it (rescaled-state form r_t = S_t / E_t, 2 FMA-pipe operations per state
+//                 element; direct form for a chunk whose decay product underflows), y stored straight from registers (a warp = 128 contiguous bytes per token)
+// An earlier version gave conversion and B / C preparation to dedicated warps: each of them ran latency-bound at ~7 cycles per instruction next to four scan
+// warps on its scheduler and the single B / C warp (3 900 cycles per chunk) paced the whole kernel (tools/front_trace.py time lines, profiles/).
 // TMEM (512 columns): 4 slots x (32 + 32) accumulator columns | weights: tile 1 hi 64, lo 64, tile 2 hi 64, lo 64 (two fp16 per column).
 // Shared memory: 128 KB ring + 32 KB B / C rows + 4 KB dt planes + 2 KB statistics = 166 KB.
 #include "gemm_tc.cuh"
@@ -46,10 +50,8 @@ constexpr int FF_P = 128;                        // d_inner = x channels = lanes
 constexpr int FF_N = 16;                         // d_state
 constexpr int FF_SLOTS = 4;
 constexpr int FF_SCAN_WARPS = 4 * FF_SLOTS;
-constexpr int FF_CONV_WARP0 = FF_SCAN_WARPS;     // 16..19
-constexpr int FF_BC_WARP = 20, FF_DT_WARP = 21;  // warp % 4 = 0 / 1: the TMEM lane quarters that hold the B / C rows and the dt row of tile 2
-constexpr int FF_TMA_WARP = 22, FF_MMA_WARP = 23;
-constexpr int FF_THREADS = 24 * 32;
+constexpr int FF_TMA_WARP = FF_SCAN_WARPS, FF_MMA_WARP = FF_SCAN_WARPS + 1;
+constexpr int FF_THREADS = (FF_SCAN_WARPS + 2) * 32;
 #ifndef FF_NST_OVERRIDE
 constexpr int FF_NST = 8;
 #else
@@ -63,14 +65,13 @@ constexpr uint32_t FF_BC = FF_RING + FF_NST * FF_STAGE_BYTES;          // [slot]
 constexpr uint32_t FF_BC_BYTES = FF_Q * 2 * FF_N * 4;                  // 4 KB per (slot, buffer)
 constexpr uint32_t FF_DD = FF_BC + FF_SLOTS * 2 * FF_BC_BYTES;         // [slot][buffer][plane: dt, decay, E, dt / E][token]
 constexpr uint32_t FF_DD_BYTES = 4 * FF_Q * 4;
-constexpr uint32_t FF_DTRAW = FF_DD + FF_SLOTS * 2 * FF_DD_BYTES;      // [token] raw dt accumulator (scratch of the dt warp)
-constexpr uint32_t FF_FLAGS = FF_DTRAW + FF_Q * 4;                     // [slot][buffer] chunk takes the direct form
+constexpr uint32_t FF_DTRAW = FF_DD + FF_SLOTS * 2 * FF_DD_BYTES;      // [slot][token] raw dt accumulator (scratch of the slot's dt warp)
+constexpr uint32_t FF_FLAGS = FF_DTRAW + FF_SLOTS * FF_Q * 4;                     // [slot][buffer] chunk takes the direct form
 constexpr uint32_t FF_STATS = FF_FLAGS + 64;                           // [stage][token] (mean, rstd): bulk-copied next to the x chunk
 constexpr uint32_t FF_BARS = FF_STATS + FF_NST * FF_Q * 8;
 constexpr uint32_t FF_SMEM = FF_BARS + 512;
 constexpr float FF_SA = 1024.f;                  // activation pre-scale behind a LayerNorm (tc_prepare)
 constexpr uint32_t FF_COL_W = 256;               // TMEM: weights behind the accumulators: + 64 job, job = 0 tile 1 hi, 1 tile 1 lo, 2 tile 2 hi, 3 tile 2 lo
-constexpr int FF_REGS_SCAN = 88, FF_REGS_OTHER = 64;
 
 struct FfParams {
   const float2* ln_stats;                        // (M) (mean, rstd)
@@ -121,8 +122,7 @@ __device__ __forceinline__ void ff_sts_u4(uint32_t addr, uint32_t a, uint32_t b,
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ float ff_silu(float z) { return z * sigmoid_fast_f(z); }
-template <int R> __device__ __forceinline__ void ff_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(R)); }
-template <int R> __device__ __forceinline__ void ff_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(R)); }
+__device__ __forceinline__ void ff_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 
 #ifdef FF_TRACE
 #define FF_TR(role, item, k) do { if (blockIdx.x == 0 && (item) < 256 && p.trace) p.trace[((role) * 256 + (item)) * 4 + (k)] = clock64(); } while (0)
@@ -148,14 +148,12 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
   const uint32_t bars = base + FF_BARS;
   const uint32_t bar_w = bars;
   auto bar_raw = [&](int s) { return bars + 8u * (1 + s); };                        // TMA landed the raw chunk
-  auto bar_op = [&](int s) { return bars + 8u * (1 + FF_NST + s); };                // converters wrote the operand
+  auto bar_op = [&](int s) { return bars + 8u * (1 + FF_NST + s); };                // the slot's threads wrote the operand
   auto bar_free = [&](int s) { return bars + 8u * (1 + 2 * FF_NST + s); };          // MMAs that read the stage retired
   constexpr int B0 = 1 + 3 * FF_NST;
   auto bar_dfull = [&](int sl) { return bars + 8u * (B0 + sl); };                   // both accumulator tiles of the slot's chunk are complete
-  auto bar_dempty = [&](int sl) { return bars + 8u * (B0 + 4 + sl); };              // scan + prep warps have pulled them into registers
-  auto bar_bcfull = [&](int sb) { return bars + 8u * (B0 + 8 + sb); };              // sb = 2 slot + buffer: B / C rows and the dt planes of the chunk are in shared memory
-  auto bar_bcfree = [&](int sb) { return bars + 8u * (B0 + 16 + sb); };             // the scan warps are done with them
-  const uint32_t tmem_slot = bars + 8u * (B0 + 24);
+  auto bar_dempty = [&](int sl) { return bars + 8u * (B0 + 4 + sl); };              // the slot's threads have pulled them into registers
+  const uint32_t tmem_slot = bars + 8u * (B0 + 8);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -164,8 +162,7 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < FF_NST; ++s) { mbar_init(bar_raw(s), 1); mbar_init(bar_op(s), 128); mbar_init(bar_free(s), 1); }
-    for (int sl = 0; sl < FF_SLOTS; ++sl) { mbar_init(bar_dfull(sl), 1); mbar_init(bar_dempty(sl), 128 + 64); }
-    for (int sb = 0; sb < 2 * FF_SLOTS; ++sb) { mbar_init(bar_bcfull(sb), 64); mbar_init(bar_bcfree(sb), 128); }
+    for (int sl = 0; sl < FF_SLOTS; ++sl) { mbar_init(bar_dfull(sl), 1); mbar_init(bar_dempty(sl), 128); }
     fence_barrier_init();
   }
   if (warp == FF_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -176,8 +173,8 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // ---- weights: global -> ring (staging) -> TMEM, once per CTA -------------------------------------------------------------------------------------------
-  // staging: tile 1 hi at 0, tile 1 lo at 32 KB: [K chunk of 64][128 rows][128 B]; tile 2 (W rows 128-191; 176+ are out of bounds and arrive as zeros)
-  // at 64 KB: per K chunk (16 KB apart) [hi 64 rows][lo 64 rows]; lanes 64-127 of tile 2 are never read
+  // staging: tile 1 hi at 0, tile 1 lo at 32 KB: [K chunk of 64][128 rows][128 B]; tile 2 (W rows 128-191: B 16, C 16, dt, zero rows; 176+ are out of
+  // bounds and arrive as zeros) at 64 KB: per K chunk (16 KB apart) [hi 64 rows][lo 64 rows]
   if (warp == FF_TMA_WARP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(bar_w, 2u * 49152u);
@@ -193,24 +190,22 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     __syncwarp();
   }
   if (warp < FF_SCAN_WARPS) {
-    const int job = warp >> 2, quarter = warp & 3;
-    const int r = quarter * 32 + lane;                                              // weight row of the tile = TMEM lane
+    const int job = warp >> 2, quarter = warp & 3;                                  // job: 0 tile 1 hi, 1 tile 1 lo, 2 tile 2 hi, 3 tile 2 lo
     mbar_wait(bar_w, 0);
-    const bool tile2 = job >= 2;
-    if (!tile2 || quarter < 2) {
-      const uint32_t src0 = base + FF_RING + (tile2 ? 65536u + (job == 3 ? 8192u : 0u) : (uint32_t)job * 32768u) + (uint32_t)r * 128u;
+    // tile 1: TMEM lane = weight row.  tile 2: quarters 0-2 each take the [B | C] rows (staging rows 0-31), quarter 3 the dt row and the zero rows (32-63)
+    const int r = job < 2 ? quarter * 32 + lane : (quarter < 3 ? lane : 32 + lane);
+    const uint32_t src0 = base + FF_RING + (job < 2 ? (uint32_t)job * 32768u : 65536u + (job == 3 ? 8192u : 0u)) + (uint32_t)r * 128u;
 #pragma unroll
-      for (int kch = 0; kch < 2; ++kch) {
-        uint32_t w[32];
+    for (int kch = 0; kch < 2; ++kch) {
+      uint32_t w[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {                                               // logical 16-byte slot q sits at physical slot q ^ (row & 7)
-          const uint4 v = ff_lds_u4(src0 + (uint32_t)kch * 16384u + (uint32_t)((q ^ (r & 7)) * 16));
-          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-        }
-        ff_tmem_st_32x32u(tmem_base + ((uint32_t)(quarter * 32) << 16) + FF_COL_W + (uint32_t)(job * 64 + kch * 32), w);
+      for (int q = 0; q < 8; ++q) {                                                 // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+        const uint4 v = ff_lds_u4(src0 + (uint32_t)kch * 16384u + (uint32_t)((q ^ (r & 7)) * 16));
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
-      tmem_st_wait();
+      ff_tmem_st_32x32u(tmem_base + ((uint32_t)(quarter * 32) << 16) + FF_COL_W + (uint32_t)(job * 64 + kch * 32), w);
     }
+    tmem_st_wait();
   }
   tc_fence_before();
   __syncthreads();                                                                  // weights are in TMEM: the ring is free for the x chunks
@@ -219,14 +214,14 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
   int nseq[FF_SLOTS];
 #pragma unroll
   for (int s = 0; s < FF_SLOTS; ++s) nseq[s] = ff_nseq(p.B, s);
-  const int nsteps = nseq[0] * nchunks;                              // slot 0 never has fewer sequences than the others
+  const int nsteps = nseq[0] * nchunks;                              // slot 0 never has fewer sequences than the others: the active slots of a step are a prefix
 
   if (warp < FF_SCAN_WARPS) {
-    // ===================================== scan warps: slot = warp / 4, thread = channel ======================================
-    ff_reg_inc<FF_REGS_SCAN>();
+    // ===================================== slot warps: slot = warp / 4, quarter = warp % 4, thread = channel ======================================
     const int slot = warp >> 2, quarter = warp & 3;
     const int ch = quarter * 32 + lane;
-    const uint32_t d_x = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 64);
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    const uint32_t d_x = tmem_base + lane_sel + (uint32_t)(slot * 64), d_bc = d_x + 32u;
     const float osc = __ldg(p.osc);
     const float Dh = p.D ? __ldg(p.D) : 0.f;
     const int kconv = p.kconv;
@@ -235,9 +230,80 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     for (int j = 0; j < 4; ++j) cw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)ch * kconv + j - (4 - kconv)) : 0.f;
     const float cb = __ldg(p.conv_b + ch);
     const float bias_x = __ldg(p.bias2 + ch);
+    // prepare role: quarters 0-2: conv channel 128 + lane (B_0..15, C_0..15); quarter 3: the dt row
+    float bw[4], bbias, bias_p, Ah = 0.f, dtb = 0.f;
+    {
+      const int bch = FF_P + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)bch * kconv + j - (4 - kconv)) : 0.f;
+      bbias = __ldg(p.conv_b + bch);
+      bias_p = quarter < 3 ? __ldg(p.bias2 + bch) : __ldg(p.bias2 + FF_P + 2 * FF_N);
+      if (quarter == 3) { Ah = -expf(__ldg(p.A_log)); dtb = __ldg(p.dt_bias); }
+    }
     const int64_t ldy = DENSE ? (int64_t)FF_P : p.ldy;
     float s[FF_N];
     float h1 = 0.f, h2 = 0.f, h3 = 0.f;                              // x of the tokens t-1, t-2, t-3 (before the conv)
+    float g1 = 0.f, g2 = 0.f, g3 = 0.f;                              // quarter 0: raw B / C values of the previous chunk's last three tokens
+
+    // ---- convert one landed x chunk in place: thread = (token r = lane, 32-column box kc = quarter) --------------------------------------------------------
+    // Each thread rewrites the 128 bytes it read -- 32 fp32 of row r of box kc -- as [fp16 hi of those 32 values (64 B) | fp16 lo (64 B)] in the same row:
+    // the box stays a [32 tokens][128 B] SWIZZLE_128B K-major tile whose first two 32-byte K steps are the hi operand and whose last two are the lo operand
+    // of K columns [32 kc, 32 kc + 32).  No thread touches another thread's bytes, so no barrier is needed between the read and the write.
+    float amax = 0.f;
+    auto convert = [&](int item, int64_t row0) {
+      const int st = item % FF_NST;
+      const uint32_t ph = (uint32_t)(item / FF_NST) & 1u;
+      const int64_t m = row0 + lane;
+      float2 stt = make_float2(0.f, 0.f);
+      if (!p.stats_bulk && m < p.M) stt = __ldg(p.ln_stats + m);
+      const uint32_t row = base + FF_RING + st * FF_STAGE_BYTES + (uint32_t)quarter * 4096u + (uint32_t)lane * 128u;
+      const int sw = lane & 7;
+      mbar_wait(bar_raw(st), ph);
+      if (p.stats_bulk && m < p.M) stt = reinterpret_cast<const float2*>(sm + FF_STATS + st * (FF_Q * 8))[lane];
+      stt.x = -stt.x * stt.y;                                        // (a - mu) rstd = fma(a, rstd, -mu rstd), as the converter of gemm_tc_ts_kernel
+      stt.x *= FF_SA; stt.y *= FF_SA;
+#ifndef FF_ABL_CONV
+      float a[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                                  // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+        const float4 v = ff_lds_f4(row + (uint32_t)((q ^ sw) * 16));
+        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) a[e] = fmaf(a[e], stt.y, stt.x);
+      uint32_t hi2[16], lo2[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
+        amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ff_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
+        ff_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
+      }
+#endif
+      fence_proxy_async();                                           // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_op(st));
+    };
+
+    // ---- B / C rows of tokens [T0, T1) of the chunk: conv + SiLU along this lane's tile 2 columns -> bc[token][lane] -----------------------------------------
+    auto prep_bc = [&](auto t0_tag, auto t1_tag, const float (&v)[32], float* __restrict__ dst) {
+      constexpr int T0 = decltype(t0_tag)::value, T1 = decltype(t1_tag)::value;
+      float raw[T1 - T0 + 3];
+#pragma unroll
+      for (int j = 0; j < T1 - T0 + 3; ++j) {
+        const int t = T0 - 3 + j;
+        raw[j] = t >= 0 ? fmaf(v[t >= 0 ? t : 0], osc, bias_p) : (t == -1 ? g1 : (t == -2 ? g2 : g3));
+      }
+#pragma unroll
+      for (int j = 0; j < T1 - T0; ++j) {
+        const float o = fmaf(bw[3], raw[j + 3], fmaf(bw[2], raw[j + 2], fmaf(bw[1], raw[j + 1], fmaf(bw[0], raw[j], bbias))));
+        dst[(T0 + j) * 2 * FF_N] = ff_silu(o);
+      }
+    };
 
     // one half chunk of FF_H tokens.  RESC: recurrence on r_t = S_t / E_t (w = x dt / E_t; y = E_t (C . r) + D x); else the direct form.
     // Per group of 8 tokens: phase A (independent of the state) conv + SiLU and the per-token scalars, phase B the state recurrence.
@@ -288,26 +354,69 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     };
 
     const int my_steps = nseq[slot] * nchunks;
+    auto nact = [&](int step) { int n = 0;
+#pragma unroll
+      for (int s2 = 0; s2 < FF_SLOTS; ++s2) n += (step < nseq[s2] * nchunks) ? 1 : 0;
+      return n; };
+    auto row_of = [&](int step) { const int k = step / nchunks, c = step - k * nchunks;
+      return ((int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + slot)) * p.T + (int64_t)c * FF_Q; };
+    int item_next = slot;                                            // ring item of this slot's chunk i + 1 (items of a step: its active slots in order)
+    if (my_steps > 0) { convert(item_next, row_of(0)); item_next += nact(0); }
     for (int i = 0; i < my_steps; ++i) {
       const int k = i / nchunks, c = i - k * nchunks;
-      const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + slot);
       const int64_t t0 = (int64_t)c * FF_Q;
       const int tc = (int)min((int64_t)FF_Q, p.T - t0);
       const int sb = 2 * slot + (i & 1);
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 0);
+      if (i + 1 < my_steps) { convert(item_next, row_of(i + 1)); item_next += nact(i + 1); }
       if (c == 0) {
 #pragma unroll
         for (int n = 0; n < FF_N; ++n) s[n] = 0.f;
-        h1 = h2 = h3 = 0.f;
+        h1 = h2 = h3 = 0.f; g1 = g2 = g3 = 0.f;
       }
-      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 0);
-      mbar_wait(bar_bcfull(sb), (uint32_t)(i >> 1) & 1u);            // the prep warps publish after their own wait on bar_dfull
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 1);
       mbar_wait(bar_dfull(slot), (uint32_t)i & 1u);
       tc_fence_after();
-      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 1);
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 2);
+      // ---- prepare: tile 2 of this chunk -> B / C rows and dt planes in shared memory (buffer i & 1) ----
+      {
+        float v[32];
+        tmem_ld_32x32(d_bc, v);
+        float* bcw = reinterpret_cast<float*>(sm + FF_BC + (uint32_t)sb * FF_BC_BYTES) + lane;
+#ifndef FF_ABL_PREP
+        if (quarter == 0) {
+          prep_bc(std::integral_constant<int, 0>{}, std::integral_constant<int, 11>{}, v, bcw);
+          g1 = fmaf(v[31], osc, bias_p); g2 = fmaf(v[30], osc, bias_p); g3 = fmaf(v[29], osc, bias_p);
+        } else if (quarter == 1) {
+          prep_bc(std::integral_constant<int, 11>{}, std::integral_constant<int, 22>{}, v, bcw);
+        } else if (quarter == 2) {
+          prep_bc(std::integral_constant<int, 22>{}, std::integral_constant<int, 32>{}, v, bcw);
+        } else {
+          float* const dtraw = reinterpret_cast<float*>(sm + FF_DTRAW) + slot * FF_Q;
+          if (lane == 0) {                                           // lane 0 of quarter 3 = TMEM lane 96 = the dt row
+#pragma unroll
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dtraw)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          const float z = fmaf(dtraw[lane], osc, bias_p);
+          __syncwarp();
+          const float d = (lane < tc) ? softplus_f(z + dtb) : 0.f;
+          const float dec = (lane < tc) ? expf(d * Ah) : 1.f;
+          float E = dec;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, E, o); if (lane >= o) E *= u; }   // inclusive product scan
+          const float Emin = __shfl_sync(0xffffffffu, E, 31);        // decays <= 1: the last product is the smallest
+          if (lane == 0) reinterpret_cast<int*>(sm + FF_FLAGS)[sb] = (Emin < 0x1p-60f || !(Emin == Emin)) ? 1 : 0;
+          float* pl = reinterpret_cast<float*>(sm + FF_DD + (uint32_t)sb * FF_DD_BYTES) + lane;
+          pl[0] = d; pl[FF_Q] = dec; pl[2 * FF_Q] = E; pl[3 * FF_Q] = d * (1.f / E);
+        }
+#endif
+      }
+      ff_bar_sync(1 + slot, 128);                                    // the chunk's rows are complete; every warp of the slot has left chunk i - 1
       const bool direct = reinterpret_cast<const int*>(sm + FF_FLAGS)[sb] != 0;
       const float4* bc4 = reinterpret_cast<const float4*>(sm + FF_BC + (uint32_t)sb * FF_BC_BYTES);
       const float4* pl4 = reinterpret_cast<const float4*>(sm + FF_DD + (uint32_t)sb * FF_DD_BYTES);
-      float* yp = p.y + (b * p.T + t0) * ldy + ch;
+      float* yp = p.y + (row_of(i)) * ldy + ch;
 #pragma unroll 1
       for (int hf = 0; hf < FF_Q / FF_H; ++hf) {
         float xr[FF_H];
@@ -335,46 +444,12 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
 #pragma unroll
         for (int n = 0; n < FF_N; ++n) s[n] *= Eend;
       }
-      mbar_arrive(bar_bcfree(sb));                                   // this thread is done with the chunk's shared rows
-      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 2);
+      if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 3);
     }
-  } else {
-    ff_reg_dec<FF_REGS_OTHER>();
-    if (warp == FF_TMA_WARP) {
-      // ===================================== TMA producer ======================================
-      if (elect_one()) {
-        int st = 0; uint32_t ph = 0;
-        for (int i = 0; i < nsteps; ++i) {
-          const int k = i / nchunks, c = i - k * nchunks;
-#pragma unroll
-          for (int s = 0; s < FF_SLOTS; ++s) {
-            if (k >= nseq[s]) continue;
-            const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + s);
-            const int row0 = (int)(b * p.T + (int64_t)c * FF_Q);
-            FF_TR(0, i * 4 + s, 0);
-            mbar_wait_one(bar_free(st), ph ^ 1);
-            FF_TR(0, i * 4 + s, 1);
-            int nst_rows = 0;
-            if (p.stats_bulk) { const int64_t left = p.M - row0; nst_rows = left < FF_Q ? (int)left : FF_Q; }    // even: T and FF_Q are
-            mbar_arrive_expect_tx(bar_raw(st), FF_STAGE_BYTES + (uint32_t)nst_rows * 8u);
-            if (nst_rows > 0) ff_bulk_load(base + FF_STATS + st * (FF_Q * 8), p.ln_stats + row0, (uint32_t)nst_rows * 8u, bar_raw(st));
-            const uint32_t dst = base + FF_RING + st * FF_STAGE_BYTES;
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) tma_load_2d(&tmapX, bar_raw(st), dst + kc * 4096, kc * 32, row0);
-            if (++st == FF_NST) { st = 0; ph ^= 1; }
-          }
-        }
-      }
-      __syncwarp();
-    } else if (warp >= FF_CONV_WARP0 && warp < FF_CONV_WARP0 + 4) {
-      // ===================================== converters: thread = (token r, 32-column box kc) ======================================
-      // Each thread rewrites the 128 bytes it read -- 32 fp32 of row r of box kc -- as [fp16 hi of those 32 values (64 B) | fp16 lo (64 B)] in the same row:
-      // the box stays a [32 tokens][128 B] SWIZZLE_128B K-major tile whose first two 32-byte K steps are the hi operand and whose last two are the lo
-      // operand of K columns [32 kc, 32 kc + 32).  No thread touches another thread's bytes, so no barrier is needed between the read and the write.
-      const int r = lane, kc = warp - FF_CONV_WARP0;
-      const int sw = r & 7;
-      const uint32_t row_off = (uint32_t)kc * 4096u + (uint32_t)r * 128u;
-      float amax = 0.f;
+    if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
+  } else if (warp == FF_TMA_WARP) {
+    // ===================================== TMA producer ======================================
+    if (elect_one()) {
       int st = 0; uint32_t ph = 0;
       for (int i = 0; i < nsteps; ++i) {
         const int k = i / nchunks, c = i - k * nchunks;
@@ -382,171 +457,61 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
         for (int s = 0; s < FF_SLOTS; ++s) {
           if (k >= nseq[s]) continue;
           const int64_t b = (int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + s);
-          const int64_t m = b * p.T + (int64_t)c * FF_Q + r;
-          float2 stt = make_float2(0.f, 0.f);
-          if (!p.stats_bulk && m < p.M) stt = __ldg(p.ln_stats + m);
-          const uint32_t row = base + FF_RING + st * FF_STAGE_BYTES + row_off;
-          if (kc == 0 && lane == 0) FF_TR(1, i * 4 + s, 0);
-          mbar_wait(bar_raw(st), ph);
-          if (kc == 0 && lane == 0) FF_TR(1, i * 4 + s, 1);
-          if (p.stats_bulk && m < p.M) stt = reinterpret_cast<const float2*>(sm + FF_STATS + st * (FF_Q * 8))[r];
-          stt.x = -stt.x * stt.y;                                    // (a - mu) rstd = fma(a, rstd, -mu rstd), as the converter of gemm_tc_ts_kernel
-          stt.x *= FF_SA; stt.y *= FF_SA;
-#ifndef FF_ABL_CONV
-          float a[32];
+          const int row0 = (int)(b * p.T + (int64_t)c * FF_Q);
+          FF_TR(0, i * 4 + s, 0);
+          mbar_wait_one(bar_free(st), ph ^ 1);
+          FF_TR(0, i * 4 + s, 1);
+          int nst_rows = 0;
+          if (p.stats_bulk) { const int64_t left = p.M - row0; nst_rows = left < FF_Q ? (int)left : FF_Q; }      // even: T and FF_Q are
+          mbar_arrive_expect_tx(bar_raw(st), FF_STAGE_BYTES + (uint32_t)nst_rows * 8u);
+          if (nst_rows > 0) ff_bulk_load(base + FF_STATS + st * (FF_Q * 8), p.ln_stats + row0, (uint32_t)nst_rows * 8u, bar_raw(st));
+          const uint32_t dst = base + FF_RING + st * FF_STAGE_BYTES;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {                              // logical 16-byte slot q sits at physical slot q ^ (row & 7)
-            const float4 v = ff_lds_f4(row + (uint32_t)((q ^ sw) * 16));
-            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-          }
-#pragma unroll
-          for (int e = 0; e < 32; ++e) a[e] = fmaf(a[e], stt.y, stt.x);
-          uint32_t hi2[16], lo2[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
-            amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
-          }
-#pragma unroll
-          for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ff_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
-            ff_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
-          }
-#endif
-          fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core (async proxy)
-          mbar_arrive(bar_op(st));
-          if (kc == 0 && lane == 0) FF_TR(1, i * 4 + s, 2);
+          for (int kc = 0; kc < 4; ++kc) tma_load_2d(&tmapX, bar_raw(st), dst + kc * 4096, kc * 32, row0);
           if (++st == FF_NST) { st = 0; ph ^= 1; }
         }
       }
-      if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
-    } else if (warp == FF_MMA_WARP) {
-      // ===================================== MMA issuer ======================================
-      if (elect_one()) {
-        const uint32_t idesc = umma_idesc_f16(128, FF_Q);
-        int st = 0; uint32_t ph = 0;
-        for (int i = 0; i < nsteps; ++i) {
-          const int k = i / nchunks;
+    }
+    __syncwarp();
+  } else if (warp == FF_MMA_WARP) {
+    // ===================================== MMA issuer ======================================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, FF_Q);
+      int st = 0; uint32_t ph = 0;
+      for (int i = 0; i < nsteps; ++i) {
+        const int k = i / nchunks;
 #pragma unroll
-          for (int s = 0; s < FF_SLOTS; ++s) {
-            if (k >= nseq[s]) continue;
-            FF_TR(2, i * 4 + s, 0);
-            mbar_wait_one(bar_op(st), ph);
-            FF_TR(2, i * 4 + s, 1);
-            mbar_wait_one(bar_dempty(s), ((uint32_t)i & 1u) ^ 1u);   // chunk i - 1 of this slot is in the scan / prep warps' registers
-            FF_TR(2, i * 4 + s, 2);
-            tc_fence_after();
-            const uint32_t stage = base + FF_RING + st * FF_STAGE_BYTES;
+        for (int s = 0; s < FF_SLOTS; ++s) {
+          if (k >= nseq[s]) continue;
+          FF_TR(2, i * 4 + s, 0);
+          mbar_wait_one(bar_op(st), ph);
+          FF_TR(2, i * 4 + s, 1);
+          mbar_wait_one(bar_dempty(s), ((uint32_t)i & 1u) ^ 1u);     // chunk i - 1 of this slot is in its threads' registers
+          FF_TR(2, i * 4 + s, 2);
+          tc_fence_after();
+          const uint32_t stage = base + FF_RING + st * FF_STAGE_BYTES;
 #pragma unroll
-            for (int tile = 0; tile < 2; ++tile) {
-              const uint32_t d = tmem_base + (uint32_t)(s * 64 + tile * 32);
-              const uint32_t a_hi = tmem_base + FF_COL_W + (uint32_t)(tile * 128), a_lo = a_hi + 64u;
+          for (int tile = 0; tile < 2; ++tile) {
+            const uint32_t d = tmem_base + (uint32_t)(s * 64 + tile * 32);
+            const uint32_t a_hi = tmem_base + FF_COL_W + (uint32_t)(tile * 128), a_lo = a_hi + 64u;
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {                       // K step of 16: weights 8 TMEM columns; activations [box of 32 columns][hi 64 B | lo 64 B]
-                const uint64_t bh = umma_desc_k_sw128(stage + (uint32_t)(ks >> 1) * 4096u) + 2u * (ks & 1), bl = bh + 4u;
+            for (int ks = 0; ks < 8; ++ks) {                         // K step of 16: weights 8 TMEM columns; activations [box of 32 columns][hi 64 B | lo 64 B]
+              const uint64_t bh = umma_desc_k_sw128(stage + (uint32_t)(ks >> 1) * 4096u) + 2u * (ks & 1), bl = bh + 4u;
 #ifndef FF_ABL_MMA                                                    // ablation builds (tools/ablate_front.sh): timing only, wrong results
-                umma_f16_ts(d, a_hi + 8u * ks, bh, idesc, ks > 0 ? 1u : 0u);
-                umma_f16_ts(d, a_lo + 8u * ks, bh, idesc, 1u);
-                umma_f16_ts(d, a_hi + 8u * ks, bl, idesc, 1u);
+              umma_f16_ts(d, a_hi + 8u * ks, bh, idesc, ks > 0 ? 1u : 0u);
+              umma_f16_ts(d, a_lo + 8u * ks, bh, idesc, 1u);
+              umma_f16_ts(d, a_hi + 8u * ks, bl, idesc, 1u);
 #endif
-              }
             }
-            umma_commit(bar_free(st));
-            umma_commit(bar_dfull(s));
-            FF_TR(2, i * 4 + s, 3);
-            if (++st == FF_NST) { st = 0; ph ^= 1; }
           }
-        }
-      }
-      __syncwarp();
-    } else if (warp == FF_BC_WARP) {
-      // ===================================== B / C rows: thread = conv channel 128 + lane (B_0..15, C_0..15) ======================================
-      const float osc = __ldg(p.osc);
-      const int kconv = p.kconv;
-      const int bch = FF_P + lane;
-      float bw[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)bch * kconv + j - (4 - kconv)) : 0.f;
-      const float bbias = __ldg(p.conv_b + bch), bias_bc = __ldg(p.bias2 + bch);
-      float g1[FF_SLOTS], g2[FF_SLOTS], g3[FF_SLOTS];                // raw values of the tokens t-1, t-2, t-3 per slot
-      for (int i = 0; i < nsteps; ++i) {
-        const int k = i / nchunks, c = i - k * nchunks;
-#pragma unroll
-        for (int s = 0; s < FF_SLOTS; ++s) {
-          if (k >= nseq[s]) continue;
-          if (c == 0) g1[s] = g2[s] = g3[s] = 0.f;
-          const int sb = 2 * s + (i & 1);
-          if (lane == 0) FF_TR(3, i * 4 + s, 0);
-          mbar_wait(bar_dfull(s), (uint32_t)i & 1u);
-          if (lane == 0) FF_TR(3, i * 4 + s, 1);
-          tc_fence_after();
-          float v[32];
-          tmem_ld_32x32(tmem_base + (uint32_t)(s * 64 + 32), v);
-          tc_fence_before();
-          mbar_arrive(bar_dempty(s));
-          mbar_wait(bar_bcfree(sb), ((uint32_t)(i >> 1) & 1u) ^ 1u);
-          if (lane == 0) FF_TR(3, i * 4 + s, 2);
-          float* dst = reinterpret_cast<float*>(sm + FF_BC + (uint32_t)sb * FF_BC_BYTES) + lane;
-          float a1 = g1[s], a2 = g2[s], a3 = g3[s];
-#ifdef FF_ABL_PREP
-          if (v[0] == 123.456f) dst[0] = v[1];
-#else
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float raw = fmaf(v[j], osc, bias_bc);
-            const float o = fmaf(bw[3], raw, fmaf(bw[2], a1, fmaf(bw[1], a2, fmaf(bw[0], a3, bbias))));
-            a3 = a2; a2 = a1; a1 = raw;
-            dst[j * 2 * FF_N] = ff_silu(o);
-          }
-#endif
-          g1[s] = a1; g2[s] = a2; g3[s] = a3;
-          mbar_arrive(bar_bcfull(sb));
-          if (lane == 0) FF_TR(3, i * 4 + s, 3);
-        }
-      }
-    } else if (warp == FF_DT_WARP) {
-      // ===================================== dt row: lane 0 of this warp = TMEM lane 32 of tile 2 ======================================
-      const float osc = __ldg(p.osc);
-      const float Ah = -expf(__ldg(p.A_log));
-      const float dtb = __ldg(p.dt_bias);
-      const float bias_dt = __ldg(p.bias2 + FF_P + 2 * FF_N);
-      float* const dtraw = reinterpret_cast<float*>(sm + FF_DTRAW);
-      for (int i = 0; i < nsteps; ++i) {
-        const int k = i / nchunks, c = i - k * nchunks;
-        const int tc = (int)min((int64_t)FF_Q, p.T - (int64_t)c * FF_Q);
-#pragma unroll
-        for (int s = 0; s < FF_SLOTS; ++s) {
-          if (k >= nseq[s]) continue;
-          const int sb = 2 * s + (i & 1);
-          mbar_wait(bar_dfull(s), (uint32_t)i & 1u);
-          tc_fence_after();
-          float v[32];
-          tmem_ld_32x32(tmem_base + (32u << 16) + (uint32_t)(s * 64 + 32), v);
-          tc_fence_before();
-          mbar_arrive(bar_dempty(s));
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dtraw)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          __syncwarp();
-          const float z = fmaf(dtraw[lane], osc, bias_dt);
-          __syncwarp();
-          const float d = (lane < tc) ? softplus_f(z + dtb) : 0.f;
-          const float dec = (lane < tc) ? expf(d * Ah) : 1.f;
-          float E = dec;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, E, o); if (lane >= o) E *= u; }   // inclusive product scan
-          const float Emin = __shfl_sync(0xffffffffu, E, 31);        // decays <= 1: the last product is the smallest
-          mbar_wait(bar_bcfree(sb), ((uint32_t)(i >> 1) & 1u) ^ 1u);
-          if (lane == 0) reinterpret_cast<int*>(sm + FF_FLAGS)[sb] = (Emin < 0x1p-60f || !(Emin == Emin)) ? 1 : 0;
-          float* pl = reinterpret_cast<float*>(sm + FF_DD + (uint32_t)sb * FF_DD_BYTES) + lane;
-          pl[0] = d; pl[FF_Q] = dec; pl[2 * FF_Q] = E; pl[3 * FF_Q] = d * (1.f / E);
-          mbar_arrive(bar_bcfull(sb));
+          umma_commit(bar_free(st));
+          umma_commit(bar_dfull(s));
+          FF_TR(2, i * 4 + s, 3);
+          if (++st == FF_NST) { st = 0; ph ^= 1; }
         }
       }
     }
+    __syncwarp();
   }
 
   tc_fence_before();

@@ -217,7 +217,8 @@ def test_prepared_weights_follow_parameter_changes(eig):
     model = Ly.MambaDev(cfg, sd, "cuda")
     X = torch.randint(0, 97, (16, 96), generator=torch.Generator().manual_seed(4)).cuda()
     for b in model.blocks:
-        b.fuse_tail = False                                                # the fused tail kernel exists for prepared operands only: compare like with like
+        b.fuse_tail = False                                                # the fused front / tail kernels exist for prepared operands only:
+        b.fuse_front = False                                               # compare like with like
     e1 = A.mamba_pass(model, X).eig_host()
     assert all(len(b._prep_ws) == 3 for b in model.blocks)                 # in_proj (+ LayerNorm), out_proj, GLU
     for b in model.blocks:

@@ -20,10 +20,9 @@ t = buf.cpu().view(8, 256, 4)
 t0 = int(t[t > 0].min())
 rel = lambda v: (int(v) - t0) if int(v) > 0 else -1
 print("item = 4 * step + slot; cycles since the first stamp")
-print("%5s | %-15s | %-23s | %-31s | %-31s" % ("item", "tma wait,issue", "conv wait,got,done", "mma start,op,dempty,done", "bc start,dfull,bcfree,done"))
-for it in range(16, 64):
-    print("%5d | %7d %7d | %7d %7d %7d | %7d %7d %7d %7d | %7d %7d %7d %7d" % ((it,) + tuple(rel(t[0, it, k]) for k in range(2)) + tuple(rel(t[1, it, k]) for k in range(3)) +
-          tuple(rel(t[2, it, k]) for k in range(4)) + tuple(rel(t[3, it, k]) for k in range(4))))
-print("scan warps (slot): chunk | wait start, wait end, chunk end")
+print("%5s | %-15s | %-31s" % ("item", "tma wait,issue", "mma start,op,dempty,done"))
+for it in range(16, 48):
+    print("%5d | %7d %7d | %7d %7d %7d %7d" % ((it,) + tuple(rel(t[0, it, k]) for k in range(2)) + tuple(rel(t[2, it, k]) for k in range(4))))
+print("slot warps: chunk | start, converted next, accumulators ready, chunk end")
 for c in range(4, 16):
-    print("%3d | " % c + " | ".join("%7d %7d %7d" % tuple(rel(t[4 + s, c, k]) for k in range(3)) for s in range(4)))
+    print("%3d | " % c + " | ".join("%7d %7d %7d %7d" % tuple(rel(t[4 + s, c, k]) for k in range(4)) for s in range(4)))
