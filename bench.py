@@ -41,6 +41,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 METRIC = "eigenvalues/sec in eval_eig"
 UNIT = "eigenvalues/s"
 NOMINAL_HBM_GBS = 8000.0
+SCAN_FMA = {}
 
 C2 = dict(layer="mamba", version="mamba2", num_layers=4, num_heads=1, input_dim=1, output_dim=8192, hidden_dim=128, state_dim=16,
           conv_dim=4, expansion=1, dropout=0.0, glu=True, norm="layer", dual=False, prenorm=True, pooling="none",
@@ -346,11 +347,17 @@ def c2_alg_bytes(tokens, D_, N_, H):
            "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): tokens * 3 * D_ * 4,
            "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): tokens * 3 * D_ * 4,
            "eigb200_out_glu_fused[D%d K%d out_proj+gelu -> glu_residual+extract]" % (D_, D_): tokens * 3 * D_ * 4,   # read y, read the skip, write x_out
+           "eigb200_mamba_front_fused[D%d P%d N%d ln+in_proj+conv+ssd]" % (D_, D_, N_): tokens * (D_ * 4 + 8 + D_ * 4),   # read x + its statistics, write y
            "eigb200_mamba2_eig_partials": tokens * (4 * H + 8)}
     flops = {"eigb200_linear_ln[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in, "eigb200_linear[N%d K%d none]" % (d_in, D_): 2.0 * tokens * D_ * d_in,
              "eigb200_linear[N%d K%d gelu]" % (D_, D_): 2.0 * tokens * D_ * D_, "eigb200_linear[N%d K%d glu_residual]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_,
              "eigb200_linear_glu_extract[N%d K%d glu_residual+extract]" % (2 * D_, D_): 2.0 * tokens * D_ * 2 * D_,
-             "eigb200_out_glu_fused[D%d K%d out_proj+gelu -> glu_residual+extract]" % (D_, D_): 2.0 * tokens * D_ * 3 * D_}
+             "eigb200_out_glu_fused[D%d K%d out_proj+gelu -> glu_residual+extract]" % (D_, D_): 2.0 * tokens * D_ * 3 * D_,
+             # in_proj on the tensor cores + the recurrence on the FMA pipe (conv 4 + state update N + output N + D x, 2 flop each, per channel and token)
+             "eigb200_mamba_front_fused[D%d P%d N%d ln+in_proj+conv+ssd]" % (D_, D_, N_): 2.0 * tokens * D_ * d_in + 2.0 * tokens * D_ * (2 * N_ + 5)}
+    global SCAN_FMA
+    SCAN_FMA = {"eigb200_mamba_front_fused[D%d P%d N%d ln+in_proj+conv+ssd]" % (D_, D_, N_): tokens * D_ * (2 * N_ + 5),
+                "eigb200_mamba_conv_ssd": tokens * D_ * (2 * N_ + 5)}
     return alg, flops
 
 
@@ -370,6 +377,14 @@ def roofline_from_profile(per, alg, flops, pk, traffic_file=True):
             "algorithmic_bytes_per_launch": alg.get(dom), "avg_launch_ms": dom_avg_ms}
     if dom in flops:
         roof["fp32_equiv_TFLOPs"] = flops[dom] / (dom_avg_ms * 1e-3) / 1e12
+    if dom in SCAN_FMA:
+        # this kernel is paced by the fp32 FMA pipe, not by HBM (profiles/: issue slots 67 % busy, DRAM 20 %): the selective-scan recurrence needs 2 N + 5 FMAs
+        # per channel and token whatever the memory system does; FMA-pipe peak = SMs x 128 lanes x clock
+        props = torch.cuda.get_device_properties(0)
+        fma_peak = props.multi_processor_count * 128 * 1.965e9
+        roof["paced_by"] = "fp32 FMA issue of the selective-scan recurrence (2 N + 5 FMAs per channel and token), not HBM"
+        roof["fma_per_s"] = SCAN_FMA[dom] / (dom_avg_ms * 1e-3)
+        roof["frac_of_fma_peak_at_1965MHz"] = roof["fma_per_s"] / fma_peak
     kernels = {k: {"launches_per_step": len(v), "ms_per_step": sum(v)} for k, v in per.items()}
     for k in kernels:
         if k in alg:

@@ -71,6 +71,8 @@ constexpr uint32_t FF_STATS = FF_FLAGS + 64;                           // [stage
 constexpr uint32_t FF_BARS = FF_STATS + FF_NST * FF_Q * 8;
 constexpr uint32_t FF_SMEM = FF_BARS + 512;
 constexpr float FF_SA = 1024.f;                  // activation pre-scale behind a LayerNorm (tc_prepare)
+// Registers: warps are allocated in fours, so 18 warps cost as much as 20 and the block gets 96 registers per thread.  Moving the issue warps' surplus to
+// the slot warps with setmaxnreg (104 / 112 registers) was measured neutral to slower: ptxas does not turn the extra registers into deeper prefetch.
 constexpr uint32_t FF_COL_W = 256;               // TMEM: weights behind the accumulators: + 64 job, job = 0 tile 1 hi, 1 tile 1 lo, 2 tile 2 hi, 3 tile 2 lo
 
 struct FfParams {
@@ -225,11 +227,17 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     const float osc = __ldg(p.osc);
     const float Dh = p.D ? __ldg(p.D) : 0.f;
     const int kconv = p.kconv;
-    float cw[4];
+    // conv over z = osc acc + bias_x (the projection's scale and folded bias): sum_k w_k z_k + b = sum_k (w_k osc) acc_k + (b + bias_x sum_k w_k),
+    // so the taps carry osc, the bias carries bias_x, and the recurrence works on the raw accumulator values (one FFMA per token less)
+    float cw[4], cb, hpad;
+    {
+      const float bias_x = __ldg(p.bias2 + ch);
+      hpad = -bias_x / osc;                                          // accumulator value whose z is the conv's zero padding: osc hpad + bias_x = 0
+      float wsum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cw[j] = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)ch * kconv + j - (4 - kconv)) : 0.f;
-    const float cb = __ldg(p.conv_b + ch);
-    const float bias_x = __ldg(p.bias2 + ch);
+      for (int j = 0; j < 4; ++j) { const float w = (j >= 4 - kconv) ? __ldg(p.conv_w + (size_t)ch * kconv + j - (4 - kconv)) : 0.f; wsum += w; cw[j] = w * osc; }
+      cb = fmaf(bias_x, wsum, __ldg(p.conv_b + ch));
+    }
     // prepare role: quarters 0-2: conv channel 128 + lane (B_0..15, C_0..15); quarter 3: the dt row
     float bw[4], bbias, bias_p, Ah = 0.f, dtb = 0.f;
     {
@@ -242,7 +250,7 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     }
     const int64_t ldy = DENSE ? (int64_t)FF_P : p.ldy;
     float s[FF_N];
-    float h1 = 0.f, h2 = 0.f, h3 = 0.f;                              // x of the tokens t-1, t-2, t-3 (before the conv)
+    float h1 = hpad, h2 = hpad, h3 = hpad;                           // raw x accumulators of the tokens t-1, t-2, t-3
     float g1 = 0.f, g2 = 0.f, g3 = 0.f;                              // quarter 0: raw B / C values of the previous chunk's last three tokens
 
     // ---- convert one landed x chunk in place: thread = (token r = lane, 32-column box kc = quarter) --------------------------------------------------------
@@ -328,13 +336,31 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
           xv[jj] = ff_silu(c);
           w0[jj] *= xv[jj];
         }
+#ifdef FF_BPREFETCH
+        float4 bn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bn[q] = bc4[(8 * g) * 8 + q];
+#endif
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int j = 8 * g + jj;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#ifdef FF_BPREFETCH
+          float4 bcur[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bcur[q] = bn[q];
+          if (jj + 1 < 8) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bn[q] = bc4[(j + 1) * 8 + q];
+          }
+#endif
 #pragma unroll
           for (int q = 0; q < FF_N / 4; ++q) {
+#ifdef FF_BPREFETCH
+            const float4 bv = bcur[q], cv = bc4[j * 8 + 4 + q];
+#else
             const float4 bv = bc4[j * 8 + q], cv = bc4[j * 8 + 4 + q];
+#endif
             if (RESC) {
               s[4 * q + 0] = fmaf(w0[jj], bv.x, s[4 * q + 0]); s[4 * q + 1] = fmaf(w0[jj], bv.y, s[4 * q + 1]);
               s[4 * q + 2] = fmaf(w0[jj], bv.z, s[4 * q + 2]); s[4 * q + 3] = fmaf(w0[jj], bv.w, s[4 * q + 3]);
@@ -354,25 +380,32 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     };
 
     const int my_steps = nseq[slot] * nchunks;
+    int steps_of[FF_SLOTS];
+#pragma unroll
+    for (int s2 = 0; s2 < FF_SLOTS; ++s2) steps_of[s2] = nseq[s2] * nchunks;
     auto nact = [&](int step) { int n = 0;
 #pragma unroll
-      for (int s2 = 0; s2 < FF_SLOTS; ++s2) n += (step < nseq[s2] * nchunks) ? 1 : 0;
+      for (int s2 = 0; s2 < FF_SLOTS; ++s2) n += (step < steps_of[s2]) ? 1 : 0;
       return n; };
-    auto row_of = [&](int step) { const int k = step / nchunks, c = step - k * nchunks;
-      return ((int64_t)blockIdx.x + (int64_t)gridDim.x * (FF_SLOTS * k + slot)) * p.T + (int64_t)c * FF_Q; };
+    const int64_t seq_stride = (int64_t)gridDim.x * FF_SLOTS * p.T;   // rows between consecutive sequences of this slot
+    int64_t row_cur = ((int64_t)blockIdx.x + (int64_t)gridDim.x * slot) * p.T;        // first row of chunk i
+    int c = 0;                                                       // chunk of the sequence
+    auto advance = [&](int64_t row, int cc, int64_t& row_n, int& c_n) {                  // (row, chunk) of the next step
+      if (cc + 1 < nchunks) { row_n = row + FF_Q; c_n = cc + 1; } else { row_n = row - (int64_t)cc * FF_Q + seq_stride; c_n = 0; }
+    };
     int item_next = slot;                                            // ring item of this slot's chunk i + 1 (items of a step: its active slots in order)
-    if (my_steps > 0) { convert(item_next, row_of(0)); item_next += nact(0); }
+    if (my_steps > 0) { convert(item_next, row_cur); item_next += nact(0); }
     for (int i = 0; i < my_steps; ++i) {
-      const int k = i / nchunks, c = i - k * nchunks;
-      const int64_t t0 = (int64_t)c * FF_Q;
-      const int tc = (int)min((int64_t)FF_Q, p.T - t0);
+      int64_t row_nx; int c_nx;
+      advance(row_cur, c, row_nx, c_nx);
+      const int tc = (int)min((int64_t)FF_Q, p.T - (int64_t)c * FF_Q);
       const int sb = 2 * slot + (i & 1);
       if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 0);
-      if (i + 1 < my_steps) { convert(item_next, row_of(i + 1)); item_next += nact(i + 1); }
+      if (i + 1 < my_steps) { convert(item_next, row_nx); item_next += nact(i + 1); }
       if (c == 0) {
 #pragma unroll
         for (int n = 0; n < FF_N; ++n) s[n] = 0.f;
-        h1 = h2 = h3 = 0.f; g1 = g2 = g3 = 0.f;
+        h1 = h2 = h3 = hpad; g1 = g2 = g3 = 0.f;
       }
       if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 1);
       mbar_wait(bar_dfull(slot), (uint32_t)i & 1u);
@@ -416,14 +449,12 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
       const bool direct = reinterpret_cast<const int*>(sm + FF_FLAGS)[sb] != 0;
       const float4* bc4 = reinterpret_cast<const float4*>(sm + FF_BC + (uint32_t)sb * FF_BC_BYTES);
       const float4* pl4 = reinterpret_cast<const float4*>(sm + FF_DD + (uint32_t)sb * FF_DD_BYTES);
-      float* yp = p.y + (row_of(i)) * ldy + ch;
+      float* yp = p.y + row_cur * ldy + ch;
 #pragma unroll 1
       for (int hf = 0; hf < FF_Q / FF_H; ++hf) {
         float xr[FF_H];
         ff_tmem_ld_32x16(d_x + (uint32_t)(hf * FF_H), xr);
         if (hf == FF_Q / FF_H - 1) { tc_fence_before(); mbar_arrive(bar_dempty(slot)); }    // the tensor core may overwrite the slot's accumulators
-#pragma unroll
-        for (int j = 0; j < FF_H; ++j) xr[j] = fmaf(xr[j], osc, bias_x);
         const float4* bch = bc4 + hf * FF_H * 8;
         const float4* plh = pl4 + hf * (FF_H / 4);
         float* yph = yp + (int64_t)(hf * FF_H) * ldy;
@@ -445,6 +476,7 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
         for (int n = 0; n < FF_N; ++n) s[n] *= Eend;
       }
       if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 3);
+      row_cur = row_nx; c = c_nx;
     }
     if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
   } else if (warp == FF_TMA_WARP) {

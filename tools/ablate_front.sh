@@ -6,7 +6,7 @@ PKG=task-level-insights-from-eigenvalues-across-sequence-models_b200
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -diag-suppress 177 -I include"
 mkdir -p ab /tmp/abl
 OBJS=$(ls $PKG/build/*.o | grep -v -e k7_front_fused.o)
-VARS=("trace:-DFF_TRACE" "scan:-DFF_ABL_SCAN" "mma:-DFF_ABL_MMA" "scanmma:-DFF_ABL_SCAN -DFF_ABL_MMA" "scanmmaprep:-DFF_ABL_SCAN -DFF_ABL_MMA -DFF_ABL_PREP" "all:-DFF_ABL_SCAN -DFF_ABL_MMA -DFF_ABL_CONV -DFF_ABL_PREP")
+VARS=("trace:-DFF_TRACE" "scan:-DFF_ABL_SCAN" "bpre:-DFF_BPREFETCH")
 for v in "${VARS[@]}"; do
   name=${v%%:*}; defs=${v#*:}
   nvcc $FLAGS $defs -c $PKG/csrc/k7_front_fused.cu -o /tmp/abl/k7_$name.o &
