@@ -149,6 +149,20 @@ def case_front(B, T=512, D=128, P=128, N=16):
     return fn, B * T * (D + P + 2) * 4, B * T
 
 
+def case_tail(M, D=128, K1=128):
+    """out_proj + GELU -> GLU + residual + extractor partials as one kernel (k4_gemm_fused.cu)."""
+    ops.set_gemm_precision("f16x3")
+    y = torch.randn(M, K1, device="cuda"); r = torch.randn(M, D, device="cuda")
+    w1 = torch.randn(D, K1, device="cuda") / K1 ** 0.5; b1 = torch.randn(D, device="cuda") * 0.3
+    w2 = torch.randn(2 * D, D, device="cuda") / D ** 0.5; b2 = torch.randn(2 * D, device="cuda")
+    wg = torch.randn(D, device="cuda") / D ** 0.5
+    ws1 = ops.linear_prepare(w1, b1, "gelu"); ws2 = ops.linear_prepare(w2, b2, "glu_residual")
+    out = torch.empty(M, D, device="cuda"); part = torch.empty(D // 16, 3, M, device="cuda")
+    def fn():
+        ops.out_glu_fused(y, ws1, b1, ws2, b2, r, wg, part, out=out)
+    return fn, M * 3 * D * 4, 2.0 * M * D * 3 * D
+
+
 def case_linear(M, N, K, epi, mode):
     a = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     nout = N // 2 if epi == "glu_residual" else N
@@ -189,6 +203,7 @@ CASES = {
     "ssd_small_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(512))[1],
     "ssd_c2_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(4096))[1],
     "ssd_small_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(512))[1],
+    "tail_c2": lambda: case_tail(M_C2),
     "front_c2": lambda: case_front(4096),
     "front_small": lambda: case_front(592),
     "ln_c2": lambda: case_ln(M_C2, 128),
