@@ -29,4 +29,8 @@ int* tc_overflow_flag();
 int launch_out_glu_fused(cudaStream_t st, const float* A, int64_t lda, const void* ws1, const float* bias1, const void* ws2, const float* bias2,
                          float* C, int64_t ldc, const float* R, int64_t ldr, int64_t M, int D, int K1, const float* eig_w, float* eig_part);
 bool out_glu_fused_supported(int D, int K1);
+// the same tail in the transposed orientation (k8_tail_fused_t.cu: weights = A operand from TMEM, 32-token chunks = B operand, three chunks in flight per CTA)
+int launch_out_glu_fused_t(cudaStream_t st, const float* A, int64_t lda, const void* ws1, const float* bias1, const void* ws2, const float* bias2,
+                           float* C, int64_t ldc, const float* R, int64_t ldr, int64_t M, int D, int K1, const float* eig_w, float* eig_part);
+bool out_glu_fused_t_supported(int D, int K1);
 }  // namespace eigb200

@@ -26,6 +26,10 @@
 // TMEM (512 columns): D1 128 | D2 128 | O hi 64 | O lo 64 | 4 operand stages x 32.  Shared memory: 192 KB weights + 32 KB ring = 224 KB.
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
+#ifndef EIGB200_TAIL_DEFAULT_T
+#define EIGB200_TAIL_DEFAULT_T 0
+#endif
 
 namespace eigb200 {
 
@@ -391,5 +395,13 @@ extern "C" int eigb200_out_glu_fused(void* stream, const float* d_y, int64_t ldy
   EIGB_CHECK_ARG(ldy >= K1 && ldc >= D && ldr >= D, "out_glu_fused: row stride smaller than the row");
   EIGB_CHECK_ARG((d_W_gate == nullptr) == (d_partials == nullptr), "out_glu_fused: the extractor needs both the gate weights and the partials buffer");
   EIGB_CHECK_ARG(tc_default_kind() == 1, "out_glu_fused: the prepared operands must be the fp16 split (EIGB200_GEMM_PRECISION=f16x3)");
+  {
+    // EIGB200_TAIL_FORM: "t" = the transposed form (k8_tail_fused_t.cu) where its shape conditions hold, "n" = this file's kernel.  Read per call (cheap next
+    // to a launch) so that the tests can switch forms.
+    const char* e = getenv("EIGB200_TAIL_FORM");
+    const bool want_t = e ? (e[0] == 't') : (EIGB200_TAIL_DEFAULT_T != 0);
+    if (want_t && out_glu_fused_t_supported(D, K1))
+      return launch_out_glu_fused_t((cudaStream_t)stream, d_y, ldy, d_ws_out, d_bias_out, d_ws_glu, d_bias_glu, d_C, ldc, d_R, ldr, M, D, K1, d_W_gate, d_partials);
+  }
   return launch_out_glu_fused((cudaStream_t)stream, d_y, ldy, d_ws_out, d_bias_out, d_ws_glu, d_bias_glu, d_C, ldc, d_R, ldr, M, D, K1, d_W_gate, d_partials);
 }

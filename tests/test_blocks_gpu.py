@@ -470,8 +470,11 @@ def test_linear_f16_split_overflow_is_loud(ops):
 
 @pytest.mark.parametrize("M,K1", [(4096, 128), (3001, 128), (129, 128), (2048, 64), (1500, 96), (40000, 32)])
 @pytest.mark.parametrize("extract", [True, False])
-def test_out_glu_fused_matches_two_kernels(ops, M, K1, extract):
-    """eigb200_out_glu_fused (GELU(out_proj) never leaves the SM) against the two-kernel form on the same prepared fp16-split operands, and against fp64."""
+@pytest.mark.parametrize("form", ["n", "t"])
+def test_out_glu_fused_matches_two_kernels(ops, M, K1, extract, form, monkeypatch):
+    """eigb200_out_glu_fused (GELU(out_proj) never leaves the SM) against the two-kernel form on the same prepared fp16-split operands, and against fp64.
+    form "t" = the transposed kernel (k8_tail_fused_t.cu) where its shape conditions hold (K1 = 128), "n" = gemm_out_glu_kernel."""
+    monkeypatch.setenv("EIGB200_TAIL_FORM", form)
     ops.set_gemm_precision("f16x3")
     try:
         D = 128

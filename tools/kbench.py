@@ -204,6 +204,7 @@ CASES = {
     "ssd_c2_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(4096))[1],
     "ssd_small_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(512))[1],
     "tail_c2": lambda: case_tail(M_C2),
+    "tail_small": lambda: case_tail(592 * 512),
     "front_c2": lambda: case_front(4096),
     "front_small": lambda: case_front(592),
     "ln_c2": lambda: case_ln(M_C2, 128),
