@@ -52,8 +52,66 @@ __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restric
   }
 }
 
+// D = 128 (the C2 / MQAR family): 8 lanes per row, the row's four float4 gathers (L2 hits) of a lane issued together and the token ids of the next trip fetched
+// one trip ahead -- the generic kernel's dependent id -> gather -> store chain per 16 bytes left it latency-bound at 59 % of the copy peak
+__global__ void __launch_bounds__(256) embedding128_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
+                                                           const float* __restrict__ pos, float* __restrict__ out,
+                                                           int64_t rows, int64_t T, int64_t vocab, float2* __restrict__ rowstats, float ln_eps) {
+  constexpr int D = 128, LPR = 8, RPW = 4;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t r0 = warp * RPW;
+  int64_t id_next = 0;
+  if (r0 < rows) id_next = ids[min(r0 + sub, rows - 1)];
+  for (; r0 < rows; r0 += nwarps * RPW) {
+    const int64_t r = r0 + sub;
+    const bool ok = r < rows;
+    const int64_t rc = ok ? r : rows - 1;
+    int64_t id = id_next;
+    const int64_t rn = r0 + nwarps * RPW;
+    if (rn < rows) id_next = ids[min(rn + sub, rows - 1)];
+    if (id < 0 || id >= vocab) id = 0;
+    const float4* w = reinterpret_cast<const float4*>(word + id * D);
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(w + l + LPR * k);
+    if (pos) {
+      const float4* pp = reinterpret_cast<const float4*>(pos + (rc % T) * D);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float4 q = __ldg(pp + l + LPR * k); v[k].x += q.x; v[k].y += q.y; v[k].z += q.z; v[k].w += q.w; }
+    }
+    float4* o = reinterpret_cast<float4*>(out + rc * D);
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stg_stream_f4(o + l + LPR * k, v[k]);
+    }
+    if (rowstats) {
+      const float shift = __shfl_sync(0xffffffffu, v[0].x, sub * LPR);           // the row's first element (lane l = 0 holds columns 0-3)
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = v[k].x - shift, bb = v[k].y - shift, cc = v[k].z - shift, d = v[k].w - shift;
+        s1 += (a + bb) + (cc + d); s2 += (a * a + bb * bb) + (cc * cc + d * d);
+      }
+#pragma unroll
+      for (int ofs = LPR / 2; ofs >= 1; ofs >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, ofs); s2 += __shfl_xor_sync(0xffffffffu, s2, ofs); }
+      if (l == 0 && ok) {
+        const float md = s1 / (float)D;
+        rowstats[r] = make_float2(shift + md, rsqrtf(fmaxf(s2 / (float)D - md * md, 0.f) + ln_eps));
+      }
+    }
+  }
+}
+
 static void launch_embedding(cudaStream_t st, const int64_t* ids, const float* word, const float* pos, float* out, int64_t rows, int64_t T, int D,
                              int64_t vocab, float2* rowstats, float ln_eps) {
+  if (D == 128) {
+    int64_t g = (rows + 31) / 32; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
+    embedding128_kernel<<<(unsigned)g, 256, 0, st>>>(ids, word, pos, out, rows, T, vocab, rowstats, ln_eps);
+    return;
+  }
   const int lpr = D <= 256 ? 8 : 32;
   const int64_t rows_per_cta = 8 * (32 / lpr);
   int64_t g = (rows + rows_per_cta - 1) / rows_per_cta; const int64_t cap = (int64_t)num_sms() * 16; if (g > cap) g = cap;
