@@ -400,12 +400,13 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
 // Epilogue of the streamed-operand kernel (a separate copy: the resident-weight kernels are sensitive to any change of their epilogue's code
 // generation -- folding the two behind a template flag cost them 10 %): the CTA walks (row tile, N tile) pairs blockIdx.x, + gridDim.x, ... with the N tile fastest; bias_s points
 // at the whole bias vector in accumulator-column order in GLOBAL memory (p.nsplit * bn entries).
-template <int EPI, bool STREAM = true>
+template <int EPI, bool STREAM = true, bool SC = false>
 __device__ __forceinline__ void tc_epilogue_stream(const TcParams& p, uint32_t tmem_base, int bn, uint32_t bar_dfull0, uint32_t bar_dempty0,
                                             const float* bias_s, int worker, int split, int warp, int lane) {
   auto bar_dfull = [&](int j) { return bar_dfull0 + 8u * j; };
   auto bar_dempty = [&](int j) { return bar_dempty0 + 8u * j; };
   constexpr bool GLU = EPI == EIGB200_EPI_GLU_RESIDUAL;
+  const float osc = SC ? __ldg(p.out_scale) : 1.f;                   // fp16 split: the accumulator carries S_a S_w
   const int nout = GLU ? p.N / 2 : p.N;
   const int cols_out = GLU ? p.bg : bn;                              // output columns produced by this CTA
   int n_cta0 = split * cols_out;
@@ -449,7 +450,9 @@ __device__ __forceinline__ void tc_epilogue_stream(const TcParams& p, uint32_t t
         if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
+        for (int i = 0; i < 16; ++i)
+          v[i] = SC ? fmaf(a[i], osc, bias_s[cg + i]) * sigmoid_fast_f(fmaf(a[16 + i], osc, bias_s[cg + 16 + i]))
+                    : (a[i] + bias_s[cg + i]) * sigmoid_fast_f(a[16 + i] + bias_s[cg + 16 + i]);
         if (r_own) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += rr[i];
@@ -502,7 +505,7 @@ __device__ __forceinline__ void tc_epilogue_stream(const TcParams& p, uint32_t t
         if (last) { tc_fence_before(); mbar_arrive(bar_dempty(j)); arrived = true; }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float vv = v[i] + bias_s[cg + i];
+          float vv = SC ? fmaf(v[i], osc, bias_s[cg + i]) : v[i] + bias_s[cg + i];
           if (EPI == EIGB200_EPI_GELU) vv = gelu_fast_f(vv);
           v[i] = vv;
         }
@@ -1009,6 +1012,30 @@ __global__ void split_a_kernel(const float* __restrict__ A, int64_t lda, const f
   reinterpret_cast<float4*>(lo)[idx] = l;
 }
 
+// fp16 split of A for the streamed-operand kernel: a' = LN(a) S_a -> hi = fp16(a'), lo = fp16(a' - hi), rows of kp64 halfs (zero padded); raises the sticky
+// overflow flag when |a'| leaves the fp16 range (the caller reruns with 3xTF32)
+__global__ void split_a_f16_kernel(const float* __restrict__ A, int64_t lda, const float2* __restrict__ stats, __half* __restrict__ hi, __half* __restrict__ lo,
+                                   int64_t M, int K, int kp64, float a_scale, int* __restrict__ ovf_flag) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;             // four halfs of the padded (M, kp64) array
+  const int kq = kp64 >> 2;
+  if (idx >= M * kq) return;
+  const int64_t m = idx / kq;
+  const int k = (int)(idx - m * kq) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < K) {                                                                     // K % 4 == 0
+    a = ldg_stream_f4(reinterpret_cast<const float4*>(A + m * lda + k));
+    float sc = a_scale, c = 0.f;
+    if (stats) { const float2 st = __ldg(stats + m); sc = st.y * a_scale; c = -st.x * st.y * a_scale; }
+    a.x = fmaf(a.x, sc, c); a.y = fmaf(a.y, sc, c); a.z = fmaf(a.z, sc, c); a.w = fmaf(a.w, sc, c);
+  }
+  const uint32_t h01 = pack_f16x2(a.x, a.y), h23 = pack_f16x2(a.z, a.w);
+  const uint32_t l01 = pack_f16x2(a.x - f16_lo_to_f32(h01), a.y - f16_hi_to_f32(h01)), l23 = pack_f16x2(a.z - f16_lo_to_f32(h23), a.w - f16_hi_to_f32(h23));
+  reinterpret_cast<uint2*>(hi)[idx] = make_uint2(h01, h23);
+  reinterpret_cast<uint2*>(lo)[idx] = make_uint2(l01, l23);
+  const float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+  if (!(amax <= 65504.f)) atomicOr(ovf_flag, 1);
+}
+
 // bias in accumulator-column order (nsplit * bn entries, zero for padding columns)
 __global__ void perm_bias_kernel(const float* __restrict__ bias, float* __restrict__ out, int N, int bn, int bg, int nsplit, int glu) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1022,7 +1049,9 @@ __global__ void perm_bias_kernel(const float* __restrict__ bias, float* __restri
 
 constexpr int SK_MAX_STAGES = 4;
 
-template <int EPI>
+// F16: operands are the scaled fp16 split (kind::f16; a stage row of 128 bytes holds 64 K values instead of 32: half the L2 traffic per product, twice the
+// tensor rate), the accumulator carries S_a S_w and the epilogue's bias FMA removes it
+template <int EPI, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_constant__ CUtensorMap tmapAlo,
                       const __grid_constant__ CUtensorMap tmapWhi, const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
@@ -1065,10 +1094,11 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
           mbar_wait_one(bar_empty(s), ph ^ 1);
           const uint32_t st0 = stage0 + s * stage_bytes;
           mbar_arrive_expect_tx(bar_full(s), stage_bytes);
-          tma_load_2d(&tmapAhi, bar_full(s), st0, c * TC_KC, (int)(tile * TC_BM));
-          tma_load_2d(&tmapAlo, bar_full(s), st0 + TC_CHUNK_BYTES, c * TC_KC, (int)(tile * TC_BM));
-          tma_load_2d(&tmapWhi, bar_full(s), st0 + 2 * TC_CHUNK_BYTES, c * TC_KC, split * bn);
-          tma_load_2d(&tmapWlo, bar_full(s), st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * TC_KC, split * bn);
+          constexpr int KSTAGE = F16 ? 64 : TC_KC;                 // K values per 128-byte row
+          tma_load_2d(&tmapAhi, bar_full(s), st0, c * KSTAGE, (int)(tile * TC_BM));
+          tma_load_2d(&tmapAlo, bar_full(s), st0 + TC_CHUNK_BYTES, c * KSTAGE, (int)(tile * TC_BM));
+          tma_load_2d(&tmapWhi, bar_full(s), st0 + 2 * TC_CHUNK_BYTES, c * KSTAGE, split * bn);
+          tma_load_2d(&tmapWlo, bar_full(s), st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * KSTAGE, split * bn);
           if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
@@ -1076,7 +1106,7 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+      const uint32_t idesc = F16 ? umma_idesc_f16(TC_BM, bn) : umma_idesc_tf32(TC_BM, bn);
       const bool three = p.nterms == 3;
       int s = 0; uint32_t ph = 0;
       int j = 0; uint32_t dph = 0;
@@ -1091,11 +1121,19 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
           const uint64_t dah0 = umma_desc_k_sw128(st0), dal0 = umma_desc_k_sw128(st0 + TC_CHUNK_BYTES);
           const uint64_t dbh0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES), dbl0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes);
 #pragma unroll
-          for (int k = 0; k < TC_KC / 8; ++k) {
-            umma_tf32(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
-            if (three) {
-              umma_tf32(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
-              umma_tf32(d_tmem, dal0 + 2u * k, dbh0 + 2u * k, idesc, 1u);
+          for (int k = 0; k < TC_KC / 8; ++k) {                      // 4 K steps of 32 bytes per stage row in either precision
+            if constexpr (F16) {
+              umma_f16_ss(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              if (three) {
+                umma_f16_ss(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
+                umma_f16_ss(d_tmem, dal0 + 2u * k, dbh0 + 2u * k, idesc, 1u);
+              }
+            } else {
+              umma_tf32(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              if (three) {
+                umma_tf32(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
+                umma_tf32(d_tmem, dal0 + 2u * k, dbh0 + 2u * k, idesc, 1u);
+              }
             }
           }
           umma_commit(bar_empty(s));
@@ -1107,7 +1145,7 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
     }
     __syncwarp();
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
-    tc_epilogue_stream<EPI>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), p.bias, 0, 0, warp - TC_EPI_WARP0, lane);
+    tc_epilogue_stream<EPI, true, F16>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), p.bias, 0, 0, warp - TC_EPI_WARP0, lane);
   }
 
   tc_fence_before();
@@ -1287,7 +1325,7 @@ static size_t stream_workspace_bytes(int64_t M, int N, int K, int epilogue) {
   const StreamPlan pl = make_stream_plan(N, K, epilogue);
   if (!pl.ok) return 0;
   const size_t wrows = (size_t)pl.nsplit * pl.bn;
-  return (2 * wrows * pl.kpad + (size_t)((N + 3) / 4 * 4) + wrows + 2 * (size_t)M * pl.kpad) * sizeof(float);
+  return (2 * wrows * pl.kpad + (size_t)((N + 3) / 4 * 4) + wrows + 2 * (size_t)M * pl.kpad) * sizeof(float) + 64;   // + the fp16 form's scale block
 }
 
 size_t tc_workspace_bytes_m(int64_t M, int N, int K) {
@@ -1334,25 +1372,25 @@ int tc_prepare(cudaStream_t st, const LinearParams& lp, void* workspace, int kin
   const TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue, kind);
   if (pl.ok) { bn = pl.bn; bg = pl.bg; nsplit = pl.nsplit; kpad = pl.kpad; }
   else {
-    kind = 0;                                                        // the streamed-operand kernel is 3xTF32 only
     const StreamPlan sp = make_stream_plan(lp.N, lp.K, lp.epilogue);
     if (!sp.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
     bn = sp.bn; bg = sp.bg; nsplit = sp.nsplit; kpad = sp.kpad;
   }
   const size_t wrows = (size_t)nsplit * bn;
+  const int kp64 = (lp.K + 63) / 64 * 64;
   if (kind == 1) {
     // [hi halfs wrows x kp64][lo halfs][bias2 floats][scal: 1/(S_a S_w), max|w| bits, S_w, S_a]
     __half* w_hi = reinterpret_cast<__half*>(workspace);
-    __half* w_lo = w_hi + wrows * pl.kp64;
-    float* bias2 = reinterpret_cast<float*>(w_lo + wrows * pl.kp64);
+    __half* w_lo = w_hi + wrows * kp64;
+    float* bias2 = reinterpret_cast<float*>(w_lo + wrows * kp64);
     float* scal = bias2 + (lp.N + 3) / 4 * 4;
     const float a_scale = ln ? 1024.f : 16.f;
     EIGB_CUDA(cudaMemsetAsync(scal, 0, 16, st));
     const int nk = lp.N * lp.K;
     absmax_weights_kernel<<<(nk + 1023) / 1024 > 64 ? 64 : (nk + 1023) / 1024, 256, 0, st>>>(lp.W, ln ? lp.ln_gamma : nullptr, lp.N, lp.K, reinterpret_cast<unsigned*>(scal) + 1);
     EIGB_LAUNCH_CHECK("absmax_weights_kernel");
-    const int total = (int)(wrows * pl.kp64);
-    split_weights_f16_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, pl.kp64, bn, bg, nsplit, glu ? 1 : 0, ln ? lp.ln_gamma : nullptr, scal, a_scale);
+    const int total = (int)(wrows * kp64);
+    split_weights_f16_kernel<<<(total + 255) / 256, 256, 0, st>>>(lp.W, w_hi, w_lo, lp.N, lp.K, kp64, bn, bg, nsplit, glu ? 1 : 0, ln ? lp.ln_gamma : nullptr, scal, a_scale);
     EIGB_LAUNCH_CHECK("split_weights_f16_kernel");
     if (ln) {
       ln_bias_kernel<<<(lp.N + 7) / 8, 256, 0, st>>>(lp.W, lp.bias, lp.ln_beta, bias2, lp.N, lp.K);
@@ -1390,48 +1428,84 @@ bool tc_prepared_layout_f16(int N, int K, int epilogue, const void* ws, TcPrepar
   return true;
 }
 
-static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace) {
+static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace, int kind) {
   if (lp.eig_part) { set_error("linear_glu_extract: not available on the streamed-operand kernel (K > 256)"); return EIGB200_EUNSUPPORTED; }
   const StreamPlan pl = make_stream_plan(lp.N, lp.K, lp.epilogue);
   if (!pl.ok) { set_error("tcgen05 GEMM: unsupported shape N=%d K=%d", lp.N, lp.K); return EIGB200_EUNSUPPORTED; }
   const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const size_t wrows = (size_t)pl.nsplit * pl.bn;
-  float* w_hi = reinterpret_cast<float*>(workspace);
-  float* w_lo = w_hi + wrows * pl.kpad;
-  float* bias2 = w_lo + wrows * pl.kpad;
-  float* bias_perm = bias2 + (lp.N + 3) / 4 * 4;
-  float* a_hi = bias_perm + wrows;
-  float* a_lo = a_hi + (size_t)lp.M * pl.kpad;
+  const bool f16 = kind == 1 && nterms == 3;
+  const int kp64 = (lp.K + 63) / 64 * 64;
+  // workspace: [W hi][W lo][bias2 = b + W beta][scal (fp16 split only)][bias in accumulator-column order][A hi][A lo]; the fp16 form needs at most the fp32 form's bytes
+  float *bias2, *bias_perm; const float* scal = nullptr;
+  void *w_hi, *w_lo, *a_hi, *a_lo;
+  if (f16) {
+    __half* wh = reinterpret_cast<__half*>(workspace);
+    __half* wl = wh + wrows * kp64;
+    bias2 = reinterpret_cast<float*>(wl + wrows * kp64);
+    scal = bias2 + (lp.N + 3) / 4 * 4;
+    bias_perm = bias2 + (lp.N + 3) / 4 * 4 + 4;
+    __half* ah = reinterpret_cast<__half*>(bias_perm + wrows);
+    w_hi = wh; w_lo = wl; a_hi = ah; a_lo = ah + (size_t)lp.M * kp64;
+  } else {
+    float* wh = reinterpret_cast<float*>(workspace);
+    float* wl = wh + wrows * pl.kpad;
+    bias2 = wl + wrows * pl.kpad;
+    bias_perm = bias2 + (lp.N + 3) / 4 * 4;
+    float* ah = bias_perm + wrows;
+    w_hi = wh; w_lo = wl; a_hi = ah; a_lo = ah + (size_t)lp.M * pl.kpad;
+  }
   if (lp.W != nullptr) {                                             // not prepared by eigb200_linear_prepare
-    int rc0 = tc_prepare(st, lp, workspace, 0);
+    int rc0 = tc_prepare(st, lp, workspace, f16 ? 1 : 0);
     if (rc0 != EIGB200_OK) return rc0;
   }
   const float* bias_eff = lp.ln_stats ? bias2 : lp.bias;
   perm_bias_kernel<<<(unsigned)((wrows + 255) / 256), 256, 0, st>>>(bias_eff, bias_perm, lp.N, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0);
   EIGB_LAUNCH_CHECK("perm_bias_kernel");
-  {
+  int* ovf = nullptr;
+  if (f16) {
+    ovf = overflow_flag_ptr();
+    if (!ovf) { set_error("tcgen05 GEMM: cannot resolve the overflow flag"); return EIGB200_ECUDA; }
+    const int64_t nq = lp.M * (kp64 / 4);
+    split_a_f16_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(lp.A, lp.lda, reinterpret_cast<const float2*>(lp.ln_stats), reinterpret_cast<__half*>(a_hi),
+                                                                    reinterpret_cast<__half*>(a_lo), lp.M, lp.K, kp64, lp.ln_stats ? 1024.f : 16.f, ovf);
+    EIGB_LAUNCH_CHECK("split_a_f16_kernel");
+  } else {
     const int64_t nq = lp.M * (pl.kpad / 4);
-    split_a_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(lp.A, lp.lda, reinterpret_cast<const float2*>(lp.ln_stats), a_hi, a_lo, lp.M, lp.K, pl.kpad);
+    split_a_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(lp.A, lp.lda, reinterpret_cast<const float2*>(lp.ln_stats), reinterpret_cast<float*>(a_hi),
+                                                                reinterpret_cast<float*>(a_lo), lp.M, lp.K, pl.kpad);
     EIGB_LAUNCH_CHECK("split_a_kernel");
   }
   CUtensorMap tAh, tAl, tWh, tWl;
   int rc;
-  if ((rc = make_tmap(&tAh, a_hi, (uint64_t)lp.M, (uint64_t)pl.kpad, (uint64_t)pl.kpad, TC_BM))) return rc;
-  if ((rc = make_tmap(&tAl, a_lo, (uint64_t)lp.M, (uint64_t)pl.kpad, (uint64_t)pl.kpad, TC_BM))) return rc;
-  if ((rc = make_tmap(&tWh, w_hi, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
-  if ((rc = make_tmap(&tWl, w_lo, wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  if (f16) {
+    if ((rc = make_tmap_f16(&tAh, a_hi, (uint64_t)lp.M, (uint64_t)kp64, TC_BM))) return rc;
+    if ((rc = make_tmap_f16(&tAl, a_lo, (uint64_t)lp.M, (uint64_t)kp64, TC_BM))) return rc;
+    if ((rc = make_tmap_f16(&tWh, w_hi, wrows, (uint64_t)kp64, (uint32_t)pl.bn))) return rc;
+    if ((rc = make_tmap_f16(&tWl, w_lo, wrows, (uint64_t)kp64, (uint32_t)pl.bn))) return rc;
+  } else {
+    if ((rc = make_tmap(&tAh, reinterpret_cast<float*>(a_hi), (uint64_t)lp.M, (uint64_t)pl.kpad, (uint64_t)pl.kpad, TC_BM))) return rc;
+    if ((rc = make_tmap(&tAl, reinterpret_cast<float*>(a_lo), (uint64_t)lp.M, (uint64_t)pl.kpad, (uint64_t)pl.kpad, TC_BM))) return rc;
+    if ((rc = make_tmap(&tWh, reinterpret_cast<float*>(w_hi), wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+    if ((rc = make_tmap(&tWl, reinterpret_cast<float*>(w_lo), wrows, (uint64_t)pl.kpad, (uint64_t)pl.kpad, (uint32_t)pl.bn))) return rc;
+  }
   TcParams p{};
   p.bias = bias_perm; p.C = lp.C; p.ldc = lp.ldc; p.R = lp.R; p.ldr = lp.ldr; p.M = lp.M; p.N = lp.N; p.K = lp.K; p.epilogue = lp.epilogue;
-  p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
+  p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = f16 ? kp64 / 64 : pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
-  p.workers = 1; p.zero = 0;
+  p.workers = 1; p.zero = 0; p.out_scale = scal; p.ovf_flag = ovf;
   p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
   const int64_t npairs = p.ntiles * p.nsplit;
   const unsigned grid = (unsigned)(npairs < (int64_t)num_sms() ? npairs : (int64_t)num_sms());
-#define SK_LAUNCH(EPI_)                                                                                                         \
-  do {                                                                                                                          \
-    EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));    \
-    gemm_tc_stream_kernel<EPI_><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                                      \
+#define SK_LAUNCH(EPI_)                                                                                                                \
+  do {                                                                                                                                 \
+    if (f16) {                                                                                                                         \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));  \
+      gemm_tc_stream_kernel<EPI_, true><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                                    \
+    } else {                                                                                                                           \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+      gemm_tc_stream_kernel<EPI_, false><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                                   \
+    }                                                                                                                                  \
   } while (0)
   switch (lp.epilogue) {
     case EIGB200_EPI_NONE: SK_LAUNCH(EIGB200_EPI_NONE); break;
@@ -1447,7 +1521,7 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
 
 int launch_linear_tc(cudaStream_t st, const LinearParams& lp, int nterms, void* workspace, int kind) {
   TcPlan pl = make_plan(lp.N, lp.K, lp.epilogue, kind);
-  if (!pl.ok) return launch_linear_stream(st, lp, nterms, workspace);   // K > 256 or a weight slice too large to stay resident
+  if (!pl.ok) return launch_linear_stream(st, lp, nterms, workspace, kind);   // K > 256 or a weight slice too large to stay resident
   if (!pl.ts) kind = 0;
   const bool glu = lp.epilogue == EIGB200_EPI_GLU_RESIDUAL;
   const size_t wrows = (size_t)pl.nsplit * pl.bn;

@@ -266,15 +266,18 @@ def test_linear_tcgen05_wide_plan(ops, prec, N, K, epi):
 @pytest.mark.parametrize("M,N,K", [(4096, 552, 512), (3000, 512, 512), (2500, 1024, 512), (1000, 96, 384), (4100, 40, 260), (2048, 1544, 512),
                                     (70000, 256, 320)])
 @pytest.mark.parametrize("epi", ["none", "gelu", "residual", "glu_residual"])
-def test_linear_tcgen05_streamed_operands(ops, M, N, K, epi):
-    """Shapes whose weight slice cannot stay resident in shared memory (K > 256): the streamed-operand kernel (A pre-split into tf32 hi / lo)."""
+@pytest.mark.parametrize("mode", ["tc3", "f16x3"])
+def test_linear_tcgen05_streamed_operands(ops, M, N, K, epi, mode):
+    """Shapes whose weight slice cannot stay resident in shared memory (K > 256): the streamed-operand kernel (A pre-split into tf32 hi / lo, or into scaled
+    fp16 hi / lo: half the operand bytes per product, kind::f16)."""
     rng = np.random.default_rng(M + N + K)
     a = rng.normal(size=(M, K)).astype(np.float32); w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
     bias = rng.normal(size=N).astype(np.float32)
     nout = N // 2 if epi == "glu_residual" else N
     ldc = (nout + 7) // 8 * 8
     r = rng.normal(size=(M, ldc)).astype(np.float32)
-    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode="tc3", ldc=ldc).cpu().numpy()
+    out = ops.linear(dev(a), dev(w), dev(bias), epilogue=epi, residual=dev(r)[:, :nout] if "residual" in epi else None, mode=mode, ldc=ldc).cpu().numpy()
+    assert not ops.gemm_overflow()
     ref = _lin_ref(a, w, bias, epi, r[:, :nout].astype(np.float64))
     # The tensor core adds every MMA into the fp32 accumulator with truncation, 3 * K / 8 times per output: the error grows linearly with K
     # (measured 3e-6 of the output scale at K = 512, against 1e-6 at K = 128) where the FFMA path's round-to-nearest sum grows like sqrt(K).
@@ -282,7 +285,28 @@ def test_linear_tcgen05_streamed_operands(ops, M, N, K, epi):
     assert np.abs(out[:, :nout] - ref).max() <= 6e-6 * np.abs(ref).max() * max(1.0, K / 256)
 
 
-def test_linear_ln_streamed_operands(ops):
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
+def test_linear_ln_streamed_operands(ops, prec):
+    ops.set_gemm_precision(prec)
+    try:
+        _linear_ln_streamed(ops)
+        assert not ops.gemm_overflow()
+    finally:
+        ops.set_gemm_precision(None)
+
+
+def test_streamed_f16_overflow_raises_the_flag(ops):
+    """An activation beyond 65504 / S_a cannot be represented in the fp16 split: the sticky flag must come up (eval_eig then reruns the pass with 3xTF32)."""
+    a = torch.ones(2048, 512, device="cuda"); a[5, 7] = 1.0e4                        # 1e4 * 16 > 65504
+    w = torch.randn(256, 512, device="cuda") / 512 ** 0.5
+    ops.gemm_overflow()                                                               # clear
+    ops.linear(a, w, None, mode="f16x3")
+    assert ops.gemm_overflow()
+    ops.linear(a, w, None, mode="tc3")
+    assert not ops.gemm_overflow()
+
+
+def _linear_ln_streamed(ops):
     rng = np.random.default_rng(3)
     M, N, K = 3000, 552, 512
     a = (rng.normal(size=(M, K)) * 2 + rng.normal(0, 1, (M, 1))).astype(np.float32)

@@ -170,7 +170,7 @@ def case_linear(M, N, K, epi, mode):
     r = torch.randn(M, nout, device="cuda") if ("residual" in epi and not epi.endswith("_nores")) else None
     epi = epi.replace("_nores", "")
     out = torch.empty(M, ldc, device="cuda")
-    ws, _ = ops.linear_workspace(N, K, "cuda")
+    ws, _ = ops.linear_workspace(N, K, "cuda", M)
     def fn():
         ops.linear(a, w, b, epilogue=epi, residual=r, mode=mode, out=out, workspace=ws)
     nbytes = M * (K + nout + (nout if r is not None else 0)) * 4
@@ -220,6 +220,10 @@ CASES = {
     "lin_glu_f16": lambda: case_linear(M_C2, 256, 128, "glu_residual", "f16x3"),
     "lin_out_none_f16": lambda: case_linear(M_C2, 128, 128, "none", "f16x3"),
     "lin_glu_nores_f16": lambda: case_linear(M_C2, 256, 128, "glu_residual_nores", "f16x3"),
+    "lin_c5_glu_tc3": lambda: case_linear(262144, 1024, 512, "glu_residual", "tc3"),
+    "lin_c5_glu_f16": lambda: case_linear(262144, 1024, 512, "glu_residual", "f16x3"),
+    "lin_c5_in_tc3": lambda: case_linear(262144, 552, 512, "none", "tc3"),
+    "lin_c5_in_f16": lambda: case_linear(262144, 552, 512, "none", "f16x3"),
     "lin_out_simt": lambda: case_linear(M_C2, 128, 128, "gelu", "simt"),
     "lin_small_tc3": lambda: case_linear(65536, 128, 128, "gelu", "tc3"),
     "lin_glu_mid_tc3": lambda: case_linear(524288, 256, 128, "glu_residual", "tc3"),
