@@ -14,10 +14,10 @@
 // (carry_c = lam^len * carry_{c-1} + end_{c-1}), pass 2 re-runs each chunk from its carry and writes h (24 B/update).
 #include "common.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace eigb200 {
 
-constexpr int DS_U = 8;
 
 struct cplx { float re, im; };
 __device__ __forceinline__ cplx cfma(cplx a, cplx h, cplx b) {      // a*h + b
@@ -28,7 +28,10 @@ __device__ __forceinline__ cplx cfma(cplx a, cplx h, cplx b) {      // a*h + b
 }
 
 // MODE 0: single pass (write h).  MODE 1: chunk end-state only.  MODE 2: start from carry, write h.
-template <int CPT, int MODE>
+// U: time steps (independent vector loads) in flight per thread.  8 when B*P fills the machine; 32 for the mid-sized case (BASELINE C3 at 128 sequences per
+// GPU: 221 threads per SM) where 8 leave 14 KB per SM in flight -- far below what HBM latency needs -- and the old answer, splitting time into chunks, paid a
+// second read of Bu (24 instead of 16 bytes per update: 0.49 of the copy peak).
+template <int CPT, int MODE, int DS_U = 8>
 __global__ void __launch_bounds__(128) diag_scan_kernel(const float* __restrict__ lam, const float* __restrict__ Bu, float* __restrict__ h,
                                                         float* __restrict__ chunk_state, int64_t Bn, int64_t T, int P, int chunk_len, int nchunks, int reverse) {
   const int pv = P / CPT;                                       // channel groups per sequence
@@ -163,7 +166,16 @@ extern "C" int eigb200_diag_scan(void* stream, const float* d_lam, const float* 
   const bool cpt2 = (P % 2 == 0) && (channels / 2 >= (int64_t)sms * 1024);
   const int cpt = cpt2 ? 2 : 1;
   const int64_t threads = channels / cpt;
+  // mid-sized batches: one pass with 32 loads in flight per thread (>= 2 warps per SM)
+  if (threads >= (int64_t)sms * 64 && threads < (int64_t)sms * 512 && getenv("EIGB200_DIAG_DEEP") == nullptr) {
+    const unsigned gx1 = (unsigned)((threads + 127) / 128);
+    if (cpt == 2) diag_scan_kernel<2, 0, 16><<<dim3(gx1, 1), 128, 0, st>>>(d_lam, d_Bu, d_h, nullptr, B, T, P, (int)T, 1, reverse);
+    else diag_scan_kernel<1, 0, 32><<<dim3(gx1, 1), 128, 0, st>>>(d_lam, d_Bu, d_h, nullptr, B, T, P, (int)T, 1, reverse);
+    EIGB_LAUNCH_CHECK("diag_scan_kernel");
+    return EIGB200_OK;
+  }
   // split time only when the channel parallelism alone leaves most of the machine idle
+  constexpr int DS_U = 8;
   int nchunks = 1;
   if (threads < (int64_t)sms * 256) {
     nchunks = (int)(((int64_t)sms * 512 + threads - 1) / threads);
