@@ -206,7 +206,25 @@ __global__ void __launch_bounds__(128) conv_silu_kernel(const float* __restrict_
     win[j] = (t >= 0 && j >= 8 - k) ? __ldg(xr + t * ldx) : 0.f;
   }
   float* orow = out + (b * T) * ldo + c;
-  for (int64_t t = t0; t < t1; ++t) {
+  // 8 tokens per trip: their loads are issued together (one load in flight per thread left the kernel latency-bound at 40 % of the copy peak)
+  constexpr int U = 8;
+  int64_t t = t0;
+  for (; t + U <= t1; t += U) {
+    float xn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xn[u] = ldg_stream_f1(xr + (t + u) * ldx);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) win[j] = win[j + 1];
+      win[7] = xn[u];
+      float acc = bb;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(wk[j], win[j], acc);
+      orow[(t + u) * ldo] = silu_f(acc);
+    }
+  }
+  for (; t < t1; ++t) {
 #pragma unroll
     for (int j = 0; j < 7; ++j) win[j] = win[j + 1];
     win[7] = __ldg(xr + t * ldx);
