@@ -290,8 +290,10 @@ def _save_results(args, conf_args, wandb_config, data_config, model_config, trai
         print(f"Permission denied: Unable to create '{out_dir}'.")
     except Exception as e:
         print(f"An error occurred: {e}")
-    for fname in RESULT_FILES:
-        np.save(os.path.join(out_dir, fname + ".npy"), arrays[fname])
+    # the two eigenvalue arrays are tens of MB each: write the ten files concurrently (np.save releases the GIL while it copies and writes)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(lambda fname: np.save(os.path.join(out_dir, fname + ".npy"), arrays[fname]), RESULT_FILES))
     with open(os.path.join(out_dir, "used_config.yaml"), "w") as file:
         yaml.dump(args, file, default_flow_style=False, sort_keys=False)
     return out_dir
