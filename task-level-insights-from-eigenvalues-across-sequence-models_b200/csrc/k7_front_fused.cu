@@ -59,7 +59,17 @@ constexpr int FF_NST = FF_NST_OVERRIDE;
 #endif
 static_assert(FF_NST >= 6, "the ring doubles as the 96 KB staging area of the weights");
 constexpr int FF_STAGE_BYTES = FF_Q * FF_K * 4;  // 16 KB: raw fp32 chunk = fp16 hi (8 KB) + lo (8 KB) operand
-constexpr int FF_H = 16;                         // tokens per unrolled half chunk of the recurrence
+#ifndef FF_H_OVERRIDE
+constexpr int FF_H = 8;                          // tokens pulled from TMEM and processed per trip of the recurrence loop (16: 1.02 ms, 8: 0.91 ms per C2 layer:
+                                                 // the 8 registers it frees let ptxas issue the shared-memory operand loads further ahead)
+#else
+constexpr int FF_H = FF_H_OVERRIDE;
+#endif
+#ifndef FF_G_OVERRIDE
+constexpr int FF_G = FF_H < 8 ? FF_H : 8;        // tokens per phase A / phase B group inside a trip
+#else
+constexpr int FF_G = FF_G_OVERRIDE;
+#endif
 constexpr uint32_t FF_RING = 0;
 constexpr uint32_t FF_BC = FF_RING + FF_NST * FF_STAGE_BYTES;          // [slot][buffer][token][B 16 | C 16] fp32
 constexpr uint32_t FF_BC_BYTES = FF_Q * 2 * FF_N * 4;                  // 4 KB per (slot, buffer)
@@ -96,6 +106,21 @@ __device__ __forceinline__ void ff_tmem_ld_32x16(uint32_t taddr, float (&v)[16])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ff_tmem_ld_32x16(uint32_t taddr, float (&v)[8]) {      // FF_H = 8 builds
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ff_tmem_ld_32x16(uint32_t taddr, float (&v)[4]) {      // FF_H = 4 builds
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void ff_tmem_st_32x32u(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -318,49 +343,31 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
     auto half = [&](auto resc_tag, auto guard_tag, const float (&xr)[FF_H], const float4* __restrict__ bc4, const float4* __restrict__ pl, float* yp, int nvalid) {
       constexpr bool RESC = decltype(resc_tag)::value, GUARD = decltype(guard_tag)::value;
 #pragma unroll
-      for (int g = 0; g < FF_H / 8; ++g) {
-        float xv[8], w0[8], ez[8];
+      for (int g = 0; g < FF_H / FF_G; ++g) {
+        float xv[FF_G], w0[FF_G], ez[FF_G];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float4 wq = pl[(RESC ? 3 : 0) * (FF_Q / 4) + 2 * g + q];   // RESC: dt / E_t; direct: dt
-          const float4 eq = pl[(RESC ? 2 : 1) * (FF_Q / 4) + 2 * g + q];   // RESC: E_t;      direct: decay
+        for (int q = 0; q < FF_G / 4; ++q) {
+          const float4 wq = pl[(RESC ? 3 : 0) * (FF_Q / 4) + (FF_G / 4) * g + q];   // RESC: dt / E_t; direct: dt
+          const float4 eq = pl[(RESC ? 2 : 1) * (FF_Q / 4) + (FF_G / 4) * g + q];   // RESC: E_t;      direct: decay
           w0[4 * q] = wq.x; w0[4 * q + 1] = wq.y; w0[4 * q + 2] = wq.z; w0[4 * q + 3] = wq.w;
           ez[4 * q] = eq.x; ez[4 * q + 1] = eq.y; ez[4 * q + 2] = eq.z; ez[4 * q + 3] = eq.w;
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = 8 * g + jj;
+        for (int jj = 0; jj < FF_G; ++jj) {
+          const int j = FF_G * g + jj;
           const float xm1 = j >= 1 ? xr[j >= 1 ? j - 1 : 0] : h1, xm2 = j >= 2 ? xr[j >= 2 ? j - 2 : 0] : (j == 1 ? h1 : h2),
                       xm3 = j >= 3 ? xr[j >= 3 ? j - 3 : 0] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
           const float c = fmaf(cw[3], xr[j], fmaf(cw[2], xm1, fmaf(cw[1], xm2, fmaf(cw[0], xm3, cb))));
           xv[jj] = ff_silu(c);
           w0[jj] *= xv[jj];
         }
-#ifdef FF_BPREFETCH
-        float4 bn[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bn[q] = bc4[(8 * g) * 8 + q];
-#endif
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = 8 * g + jj;
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#ifdef FF_BPREFETCH
-          float4 bcur[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bcur[q] = bn[q];
-          if (jj + 1 < 8) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) bn[q] = bc4[(j + 1) * 8 + q];
-          }
-#endif
+        for (int jj = 0; jj < FF_G; ++jj) {
+          const int j = FF_G * g + jj;
+          float a0 = 0.f, a1 = 0.f;
 #pragma unroll
           for (int q = 0; q < FF_N / 4; ++q) {
-#ifdef FF_BPREFETCH
-            const float4 bv = bcur[q], cv = bc4[j * 8 + 4 + q];
-#else
             const float4 bv = bc4[j * 8 + q], cv = bc4[j * 8 + 4 + q];
-#endif
             if (RESC) {
               s[4 * q + 0] = fmaf(w0[jj], bv.x, s[4 * q + 0]); s[4 * q + 1] = fmaf(w0[jj], bv.y, s[4 * q + 1]);
               s[4 * q + 2] = fmaf(w0[jj], bv.z, s[4 * q + 2]); s[4 * q + 3] = fmaf(w0[jj], bv.w, s[4 * q + 3]);
@@ -368,10 +375,10 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
               s[4 * q + 0] = fmaf(ez[jj], s[4 * q + 0], w0[jj] * bv.x); s[4 * q + 1] = fmaf(ez[jj], s[4 * q + 1], w0[jj] * bv.y);
               s[4 * q + 2] = fmaf(ez[jj], s[4 * q + 2], w0[jj] * bv.z); s[4 * q + 3] = fmaf(ez[jj], s[4 * q + 3], w0[jj] * bv.w);
             }
-            a0 = fmaf(cv.x, s[4 * q + 0], a0); a1 = fmaf(cv.y, s[4 * q + 1], a1);
-            a2 = fmaf(cv.z, s[4 * q + 2], a2); a3 = fmaf(cv.w, s[4 * q + 3], a3);
+            a0 = fmaf(cv.x, s[4 * q + 0], a0); a1 = fmaf(cv.y, s[4 * q + 1], a1);       // two chains: 4 measured 1.6 % slower (2 registers, 2 FADDs more)
+            a0 = fmaf(cv.z, s[4 * q + 2], a0); a1 = fmaf(cv.w, s[4 * q + 3], a1);
           }
-          const float dot = (a0 + a1) + (a2 + a3);
+          const float dot = a0 + a1;
           const float yv = fmaf(Dh, xv[jj], RESC ? ez[jj] * dot : dot);
           if (!GUARD || j < nvalid) yp[(int64_t)j * ldy] = yv;
         }
