@@ -274,7 +274,11 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
       if (quarter == 3) { Ah = -expf(__ldg(p.A_log)); dtb = __ldg(p.dt_bias); }
     }
     const int64_t ldy = DENSE ? (int64_t)FF_P : p.ldy;
+#ifndef FF_FMA2
     float s[FF_N];
+#else
+    uint64_t s2[FF_N / 2];                                           // the state row as fp32 pairs: the recurrence runs on FFMA2 (half the issue slots)
+#endif
     float h1 = hpad, h2 = hpad, h3 = hpad;                           // raw x accumulators of the tokens t-1, t-2, t-3
     float g1 = 0.f, g2 = 0.f, g3 = 0.f;                              // quarter 0: raw B / C values of the previous chunk's last three tokens
 
@@ -364,6 +368,7 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
 #pragma unroll
         for (int jj = 0; jj < FF_G; ++jj) {
           const int j = FF_G * g + jj;
+#ifndef FF_FMA2
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
           for (int q = 0; q < FF_N / 4; ++q) {
@@ -378,6 +383,24 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
             a0 = fmaf(cv.x, s[4 * q + 0], a0); a1 = fmaf(cv.y, s[4 * q + 1], a1);       // two chains: 4 measured 1.6 % slower (2 registers, 2 FADDs more)
             a0 = fmaf(cv.z, s[4 * q + 2], a0); a1 = fmaf(cv.w, s[4 * q + 3], a1);
           }
+#else
+          // packed form: (s_2i, s_2i+1) pairs, w0 / ez as broadcast operands; the pair accumulator is the scalar form's two chains a0 (even n), a1 (odd n)
+          const uint64_t w2 = pk2(w0[jj], w0[jj]), ez2 = pk2(ez[jj], ez[jj]);
+          const ulonglong2* bc2 = reinterpret_cast<const ulonglong2*>(bc4);
+          uint64_t acc = 0ull;
+#pragma unroll
+          for (int q = 0; q < FF_N / 4; ++q) {
+            const ulonglong2 bv = bc2[j * 8 + q], cv = bc2[j * 8 + 4 + q];
+            if (RESC) {
+              s2[2 * q] = fma2(w2, bv.x, s2[2 * q]); s2[2 * q + 1] = fma2(w2, bv.y, s2[2 * q + 1]);
+            } else {
+              s2[2 * q] = fma2(ez2, s2[2 * q], mul2(w2, bv.x)); s2[2 * q + 1] = fma2(ez2, s2[2 * q + 1], mul2(w2, bv.y));
+            }
+            acc = fma2(cv.x, s2[2 * q], acc); acc = fma2(cv.y, s2[2 * q + 1], acc);
+          }
+          float a0, a1;
+          upk2(acc, a0, a1);
+#endif
           const float dot = a0 + a1;
           const float yv = fmaf(Dh, xv[jj], RESC ? ez[jj] * dot : dot);
           if (!GUARD || j < nvalid) yp[(int64_t)j * ldy] = yv;
@@ -410,8 +433,13 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
       if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 0);
       if (i + 1 < my_steps) { convert(item_next, row_nx); item_next += nact(i + 1); }
       if (c == 0) {
+#ifndef FF_FMA2
 #pragma unroll
         for (int n = 0; n < FF_N; ++n) s[n] = 0.f;
+#else
+#pragma unroll
+        for (int n = 0; n < FF_N / 2; ++n) s2[n] = 0ull;
+#endif
         h1 = h2 = h3 = hpad; g1 = g2 = g3 = 0.f;
       }
       if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 1);
@@ -479,8 +507,14 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
       }
       if (!direct) {                                                 // back to the true state: S = r E
         const float Eend = reinterpret_cast<const float*>(pl4)[2 * FF_Q + FF_Q - 1];
+#ifndef FF_FMA2
 #pragma unroll
         for (int n = 0; n < FF_N; ++n) s[n] *= Eend;
+#else
+        const uint64_t Eend2 = pk2(Eend, Eend);
+#pragma unroll
+        for (int n = 0; n < FF_N / 2; ++n) s2[n] = mul2(s2[n], Eend2);
+#endif
       }
       if (quarter == 0 && lane == 0) FF_TR(4 + slot, i, 3);
       row_cur = row_nx; c = c_nx;
