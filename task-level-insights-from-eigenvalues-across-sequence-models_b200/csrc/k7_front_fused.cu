@@ -274,10 +274,13 @@ mamba_front_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_const
       if (quarter == 3) { Ah = -expf(__ldg(p.A_log)); dtb = __ldg(p.dt_bias); }
     }
     const int64_t ldy = DENSE ? (int64_t)FF_P : p.ldy;
+    // -DFF_FMA2: the state row as fp32 pairs, the recurrence on fma.rn.f32x2 (FFMA2: 16 instead of 32 issue slots per channel-token, bit-identical results).
+    // Measured 8 % SLOWER (0.965 against 0.893 ms per C2 layer, profiles/r2_front_ffma2_ab.txt): an FFMA2 holds the FMA pipe for two passes, so the pipe -- not
+    // the issue slot -- is what the recurrence saturates, and the 64-bit register pairs cost ptxas its scheduling freedom.  Kept as an opt-in build.
 #ifndef FF_FMA2
     float s[FF_N];
 #else
-    uint64_t s2[FF_N / 2];                                           // the state row as fp32 pairs: the recurrence runs on FFMA2 (half the issue slots)
+    uint64_t s2[FF_N / 2];
 #endif
     float h1 = hpad, h2 = hpad, h3 = hpad;                           // raw x accumulators of the tokens t-1, t-2, t-3
     float g1 = 0.f, g2 = 0.f, g3 = 0.f;                              // quarter 0: raw B / C values of the previous chunk's last three tokens
