@@ -289,6 +289,16 @@ int eigb200_conv_silu(void* stream, const float* d_x, int64_t ldx, const float* 
 int eigb200_linattn_forward(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld,
                             const float* d_gate, int phi_elu, int normalise, float kscale,
                             float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv);
+/* The same layer with the depthwise causal conv + SiLU of MHA.forward / MHNA.forward (models/attention.py:153-156; norm_attention.py:236-239) fused
+ * into the tile loader: d_q / d_k / d_v point at the RAW projection columns, d_conv_w (C, kconv) / d_conv_b (C) are conv1d's parameters and conv_ch_* the
+ * conv channel of each matrix's first column (head 0), < 0 = that matrix is not convolved (conv_type != "full" leaves v as it is).  Chunked tensor-core
+ * kernel only: d = dv = 64, kconv <= 4, ld % 4 == 0, 16-byte aligned q / k / v, 8-byte aligned out -- eigb200_linattn_conv_fusable returns 1 when the call
+ * is possible, otherwise run eigb200_conv_silu + eigb200_linattn_forward (EIGB200_EINVAL here). */
+int eigb200_linattn_conv_fusable(const float* d_q, const float* d_k, const float* d_v, int64_t ld, const float* d_out, int64_t ldo, int d, int dv, int kconv);
+int eigb200_linattn_forward_conv(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld,
+                                 const float* d_gate, int phi_elu, int normalise, float kscale,
+                                 const float* d_conv_w, const float* d_conv_b, int kconv, int conv_ch_q, int conv_ch_k, int conv_ch_v,
+                                 float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv);
 /* elementwise helpers of the transformer block (models/transformer.py:90-111): out = a + b; out = y * silu(z) etc. */
 int eigb200_add(void* stream, const float* d_a, const float* d_b, float* d_out, int64_t n);
 int eigb200_mul_silu(void* stream, const float* d_y, const float* d_z, float* d_out, int64_t n);

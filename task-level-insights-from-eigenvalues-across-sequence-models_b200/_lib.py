@@ -70,6 +70,8 @@ SIGNATURES = {
     "eigb200_layernorm": [_vp, _vp, _vp, _vp, _f, _vp, _i64, _i],
     "eigb200_conv_silu": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _i64, _i64, _i64, _i],
     "eigb200_linattn_forward": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _f, _vp, _i64, _i64, _i64, _i, _i, _i],
+    "eigb200_linattn_conv_fusable": [_vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i],
+    "eigb200_linattn_forward_conv": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _f, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _i64, _i, _i, _i],
     "eigb200_add": [_vp, _vp, _vp, _vp, _i64],
     "eigb200_mul_silu": [_vp, _vp, _vp, _vp, _i64],
     "eigb200_gelu": [_vp, _vp, _vp, _i64],

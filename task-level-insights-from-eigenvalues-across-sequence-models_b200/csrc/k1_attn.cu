@@ -6,7 +6,9 @@
 //   SelfLinAttention.forward  models/attention.py:63-83    kv cumsum materialised as (B,T,H,d,dv)
 //   SelfNormAttention.forward models/norm_attention.py:61-89
 // Roofline: HBM for nu (2*d*4 bytes read per eigenvalue, 8 written); FMA-pipe for the layer forward (2*d*dv FMA per token).
-#include "common.cuh"
+#include "linattn.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace eigb200 {
 
@@ -62,11 +64,6 @@ __global__ void __launch_bounds__(NU_WARPS * 32) linattn_nu_kernel(const float* 
 constexpr int LA_THREADS = 256;
 constexpr int LA_TC = 16;             // tokens per staging round
 
-struct LinAttnParams {
-  const float* q; const float* k; const float* v; int64_t ld; const float* gate;
-  int phi_elu, normalise; float kscale;
-  float* out; int64_t ldo; int64_t T; int H, d, dv;
-};
 
 template <int RI>
 __global__ void __launch_bounds__(LA_THREADS) linattn_forward_kernel(const LinAttnParams p) {
@@ -418,7 +415,16 @@ extern "C" int eigb200_linattn_forward(void* stream, const float* d_q, const flo
   EIGB_CHECK_ARG(d % groups == 0, "linattn_forward: key head dim %d must be a multiple of %d (= 256 / dv)", d, groups);
   const int ri = d / groups;
   EIGB_CHECK_ARG(ri >= 1 && ri <= 64 && (ri & (ri - 1)) == 0, "linattn_forward: d*dv/256 = %d must be a power of two <= 64", ri);
-  LinAttnParams p{d_q, d_k, d_v, ld, d_gate, phi_elu, normalise, kscale, d_out, ldo, T, H, d, dv};
+  LinAttnParams p{d_q, d_k, d_v, ld, d_gate, phi_elu, normalise, kscale, d_out, ldo, T, H, d, dv, nullptr, nullptr, 0, -1, -1, -1};
+  {
+    // chunked tensor-core form (k9_linattn_mma.cu) for d = dv = 64 (the C1 / C5 heads); EIGB200_LINATTN_FORM=col keeps the recurrent column-owner kernel
+    const char* form = getenv("EIGB200_LINATTN_FORM");
+    if (!(form && strcmp(form, "col") == 0) && linattn_mma_supported(p)) {
+      const cudaError_t e = linattn_mma_launch(p, B, (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_fail(e, "linattn_mma_kernel");
+      return EIGB200_OK;
+    }
+  }
   const bool al16 = ld % 4 == 0 && (((uintptr_t)d_q | (uintptr_t)d_k | (uintptr_t)d_v) & 15) == 0 && d % 4 == 0;   // cp.async 16-byte pieces
   if ((d == 16 || d == 32 || d == 64 || d == 128) && dv % 32 == 0 && dv <= 256 && al16) {     // column-owner kernel: dv threads per (b,h)
     const size_t smem2 = sizeof(float) * (2 * (size_t)LC_TC * (2 * d + dv) + LC_TC + d);
@@ -445,6 +451,24 @@ extern "C" int eigb200_linattn_forward(void* stream, const float* d_q, const flo
   return EIGB200_OK;
 }
 
+extern "C" int eigb200_linattn_conv_fusable(const float* d_q, const float* d_k, const float* d_v, int64_t ld, const float* d_out, int64_t ldo, int d, int dv, int kconv) {
+  LinAttnParams p{d_q, d_k, d_v, ld, nullptr, 1, 0, 1.f, const_cast<float*>(d_out), ldo, 1, 1, d, dv, d_q, d_q, kconv, 0, 0, 0};
+  return linattn_mma_supported(p) ? 1 : 0;
+}
+
+extern "C" int eigb200_linattn_forward_conv(void* stream, const float* d_q, const float* d_k, const float* d_v, int64_t ld,
+                                            const float* d_gate, int phi_elu, int normalise, float kscale,
+                                            const float* d_conv_w, const float* d_conv_b, int kconv, int conv_ch_q, int conv_ch_k, int conv_ch_v,
+                                            float* d_out, int64_t ldo, int64_t B, int64_t T, int H, int d, int dv) {
+  EIGB_CHECK_ARG(d_q && d_k && d_v && d_out && d_conv_w && d_conv_b, "linattn_forward_conv: null pointer");
+  EIGB_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && H > 0 && d > 0 && dv > 0, "linattn_forward_conv: bad shape");
+  LinAttnParams p{d_q, d_k, d_v, ld, d_gate, phi_elu, normalise, kscale, d_out, ldo, T, H, d, dv, d_conv_w, d_conv_b, kconv, conv_ch_q, conv_ch_k, conv_ch_v};
+  EIGB_CHECK_ARG(linattn_mma_supported(p), "linattn_forward_conv: needs d = dv = 64, conv taps <= 4, 16-byte aligned q / k / v rows (ld %% 4 == 0) and an 8-byte aligned output "
+                 "(got d %d dv %d k %d ld %lld): run eigb200_conv_silu + eigb200_linattn_forward instead", d, dv, kconv, (long long)ld);
+  const cudaError_t e = linattn_mma_launch(p, B, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "linattn_mma_kernel<conv>");
+  return EIGB200_OK;
+}
 
 extern "C" int eigb200_softmax_nu(void* stream, const float* d_q, const float* d_k, int64_t ld, int64_t B, int64_t T, int H, int d,
                                   double* d_nu, float* d_m) {

@@ -277,6 +277,12 @@ class AttentionDev:
         ops.conv_silu(buf[:, col0:], ld, self.conv_w, self.conv_b, B, T, ncols, out=out[:, col0:], ldo=ld)
         return out
 
+    def _fuse_conv(self, buf, ld, q_off, k_off, v_off, H, d, dv):
+        """The conv + SiLU rides in the chunked attention kernel when that kernel takes the shape (EIGB200_LINATTN_FORM=col / EIGB200_LINATTN_CONV=split: no)."""
+        if os.environ.get("EIGB200_LINATTN_FORM") == "col" or os.environ.get("EIGB200_LINATTN_CONV") == "split":
+            return False
+        return ops.linattn_conv_fusable(buf, ld, q_off, k_off, v_off, H, d, dv, int(self.conv_w.shape[1]))
+
     def forward_residual(self, xn, skip):
         """out_proj(attention(xn)) + skip   (MHA.forward models/attention.py:149-182 / MHNA.forward norm_attention.py:230-258)."""
         B, T, D = xn.shape
@@ -284,21 +290,33 @@ class AttentionDev:
         if self.kind == "lin-attention":
             ld = 2 * dqk + D
             buf = ops.linear(xn, self.Wqkv.weight, self.Wqkv.bias)
-            if self.conv_w is not None:
-                buf = self._conv(buf, ld, 0, ld if self.conv_type == "full" else 2 * dqk, B, T)
-            ctx = ops.linattn_forward(buf, ld, 0, dqk, 2 * dqk, B, T, H, d, dv, phi_elu=True, normalise=True)
+            if self.conv_w is not None and self._fuse_conv(buf, ld, 0, dqk, 2 * dqk, H, d, dv):
+                # conv + SiLU inside the attention kernel's tile loader: q at conv channel 0, k at dqk, v at 2 dqk ("full") or untouched
+                ctx = ops.linattn_forward_conv(buf, ld, 0, dqk, 2 * dqk, B, T, H, d, dv, self.conv_w, self.conv_b, 0, dqk,
+                                               2 * dqk if self.conv_type == "full" else -1, phi_elu=True, normalise=True)
+            else:
+                if self.conv_w is not None:
+                    buf = self._conv(buf, ld, 0, ld if self.conv_type == "full" else 2 * dqk, B, T)
+                ctx = ops.linattn_forward(buf, ld, 0, dqk, 2 * dqk, B, T, H, d, dv, phi_elu=True, normalise=True)
         elif self.kind == "norm-attention":
             ld = D + 2 * dqk + H
             buf = ops.linear(xn, self.Wvqkn.weight, self.Wvqkn.bias)
             gate = ops.normattn_gate(xn, self.W_n, self.b_n, self.inner_attn.offset, self.norm_fn)
-            if self.conv_w is not None:
-                if self.conv_type == "full":
-                    buf = self._conv(buf, ld, 0, D + 2 * dqk, B, T)
-                else:
-                    buf = self._conv(buf, ld, D, 2 * dqk, B, T)
             kscale = 1.0 / math.sqrt(d) if self.scale_B else 1.0
-            ctx = ops.linattn_forward(buf, ld, D, D + dqk, 0, B, T, H, d, dv, gate=gate, phi_elu=(self.approx_fn == "elu"),
-                                      normalise=False, kscale=kscale)
+            if self.conv_w is not None and self._fuse_conv(buf, ld, D, D + dqk, 0, H, d, dv):
+                # buffer columns [v | q | k | n]; "full": conv channel = column, else the conv covers q, k only (channel = column - D)
+                full = self.conv_type == "full"
+                ctx = ops.linattn_forward_conv(buf, ld, D, D + dqk, 0, B, T, H, d, dv, self.conv_w, self.conv_b,
+                                               D if full else 0, D + dqk if full else dqk, 0 if full else -1,
+                                               gate=gate, phi_elu=(self.approx_fn == "elu"), normalise=False, kscale=kscale)
+            else:
+                if self.conv_w is not None:
+                    if self.conv_type == "full":
+                        buf = self._conv(buf, ld, 0, D + 2 * dqk, B, T)
+                    else:
+                        buf = self._conv(buf, ld, D, 2 * dqk, B, T)
+                ctx = ops.linattn_forward(buf, ld, D, D + dqk, 0, B, T, H, d, dv, gate=gate, phi_elu=(self.approx_fn == "elu"),
+                                          normalise=False, kscale=kscale)
         elif self.kind == "sm-attention":
             # SelfAttention.forward (models/attention.py:14-35), the float32 "naive" path; with use_flash the reference rounds q,k,v to fp16 first
             ld = 2 * dqk + D

@@ -283,6 +283,31 @@ def linattn_forward(buf, ld, q_off, k_off, v_off, B, T, H, d, dv, gate=None, phi
     return out
 
 
+def linattn_conv_fusable(buf, ld, q_off, k_off, v_off, H, d, dv, kconv) -> bool:
+    """True when linattn_forward_conv takes this shape (chunked tensor-core kernel: d = dv = 64, taps <= 4, aligned rows)."""
+    lib = _enter(buf)
+    base = buf.data_ptr()
+    fn = lib.eigb200_linattn_conv_fusable
+    return bool(fn(C.c_void_p(base + 4 * q_off), C.c_void_p(base + 4 * k_off), C.c_void_p(base + 4 * v_off), ld, C.c_void_p(256), H * dv, d, dv, kconv))
+
+
+def linattn_forward_conv(buf, ld, q_off, k_off, v_off, B, T, H, d, dv, conv_w, conv_b, conv_ch_q, conv_ch_k, conv_ch_v,
+                         gate=None, phi_elu=True, normalise=True, kscale=1.0):
+    """conv1d + SiLU (depthwise, causal) of the q / k / v columns fused into the causal linear attention: buf holds the RAW projection.
+    conv_w (C, k), conv_b (C); conv_ch_* = conv channel of each matrix's first column, -1 = not convolved."""
+    buf = _prep(buf, torch.float32)
+    conv_w = _prep(conv_w, torch.float32); conv_b = _prep(conv_b, torch.float32)
+    lib = _enter(buf)
+    out = torch.empty(B, T, H * dv, dtype=torch.float32, device=buf.device)
+    base = buf.data_ptr()
+    gate = _prep(gate, torch.float32) if gate is not None else None
+    _call(lib, "eigb200_linattn_forward_conv", _stream(buf), C.c_void_p(base + 4 * q_off), C.c_void_p(base + 4 * k_off),
+          C.c_void_p(base + 4 * v_off), ld, _p(gate), int(phi_elu), int(normalise), float(kscale),
+          _p(conv_w), _p(conv_b), int(conv_w.shape[1]), int(conv_ch_q), int(conv_ch_k), int(conv_ch_v),
+          _p(out), H * dv, B, T, H, d, dv)
+    return out
+
+
 # ---- K2 scans -----------------------------------------------------------------------------------------------------
 def diag_scan(lam, Bu, reverse=False):
     """lam (P,) complex64, Bu (B,T,P) complex64 -> h (B,T,P) complex64  (h_t = lam h_{t-1} + Bu_t)."""

@@ -134,6 +134,74 @@ def test_linattn_forward_column_owner_tail(ops, T, H, d, dv, normalise):
     np.testing.assert_allclose(out.reshape(B, T, H, dv), ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
 
 
+def _linattn_ref(buf, B, T, H, d, dv, q_off, k_off, v_off, normalise, gate, kscale, phi=True):
+    b3 = buf.reshape(B, T, -1).astype(np.float64)
+    q = b3[..., q_off:q_off + H * d].reshape(B, T, H, d); k = b3[..., k_off:k_off + H * d].reshape(B, T, H, d)
+    if phi:
+        q = O.elu(q) + 1; k = O.elu(k) + 1
+    v = b3[..., v_off:v_off + H * dv].reshape(B, T, H, dv)
+    kv = np.cumsum(np.einsum("bthd,bthe->bthde", k * kscale, v), axis=1)
+    num = np.einsum("bthd,bthde->bthe", q, kv)
+    if normalise:
+        return num / np.einsum("bthd,bthd->bth", q, np.cumsum(k, axis=1))[..., None]
+    return num * gate[..., None]
+
+
+@pytest.mark.parametrize("T", [200, 64, 130, 1])
+@pytest.mark.parametrize("H,normalise,phi", [(3, True, True), (2, False, True), (1, False, False)])
+def test_linattn_forward_chunked_mma(ops, T, H, normalise, phi, monkeypatch):
+    """The chunked tensor-core form (k9_linattn_mma.cu: d = dv = 64, the C1 / C5 heads): several chunks, a partial last chunk, both scalings, against
+    float64 and against the recurrent column-owner kernel (EIGB200_LINATTN_FORM=col)."""
+    rng = np.random.default_rng(77 * T + H)
+    B, d, dv = 2, 64, 64
+    ld = 2 * H * d + H * dv + 4
+    buf = rng.normal(size=(B * T, ld)).astype(np.float32)
+    if not phi:
+        buf = np.abs(buf) + 0.05                                   # raw positive features
+    gate = rng.uniform(0.1, 1.0, (B, T, H)).astype(np.float32)
+    kw = dict(gate=None if normalise else dev(gate), phi_elu=phi, normalise=normalise, kscale=1.0 if normalise else 0.125)
+    out = ops.linattn_forward(dev(buf), ld, 0, H * d, 2 * H * d, B, T, H, d, dv, **kw).cpu().numpy()
+    ref = _linattn_ref(buf, B, T, H, d, dv, 0, H * d, 2 * H * d, normalise, gate, kw["kscale"], phi)
+    np.testing.assert_allclose(out.reshape(B, T, H, dv), ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
+    monkeypatch.setenv("EIGB200_LINATTN_FORM", "col")
+    col = ops.linattn_forward(dev(buf), ld, 0, H * d, 2 * H * d, B, T, H, d, dv, **kw).cpu().numpy()
+    np.testing.assert_allclose(out, col, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
+    e_mma = np.abs(out.reshape(ref.shape) - ref).max() / np.abs(ref).max(); e_col = np.abs(col.reshape(ref.shape) - ref).max() / np.abs(ref).max()
+    print("linattn T=%d: max err / max |ref|: chunked mma %.2e, recurrent fp32 %.2e" % (T, e_mma, e_col))
+
+
+@pytest.mark.parametrize("T", [150, 64, 5])
+@pytest.mark.parametrize("kconv,full,normalise", [(4, True, False), (3, False, False), (4, True, True), (2, False, True)])
+def test_linattn_forward_conv_fused(ops, T, kconv, full, normalise):
+    """conv1d + SiLU fused into the chunked kernel's loader == eigb200_conv_silu followed by eigb200_linattn_forward (same FMA order, approximate-unit SiLU), for the norm-attention column order [v | q | k | n] and the linear-attention order [q | k | v], conv over everything or over q, k only."""
+    rng = np.random.default_rng(5 * T + kconv)
+    B, H, d, dv = 2, 2, 64, 64
+    D = dqk = H * d
+    if normalise:                                                  # lin-attention: [q | k | v]
+        ld = 2 * dqk + D
+        q_off, k_off, v_off = 0, dqk, 2 * dqk
+        ncv = ld if full else 2 * dqk; col0 = 0
+        chq, chk, chv = 0, dqk, (2 * dqk if full else -1)
+    else:                                                          # norm-attention: [v | q | k | n]
+        ld = D + 2 * dqk + 4
+        q_off, k_off, v_off = D, D + dqk, 0
+        ncv = D + 2 * dqk if full else 2 * dqk; col0 = 0 if full else D
+        chq, chk, chv = (D, D + dqk, 0) if full else (0, dqk, -1)
+    buf = rng.normal(size=(B * T, ld)).astype(np.float32)
+    cw = (rng.normal(size=(ncv, kconv)) * 0.5).astype(np.float32); cb = (rng.normal(size=ncv) * 0.2).astype(np.float32)
+    gate = rng.uniform(0.1, 1.0, (B, T, H)).astype(np.float32)
+    kw = dict(gate=None if normalise else dev(gate), phi_elu=True, normalise=normalise, kscale=1.0 if normalise else 0.125)
+    assert ops.linattn_conv_fusable(dev(buf), ld, q_off, k_off, v_off, H, d, dv, kconv)
+    fused = ops.linattn_forward_conv(dev(buf), ld, q_off, k_off, v_off, B, T, H, d, dv, dev(cw), dev(cb), chq, chk, chv, **kw).cpu().numpy()
+    cbuf = dev(buf).clone()
+    ops.conv_silu(dev(buf)[:, col0:], ld, dev(cw), dev(cb), B, T, ncv, out=cbuf[:, col0:], ldo=ld)
+    split = ops.linattn_forward(cbuf, ld, q_off, k_off, v_off, B, T, H, d, dv, **kw).cpu().numpy()
+    ref = _linattn_ref(cbuf.cpu().numpy(), B, T, H, d, dv, q_off, k_off, v_off, normalise, gate, kw["kscale"])
+    # the same attention kernel; the fused loader's SiLU uses ex2.approx / rcp.approx (~3 ulp) where eigb200_conv_silu divides
+    np.testing.assert_allclose(fused, split, rtol=5e-6, atol=2e-6 * np.abs(ref).max())
+    np.testing.assert_allclose(fused.reshape(B, T, H, dv), ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
+
+
 def test_linattn_nu_and_eta(ops):
     from conftest import load_golden
     g = load_golden("lin_softmax_extractor")

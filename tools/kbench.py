@@ -195,8 +195,42 @@ def case_ln(M, D):
     return fn, 2 * M * D * 4, M
 
 
+def case_linattn(B, T, H, form, conv=False):
+    """Norm-attention layer core at the C5 head shape (d = dv = 64): projection buffer [v | q | k | n] -> gated causal linear attention."""
+    if form:
+        os.environ["EIGB200_LINATTN_FORM"] = form
+    else:
+        os.environ.pop("EIGB200_LINATTN_FORM", None)
+    d = dv = 64; D = H * d
+    ld = 3 * D + 8
+    buf = torch.randn(B * T, ld, device="cuda")
+    gate = torch.rand(B, T, H, device="cuda")
+    cw = torch.randn(3 * D, 4, device="cuda") * 0.5; cb = torch.randn(3 * D, device="cuda") * 0.2
+    if conv:
+        def fn():
+            ops.linattn_forward_conv(buf, ld, D, 2 * D, 0, B, T, H, d, dv, cw, cb, D, 2 * D, 0, gate=gate, phi_elu=True, normalise=False, kscale=0.125)
+    else:
+        def fn():
+            ops.linattn_forward(buf, ld, D, 2 * D, 0, B, T, H, d, dv, gate=gate, phi_elu=True, normalise=False, kscale=0.125)
+    return fn, B * T * 4 * D * 4, B * T * H
+
+
+def case_conv(B, T, Cn):
+    ld = Cn + 8
+    buf = torch.randn(B * T, ld, device="cuda"); out = torch.empty_like(buf)
+    cw = torch.randn(Cn, 4, device="cuda") * 0.5; cb = torch.randn(Cn, device="cuda") * 0.2
+    def fn():
+        ops.conv_silu(buf, ld, cw, cb, B, T, Cn, out=out, ldo=ld)
+    return fn, 2 * B * T * Cn * 4, B * T
+
+
 M_C2 = 4096 * 512
 CASES = {
+    "linattn_c5": lambda: case_linattn(1024, 1024, 8, None),
+    "linattn_c5_col": lambda: case_linattn(1024, 1024, 8, "col"),
+    "linattn_c5_conv": lambda: case_linattn(1024, 1024, 8, None, conv=True),
+    "linattn_small": lambda: case_linattn(128, 1024, 8, None),
+    "conv_c5": lambda: case_conv(1024, 1024, 1536),
     "ssd_c2": lambda: case_ssd(4096),
     "ssd_small": lambda: case_ssd(512),
     "ssd_c2_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(4096))[1],
