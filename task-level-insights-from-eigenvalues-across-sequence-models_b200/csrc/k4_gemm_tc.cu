@@ -1310,6 +1310,17 @@ static StreamPlan make_stream_plan(int N, int K, int epilogue) {
   const int nout = glu ? N / 2 : N;
   if (glu) { pl.bg = 64; pl.bn = 128; }
   else { pl.bn = nout >= 128 ? 128 : (nout + 31) / 32 * 32; pl.bg = pl.bn; }
+  {
+    // 256 accumulator columns per N tile: the A stage (32 KB per 64 K values) is then shared by twice the products -- 48 KB instead of 64 KB from L2 per
+    // 128 x 128 x 64 block, which is what bounds this kernel (the L2 slices deliver ~43 B per clock and SM, the tensor core wants 80 at 128 columns).
+    // Taken when the padded width does not grow by more than 1/8 (EIGB200_STREAM_BN=128 / 256 forces either).
+    static const char* force = getenv("EIGB200_STREAM_BN");
+    const int bg256 = glu ? 128 : 256;
+    const int pad128 = (nout + pl.bg - 1) / pl.bg * pl.bg, pad256 = (nout + bg256 - 1) / bg256 * bg256;
+    bool wide = nout >= bg256 && 8 * pad256 <= 9 * pad128;
+    if (force) wide = atoi(force) == 256 && nout >= bg256;
+    if (wide) { pl.bg = bg256; pl.bn = 256; }
+  }
   pl.nsplit = (nout + pl.bg - 1) / pl.bg;
   const size_t stage_bytes = 2 * (size_t)TC_CHUNK_BYTES + 2 * (size_t)pl.bn * 128;
   int nst = (int)((TC_SMEM_LIMIT - 2048) / stage_bytes);
