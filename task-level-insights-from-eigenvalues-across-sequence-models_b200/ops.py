@@ -3,6 +3,7 @@ the current stream; every computation below is a hand-written sm_100a kernel ins
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -418,6 +419,9 @@ def linear_prepare(weight, bias=None, epilogue="none", ln_gamma=None, ln_beta=No
     return ws
 
 
+K_SLABS = os.environ.get("EIGB200_K_SLABS", "1") != "0"          # narrow GEMMs with K > 256 as K slabs on the resident-weight kernel (see linear)
+
+
 def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", out=None, ldc=None, workspace=None, prepared=None):
     """a (..., K) with a.stride(-2) as the row stride -> epilogue(a W^T + bias).  weight (N,K) torch layout.
     prepared: workspace from linear_prepare(weight, bias, epilogue) -- no per-call weight preparation kernels (tensor-core path only)."""
@@ -434,6 +438,20 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     N = weight.shape[0]
     assert weight.shape[1] == K
     bias = _prep(bias, torch.float32) if bias is not None else None
+    if (K > 256 and N <= 128 and epilogue in ("none", "residual") and mode in ("auto", "f16x3", "tc3") and M >= 1024 and prepared is None
+            and K_SLABS and a2.data_ptr() % 16 == 0 and lda % 4 == 0):
+        # K in slabs of <= 256 columns through the RESIDENT-weight kernel, each slab accumulating onto the previous result through the residual epilogue:
+        # that kernel reads the raw fp32 rows by TMA (row stride lda) and splits them on the SM, where the streamed-operand kernel (K > 256) first writes and
+        # re-reads a split copy of A -- 3x the bytes of A, which is all this shape costs (the C h projection of LRU / S5: 0.48 -> 0.27 ms at C3).
+        nsl = (K + 255) // 256
+        step = ((K + nsl - 1) // nsl + 3) // 4 * 4
+        acc = residual if epilogue == "residual" else None
+        for i, k0 in enumerate(range(0, K, step)):
+            k1 = min(K, k0 + step)
+            last = k1 == K
+            acc = linear(a2[:, k0:k1], weight[:, k0:k1].contiguous(), bias if i == 0 else None, epilogue="residual" if acc is not None else "none",
+                         residual=acc, mode=mode, out=out if last else None, ldc=ldc if last else None)
+        return acc
     nout = N // 2 if epilogue == "glu_residual" else N
     lib = _enter(a)
     if out is None:
