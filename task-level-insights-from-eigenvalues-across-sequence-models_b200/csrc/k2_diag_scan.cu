@@ -31,7 +31,7 @@ __device__ __forceinline__ cplx cfma(cplx a, cplx h, cplx b) {      // a*h + b
 // U: time steps (independent vector loads) in flight per thread.  8 when B*P fills the machine; 32 for the mid-sized case (BASELINE C3 at 128 sequences per
 // GPU: 221 threads per SM) where 8 leave 14 KB per SM in flight -- far below what HBM latency needs -- and the old answer, splitting time into chunks, paid a
 // second read of Bu (24 instead of 16 bytes per update: 0.49 of the copy peak).
-template <int CPT, int MODE, int DS_U = 8>
+template <int CPT, int MODE, int DS_U = 8, bool PIPE = false>
 __global__ void __launch_bounds__(128) diag_scan_kernel(const float* __restrict__ lam, const float* __restrict__ Bu, float* __restrict__ h,
                                                         float* __restrict__ chunk_state, int64_t Bn, int64_t T, int P, int chunk_len, int nchunks, int reverse) {
   const int pv = P / CPT;                                       // channel groups per sequence
@@ -61,8 +61,7 @@ __global__ void __launch_bounds__(128) diag_scan_kernel(const float* __restrict_
   const size_t vbase = base / CPT;
   const size_t vstride = (size_t)P / CPT;
 
-  for (int64_t k = k0; k < k1; k += DS_U) {
-    vec_t v[DS_U];
+  auto load = [&](vec_t (&v)[DS_U], int64_t k) {
 #pragma unroll
     for (int u = 0; u < DS_U; ++u) {
       const int64_t kk = k + u;
@@ -71,6 +70,20 @@ __global__ void __launch_bounds__(128) diag_scan_kernel(const float* __restrict_
         if constexpr (CPT == 2) v[u] = ldg_stream_f4(src + vbase + (size_t)t * vstride);
         else v[u] = ldg_stream_f2(src + vbase + (size_t)t * vstride);
       }
+    }
+  };
+  // PIPE: the next trip's loads are issued before this trip's recurrence (two register sets): a thread always has DS_U .. 2 DS_U loads in flight instead
+  // of alternating between "all in flight" and "none" -- the mid-sized case has too few warps per SM to cover that bubble with other warps
+  vec_t vn[PIPE ? DS_U : 1];
+  if constexpr (PIPE) load(vn, k0);
+  for (int64_t k = k0; k < k1; k += DS_U) {
+    vec_t v[DS_U];
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int u = 0; u < DS_U; ++u) v[u] = vn[u];
+      if (k + DS_U < k1) load(vn, k + DS_U);
+    } else {
+      load(v, k);
     }
 #pragma unroll
     for (int u = 0; u < DS_U; ++u) {
@@ -169,8 +182,10 @@ extern "C" int eigb200_diag_scan(void* stream, const float* d_lam, const float* 
   // mid-sized batches: one pass with 32 loads in flight per thread (>= 2 warps per SM)
   if (threads >= (int64_t)sms * 64 && threads < (int64_t)sms * 512 && getenv("EIGB200_DIAG_DEEP") == nullptr) {
     const unsigned gx1 = (unsigned)((threads + 127) / 128);
+    static const bool nopipe = getenv("EIGB200_DIAG_NOPIPE") != nullptr;
     if (cpt == 2) diag_scan_kernel<2, 0, 16><<<dim3(gx1, 1), 128, 0, st>>>(d_lam, d_Bu, d_h, nullptr, B, T, P, (int)T, 1, reverse);
-    else diag_scan_kernel<1, 0, 32><<<dim3(gx1, 1), 128, 0, st>>>(d_lam, d_Bu, d_h, nullptr, B, T, P, (int)T, 1, reverse);
+    else if (nopipe) diag_scan_kernel<1, 0, 32><<<dim3(gx1, 1), 128, 0, st>>>(d_lam, d_Bu, d_h, nullptr, B, T, P, (int)T, 1, reverse);
+    else diag_scan_kernel<1, 0, 32, true><<<dim3(gx1, 1), 128, 0, st>>>(d_lam, d_Bu, d_h, nullptr, B, T, P, (int)T, 1, reverse);
     EIGB_LAUNCH_CHECK("diag_scan_kernel");
     return EIGB200_OK;
   }
