@@ -34,12 +34,30 @@ __device__ __forceinline__ void lm_mma(float (&d)[4], const uint32_t (&a)[4], ui
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// tf32 split, hi rounded to nearest (integer add of half an ulp of tf32, then truncation): lo = v - hi is exact, signed and <= 2^-12 |v|; the tensor core
-// truncates lo's own low bits (2^-22 |v|, either sign) and the dropped lo x lo term is <= 2^-24.  3 instructions per element; with hi = trunc19(v) the lo
-// parts of positive operands are all positive and the dropped term is a bias (measured 4e-6 of max |out| against 4e-7 for this form).
+// tf32 split.  The tensor core reads only the upper 19 bits of an operand register and truncates lo's own low bits the same way.
+//   lm_split    hi rounded to nearest (integer add of half a tf32 ulp, then the mask): lo = v - hi is exact and SIGNED, so the hardware's truncation of lo
+//               is unbiased.  3 instructions.  Used for the all-positive operands (phi(q), phi(k), P).
+//   lm_split_tr hi = the fp32 word itself (no instruction), lo = v - trunc19(v): 2 instructions; on an all-positive operand the truncated lo is a one-sided
+//               error, on the signed operands (v, the state) it has no preferred sign -- used there.
+// The split is 40 % of this kernel's non-MMA instructions, and those ADD to its HMMA time rather than hide under it (ablations in profiles/).  Measured at the
+// C5 layer shape / as activation deviation after 12 norm-attention blocks (tests/test_parity_fullshape_gpu.py; the fp32 recurrent kernel: 6.70 ms, 4.7e-6):
+// nearest everywhere (-DLM_SPLIT_RN) 4.95 ms, 5.5e-6; this mix 4.79 ms, 6.3e-6; truncation everywhere (-DLM_SPLIT_TR) 4.57 ms, 7.5e-6.
 __device__ __forceinline__ void lm_split(float v, uint32_t& hi, uint32_t& lo) {
+#ifdef LM_SPLIT_TR
+  hi = __float_as_uint(v);
+  lo = __float_as_uint(v - __uint_as_float(hi & 0xffffe000u));
+#else
   hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(v - __uint_as_float(hi));
+#endif
+}
+__device__ __forceinline__ void lm_split_tr(float v, uint32_t& hi, uint32_t& lo) {
+#ifdef LM_SPLIT_RN
+  lm_split(v, hi, lo);
+#else
+  hi = __float_as_uint(v);
+  lo = __float_as_uint(v - __uint_as_float(hi & 0xffffe000u));
+#endif
 }
 // D[i] += A B_i for four n-tiles, A = ah + al, B_i = bh + bl: small terms first, the three dependent MMAs of a tile four instructions apart
 __device__ __forceinline__ void lm_mma3x4(float (&d0)[4], float (&d1)[4], float (&d2)[4], float (&d3)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
@@ -52,10 +70,10 @@ __device__ __forceinline__ void lm_mma3x4(float (&d0)[4], float (&d1)[4], float 
 __device__ __forceinline__ void lm_afrag(float a0, float a1, float a2, float a3, uint32_t (&ah)[4], uint32_t (&al)[4]) {
   lm_split(a0, ah[0], al[0]); lm_split(a1, ah[1], al[1]); lm_split(a2, ah[2], al[2]); lm_split(a3, ah[3], al[3]);
 }
-// B fragments of four n-tiles: element pair (p0[8 i], p1[8 i]) for tile i
+// B fragments of four n-tiles of a SIGNED operand (v, the state): element pair (p0[8 i], p1[8 i]) for tile i
 __device__ __forceinline__ void lm_bfrag4(const float* __restrict__ p0, const float* __restrict__ p1, uint32_t (&bh)[8], uint32_t (&bl)[8]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { lm_split(p0[8 * i], bh[2 * i], bl[2 * i]); lm_split(p1[8 * i], bh[2 * i + 1], bl[2 * i + 1]); }
+  for (int i = 0; i < 4; ++i) { lm_split_tr(p0[8 * i], bh[2 * i], bl[2 * i]); lm_split_tr(p1[8 * i], bh[2 * i + 1], bl[2 * i + 1]); }
 }
 // phi = elu + 1 = x + 1 (x > 0), e^x (x <= 0): one expf instead of expm1f + 1 (each within an ulp of the exact value)
 // (both sides are computed and selected: a per-element branch diverges on half the lanes)
@@ -302,11 +320,10 @@ __global__ void __launch_bounds__(LM_THREADS, 3) linattn_mma_kernel(const LinAtt
           }
         }
       }
+      // the chunk's K^T V goes into a ZEROED accumulator and is added to the state with round-to-nearest FADDs: the tensor core's own fp32 accumulation
+      // truncates, and 16 chunks x 24 MMAs into one accumulator left a one-sided ~2e-5 on the state (activation deviation after 12 blocks 1.4e-5 -> 5.5e-6)
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const float2 a = *reinterpret_cast<const float2*>(srow0 + 8 * nt), c = *reinterpret_cast<const float2*>(srow1 + 8 * nt);
-        S[nt][0] = a.x; S[nt][1] = a.y; S[nt][2] = c.x; S[nt][3] = c.y;
-      }
+      for (int nt = 0; nt < 8; ++nt) { S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f; }
 #pragma unroll 1
       for (int kb8 = 0; kb8 < 8; ++kb8) {
         const float* v0 = Vs + (8 * kb8 + 2 * t4) * LM_LD + g;      // token 2 t4 (K index t4) and 2 t4 + 1 (K index t4 + 4) of the block
@@ -319,6 +336,13 @@ __global__ void __launch_bounds__(LM_THREADS, 3) linattn_mma_kernel(const LinAtt
           lm_bfrag4(v0 + 32 * hf, v0 + LM_LD + 32 * hf, bh, bl);
           lm_mma3x4(S[4 * hf], S[4 * hf + 1], S[4 * hf + 2], S[4 * hf + 3], kh, kl, bh, bl);
         }
+      }
+    }
+    if (t0 + LM_C < p.T) {                                          // S = S0 + K^T V (the state rows of this role are read by the other warps until the barrier)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 a = *reinterpret_cast<const float2*>(srow0 + 8 * nt), c = *reinterpret_cast<const float2*>(srow1 + 8 * nt);
+        S[nt][0] += a.x; S[nt][1] += a.y; S[nt][2] += c.x; S[nt][3] += c.y;
       }
     }
     __syncthreads();                                                // every warp is done with the tiles and the state at the chunk start

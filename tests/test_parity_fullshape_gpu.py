@@ -213,7 +213,7 @@ def test_c5_norm_attention_full_depth_vs_oracle(eig):
     rel = np.abs(e[fin] - ref[fin]) / np.abs(ref[fin])
     print("C5 norm-attention T=1024 x 12 layers: activation deviation %.2e of scale; eta relative error: median %.2e, 99 %% %.2e, worst %.2e"
           % (dev, np.median(rel), np.quantile(rel, 0.99), rel.max()))
-    assert dev <= 5e-5                                             # measured 9.0e-6 after 12 blocks
+    assert dev <= 2.5e-5                                           # measured after 12 blocks: 6.3e-6 (chunked tensor-core attention), 4.7e-6 (EIGB200_LINATTN_FORM=col)
     # eta = n_{t+1} / n_t with n = exp(-softplus(z + offset)), offsets 4..9: d ln eta = dz_{t+1} - dz_t and dz = W_n . dx, so the activation deviation
     # above (x |W_n| sqrt(D)) is amplified into a ~1e-3 tail -- conditioning of the quantity, not of the kernel.  The kernel itself: eta from the DEVICE's
     # last-layer activations against the fp64 formula on the same activations holds the conditioning-aware 1e-5 (below).
