@@ -77,7 +77,7 @@ __device__ __forceinline__ void lm_bfrag4(const float* __restrict__ p0, const fl
 }
 // phi = elu + 1 = x + 1 (x > 0), e^x (x <= 0): one expf instead of expm1f + 1 (each within an ulp of the exact value)
 // (both sides are computed and selected: a per-element branch diverges on half the lanes)
-__device__ __forceinline__ float lm_phi(float x) { const float e = expf(fminf(x, 0.f)), l = x + 1.f; return x > 0.f ? l : e; }
+__device__ __forceinline__ float lm_phi(float x) { const float e = expf(x), l = x + 1.f; return x > 0.f ? l : e; }   // (e may be +inf for large x: not selected)
 
 // SiLU with ex2.approx / rcp.approx (as the Mamba conv, k2_ssd_scan.cu): ~3 ulp, no division slow path -- 96 activations per thread and chunk
 __device__ __forceinline__ float lm_silu(float z) { return z * sigmoid_fast_f(z); }
@@ -94,8 +94,13 @@ __device__ __forceinline__ void lm_issue(const LinAttnParams& p, const float* __
   const float* g = src + (row0_global + 8 * seg) * p.ld + 4 * c4;
   // branch-free loads: a row beyond the sequence end is clamped to the last valid row and zeroed in lm_finish (per-row guards cost a branch region per load)
   const int rlast = max(tc - 1 - 8 * seg, -8 * seg);                // last valid row of this segment, relative to its first row (may be < 0; >= row 0 of the chunk)
+  if (tc == LM_C) {                                                 // full chunk (all but the last of a sequence): constant-stride addresses, no clamps
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r.cur[i] = __ldg(reinterpret_cast<const float4*>(g + (int64_t)min(i, rlast) * p.ld));
+    for (int i = 0; i < 8; ++i) r.cur[i] = __ldg(reinterpret_cast<const float4*>(g + (int64_t)i * p.ld));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.cur[i] = __ldg(reinterpret_cast<const float4*>(g + (int64_t)min(i, rlast) * p.ld));
+  }
   if (CONV && conv_ch >= 0) {
     const int64_t rfirst = -(seq_row0 + 8 * seg);                   // first row of the sequence relative to this segment's first row (<= 0)
 #pragma unroll
@@ -310,13 +315,20 @@ __global__ void __launch_bounds__(LM_THREADS, 3) linattn_mma_kernel(const LinAtt
       {                                                             // next chunk's rows -> L2, in flight under the state update
         const int tcn = (int)min((int64_t)LM_C, p.T - t0 - LM_C);
         const int c4 = tid & 15, seg = tid >> 4;
-        if (c4 == 0 || c4 == 8) {                                   // one prefetch per 128-byte half row
+        // one prefetch per 128-byte half row and tile: the threads with c4 = 0, 8 of each row segment
+        if ((c4 & 7) == 0) {
+          const int64_t row0 = rowbase + t0 + LM_C + 8 * seg;
+          const int nrow = min(8, tcn - 8 * seg);                   // rows of this segment that exist
+          const float* pq = qbase + row0 * p.ld + 4 * c4;
+          const int64_t dk = kbase - qbase, dv = vbase - qbase;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int64_t row = rowbase + t0 + LM_C + min(8 * seg + i, tcn - 1);
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(qbase + row * p.ld + 4 * c4));
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(kbase + row * p.ld + 4 * c4));
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(vbase + row * p.ld + 4 * c4));
+            if (i < nrow) {
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(pq));
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(pq + dk));
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(pq + dv));
+            }
+            pq += p.ld;
           }
         }
       }
