@@ -1049,9 +1049,22 @@ __global__ void perm_bias_kernel(const float* __restrict__ bias, float* __restri
 
 constexpr int SK_MAX_STAGES = 4;
 
+__device__ __forceinline__ float4 sk_lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sk_sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // F16: operands are the scaled fp16 split (kind::f16; a stage row of 128 bytes holds 64 K values instead of 32: half the L2 traffic per product, twice the
-// tensor rate), the accumulator carries S_a S_w and the epilogue's bias FMA removes it
-template <int EPI, bool F16 = false>
+// tensor rate), the accumulator carries S_a S_w and the epilogue's bias FMA removes it.
+// RAWA (F16 only): A arrives as RAW fp32 -- tmapAhi is the fp32 map of A (row stride lda), two 32-column boxes per stage in the 32 KB the hi / lo operands
+// took -- and the four converter warps rewrite every landed row IN PLACE as [fp16 hi of its 32 values (64 B) | fp16 lo (64 B)] (thread = row; the box stays a
+// SWIZZLE_128B K-major tile whose first two 32-byte K steps are the hi operand and whose last two are the lo operand, as in k7_front_fused.cu), LayerNorm
+// folded in.  That removes split_a_f16_kernel -- A read, written as hi / lo and read again: a quarter of every call at K = 512 -- and its 2 M K workspace bytes.
+template <int EPI, bool F16 = false, bool RAWA = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_constant__ CUtensorMap tmapAlo,
                       const __grid_constant__ CUtensorMap tmapWhi, const __grid_constant__ CUtensorMap tmapWlo, const TcParams p) {
@@ -1067,13 +1080,14 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
   auto bar_dfull = [&](int j) { return bars + 8u * (2 * SK_MAX_STAGES + j); };
   auto bar_dempty = [&](int j) { return bars + 8u * (2 * SK_MAX_STAGES + 2 + j); };
   const uint32_t tmem_slot = bars + 8u * (2 * SK_MAX_STAGES + 4);
+  auto bar_raw = [&](int s) { return bars + 8u * (2 * SK_MAX_STAGES + 8 + s); };   // RAWA: TMA landed the raw stage (bar_full then = converted, 128 arrivals)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (2 * bn <= 32) ? 32 : (2 * bn <= 64) ? 64 : (2 * bn <= 128) ? 128 : (2 * bn <= 256) ? 256 : 512;
   const int64_t npairs = p.ntiles * p.nsplit;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), RAWA ? 128 : 1); mbar_init(bar_empty(s), 1); if (RAWA) mbar_init(bar_raw(s), 1); }
     for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), TC_EPI_WARPS * 32); }
     fence_barrier_init();
   }
@@ -1093,12 +1107,18 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
         for (int c = 0; c < kch; ++c) {
           mbar_wait_one(bar_empty(s), ph ^ 1);
           const uint32_t st0 = stage0 + s * stage_bytes;
-          mbar_arrive_expect_tx(bar_full(s), stage_bytes);
+          const uint32_t bar_land = RAWA ? bar_raw(s) : bar_full(s);
+          mbar_arrive_expect_tx(bar_land, stage_bytes);
           constexpr int KSTAGE = F16 ? 64 : TC_KC;                 // K values per 128-byte row
-          tma_load_2d(&tmapAhi, bar_full(s), st0, c * KSTAGE, (int)(tile * TC_BM));
-          tma_load_2d(&tmapAlo, bar_full(s), st0 + TC_CHUNK_BYTES, c * KSTAGE, (int)(tile * TC_BM));
-          tma_load_2d(&tmapWhi, bar_full(s), st0 + 2 * TC_CHUNK_BYTES, c * KSTAGE, split * bn);
-          tma_load_2d(&tmapWlo, bar_full(s), st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * KSTAGE, split * bn);
+          if constexpr (RAWA) {                                    // two raw fp32 boxes: K columns [64 c, 64 c + 32) and [64 c + 32, 64 c + 64) (zero-filled beyond K)
+            tma_load_2d(&tmapAhi, bar_land, st0, c * KSTAGE, (int)(tile * TC_BM));
+            tma_load_2d(&tmapAhi, bar_land, st0 + TC_CHUNK_BYTES, c * KSTAGE + TC_KC, (int)(tile * TC_BM));
+          } else {
+            tma_load_2d(&tmapAhi, bar_land, st0, c * KSTAGE, (int)(tile * TC_BM));
+            tma_load_2d(&tmapAlo, bar_land, st0 + TC_CHUNK_BYTES, c * KSTAGE, (int)(tile * TC_BM));
+          }
+          tma_load_2d(&tmapWhi, bar_land, st0 + 2 * TC_CHUNK_BYTES, c * KSTAGE, split * bn);
+          tma_load_2d(&tmapWlo, bar_land, st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * KSTAGE, split * bn);
           if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
@@ -1122,7 +1142,12 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
           const uint64_t dbh0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES), dbl0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes);
 #pragma unroll
           for (int k = 0; k < TC_KC / 8; ++k) {                      // 4 K steps of 32 bytes per stage row in either precision
-            if constexpr (F16) {
+            if constexpr (F16 && RAWA) {                             // box k / 2 holds [hi K steps 0, 1 | lo K steps 0, 1] of its 32 K values
+              const uint64_t ah = (k < 2 ? dah0 : dal0) + 2u * (k & 1), al = ah + 4u;
+              umma_f16_ss(d_tmem, ah, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ss(d_tmem, ah, dbl0 + 2u * k, idesc, 1u);
+              umma_f16_ss(d_tmem, al, dbh0 + 2u * k, idesc, 1u);
+            } else if constexpr (F16) {
               umma_f16_ss(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
               if (three) {
                 umma_f16_ss(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
@@ -1144,6 +1169,50 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
       }
     }
     __syncwarp();
+  } else if (RAWA && warp >= TC_CONV_WARP0 && warp < TC_CONV_WARP0 + 4) {
+    // ===================================== converters: one row of the tile per thread, in place ======================================
+    const int r = threadIdx.x - TC_CONV_WARP0 * 32;
+    const int sw = r & 7;
+    const float S_a = p.ln_stats ? 1024.f : 16.f;                    // activation pre-scale (split_a_f16_kernel's)
+    float amax = 0.f;
+    int s = 0; uint32_t ph = 0;
+    for (int64_t it = blockIdx.x; it < npairs; it += gridDim.x) {
+      const int64_t tile = it / p.nsplit;
+      const int64_t m = tile * TC_BM + r;
+      float sc = S_a, cc = 0.f;
+      if (p.ln_stats && m < p.M) { const float2 stt = __ldg(p.ln_stats + m); sc = stt.y * S_a; cc = -stt.x * stt.y * S_a; }
+      for (int c = 0; c < kch; ++c) {
+        const uint32_t st0 = stage0 + s * stage_bytes;
+        mbar_wait(bar_raw(s), ph);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t row = st0 + (uint32_t)b * TC_CHUNK_BYTES + (uint32_t)r * 128u;
+          float a[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {                              // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+            const float4 v = sk_lds_f4(row + (uint32_t)((q ^ sw) * 16));
+            a[4 * q] = fmaf(v.x, sc, cc); a[4 * q + 1] = fmaf(v.y, sc, cc); a[4 * q + 2] = fmaf(v.z, sc, cc); a[4 * q + 3] = fmaf(v.w, sc, cc);
+          }
+          uint32_t hi2[16], lo2[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
+            amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sk_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
+            sk_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
+          }
+        }
+        fence_proxy_async();                                         // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar_full(s));
+        if (++s == nst) { s = 0; ph ^= 1; }
+      }
+    }
+    if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_EPI_WARPS) {
     tc_epilogue_stream<EPI, true, F16>(p, tmem_base, bn, bar_dfull(0), bar_dempty(0), p.bias, 0, 0, warp - TC_EPI_WARP0, lane);
   }
@@ -1474,7 +1543,12 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   perm_bias_kernel<<<(unsigned)((wrows + 255) / 256), 256, 0, st>>>(bias_eff, bias_perm, lp.N, pl.bn, pl.bg, pl.nsplit, glu ? 1 : 0);
   EIGB_LAUNCH_CHECK("perm_bias_kernel");
   int* ovf = nullptr;
-  if (f16) {
+  static const bool rawa_off = getenv("EIGB200_STREAM_RAWA") != nullptr && atoi(getenv("EIGB200_STREAM_RAWA")) == 0;
+  const bool rawa = f16 && !rawa_off;                                // A converted on the SM (gemm_tc_stream_kernel<EPI, true, true>): no split pre-pass
+  if (f16 && rawa) {
+    ovf = overflow_flag_ptr();
+    if (!ovf) { set_error("tcgen05 GEMM: cannot resolve the overflow flag"); return EIGB200_ECUDA; }
+  } else if (f16) {
     ovf = overflow_flag_ptr();
     if (!ovf) { set_error("tcgen05 GEMM: cannot resolve the overflow flag"); return EIGB200_ECUDA; }
     const int64_t nq = lp.M * (kp64 / 4);
@@ -1490,8 +1564,13 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   CUtensorMap tAh, tAl, tWh, tWl;
   int rc;
   if (f16) {
-    if ((rc = make_tmap_f16(&tAh, a_hi, (uint64_t)lp.M, (uint64_t)kp64, TC_BM))) return rc;
-    if ((rc = make_tmap_f16(&tAl, a_lo, (uint64_t)lp.M, (uint64_t)kp64, TC_BM))) return rc;
+    if (rawa) {
+      if ((rc = make_tmap(&tAh, lp.A, (uint64_t)lp.M, (uint64_t)lp.K, (uint64_t)lp.lda, TC_BM))) return rc;
+      tAl = tAh;
+    } else {
+      if ((rc = make_tmap_f16(&tAh, a_hi, (uint64_t)lp.M, (uint64_t)kp64, TC_BM))) return rc;
+      if ((rc = make_tmap_f16(&tAl, a_lo, (uint64_t)lp.M, (uint64_t)kp64, TC_BM))) return rc;
+    }
     if ((rc = make_tmap_f16(&tWh, w_hi, wrows, (uint64_t)kp64, (uint32_t)pl.bn))) return rc;
     if ((rc = make_tmap_f16(&tWl, w_lo, wrows, (uint64_t)kp64, (uint32_t)pl.bn))) return rc;
   } else {
@@ -1505,12 +1584,16 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = f16 ? kp64 / 64 : pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
   p.workers = 1; p.zero = 0; p.out_scale = scal; p.ovf_flag = ovf;
+  if (rawa) p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats);
   p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
   const int64_t npairs = p.ntiles * p.nsplit;
   const unsigned grid = (unsigned)(npairs < (int64_t)num_sms() ? npairs : (int64_t)num_sms());
 #define SK_LAUNCH(EPI_)                                                                                                                \
   do {                                                                                                                                 \
-    if (f16) {                                                                                                                         \
+    if (f16 && rawa) {                                                                                                                 \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+      gemm_tc_stream_kernel<EPI_, true, true><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                              \
+    } else if (f16) {                                                                                                                  \
       EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));  \
       gemm_tc_stream_kernel<EPI_, true><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                                    \
     } else {                                                                                                                           \
