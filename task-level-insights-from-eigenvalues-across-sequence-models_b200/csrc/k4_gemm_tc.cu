@@ -1380,15 +1380,22 @@ static StreamPlan make_stream_plan(int N, int K, int epilogue) {
   if (glu) { pl.bg = 64; pl.bn = 128; }
   else { pl.bn = nout >= 128 ? 128 : (nout + 31) / 32 * 32; pl.bg = pl.bn; }
   {
-    // 256 accumulator columns per N tile: the A stage (32 KB per 64 K values) is then shared by twice the products -- 48 KB instead of 64 KB from L2 per
-    // 128 x 128 x 64 block, which is what bounds this kernel (the L2 slices deliver ~43 B per clock and SM, the tensor core wants 80 at 128 columns).
-    // Taken when the padded width does not grow by more than 1/8 (EIGB200_STREAM_BN=128 / 256 forces either).
+    // Wider N tiles: the A stage (32 KB per 64 K values, converted once per (row tile, N tile) pair) is shared by more products -- 48 instead of 64 KB from L2
+    // per 128 x 128 x 64 block at 256 columns, which is what bounds this kernel (the L2 slices deliver ~43 B per clock and SM, the tensor core wants 80 at 128
+    // columns).  Measured cost per PADDED output column at K = 512 (profiles/r2_stream_bn_sweep.txt): 1.00 / 0.88 / 0.76 at 128 / 192 / 256 columns; the plan
+    // takes the width with the smallest padded width x cost (N 552 -> 3 x 192, N 1544 -> 7 x 256, N 512 / GLU 1024 -> 2 / 4 x 256).  EIGB200_STREAM_BN forces one.
     static const char* force = getenv("EIGB200_STREAM_BN");
-    const int bg256 = glu ? 128 : 256;
-    const int pad128 = (nout + pl.bg - 1) / pl.bg * pl.bg, pad256 = (nout + bg256 - 1) / bg256 * bg256;
-    bool wide = nout >= bg256 && 8 * pad256 <= 9 * pad128;
-    if (force) wide = atoi(force) == 256 && nout >= bg256;
-    if (wide) { pl.bg = bg256; pl.bn = 256; }
+    const int widths[3] = {128, 192, 256};
+    const double cost[3] = {1.0, 0.88, 0.76};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+      const int bn = widths[i], bg = glu ? bn / 2 : bn;
+      if (nout < bg && i > 0) continue;
+      if (force && atoi(force) != bn && nout >= bg) continue;
+      if (!glu && i == 0 && nout < 128) { best = 0; break; }          // narrow outputs keep the rounded-up single tile chosen above
+      const double c = (double)((nout + bg - 1) / bg * bg) * cost[i];
+      if (c < best) { best = c; pl.bn = bn; pl.bg = bg; }
+    }
   }
   pl.nsplit = (nout + pl.bg - 1) / pl.bg;
   const size_t stage_bytes = 2 * (size_t)TC_CHUNK_BYTES + 2 * (size_t)pl.bn * 128;

@@ -419,7 +419,9 @@ def linear_prepare(weight, bias=None, epilogue="none", ln_gamma=None, ln_beta=No
     return ws
 
 
-K_SLABS = os.environ.get("EIGB200_K_SLABS", "1") != "0"          # narrow GEMMs with K > 256 as K slabs on the resident-weight kernel (see linear)
+# narrow GEMMs with K > 256 as K slabs on the resident-weight kernel (see linear): opt-in since the streamed-operand kernel converts A on the SM
+# (no split pre-pass): 0.229 ms against 0.305 ms for two slabs at the C h projection of C3 (262 144 x 128 x 512)
+K_SLABS = os.environ.get("EIGB200_K_SLABS", "0") == "1"
 
 
 def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", out=None, ldc=None, workspace=None, prepared=None):
@@ -441,8 +443,8 @@ def linear(a, weight, bias=None, epilogue="none", residual=None, mode="auto", ou
     if (K > 256 and N <= 128 and epilogue in ("none", "residual") and mode in ("auto", "f16x3", "tc3") and M >= 1024 and prepared is None
             and K_SLABS and a2.data_ptr() % 16 == 0 and lda % 4 == 0):
         # K in slabs of <= 256 columns through the RESIDENT-weight kernel, each slab accumulating onto the previous result through the residual epilogue:
-        # that kernel reads the raw fp32 rows by TMA (row stride lda) and splits them on the SM, where the streamed-operand kernel (K > 256) first writes and
-        # re-reads a split copy of A -- 3x the bytes of A, which is all this shape costs (the C h projection of LRU / S5: 0.48 -> 0.27 ms at C3).
+        # that kernel reads the raw fp32 rows by TMA (row stride lda) and splits them on the SM.  It beat the streamed-operand kernel while that one wrote and
+        # re-read a split copy of A (0.48 -> 0.27 ms at the C h projection of C3); the streamed kernel now converts on the SM too and is faster (0.23 ms).
         nsl = (K + 255) // 256
         step = ((K + nsl - 1) // nsl + 3) // 4 * 4
         acc = residual if epilogue == "residual" else None

@@ -254,6 +254,8 @@ CASES = {
     "lin_glu_f16": lambda: case_linear(M_C2, 256, 128, "glu_residual", "f16x3"),
     "lin_out_none_f16": lambda: case_linear(M_C2, 128, 128, "none", "f16x3"),
     "lin_glu_nores_f16": lambda: case_linear(M_C2, 256, 128, "glu_residual_nores", "f16x3"),
+    "lin_c5_qkv_f16": lambda: case_linear(262144, 1544, 512, "none", "f16x3"),
+    "lin_c5_out_f16": lambda: case_linear(262144, 512, 512, "residual", "f16x3"),
     "lin_c3_out": lambda: case_linear(262144, 128, 512, "residual", "auto"),
     "lin_c5_glu_tc3": lambda: case_linear(262144, 1024, 512, "glu_residual", "tc3"),
     "lin_c5_glu_f16": lambda: case_linear(262144, 1024, 512, "glu_residual", "f16x3"),
