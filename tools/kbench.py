@@ -233,6 +233,7 @@ CASES = {
     "conv_c5": lambda: case_conv(1024, 1024, 1536),
     "ssd_c2": lambda: case_ssd(4096),
     "ssd_small": lambda: case_ssd(512),
+    "ssd_c5": lambda: case_ssd(1024, T=1024, H=8, P=64),
     "ssd_c2_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(4096))[1],
     "ssd_small_tc": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "tc"), case_ssd(512))[1],
     "ssd_c2_scan": lambda: (os.environ.__setitem__("EIGB200_SSD_FORM", "scan"), case_ssd(4096))[1],
