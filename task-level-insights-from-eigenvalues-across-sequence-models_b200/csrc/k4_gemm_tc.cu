@@ -63,6 +63,7 @@ struct TcParams {
   // fp16-split operands (kind::f16, see "fp16 split" below): weight chunks of 64 K-values, activation pre-scale S_a (a power of two; folded into the
   // LayerNorm constants when there is one), 1 / (S_a S_w) for the epilogue (device scalar written by the weight preparation), sticky overflow flag
   int kch_w; float a_scale; const float* out_scale; int* ovf_flag;
+  int na_stages;     // streamed kernel with on-SM conversion: raw A boxes (16 KB) in the ring in front of the W stages
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -1072,22 +1073,29 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int bn = p.bn, kch = p.kchunks, nst = p.nstages;
   const uint32_t w_chunk_bytes = (uint32_t)bn * 128u;
-  const uint32_t stage_bytes = 2u * TC_CHUNK_BYTES + 2u * w_chunk_bytes;          // [A_hi 16K][A_lo 16K][W_hi][W_lo]
-  const uint32_t stage0 = base;
+  const uint32_t stage_bytes = RAWA ? 2u * w_chunk_bytes : 2u * TC_CHUNK_BYTES + 2u * w_chunk_bytes;   // [A_hi 16K][A_lo 16K][W_hi][W_lo]; RAWA: [W_hi][W_lo]
+  // RAWA: the raw A boxes (32 K columns, 16 KB) have their own, deeper ring in front of the W ring: a box goes TMA -> converters -> MMA, the weights only
+  // TMA -> MMA, and with both in one 96 KB stage (two stages at 256 columns) the conversion sat in the critical path (tensor pipe 55 %)
+  const int na = RAWA ? p.na_stages : 0;
+  const uint32_t aring = base;
+  const uint32_t stage0 = base + (uint32_t)na * TC_CHUNK_BYTES;
   const uint32_t bars = stage0 + nst * stage_bytes;
   auto bar_full = [&](int s) { return bars + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 8u * (SK_MAX_STAGES + s); };
   auto bar_dfull = [&](int j) { return bars + 8u * (2 * SK_MAX_STAGES + j); };
   auto bar_dempty = [&](int j) { return bars + 8u * (2 * SK_MAX_STAGES + 2 + j); };
   const uint32_t tmem_slot = bars + 8u * (2 * SK_MAX_STAGES + 4);
-  auto bar_raw = [&](int s) { return bars + 8u * (2 * SK_MAX_STAGES + 8 + s); };   // RAWA: TMA landed the raw stage (bar_full then = converted, 128 arrivals)
+  auto bar_araw = [&](int i) { return bars + 8u * (24 + i); };      // RAWA: TMA landed raw box i | converted (128 arrivals) | its MMAs retired
+  auto bar_afull = [&](int i) { return bars + 8u * (32 + i); };
+  auto bar_aempty = [&](int i) { return bars + 8u * (40 + i); };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (2 * bn <= 32) ? 32 : (2 * bn <= 64) ? 64 : (2 * bn <= 128) ? 128 : (2 * bn <= 256) ? 256 : 512;
   const int64_t npairs = p.ntiles * p.nsplit;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), RAWA ? 128 : 1); mbar_init(bar_empty(s), 1); if (RAWA) mbar_init(bar_raw(s), 1); }
+    for (int s = 0; s < nst; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int i = 0; i < na; ++i) { mbar_init(bar_araw(i), 1); mbar_init(bar_afull(i), 128); mbar_init(bar_aempty(i), 1); }
     for (int j = 0; j < 2; ++j) { mbar_init(bar_dfull(j), 1); mbar_init(bar_dempty(j), TC_EPI_WARPS * 32); }
     fence_barrier_init();
   }
@@ -1101,24 +1109,33 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
   if (warp == TC_TMA_WARP) {
     if (elect_one()) {
       int s = 0; uint32_t ph = 0;
+      int ai = 0; uint32_t aph = 0;
       for (int64_t it = blockIdx.x; it < npairs; it += gridDim.x) {
         const int64_t tile = it / p.nsplit;
         const int split = (int)(it - tile * p.nsplit);
         for (int c = 0; c < kch; ++c) {
-          mbar_wait_one(bar_empty(s), ph ^ 1);
-          const uint32_t st0 = stage0 + s * stage_bytes;
-          const uint32_t bar_land = RAWA ? bar_raw(s) : bar_full(s);
-          mbar_arrive_expect_tx(bar_land, stage_bytes);
           constexpr int KSTAGE = F16 ? 64 : TC_KC;                 // K values per 128-byte row
           if constexpr (RAWA) {                                    // two raw fp32 boxes: K columns [64 c, 64 c + 32) and [64 c + 32, 64 c + 64) (zero-filled beyond K)
-            tma_load_2d(&tmapAhi, bar_land, st0, c * KSTAGE, (int)(tile * TC_BM));
-            tma_load_2d(&tmapAhi, bar_land, st0 + TC_CHUNK_BYTES, c * KSTAGE + TC_KC, (int)(tile * TC_BM));
-          } else {
-            tma_load_2d(&tmapAhi, bar_land, st0, c * KSTAGE, (int)(tile * TC_BM));
-            tma_load_2d(&tmapAlo, bar_land, st0 + TC_CHUNK_BYTES, c * KSTAGE, (int)(tile * TC_BM));
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              mbar_wait_one(bar_aempty(ai), aph ^ 1);
+              mbar_arrive_expect_tx(bar_araw(ai), TC_CHUNK_BYTES);
+              tma_load_2d(&tmapAhi, bar_araw(ai), aring + (uint32_t)ai * TC_CHUNK_BYTES, c * KSTAGE + b * TC_KC, (int)(tile * TC_BM));
+              if (++ai == na) { ai = 0; aph ^= 1; }
+            }
           }
-          tma_load_2d(&tmapWhi, bar_land, st0 + 2 * TC_CHUNK_BYTES, c * KSTAGE, split * bn);
-          tma_load_2d(&tmapWlo, bar_land, st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * KSTAGE, split * bn);
+          mbar_wait_one(bar_empty(s), ph ^ 1);
+          const uint32_t st0 = stage0 + s * stage_bytes;
+          mbar_arrive_expect_tx(bar_full(s), stage_bytes);
+          if constexpr (RAWA) {
+            tma_load_2d(&tmapWhi, bar_full(s), st0, c * KSTAGE, split * bn);
+            tma_load_2d(&tmapWlo, bar_full(s), st0 + w_chunk_bytes, c * KSTAGE, split * bn);
+          } else {
+            tma_load_2d(&tmapAhi, bar_full(s), st0, c * KSTAGE, (int)(tile * TC_BM));
+            tma_load_2d(&tmapAlo, bar_full(s), st0 + TC_CHUNK_BYTES, c * KSTAGE, (int)(tile * TC_BM));
+            tma_load_2d(&tmapWhi, bar_full(s), st0 + 2 * TC_CHUNK_BYTES, c * KSTAGE, split * bn);
+            tma_load_2d(&tmapWlo, bar_full(s), st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes, c * KSTAGE, split * bn);
+          }
           if (++s == nst) { s = 0; ph ^= 1; }
         }
       }
@@ -1129,6 +1146,7 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
       const uint32_t idesc = F16 ? umma_idesc_f16(TC_BM, bn) : umma_idesc_tf32(TC_BM, bn);
       const bool three = p.nterms == 3;
       int s = 0; uint32_t ph = 0;
+      int ai = 0; uint32_t aph = 0;
       int j = 0; uint32_t dph = 0;
       for (int64_t it = blockIdx.x; it < npairs; it += gridDim.x) {
         mbar_wait_one(bar_dempty(j), dph ^ 1);
@@ -1138,16 +1156,29 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
           mbar_wait_one(bar_full(s), ph);
           tc_fence_after();
           const uint32_t st0 = stage0 + s * stage_bytes;
+          if constexpr (F16 && RAWA) {
+            const uint64_t dbh0 = umma_desc_k_sw128(st0), dbl0 = umma_desc_k_sw128(st0 + w_chunk_bytes);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {                            // box b: [hi K steps 0, 1 | lo K steps 0, 1] of K values [64 c + 32 b, + 32)
+              mbar_wait_one(bar_afull(ai), aph);
+              tc_fence_after();
+              const uint64_t da = umma_desc_k_sw128(aring + (uint32_t)ai * TC_CHUNK_BYTES);
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const uint32_t k = 2u * b + jj;
+                umma_f16_ss(d_tmem, da + 2u * jj, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ss(d_tmem, da + 2u * jj, dbl0 + 2u * k, idesc, 1u);
+                umma_f16_ss(d_tmem, da + 4u + 2u * jj, dbh0 + 2u * k, idesc, 1u);
+              }
+              umma_commit(bar_aempty(ai));
+              if (++ai == na) { ai = 0; aph ^= 1; }
+            }
+          } else {
           const uint64_t dah0 = umma_desc_k_sw128(st0), dal0 = umma_desc_k_sw128(st0 + TC_CHUNK_BYTES);
           const uint64_t dbh0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES), dbl0 = umma_desc_k_sw128(st0 + 2 * TC_CHUNK_BYTES + w_chunk_bytes);
 #pragma unroll
           for (int k = 0; k < TC_KC / 8; ++k) {                      // 4 K steps of 32 bytes per stage row in either precision
-            if constexpr (F16 && RAWA) {                             // box k / 2 holds [hi K steps 0, 1 | lo K steps 0, 1] of its 32 K values
-              const uint64_t ah = (k < 2 ? dah0 : dal0) + 2u * (k & 1), al = ah + 4u;
-              umma_f16_ss(d_tmem, ah, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
-              umma_f16_ss(d_tmem, ah, dbl0 + 2u * k, idesc, 1u);
-              umma_f16_ss(d_tmem, al, dbh0 + 2u * k, idesc, 1u);
-            } else if constexpr (F16) {
+            if constexpr (F16) {
               umma_f16_ss(d_tmem, dah0 + 2u * k, dbh0 + 2u * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
               if (three) {
                 umma_f16_ss(d_tmem, dah0 + 2u * k, dbl0 + 2u * k, idesc, 1u);
@@ -1160,6 +1191,7 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
                 umma_tf32(d_tmem, dal0 + 2u * k, dbh0 + 2u * k, idesc, 1u);
               }
             }
+          }
           }
           umma_commit(bar_empty(s));
           if (c == kch - 1) umma_commit(bar_dfull(j));
@@ -1175,41 +1207,37 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
     const int sw = r & 7;
     const float S_a = p.ln_stats ? 1024.f : 16.f;                    // activation pre-scale (split_a_f16_kernel's)
     float amax = 0.f;
-    int s = 0; uint32_t ph = 0;
+    int ai = 0; uint32_t aph = 0;
     for (int64_t it = blockIdx.x; it < npairs; it += gridDim.x) {
       const int64_t tile = it / p.nsplit;
       const int64_t m = tile * TC_BM + r;
       float sc = S_a, cc = 0.f;
       if (p.ln_stats && m < p.M) { const float2 stt = __ldg(p.ln_stats + m); sc = stt.y * S_a; cc = -stt.x * stt.y * S_a; }
-      for (int c = 0; c < kch; ++c) {
-        const uint32_t st0 = stage0 + s * stage_bytes;
-        mbar_wait(bar_raw(s), ph);
+      for (int cb = 0; cb < 2 * kch; ++cb) {                         // raw boxes in K order
+        const uint32_t row = aring + (uint32_t)ai * TC_CHUNK_BYTES + (uint32_t)r * 128u;
+        mbar_wait(bar_araw(ai), aph);
+        float a[32];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const uint32_t row = st0 + (uint32_t)b * TC_CHUNK_BYTES + (uint32_t)r * 128u;
-          float a[32];
+        for (int q = 0; q < 8; ++q) {                                // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+          const float4 v = sk_lds_f4(row + (uint32_t)((q ^ sw) * 16));
+          a[4 * q] = fmaf(v.x, sc, cc); a[4 * q + 1] = fmaf(v.y, sc, cc); a[4 * q + 2] = fmaf(v.z, sc, cc); a[4 * q + 3] = fmaf(v.w, sc, cc);
+        }
+        uint32_t hi2[16], lo2[16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {                              // logical 16-byte slot q sits at physical slot q ^ (row & 7)
-            const float4 v = sk_lds_f4(row + (uint32_t)((q ^ sw) * 16));
-            a[4 * q] = fmaf(v.x, sc, cc); a[4 * q + 1] = fmaf(v.y, sc, cc); a[4 * q + 2] = fmaf(v.z, sc, cc); a[4 * q + 3] = fmaf(v.w, sc, cc);
-          }
-          uint32_t hi2[16], lo2[16];
+        for (int e = 0; e < 16; ++e) {
+          hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
+          amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
+        }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
-            amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
-          }
+        for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
 #pragma unroll
-          for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sk_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
-            sk_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          sk_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
+          sk_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
         }
         fence_proxy_async();                                         // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(bar_full(s));
-        if (++s == nst) { s = 0; ph ^= 1; }
+        mbar_arrive(bar_afull(ai));
+        if (++ai == na) { ai = 0; aph ^= 1; }
       }
     }
     if (!(amax <= 65504.f)) atomicOr(p.ovf_flag, 1);
@@ -1591,15 +1619,25 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   p.bn = pl.bn; p.bg = pl.bg; p.nsplit = pl.nsplit; p.kchunks = f16 ? kp64 / 64 : pl.kchunks; p.nstages = pl.nstages; p.nterms = nterms;
   p.ntiles = (lp.M + TC_BM - 1) / TC_BM;
   p.workers = 1; p.zero = 0; p.out_scale = scal; p.ovf_flag = ovf;
-  if (rawa) p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats);
+  size_t smem_bytes = pl.smem;
+  if (rawa) {                                                        // separate rings: raw A boxes (16 KB each) in front of the [W hi | W lo] stages
+    p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats);
+    const size_t wstage = 2 * (size_t)pl.bn * 128;
+    const int nw = pl.bn <= 128 ? 3 : 2;
+    int na = (int)((TC_SMEM_LIMIT - 2048 - nw * wstage) / TC_CHUNK_BYTES);
+    if (na > 8) na = 8;
+    if (na < 2) { set_error("tcgen05 GEMM: no room for the raw A ring (bn %d)", pl.bn); return EIGB200_EUNSUPPORTED; }
+    p.nstages = nw; p.na_stages = na;
+    smem_bytes = (size_t)na * TC_CHUNK_BYTES + nw * wstage + 1024 /*alignment*/ + 1024 /*barriers*/;
+  }
   p.r_v8 = (lp.R && (((uintptr_t)lp.R & 31) == 0) && lp.ldr % 8 == 0) ? 1 : 0;
   const int64_t npairs = p.ntiles * p.nsplit;
   const unsigned grid = (unsigned)(npairs < (int64_t)num_sms() ? npairs : (int64_t)num_sms());
 #define SK_LAUNCH(EPI_)                                                                                                                \
   do {                                                                                                                                 \
     if (f16 && rawa) {                                                                                                                 \
-      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-      gemm_tc_stream_kernel<EPI_, true, true><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                              \
+      EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+      gemm_tc_stream_kernel<EPI_, true, true><<<grid, TC_THREADS, smem_bytes, st>>>(tAh, tAl, tWh, tWl, p);                           \
     } else if (f16) {                                                                                                                  \
       EIGB_CUDA(cudaFuncSetAttribute(gemm_tc_stream_kernel<EPI_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));  \
       gemm_tc_stream_kernel<EPI_, true><<<grid, TC_THREADS, pl.smem, st>>>(tAh, tAl, tWh, tWl, p);                                    \
