@@ -1216,6 +1216,7 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
       for (int cb = 0; cb < 2 * kch; ++cb) {                         // raw boxes in K order
         const uint32_t row = aring + (uint32_t)ai * TC_CHUNK_BYTES + (uint32_t)r * 128u;
         mbar_wait(bar_araw(ai), aph);
+#ifndef SK_ABL_CONV                                                  // timing-only ablation: operands left as raw bytes (wrong results)
         float a[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {                                // logical 16-byte slot q sits at physical slot q ^ (row & 7)
@@ -1235,6 +1236,7 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
           sk_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
           sk_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
         }
+#endif
         fence_proxy_async();                                         // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar_afull(ai));
         if (++ai == na) { ai = 0; aph ^= 1; }
@@ -1623,7 +1625,8 @@ static int launch_linear_stream(cudaStream_t st, const LinearParams& lp, int nte
   if (rawa) {                                                        // separate rings: raw A boxes (16 KB each) in front of the [W hi | W lo] stages
     p.ln_stats = reinterpret_cast<const float2*>(lp.ln_stats);
     const size_t wstage = 2 * (size_t)pl.bn * 128;
-    const int nw = pl.bn <= 128 ? 3 : 2;
+    int nw = pl.bn <= 128 ? 3 : 2;
+    if (const char* e = getenv("EIGB200_STREAM_NW")) { const int v = atoi(e); if (v >= 2 && v <= SK_MAX_STAGES) nw = v; }   // experiment hook
     int na = (int)((TC_SMEM_LIMIT - 2048 - nw * wstage) / TC_CHUNK_BYTES);
     if (na > 8) na = 8;
     if (na < 2) { set_error("tcgen05 GEMM: no room for the raw A ring (bn %d)", pl.bn); return EIGB200_EUNSUPPORTED; }
