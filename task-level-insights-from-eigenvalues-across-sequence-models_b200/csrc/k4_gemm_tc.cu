@@ -1217,25 +1217,31 @@ gemm_tc_stream_kernel(const __grid_constant__ CUtensorMap tmapAhi, const __grid_
         const uint32_t row = aring + (uint32_t)ai * TC_CHUNK_BYTES + (uint32_t)r * 128u;
         mbar_wait(bar_araw(ai), aph);
 #ifndef SK_ABL_CONV                                                  // timing-only ablation: operands left as raw bytes (wrong results)
-        float a[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {                                // logical 16-byte slot q sits at physical slot q ^ (row & 7)
-          const float4 v = sk_lds_f4(row + (uint32_t)((q ^ sw) * 16));
-          a[4 * q] = fmaf(v.x, sc, cc); a[4 * q + 1] = fmaf(v.y, sc, cc); a[4 * q + 2] = fmaf(v.z, sc, cc); a[4 * q + 3] = fmaf(v.w, sc, cc);
-        }
+        // two half rows (16 values each): every slot is read before it is overwritten -- hi goes to logical slots 0-3, lo to 4-7 -- and the live set stays
+        // at 48 registers (the whole row at once spilled under this kernel's 80-register cap)
         uint32_t hi2[16], lo2[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          hi2[e] = pack_f16x2(a[2 * e], a[2 * e + 1]);
-          amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
+        for (int hf = 0; hf < 2; ++hf) {
+          float a[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                              // logical 16-byte slot q sits at physical slot q ^ (row & 7)
+            const float4 v = sk_lds_f4(row + (uint32_t)(((4 * hf + q) ^ sw) * 16));
+            a[4 * q] = fmaf(v.x, sc, cc); a[4 * q + 1] = fmaf(v.y, sc, cc); a[4 * q + 2] = fmaf(v.z, sc, cc); a[4 * q + 3] = fmaf(v.w, sc, cc);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t h = pack_f16x2(a[2 * e], a[2 * e + 1]);
+            hi2[8 * hf + e] = h;
+            amax = fmaxf(amax, fmaxf(fabsf(a[2 * e]), fabsf(a[2 * e + 1])));
+            lo2[8 * hf + e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(h), a[2 * e + 1] - f16_hi_to_f32(h));
+          }
+          if (hf == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sk_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
+          }
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) lo2[e] = pack_f16x2(a[2 * e] - f16_lo_to_f32(hi2[e]), a[2 * e + 1] - f16_hi_to_f32(hi2[e]));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sk_sts_u4(row + (uint32_t)((j ^ sw) * 16), hi2[4 * j], hi2[4 * j + 1], hi2[4 * j + 2], hi2[4 * j + 3]);
-          sk_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
-        }
+        for (int j = 0; j < 4; ++j) sk_sts_u4(row + (uint32_t)(((4 + j) ^ sw) * 16), lo2[4 * j], lo2[4 * j + 1], lo2[4 * j + 2], lo2[4 * j + 3]);
 #endif
         fence_proxy_async();                                         // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar_afull(ai));

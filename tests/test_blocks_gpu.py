@@ -353,6 +353,22 @@ def test_linear_tcgen05_streamed_operands(ops, M, N, K, epi, mode):
     assert np.abs(out[:, :nout] - ref).max() <= 6e-6 * np.abs(ref).max() * max(1.0, K / 256)
 
 
+@pytest.mark.parametrize("mode", ["tc3", "f16x3"])
+def test_linear_streamed_strided_input(ops, mode):
+    """K > 256 on a column slice of a wider buffer (row stride 600): the fp16-split form reads the raw fp32 rows by TMA with that stride and converts them on the SM
+    (gemm_tc_stream_kernel<EPI, true, true>); rows beyond M and columns beyond K are zero-filled by the tensor map."""
+    rng = np.random.default_rng(11)
+    M, N, K = 3001, 200, 324
+    big = rng.normal(size=(M, 600)).astype(np.float32)
+    w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32); bias = rng.normal(size=N).astype(np.float32)
+    r = rng.normal(size=(M, N)).astype(np.float32)
+    a = dev(big)[:, 8:8 + K]
+    out = ops.linear(a, dev(w), dev(bias), epilogue="residual", residual=dev(r), mode=mode).cpu().numpy()
+    assert not ops.gemm_overflow()
+    ref = _lin_ref(big[:, 8:8 + K], w, bias, "residual", r.astype(np.float64))
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
+
+
 @pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
 def test_linear_ln_streamed_operands(ops, prec):
     ops.set_gemm_precision(prec)
