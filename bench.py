@@ -598,6 +598,7 @@ def run_other(args, rank, local, world):
             "e2e": {"value": wl.units * world * args.steps / (e2e_ms * 1e-3), "unit": wl.unit, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": wl.h2d * world, "d2h_bytes_per_step": wl.d2h * world, "mode": "serial copy-pass-copy"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
+    line["runtime"] = {"launch": getattr(wl, "launch", "eager: one C-ABI call per kernel from Python")}
     if not args.no_cpu_baseline and world == 1:
         threads = len(os.sched_getaffinity(0))
         u, s = wl.cpu(WL.CPU_SAMPLE[kind], threads)

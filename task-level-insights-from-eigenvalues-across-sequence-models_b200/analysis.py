@@ -156,6 +156,37 @@ class MambaPassGraph:
         return self.result
 
 
+class TransformerPassGraph:
+    """transformer_pass captured as a CUDA graph, as MambaPassGraph: a small analysis batch (the reference's C1 run: 8 sequences x 64 tokens, 17 kernels of a few
+    microseconds each) is bound by launch latency and host work between the kernels, not by the device; one replay removes both.  run(X) copies the token ids
+    into the static input and replays; the returned PassResult is overwritten by the next run()."""
+
+    def __init__(self, model: "Ly.TransformerDev", X_example, cfg, want_eig=True, compare="float64", warmup=2):
+        if not X_example.is_cuda:
+            raise L.Eigb200Error("TransformerPassGraph: the example batch must live on the CUDA device")
+        self.X = X_example.clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):                       # first calls set function attributes / fill caches: outside the capture
+                transformer_pass(model, self.X, cfg, want_eig=want_eig, compare=compare)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = ops.LAUNCHES["n"]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = transformer_pass(model, self.X, cfg, want_eig=want_eig, compare=compare)
+        self.launches_per_run = ops.LAUNCHES["n"] - n0
+
+    def run(self, X=None) -> PassResult:
+        if X is not None:
+            self.X.copy_(X, non_blocking=True)
+        self.graph.replay()
+        ops.LAUNCHES["n"] += self.launches_per_run
+        return self.result
+
+
 def transformer_pass(model: "Ly.TransformerDev", X, cfg, want_eig=True, compare="float64") -> PassResult:
     """eval_eig.py:528-564 / :627-663."""
     x = model.encoder(X)

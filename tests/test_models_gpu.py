@@ -334,3 +334,27 @@ def test_fp16_split_range_fallback(eig):
     ocfg = dict(num_layers=2, d_inner=128, ngroups=1, d_state=16, nheads=1, headdim=128, prenorm=True)
     ref, _ = O.mamba_eval_pass(X.cpu().numpy(), {k: v.numpy() for k, v in sd.items()}, ocfg, np.float64)
     assert_eig_close(res.eig_host(), ref, rtol=3e-5)
+
+
+@pytest.mark.gpu
+def test_transformer_pass_graph_equals_eager():
+    """TransformerPassGraph (the launch-bound C1 batch replayed as one CUDA graph) returns exactly what the eager pass returns, also for a new batch of ids."""
+    import json
+    import torch
+    import eigb200.analysis as A
+    import eigb200.layers as Ly
+    from conftest import load_golden
+    g = load_golden("c1_linattn_mqar")
+    cfg = json.loads(bytes(g["cfg_json"]).decode())
+    sd = Ly.init_transformer_state_dict(cfg, 1919)
+    model = Ly.TransformerDev(cfg, sd, "cuda")
+    gen = torch.Generator().manual_seed(3)
+    X0 = torch.randint(0, cfg["vocab_size"], (8, 64), generator=gen).cuda()
+    X1 = torch.randint(0, cfg["vocab_size"], (8, 64), generator=gen).cuda()
+    pg = A.TransformerPassGraph(model, X0, cfg)
+    for X in (X0, X1, X0):
+        ref = A.transformer_pass(model, X, cfg)
+        res = pg.run(X)
+        torch.cuda.synchronize()
+        assert torch.equal(res.eig, ref.eig) and torch.equal(res.counts, ref.counts)
+
