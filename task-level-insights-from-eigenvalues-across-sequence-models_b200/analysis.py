@@ -156,6 +156,36 @@ class MambaPassGraph:
         return self.result
 
 
+class PassGraph:
+    """Any stream-ordered pass `fn(X) -> result` over a batch of fixed shape (the LRU / S5 layer stack with its eigenvalue counts, a user's own composition of
+    the layer calls) captured as a CUDA graph: run(X) copies X into the static input and replays; the returned result is overwritten by the next run()."""
+
+    def __init__(self, fn, X_example, warmup=2):
+        if not X_example.is_cuda:
+            raise L.Eigb200Error("PassGraph: the example batch must live on the CUDA device")
+        self.X = X_example.clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):                       # first calls set function attributes / fill caches: outside the capture
+                fn(self.X)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = ops.LAUNCHES["n"]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fn(self.X)
+        self.launches_per_run = ops.LAUNCHES["n"] - n0
+
+    def run(self, X=None):
+        if X is not None:
+            self.X.copy_(X, non_blocking=True)
+        self.graph.replay()
+        ops.LAUNCHES["n"] += self.launches_per_run
+        return self.result
+
+
 class TransformerPassGraph:
     """transformer_pass captured as a CUDA graph, as MambaPassGraph: a small analysis batch (the reference's C1 run: 8 sequences x 64 tokens, 17 kernels of a few
     microseconds each) is bound by launch latency and host work between the kernels, not by the device; one replay removes both.  run(X) copies the token ids

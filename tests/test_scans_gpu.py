@@ -157,3 +157,35 @@ def test_mamba_conv_ssd_tcgen05_form(ops, monkeypatch, B, T, H, G, kconv):
     assert (np.abs(y[sel].reshape(len(sel), T, H, P) - ref) <= 1e-5 * scale + 1e-6).all()
     sc2 = np.abs(y_scan).reshape(B, T, H * P).max(axis=1, keepdims=True)
     assert (np.abs(y - y_scan) <= 2e-5 * sc2 + 1e-6).all()
+
+
+@pytest.mark.gpu
+def test_pass_graph_lru_stack_equals_eager():
+    """analysis.PassGraph: two LRU layer calls captured as one CUDA graph return exactly the eager result, also for a new input."""
+    import torch
+    import eigb200.analysis as A
+    import eigb200.ssm as S
+    rng = np.random.default_rng(5)
+    P, Hd, B, T = 64, 32, 16, 96
+    def mk():
+        return {"nu_log": torch.from_numpy(np.log(-np.log(rng.uniform(0.8, 0.99, P))).astype(np.float32)).cuda(),
+                "theta_log": torch.from_numpy(np.log(rng.uniform(0.01, 3.0, P)).astype(np.float32)).cuda(),
+                "gamma_log": torch.from_numpy(rng.normal(-1, 0.2, P).astype(np.float32)).cuda(),
+                "B_re": torch.from_numpy((rng.normal(size=(P, Hd)) / np.sqrt(2 * Hd)).astype(np.float32)).cuda(),
+                "B_im": torch.from_numpy((rng.normal(size=(P, Hd)) / np.sqrt(2 * Hd)).astype(np.float32)).cuda(),
+                "C_re": torch.from_numpy((rng.normal(size=(Hd, P)) / np.sqrt(P)).astype(np.float32)).cuda(),
+                "C_im": torch.from_numpy((rng.normal(size=(Hd, P)) / np.sqrt(P)).astype(np.float32)).cuda(),
+                "D": torch.from_numpy(rng.normal(size=Hd).astype(np.float32)).cuda()}
+    layers = [mk(), mk()]
+    def fn(u):
+        for p in layers:
+            u = S.lru_forward(p, u)
+        return u
+    u0 = torch.randn(B, T, Hd, device="cuda"); u1 = torch.randn(B, T, Hd, device="cuda")
+    pg = A.PassGraph(fn, u0)
+    for u in (u0, u1, u0):
+        ref = fn(u)
+        out = pg.run(u)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+

@@ -217,12 +217,24 @@ class DiagSsmWorkload(_Base):
         _, counts = ops.ratio_hist(rad, L.RATIO_NONE, want_out=False)
         return lam, counts
 
-    def step(self, u=None):
+    def _pass(self, x):
         import eigb200.ssm as S
         lam, counts = self._eigs()
-        x = self.u if u is None else u
         for p in self.params:
             x = S.lru_forward(p, x) if self.layer == "lru" else S.s5_forward(p, x)
+        return x, lam, counts
+
+    def step(self, u=None):
+        import eigb200.analysis as A
+        import eigb200.ops as ops
+        # one CUDA graph per pass (37 launches of 70 - 200 us each: the launch gaps are 8 % of the eager pass); the per-kernel profile needs eager launches
+        if ops.PROFILE is None and os.environ.get("EIGB200_BENCH_GRAPH", "1") != "0":
+            if getattr(self, "_graph", None) is None:
+                self._graph = A.PassGraph(self._pass, self.u)
+                self.launch = "cuda-graph replay (one launch per pass)"
+            x, lam, counts = self._graph.run(u)
+        else:
+            x, lam, counts = self._pass(self.u if u is None else u)
         self.last = (lam, counts)
         return x
 
