@@ -16,7 +16,10 @@ WANT = [("k1_row8_kernel", r"k1_row8_kernel<"), ("k1_partials_kernel", r"k1_part
         ("diag_scan_kernel", r"diag_scan_kernel"), ("eigvals_kernel", r"eigvals_kernel"), ("dplr_abar_kernel", r"dplr_abar"),
         ("gemm_tc_ts_kernel_inproj_f16", r"gemm_tc_ts_kernel<0, false, 4, true>"),
         ("gemm_tc_ts_kernel_glu_tf32", r"gemm_tc_ts_kernel<2, false, 4, false>"),
-        ("gemm_out_glu_kernel", r"gemm_out_glu_kernel"), ("mamba_front_kernel", r"mamba_front_kernel<true>"), ("gemm_tc_stream_kernel", r"gemm_tc_stream_kernel<0>"),
+        ("gemm_out_glu_kernel", r"gemm_out_glu_kernel"), ("mamba_front_kernel", r"mamba_front_kernel<true>"), ("gemm_tc_stream_kernel", r"gemm_tc_stream_kernel<0, false"),
+        ("gemm_tc_stream_kernel_glu_f16_rawa", r"gemm_tc_stream_kernel<2, true, true>"), ("linattn_mma_kernel", r"linattn_mma_kernel<false>"),
+        ("linattn_mma_kernel_conv", r"linattn_mma_kernel<true>"), ("diag_scan_kernel_pipelined", r"diag_scan_kernel<1, 0, 32, true>"),
+        ("embedding128_kernel", r"embedding128_kernel"),
         ("embedding_kernel", r"embedding_kernel<8>"), ("count_moments_kernel", r"count_moments_kernel"), ("ratio_hist_kernel", r"ratio_hist_kernel"),
         ("linattn_forward_col_kernel", r"linattn_forward_col_kernel<64>"), ("softmax_nu_kernel", r"softmax_nu_kernel")]
 KEY = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "ELECT", "LDGSTS", "HMMA", "FFMA", "DFMA", "MUFU", "LDG", "STG", "LDS", "STS", "ATOM", "RED", "SHFL"]
