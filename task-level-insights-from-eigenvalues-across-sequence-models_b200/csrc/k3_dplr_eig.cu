@@ -154,33 +154,47 @@ __device__ void warp_eigvals(cd* H, cd* vec, double* rc, int n, int ld, int lane
     for (int i = lane; i <= en; i += 32) HH(i, i) = csub(HH(i, i), sh);
     t = cadd(t, sh);
     __syncwarp();
-    // row pass: H <- G_k H, k = l .. en-1 (columns k .. en)
-    for (int k = l; k < en; ++k) {
-      const cd a = HH(k, k), b = HH(k + 1, k);
-      const double aa = cabsd(a), ab = cabsd(b);
-      const double r = hypot(aa, ab);
+    // H <- G_{en-1} .. G_l H G_l^H .. G_{en-1}^H.  EISPACK runs a row pass (H <- G_k H, columns k .. en) and then a column pass (H <- H G_k^H, rows
+    // l .. min(k+1, en)); here step k does the row rotation G_k AND the column rotation G_{k-2}^H: the two touch disjoint elements (columns >= k against
+    // columns k-2, k-1), rows <= k-1 have seen all their row rotations by then, and every element still receives its updates in EISPACK's order, so the
+    // results are bit-identical -- but the serial chain is half as long, and the column update's loads run under the hypot / divisions of the next rotation.
+    for (int k = l; k < en + 2; ++k) {
+      const bool do_row = k < en;
       double cth = 1.0; cd sn = cmk(0.0, 0.0);
-      if (r != 0.0) {
-        if (aa == 0.0) { cth = 0.0; sn = cscale(cconj(b), 1.0 / ab); }
-        else { cth = aa / r; sn = cscale(cmulc(cscale(a, 1.0 / aa), b), 1.0 / r); }      // (a/|a|) conj(b) / r
+      if (do_row) {
+        // c = |a| / r, s = (a / |a|) conj(b) / r, r = sqrt(|a|^2 + |b|^2): the step's serial chain.  Two independent rsqrt (|a|^2 and r^2) and products
+        // instead of three hypot and three divisions (~500 -> ~100 cycles per step); the squares cannot leave the double range for a balanced matrix whose
+        // negligible subdiagonals have been deflated (|.| >= eps * local scale), and (c, s) are unitary to rounding as before.
+        const cd a = HH(k, k), b = HH(k + 1, k);
+        const double aa2 = cabs2(a), ab2 = cabs2(b);
+        const double r2 = aa2 + ab2;
+        if (r2 != 0.0) {
+          if (aa2 == 0.0) { cth = 0.0; sn = cscale(cconj(b), rsqrt(ab2)); }
+          else {
+            const double ia = rsqrt(aa2), ir = rsqrt(r2);
+            cth = aa2 * ia * ir;                                                           // |a| / r
+            sn = cscale(cmulc(a, b), ia * ir);                                             // a conj(b) / (|a| r)
+          }
+        }
       }
       __syncwarp();                                          // everyone has read a, b before they are overwritten
-      for (int j = k + lane; j <= en; j += 32) {
-        const cd top = HH(k, j), bot = HH(k + 1, j);
-        HH(k, j) = cadd(cscale(top, cth), cmul(sn, bot));
-        HH(k + 1, j) = j == k ? cmk(0.0, 0.0) : csub(cscale(bot, cth), cmul(cconj(sn), top));
+      if (do_row) {
+        for (int j = k + lane; j <= en; j += 32) {
+          const cd top = HH(k, j), bot = HH(k + 1, j);
+          HH(k, j) = cadd(cscale(top, cth), cmul(sn, bot));
+          HH(k + 1, j) = j == k ? cmk(0.0, 0.0) : csub(cscale(bot, cth), cmul(cconj(sn), top));
+        }
+        if (lane == 0) { rc[k] = cth; vec[k] = sn; }
       }
-      if (lane == 0) { rc[k] = cth; vec[k] = sn; }
-      __syncwarp();
-    }
-    // column pass: H <- H G_k^H (rows l .. min(k+1, en))
-    for (int k = l; k < en; ++k) {
-      const double cth = rc[k]; const cd sn = vec[k];
-      const int hi = min(k + 1, en);
-      for (int i = l + lane; i <= hi; i += 32) {
-        const cd c0 = HH(i, k), c1 = HH(i, k + 1);
-        HH(i, k) = cadd(cscale(c0, cth), cmul(cconj(sn), c1));
-        HH(i, k + 1) = csub(cscale(c1, cth), cmul(sn, c0));
+      const int kc = k - 2;
+      if (kc >= l) {                                         // column rotation kc: its (c, s) were stored two steps ago
+        const double c2 = rc[kc]; const cd s2 = vec[kc];
+        const int hi = min(kc + 1, en);
+        for (int i = l + lane; i <= hi; i += 32) {
+          const cd c0 = HH(i, kc), c1 = HH(i, kc + 1);
+          HH(i, kc) = cadd(cscale(c0, c2), cmul(cconj(s2), c1));
+          HH(i, kc + 1) = csub(cscale(c1, c2), cmul(s2, c0));
+        }
       }
       __syncwarp();
     }
@@ -266,11 +280,10 @@ extern "C" int eigb200_eigvals_c64(void* stream, float* d_A, int64_t nmat, int N
   const size_t per_warp = (((size_t)N * (N + 1) + N) * sizeof(double2) + (size_t)N * sizeof(double) + 15) & ~(size_t)15;
   cudaStream_t st = (cudaStream_t)stream;
   // warps per CTA: as many matrices as fit in ~200 KB of shared memory, at most 8
-  int wpb = (int)((200 * 1024) / per_warp);
+  int wpb = (int)((224 * 1024) / per_warp);
   if (wpb > 8) wpb = 8;
   if (wpb >= 4 && wpb < 8) wpb = 4;
-  if (wpb == 3) wpb = 2;
-  if (wpb < 1) wpb = 1;
+  if (wpb < 1) wpb = 1;                                              // N = 64: 3 matrices (3 x 66.5 KB) per SM -- the solver is latency-bound, every resident warp counts
   const size_t smem = per_warp * wpb;
   int64_t grid = (nmat + wpb - 1) / wpb;
   const int64_t cap = (int64_t)num_sms() * 4;
@@ -280,7 +293,7 @@ extern "C" int eigb200_eigvals_c64(void* stream, float* d_A, int64_t nmat, int N
     if (smem > 48 * 1024) EIGB_CUDA(cudaFuncSetAttribute(eigvals_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     eigvals_kernel<W_><<<(unsigned)grid, W_ * 32, smem, st>>>((const float2*)d_A, nmat, N, (float2*)d_eig, d_info);       \
   } while (0)
-  switch (wpb) { case 8: EIG_LAUNCH(8); break; case 4: EIG_LAUNCH(4); break; case 2: EIG_LAUNCH(2); break; default: EIG_LAUNCH(1); break; }
+  switch (wpb) { case 8: EIG_LAUNCH(8); break; case 4: EIG_LAUNCH(4); break; case 3: EIG_LAUNCH(3); break; case 2: EIG_LAUNCH(2); break; default: EIG_LAUNCH(1); break; }
 #undef EIG_LAUNCH
   EIGB_LAUNCH_CHECK("eigvals_kernel");
   return EIGB200_OK;
