@@ -260,6 +260,10 @@ class AttentionDev:
             lo = self.d_model + 2 * self.d_qk
             self.W_n = self.Wvqkn.weight[lo:lo + self.num_heads].contiguous()
             self.b_n = self.Wvqkn.bias[lo:lo + self.num_heads].contiguous()
+            # the layer forward projects only [v | q | k]: the H gate columns come from eigb200_normattn_gate (fp32 dot products, the extractor's arithmetic), so
+            # the GEMM drops them -- at C5 that is N = 1536 = 6 tiles of 256 columns instead of 1544 = 7 tiles (one of them 97 % padding)
+            self.W_vqk = self.Wvqkn.weight[:lo].contiguous()
+            self.b_vqk = self.Wvqkn.bias[:lo].contiguous() if self.Wvqkn.bias is not None else None
         elif self.kind in ("lin-attention", "sm-attention"):
             self.Wqkv = _Lin(_dev(sd, prefix + "Wqkv.weight", device), _dev(sd, prefix + "Wqkv.bias", device))
             self.W_qk = self.Wqkv.weight[: 2 * self.d_qk].contiguous()
@@ -299,12 +303,12 @@ class AttentionDev:
                     buf = self._conv(buf, ld, 0, ld if self.conv_type == "full" else 2 * dqk, B, T)
                 ctx = ops.linattn_forward(buf, ld, 0, dqk, 2 * dqk, B, T, H, d, dv, phi_elu=True, normalise=True)
         elif self.kind == "norm-attention":
-            ld = D + 2 * dqk + H
-            buf = ops.linear(xn, self.Wvqkn.weight, self.Wvqkn.bias)
+            ld = D + 2 * dqk
+            buf = ops.linear(xn, self.W_vqk, self.b_vqk)
             gate = ops.normattn_gate(xn, self.W_n, self.b_n, self.inner_attn.offset, self.norm_fn)
             kscale = 1.0 / math.sqrt(d) if self.scale_B else 1.0
             if self.conv_w is not None and self._fuse_conv(buf, ld, D, D + dqk, 0, H, d, dv):
-                # buffer columns [v | q | k | n]; "full": conv channel = column, else the conv covers q, k only (channel = column - D)
+                # buffer columns [v | q | k]; "full": conv channel = column, else the conv covers q, k only (channel = column - D)
                 full = self.conv_type == "full"
                 ctx = ops.linattn_forward_conv(buf, ld, D, D + dqk, 0, B, T, H, d, dv, self.conv_w, self.conv_b,
                                                D if full else 0, D + dqk if full else dqk, 0 if full else -1,
